@@ -1,0 +1,199 @@
+/*
+ * pz_b200.h -- C ABI of the B200-native `PiZero.infer_action` hot path.
+ *
+ * The reference (shroglck/open-pi-zero) is pure Python/PyTorch and exposes no
+ * FFI layer; its boundary for this path is the Python class surface
+ * (SURVEY.md section 8b).  This header is what the Python look-alike in
+ * `open-pi-zero_b200/pizero.py` binds through ctypes, and what any other host
+ * language would bind.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named `d_*` / inside pz_weights is a
+ *     DEVICE pointer owned by the caller (torch allocations); the library never
+ *     frees, reallocates or retains them beyond the handle's lifetime.
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as
+ *     void*); no entry point synchronises or allocates device memory unless
+ *     its comment says so.
+ *   - return value: 0 = ok, negative = error (see pz_status); the message is
+ *     available through pz_last_error().  Nothing throws or aborts.
+ *   - one handle may be used by one host thread at a time.
+ */
+#ifndef PZ_B200_H
+#define PZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZ_ABI_VERSION 3
+
+typedef enum pz_status {
+    PZ_OK = 0,
+    PZ_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    PZ_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+    PZ_ERR_UNBOUND = -3,      /* weights not bound */
+    PZ_ERR_WORKSPACE = -4     /* workspace too small */
+} pz_status;
+
+typedef enum pz_dtype { PZ_F32 = 0, PZ_BF16 = 1 } pz_dtype;
+
+/* Model dimensions: config/train/bridge.yaml:85-181 of the reference, as read
+ * by PiZero.__init__ (src/model/vla/pizero.py:30-103) and JointModel.__init__
+ * (src/model/vla/joint_model.py:309-323). */
+typedef struct pz_config {
+    int32_t dtype;              /* pz_dtype: storage type of weights/activations */
+    int32_t vocab_size, pad_token_id, image_token_index;
+    int32_t s_vlm;              /* max_image_text_tokens (276) */
+    int32_t n_img_tokens;       /* tokens per image (256) */
+    int32_t n_images;           /* 1 (3 for the pi0-paper shape) */
+    int32_t cond_steps, horizon, action_dim, proprio_dim;
+    int32_t n_steps;            /* num_inference_steps (10) */
+    float   clip;               /* final_action_clip_value; < 0 = none */
+    int32_t n_layers, n_heads, n_kv_heads, head_dim;
+    int32_t vlm_hidden, vlm_inter, act_hidden, act_inter;
+    int32_t vit_hidden, vit_inter, vit_layers, vit_heads, image_size, patch_size;
+    int32_t patch_k_pad;        /* K of the packed patch-embedding matrix (>= 3*p*p, mult of 8) */
+    int32_t max_batch;          /* largest B any call will use (sizes the workspace) */
+    int32_t flags;              /* PZ_FLAG_* */
+} pz_config;
+
+#define PZ_FLAG_SIMPLE_KERNELS 1   /* debug: run every op through the plain SIMT kernels */
+
+/* One SigLIP encoder layer (src/model/paligemma/siglip.py:197-238).  Matrices
+ * are `[out,in]` row-major in the handle dtype; vectors are fp32. */
+typedef struct pz_vit_layer {
+    const float *ln1_w, *ln1_b;
+    const void  *w_qkv;  const float *b_qkv;   /* [3*V, V]: q | k | v rows */
+    const void  *w_o;    const float *b_o;     /* [V, V] */
+    const float *ln2_w, *ln2_b;
+    const void  *w_fc1;  const float *b_fc1;   /* [VI, V] */
+    const void  *w_fc2;  const float *b_fc2;   /* [V, VI] */
+} pz_vit_layer;
+
+/* One mixture decoder layer (src/model/vla/mixture.py:80-218,
+ * src/model/paligemma/modules.py:70-95).  No biases. */
+typedef struct pz_mix_layer {
+    const float *norm_in;      /* input_layernorm.weight [hidden] (raw w; kernels use 1+w) */
+    const void  *w_qkv;        /* [(nh+2*nkv)*hd, hidden]: q | k | v rows */
+    const void  *w_o;          /* [hidden, nh*hd] */
+    const float *norm_post;    /* post_attention_layernorm.weight */
+    const void  *w_gate_up;    /* [2*inter, hidden], blocks of PZ_GU_BLOCK gate rows then PZ_GU_BLOCK up rows */
+    const void  *w_down;       /* [hidden, inter] */
+} pz_mix_layer;
+
+#define PZ_GU_BLOCK 128
+
+typedef struct pz_weights {
+    const void  *embed;                 /* embed_tokens.weight [vocab, H] */
+    const void  *patch_w;               /* patch_embedding.weight as [V, patch_k_pad] (c,ky,kx order, zero pad) */
+    const float *patch_b;               /* [V] */
+    const float *pos_emb;               /* position_embedding.weight [n_img_tokens, V] fp32 */
+    const pz_vit_layer *vit;            /* HOST array [vit_layers] */
+    const float *post_ln_w, *post_ln_b;
+    const void  *proj_w; const float *proj_b;      /* multi_modal_projector [H, V] */
+    const pz_mix_layer *vlm, *proprio, *action;    /* HOST arrays [n_layers] */
+    const float *action_final_norm;     /* joint_model.mixtures.action.norm.weight */
+    const void  *enc_w1; const float *enc_b1;      /* action_encoder.linear_1 [A, action_dim_pad] */
+    const void  *enc_w2a;               /* action_encoder.linear_2.weight[:, A:] -> [A, A] (action half) */
+    const float *enc_time_bias;         /* [n_steps, A] fp32: W2[:, :A] . time_emb(t_i) + b2 (constant per step) */
+    const void  *enc_w3; const float *enc_b3;      /* [A, A] */
+    const void  *prop_w; const float *prop_b;      /* proprio_encoder [A, proprio_dim_pad] */
+    const void  *dec_w;  const float *dec_b;       /* action_decoder [action_dim_pad8, A] */
+    const float *rope_vlm_cos, *rope_vlm_sin;      /* [s_vlm, hd/2] fp32, positions 1..s_vlm */
+    const float *rope_act_cos, *rope_act_sin;      /* [cond+horizon, hd/2] fp32, positions 1.. */
+    int32_t small_k_pad;                /* padded K of enc_w1 / prop_w (>= action_dim, proprio_dim; mult of 8) */
+} pz_weights;
+
+/* Optional capture taps for per-layer parity tests (all fp32 device buffers,
+ * any may be NULL).  They mirror what wrapping
+ * `joint_model.forward_mixture_layers` records on the reference side. */
+typedef struct pz_capture {
+    float *vit_out;          /* [B*n_images*n_img_tokens, V] after post_layernorm */
+    float *image_features;   /* [B*n_images*n_img_tokens, H] projector output (before /sqrt(H)) */
+    float *prefix_embeds;    /* [B, s_vlm, H] residual stream entering layer 0 (= merged embedding * sqrt(H)) */
+    float *prefix_vlm;       /* [n_layers-1, B, s_vlm, H] residual stream after each layer */
+    float *prefix_proprio;   /* [n_layers-1, B, cond, A] */
+    float *denoise_action;   /* [n_steps, n_layers, B, horizon, A] */
+    float *velocities;       /* [n_steps, B, horizon, action_dim] */
+    float *action_preclip;   /* [B, horizon, action_dim] */
+} pz_capture;
+
+typedef struct pz_handle pz_handle;
+
+int pz_abi_version(void);
+
+/* PiZero.__init__ (pizero.py:30-103): validates the configuration. Host only. */
+int pz_create(const pz_config *cfg, pz_handle **out);
+void pz_destroy(pz_handle *h);
+const char *pz_last_error(const pz_handle *h);   /* h may be NULL: last create error */
+
+/* load_state_dict (eval.py:182-188) after host-side packing: records device
+ * pointers; builds TMA descriptors (host only, no device work). */
+int pz_bind_weights(pz_handle *h, const pz_weights *w);
+
+/* Bytes of scratch `pz_infer_action` needs for batch B (<= max_batch). */
+size_t pz_workspace_bytes(const pz_handle *h, int batch);
+
+/* Where the prefix KV cache lives inside the workspace (for parity tests):
+ * K and V are each [n_layers][B][s_vlm+cond][head_dim] in the handle dtype
+ * (replaces src/model/kv_cache.py: list-of-tensors growing by torch.cat). */
+int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,
+                 size_t *layer_stride_elems);
+
+/* PiZero.infer_action (pizero.py:416-490), whole call.
+ *   d_input_ids  int64 [B, s_vlm]
+ *   d_pixels     handle dtype [B*n_images, 3, image, image], already normalised
+ *   d_valid_len  int32 [B]: number of image+text tokens per sample (what the
+ *                dense masks of build_causal_mask_and_position_ids encode)
+ *   d_proprio    fp32 [B, cond, proprio_dim]
+ *   d_noise      fp32 [B, horizon, action_dim]  (the reference's torch.randn, pizero.py:454)
+ *   d_action_out fp32 [B, horizon, action_dim]
+ *   cap          optional taps (NULL in production)                              */
+int pz_infer_action(pz_handle *h, const int64_t *d_input_ids, const void *d_pixels,
+                    const int32_t *d_valid_len, const float *d_proprio, const float *d_noise,
+                    float *d_action_out, void *d_workspace, size_t workspace_bytes, int batch,
+                    const pz_capture *cap, void *stream);
+
+/* The three stages of the call, separately (bench / profiling / tests).
+ * pz_embed_prefix  = _forward_siglip_and_text_embedding (pizero.py:376-414)
+ * pz_prefill       = proprio_encoder + prefix JointModel.forward (pizero.py:436-451)
+ * pz_denoise       = the Euler loop (pizero.py:454-489)
+ * They communicate through the workspace and must run in this order. */
+int pz_embed_prefix(pz_handle *h, const int64_t *d_input_ids, const void *d_pixels,
+                    void *d_workspace, size_t workspace_bytes, int batch,
+                    const pz_capture *cap, void *stream);
+int pz_prefill(pz_handle *h, const int32_t *d_valid_len, const float *d_proprio,
+               void *d_workspace, size_t workspace_bytes, int batch,
+               const pz_capture *cap, void *stream);
+int pz_denoise(pz_handle *h, const int32_t *d_valid_len, const float *d_noise,
+               float *d_action_out, void *d_workspace, size_t workspace_bytes, int batch,
+               const pz_capture *cap, void *stream);
+
+/* Number of kernels the last call on this handle launched (bench: gpu_launches). */
+int64_t pz_launch_count(const pz_handle *h);
+
+/* ---- single-op entry points (unit tests of the hand-written kernels) ---- */
+
+/* C = alpha * epilogue(A[M,K] . W[N,K]^T + bias[N]).  impl: 0 = SIMT reference
+ * kernel, 1 = tcgen05/TMA kernel (bf16 only), 2 = skinny weight-streaming
+ * kernel (bf16, M <= 64).  flags: 1 gelu-tanh, 2 C is fp32 (else `dtype`),
+ * 4 accumulate into fp32 C, 8 GeGLU over [128 gate | 128 up] row blocks of W
+ * (C is [M, N/2]), 16 SiLU. */
+int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const float *d_bias,
+                 void *d_c, int M, int N, int K, int lda, int ldc, int flags, float alpha,
+                 void *stream);
+
+/* Block-masked attention over [cache | fresh] keys; see csrc/attention.cuh. */
+int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
+                    const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
+                    int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,
+                    int s_vlm, int n_fresh, int kv_heads, float scale, float softcap,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PZ_B200_H */

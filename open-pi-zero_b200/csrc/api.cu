@@ -1,0 +1,550 @@
+// api.cu -- the C ABI (include/pz_b200.h) and the orchestration of
+// PiZero.infer_action (reference: src/model/vla/pizero.py:416-490,
+// src/model/vla/joint_model.py:24-383, src/model/paligemma/siglip.py).
+//
+// Everything here is host code that enqueues kernels on the caller's stream;
+// no allocation, no synchronisation, no hidden state besides the handle.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+thread_local LaunchCounter *g_launch_counter = nullptr;
+static thread_local std::string g_create_error;
+
+struct pz_handle {
+    pz_config cfg;
+    pz_weights w;
+    bool bound = false;
+    std::vector<pz_vit_layer> vit;
+    std::vector<pz_mix_layer> vlm, proprio, action;
+    std::string err;
+    LaunchCounter lc;
+    int prefix_chunk = 64;
+};
+
+static int fail(pz_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+// ------------------------------------------------------------ workspace ---
+struct Bump {
+    size_t off = 0;
+    char *base = nullptr;
+    template <typename P> P *take(size_t bytes) {
+        size_t o = (off + 1023) & ~(size_t)1023;   // 1 KiB alignment (TMA / vector loads)
+        off = o + bytes;
+        return base ? reinterpret_cast<P *>(base + o) : nullptr;
+    }
+};
+
+struct Workspace {
+    // persistent between the stages
+    void *kcache, *vcache;   // [L][B][S_c][hd] T
+    float *x;                // [B][S_v][H] fp32: prefix residual stream
+    // SigLIP scratch (per chunk)
+    void *patches, *hv, *qkvv, *av, *mv;
+    float *xv, *feats;
+    // prefix scratch (per chunk)
+    void *h, *qkv, *q, *att, *mlp;
+    void *pp, *hp, *qkvp, *qp, *attp, *mlpp;
+    float *xp;
+    // denoise scratch (whole batch)
+    void *a_in, *e1, *z, *ha, *qkva, *qa, *ka, *va, *atta, *mlpa;
+    float *act, *xa, *vel;
+    size_t total;
+};
+
+static Workspace carve(const pz_config &c, int B, int chunk, void *base) {
+    Workspace w;
+    Bump b;
+    b.base = (char *)base;
+    size_t es = c.dtype == PZ_BF16 ? 2 : 4;
+    int Bc = B < chunk ? B : chunk;
+    size_t S_c = c.s_vlm + c.cond_steps;
+    size_t qkvd = (size_t)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+    size_t qd = (size_t)c.n_heads * c.head_dim;
+    w.kcache = b.take<void>((size_t)c.n_layers * B * S_c * c.head_dim * es);
+    w.vcache = b.take<void>((size_t)c.n_layers * B * S_c * c.head_dim * es);
+    w.x = b.take<float>((size_t)B * c.s_vlm * c.vlm_hidden * 4);
+    size_t Mv = (size_t)Bc * c.n_images * c.n_img_tokens;
+    w.patches = b.take<void>(Mv * c.patch_k_pad * es);
+    w.xv = b.take<float>(Mv * c.vit_hidden * 4);
+    w.hv = b.take<void>(Mv * c.vit_hidden * es);
+    w.qkvv = b.take<void>(Mv * 3 * c.vit_hidden * es);
+    w.av = b.take<void>(Mv * c.vit_hidden * es);
+    w.mv = b.take<void>(Mv * c.vit_inter * es);
+    w.feats = b.take<float>(Mv * c.vlm_hidden * 4);
+    size_t M = (size_t)Bc * c.s_vlm, Mp = (size_t)Bc * c.cond_steps;
+    w.h = b.take<void>(M * c.vlm_hidden * es);
+    w.qkv = b.take<void>(M * qkvd * es);
+    w.q = b.take<void>(M * qd * es);
+    w.att = b.take<void>(M * qd * es);
+    w.mlp = b.take<void>(M * c.vlm_inter * es);
+    w.pp = b.take<void>(Mp * 64 * es);
+    w.xp = b.take<float>(Mp * c.act_hidden * 4);
+    w.hp = b.take<void>(Mp * c.act_hidden * es);
+    w.qkvp = b.take<void>(Mp * qkvd * es);
+    w.qp = b.take<void>(Mp * qd * es);
+    w.attp = b.take<void>(Mp * qd * es);
+    w.mlpp = b.take<void>(Mp * c.act_inter * es);
+    size_t Ma = (size_t)B * c.horizon;
+    w.act = b.take<float>(Ma * c.action_dim * 4);
+    w.a_in = b.take<void>(Ma * 64 * es);
+    w.e1 = b.take<void>(Ma * c.act_hidden * es);
+    w.z = b.take<void>(Ma * c.act_hidden * es);
+    w.xa = b.take<float>(Ma * c.act_hidden * 4);
+    w.ha = b.take<void>(Ma * c.act_hidden * es);
+    w.qkva = b.take<void>(Ma * qkvd * es);
+    w.qa = b.take<void>(Ma * qd * es);
+    w.ka = b.take<void>(Ma * c.head_dim * es);
+    w.va = b.take<void>(Ma * c.head_dim * es);
+    w.atta = b.take<void>(Ma * qd * es);
+    w.mlpa = b.take<void>(Ma * c.act_inter * es);
+    w.vel = b.take<float>(Ma * 8 * 4);
+    w.total = (b.off + 1023) & ~(size_t)1023;
+    return w;
+}
+
+// --------------------------------------------------------------- dispatch --
+template <typename T> struct Ops;
+
+template <> struct Ops<float> {
+    static int linear(pz_handle *, const LinearArgs &a, cudaStream_t st) {
+        launch_linear_simple<float>(a, st);
+        return 0;
+    }
+    static int attention(pz_handle *, const AttnArgs &a, cudaStream_t st) {
+        launch_attn_simple<float>(a, st);
+        return 0;
+    }
+};
+
+template <> struct Ops<bf16> {
+    static int linear(pz_handle *h, const LinearArgs &a, cudaStream_t st) {
+        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS)) {
+            if (skinny_supported(a)) return launch_linear_skinny(a, st);
+            if (gemm_tc_supported(a)) {
+                const char *e = nullptr;
+                int rc = launch_linear_tc(a, st, &e);
+                if (rc) return fail(h, rc, e ? e : "tcgen05 gemm launch failed");
+                return 0;
+            }
+        }
+        launch_linear_simple<bf16>(a, st);
+        return 0;
+    }
+    static int attention(pz_handle *h, const AttnArgs &a, cudaStream_t st) {
+        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_mma_supported(a))
+            return launch_attn_mma(a, st);
+        launch_attn_simple<bf16>(a, st);
+        return 0;
+    }
+};
+
+static LinearArgs lin(const void *A, int lda, const void *W, const float *bias, void *C, int ldc,
+                      int M, int N, int K, int flags = 0, float alpha = 1.f) {
+    LinearArgs a;
+    a.A = A; a.W = W; a.bias = bias; a.C = C;
+    a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldc = ldc;
+    a.alpha = alpha; a.flags = flags;
+    return a;
+}
+
+#define PZ_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+static void copy_f32(float *dst, const float *src, size_t n, cudaStream_t st) {
+    cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+}
+
+// ------------------------------------------------------ stage 1: SigLIP ----
+template <typename T>
+static int run_embed_prefix(pz_handle *h, const int64_t *ids, const void *pixels, void *wsp, int B,
+                            const pz_capture *cap, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int V = c.vit_hidden, VI = c.vit_inter, H = c.vlm_hidden, P = c.n_img_tokens;
+    const int hdv = V / c.vit_heads;
+    const size_t img_elems = (size_t)3 * c.image_size * c.image_size;
+    for (int b0 = 0; b0 < B; b0 += h->prefix_chunk) {
+        int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
+        int n_img = nb * c.n_images;
+        int Mv = n_img * P;
+        const T *pix = (const T *)pixels + (size_t)b0 * c.n_images * img_elems;
+        // patch embedding (siglip.py:59-78): conv as GEMM over im2col rows, + bias + position table
+        launch_im2col<T>(pix, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+        launch_bcast_rows(ws.xv, w.pos_emb, Mv, V, P, st);
+        PZ_TRY(Ops<T>::linear(h, lin(ws.patches, c.patch_k_pad, w.patch_w, w.patch_b, ws.xv, V, Mv, V,
+                                     c.patch_k_pad, LIN_OUT_F32 | LIN_ACCUM), st));
+        for (int l = 0; l < c.vit_layers; ++l) {   // siglip.py:220-238
+            const pz_vit_layer &L = h->vit[l];
+            launch_layernorm<T>(ws.xv, L.ln1_w, L.ln1_b, (T *)ws.hv, Mv, V, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.hv, V, L.w_qkv, L.b_qkv, ws.qkvv, 3 * V, Mv, 3 * V, V), st));
+            AttnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Q = ws.qkvv; a.q_batch_stride = (long)P * 3 * V; a.q_row_stride = 3 * V; a.q_head_stride = hdv;
+            a.K = (const T *)ws.qkvv + V; a.V = (const T *)ws.qkvv + 2 * V;
+            a.kv_batch_stride = (long)P * 3 * V; a.kv_row_stride = 3 * V; a.kv_head_stride = hdv;
+            a.O = ws.av; a.o_batch_stride = (long)P * V; a.o_row_stride = V; a.o_head_stride = hdv;
+            a.batch = n_img; a.n_heads = c.vit_heads; a.head_dim = hdv; a.q_rows = P; a.q_row0 = 0;
+            a.s_cache = P; a.s_vlm = P; a.n_fresh = 0;
+            a.scale = 1.0f / sqrtf((float)hdv); a.softcap = 0.f;
+            PZ_TRY(Ops<T>::attention(h, a, st));
+            PZ_TRY(Ops<T>::linear(h, lin(ws.av, V, L.w_o, L.b_o, ws.xv, V, Mv, V, V,
+                                         LIN_OUT_F32 | LIN_ACCUM), st));
+            launch_layernorm<T>(ws.xv, L.ln2_w, L.ln2_b, (T *)ws.hv, Mv, V, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.hv, V, L.w_fc1, L.b_fc1, ws.mv, VI, Mv, VI, V, LIN_GELU), st));
+            PZ_TRY(Ops<T>::linear(h, lin(ws.mv, VI, L.w_fc2, L.b_fc2, ws.xv, V, Mv, V, VI,
+                                         LIN_OUT_F32 | LIN_ACCUM), st));
+        }
+        launch_layernorm<T>(ws.xv, w.post_ln_w, w.post_ln_b, (T *)ws.hv, Mv, V, 1e-6f, st);
+        if (cap && cap->vit_out)
+            launch_to_f32<T>((const T *)ws.hv, cap->vit_out + (size_t)b0 * c.n_images * P * V,
+                             (long)Mv * V, st);
+        // projector (siglip.py:28-31)
+        PZ_TRY(Ops<T>::linear(h, lin(ws.hv, V, w.proj_w, w.proj_b, ws.feats, H, Mv, H, V, LIN_OUT_F32), st));
+        if (cap && cap->image_features)
+            copy_f32(cap->image_features + (size_t)b0 * c.n_images * P * H, ws.feats, (size_t)Mv * H, st);
+        float *x = ws.x + (size_t)b0 * c.s_vlm * H;
+        launch_embed_merge<T>(ids + (size_t)b0 * c.s_vlm, (const T *)w.embed, ws.feats, x, nb, c.s_vlm,
+                              H, c.n_images * P, c.image_token_index, c.pad_token_id,
+                              sqrtf((float)H), st);
+        if (cap && cap->prefix_embeds)
+            copy_f32(cap->prefix_embeds + (size_t)b0 * c.s_vlm * H, x, (size_t)nb * c.s_vlm * H, st);
+    }
+    return 0;
+}
+
+// ------------------------------------- one mixture's post-attention half ----
+// x += o_proj(att); x += down(gelu(gate(n)) * up(n)), n = rmsnorm(x)
+// (joint_model.py:65-127, mixture.py:217-218, paligemma/modules.py:86-95)
+template <typename T>
+static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *hbuf, void *att,
+                          void *mlp, int M, int hidden, int inter, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    int qd = c.n_heads * c.head_dim;
+    PZ_TRY(Ops<T>::linear(h, lin(att, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
+                                 LIN_OUT_F32 | LIN_ACCUM), st));
+    launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
+    PZ_TRY(Ops<T>::linear(h, lin(hbuf, hidden, L.w_gate_up, nullptr, mlp, inter, M, 2 * inter, hidden,
+                                 LIN_GEGLU), st));
+    PZ_TRY(Ops<T>::linear(h, lin(mlp, inter, L.w_down, nullptr, x, hidden, M, hidden, inter,
+                                 LIN_OUT_F32 | LIN_ACCUM), st));
+    return 0;
+}
+
+// ------------------------------------------------ stage 2: prefix pass ------
+template <typename T>
+static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *proprio, void *wsp,
+                       int B, const pz_capture *cap, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int H = c.vlm_hidden, A = c.act_hidden, hd = c.head_dim, nh = c.n_heads;
+    const int S_v = c.s_vlm, S_p = c.cond_steps, S_c = S_v + S_p;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)S_c * hd;
+    for (int b0 = 0; b0 < B; b0 += h->prefix_chunk) {
+        int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
+        int M = nb * S_v, Mp = nb * S_p;
+        float *x = ws.x + (size_t)b0 * S_v * H;
+        // proprio encoder (pizero.py:436) and the sqrt(hidden) embed scale (joint_model.py:348-355)
+        launch_cast_pad<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
+                           w.small_k_pad, st);
+        PZ_TRY(Ops<T>::linear(h, lin(ws.pp, w.small_k_pad, w.prop_w, w.prop_b, ws.xp, A, Mp, A,
+                                     w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), st));
+        for (int l = 0; l < c.n_layers; ++l) {
+            bool last = l == c.n_layers - 1;
+            T *Kc = (T *)ws.kcache + ((size_t)l * B + b0) * kv_bs;
+            T *Vc = (T *)ws.vcache + ((size_t)l * B + b0) * kv_bs;
+            // vlm block: norm -> fused QKV projection -> RoPE; K (post-RoPE) and V go to the cache
+            launch_rmsnorm<T>(x, h->vlm[l].norm_in, (T *)ws.h, M, H, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.h, H, h->vlm[l].w_qkv, nullptr, ws.qkv, qkvd, M, qkvd, H), st));
+            launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)S_v * qd, Kc, Vc, kv_bs,
+                                 w.rope_vlm_cos, w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
+            // proprio block through the action-expert-shaped weights
+            launch_rmsnorm<T>(ws.xp, h->proprio[l].norm_in, (T *)ws.hp, Mp, A, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.hp, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), st));
+            launch_rope_split<T>((const T *)ws.qkvp, qkvd, (T *)ws.qp, (long)S_p * qd, Kc + (size_t)S_v * hd,
+                                 Vc + (size_t)S_v * hd, kv_bs, w.rope_act_cos, w.rope_act_sin, nb, S_p,
+                                 0, nh, hd, st);
+            // last layer: the reference computes attention for vlm/proprio and drops it
+            // (joint_model.py:297-299); only the K/V above are kept.
+            if (last) break;
+            AttnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.K = Kc; a.V = Vc; a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+            a.valid_len = valid_len + b0;
+            a.batch = nb; a.n_heads = nh; a.head_dim = hd; a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = 0;
+            a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;   // joint_model.py:139,261-268
+            a.q_row_stride = qd; a.q_head_stride = hd; a.o_row_stride = qd; a.o_head_stride = hd;
+            AttnArgs av = a;   // image/text rows
+            av.Q = ws.q; av.q_batch_stride = (long)S_v * qd; av.O = ws.att; av.o_batch_stride = (long)S_v * qd;
+            av.q_rows = S_v; av.q_row0 = 0;
+            PZ_TRY(Ops<T>::attention(h, av, st));
+            AttnArgs ap = a;   // proprio rows
+            ap.Q = ws.qp; ap.q_batch_stride = (long)S_p * qd; ap.O = ws.attp; ap.o_batch_stride = (long)S_p * qd;
+            ap.q_rows = S_p; ap.q_row0 = S_v;
+            PZ_TRY(Ops<T>::attention(h, ap, st));
+            PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, M, H, c.vlm_inter, st));
+            PZ_TRY(post_attention<T>(h, h->proprio[l], ws.xp, ws.hp, ws.attp, ws.mlpp, Mp, A, c.act_inter, st));
+            if (cap && cap->prefix_vlm)
+                copy_f32(cap->prefix_vlm + ((size_t)l * B + b0) * S_v * H, x, (size_t)M * H, st);
+            if (cap && cap->prefix_proprio)
+                copy_f32(cap->prefix_proprio + ((size_t)l * B + b0) * S_p * A, ws.xp, (size_t)Mp * A, st);
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------- stage 3: Euler sampler -------
+template <typename T>
+static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *noise, float *out,
+                       void *wsp, int B, const pz_capture *cap, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int A = c.act_hidden, hd = c.head_dim, nh = c.n_heads, Hz = c.horizon;
+    const int S_v = c.s_vlm, S_p = c.cond_steps, S_c = S_v + S_p;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)S_c * hd;
+    const int Ma = B * Hz;
+    const float dt = (float)(1.0 / c.n_steps);
+    copy_f32(ws.act, noise, (size_t)Ma * c.action_dim, st);
+    for (int step = 0; step < c.n_steps; ++step) {
+        // action encoder (vla/modules.py:39-53); the time half of linear_2 is the
+        // per-step constant enc_time_bias[step]
+        launch_cast_pad<T>(ws.act, (T *)ws.a_in, Ma, c.action_dim, w.small_k_pad, st);
+        PZ_TRY(Ops<T>::linear(h, lin(ws.a_in, w.small_k_pad, w.enc_w1, w.enc_b1, ws.e1, A, Ma, A,
+                                     w.small_k_pad), st));
+        PZ_TRY(Ops<T>::linear(h, lin(ws.e1, A, w.enc_w2a, w.enc_time_bias + (size_t)step * A, ws.z, A,
+                                     Ma, A, A, LIN_SILU), st));
+        PZ_TRY(Ops<T>::linear(h, lin(ws.z, A, w.enc_w3, w.enc_b3, ws.xa, A, Ma, A, A, LIN_OUT_F32,
+                                     sqrtf((float)A)), st));
+        for (int l = 0; l < c.n_layers; ++l) {
+            const pz_mix_layer &L = h->action[l];
+            launch_rmsnorm<T>(ws.xa, L.norm_in, (T *)ws.ha, Ma, A, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.ha, A, L.w_qkv, nullptr, ws.qkva, qkvd, Ma, qkvd, A), st));
+            launch_rope_split<T>((const T *)ws.qkva, qkvd, (T *)ws.qa, (long)Hz * qd, (T *)ws.ka,
+                                 (T *)ws.va, (long)Hz * hd, w.rope_act_cos, w.rope_act_sin, B, Hz, S_p,
+                                 nh, hd, st);
+            AttnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Q = ws.qa; a.q_batch_stride = (long)Hz * qd; a.q_row_stride = qd; a.q_head_stride = hd;
+            a.K = (T *)ws.kcache + (size_t)l * B * kv_bs; a.V = (T *)ws.vcache + (size_t)l * B * kv_bs;
+            a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+            a.K2 = ws.ka; a.V2 = ws.va; a.kv2_batch_stride = (long)Hz * hd; a.kv2_row_stride = hd;
+            a.valid_len = valid_len;
+            a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
+            a.batch = B; a.n_heads = nh; a.head_dim = hd; a.q_rows = Hz; a.q_row0 = S_c;
+            a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = Hz;
+            a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+            PZ_TRY(Ops<T>::attention(h, a, st));
+            PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st));
+            if (cap && cap->denoise_action)
+                copy_f32(cap->denoise_action + ((size_t)step * c.n_layers + l) * Ma * A, ws.xa,
+                         (size_t)Ma * A, st);
+        }
+        // final norm + decoder + Euler step (joint_model.py:375-380, pizero.py:479-481)
+        launch_rmsnorm<T>(ws.xa, w.action_final_norm, (T *)ws.ha, Ma, A, 1e-6f, st);
+        PZ_TRY(Ops<T>::linear(h, lin(ws.ha, A, w.dec_w, w.dec_b, ws.vel, 8, Ma, c.action_dim, A,
+                                     LIN_OUT_F32), st));
+        launch_euler(ws.act, ws.vel, 8, dt, Ma, c.action_dim,
+                     (cap && cap->velocities) ? cap->velocities + (size_t)step * Ma * c.action_dim : nullptr,
+                     st);
+    }
+    if (cap && cap->action_preclip) copy_f32(cap->action_preclip, ws.act, (size_t)Ma * c.action_dim, st);
+    launch_clamp_copy(ws.act, out, (long)Ma * c.action_dim, c.clip, st);
+    return 0;
+}
+
+// ------------------------------------------------------------------- ABI ----
+extern "C" {
+
+int pz_abi_version(void) { return PZ_ABI_VERSION; }
+
+const char *pz_last_error(const pz_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pz_create(const pz_config *cfg, pz_handle **out) {
+    if (!cfg || !out) return fail(nullptr, PZ_ERR_INVALID, "null argument");
+    const pz_config &c = *cfg;
+    if (c.dtype != PZ_F32 && c.dtype != PZ_BF16) return fail(nullptr, PZ_ERR_INVALID, "dtype must be 0 (f32) or 1 (bf16)");
+    if (c.n_kv_heads != 1) return fail(nullptr, PZ_ERR_INVALID, "only num_key_value_heads == 1 (MQA) is supported");
+    if (c.head_dim % 2 || c.head_dim > 256) return fail(nullptr, PZ_ERR_INVALID, "head_dim must be even and <= 256");
+    if (c.vit_hidden % c.vit_heads) return fail(nullptr, PZ_ERR_INVALID, "vit hidden_size % num_heads != 0");
+    if (c.vlm_hidden % 4 || c.act_hidden % 4) return fail(nullptr, PZ_ERR_INVALID, "hidden sizes must be multiples of 4");
+    if (c.vlm_inter % PZ_GU_BLOCK || c.act_inter % PZ_GU_BLOCK)   // packed gate|up layout: blocks of PZ_GU_BLOCK rows
+        return fail(nullptr, PZ_ERR_INVALID, "intermediate sizes must be multiples of 128");
+    if (c.action_dim > 8 || c.proprio_dim > 64) return fail(nullptr, PZ_ERR_INVALID, "action_dim <= 8 and proprio_dim <= 64 required");
+    if (c.n_img_tokens != (c.image_size / c.patch_size) * (c.image_size / c.patch_size))
+        return fail(nullptr, PZ_ERR_INVALID, "num_image_tokens must equal (image_size/patch_size)^2");
+    if (c.s_vlm < c.n_images * c.n_img_tokens) return fail(nullptr, PZ_ERR_INVALID, "max_image_text_tokens smaller than the image tokens");
+    if (c.patch_k_pad < 3 * c.patch_size * c.patch_size || c.patch_k_pad % 8) return fail(nullptr, PZ_ERR_INVALID, "bad patch_k_pad");
+    if (c.max_batch < 1) return fail(nullptr, PZ_ERR_INVALID, "max_batch must be >= 1");
+    pz_handle *h = new pz_handle();
+    h->cfg = c;
+    const char *e = getenv("PZ_PREFIX_CHUNK");
+    if (e && atoi(e) > 0) h->prefix_chunk = atoi(e);
+    *out = h;
+    return PZ_OK;
+}
+
+void pz_destroy(pz_handle *h) { delete h; }
+
+int pz_bind_weights(pz_handle *h, const pz_weights *w) {
+    if (!h || !w) return PZ_ERR_INVALID;
+    if (!w->vit || !w->vlm || !w->proprio || !w->action) return fail(h, PZ_ERR_INVALID, "layer tables missing");
+    if (w->small_k_pad < h->cfg.action_dim || w->small_k_pad < h->cfg.proprio_dim || w->small_k_pad > 64 || w->small_k_pad % 8)
+        return fail(h, PZ_ERR_INVALID, "bad small_k_pad");
+    h->w = *w;
+    h->vit.assign(w->vit, w->vit + h->cfg.vit_layers);
+    h->vlm.assign(w->vlm, w->vlm + h->cfg.n_layers);
+    h->proprio.assign(w->proprio, w->proprio + h->cfg.n_layers);
+    h->action.assign(w->action, w->action + h->cfg.n_layers);
+    h->w.vit = h->vit.data(); h->w.vlm = h->vlm.data();
+    h->w.proprio = h->proprio.data(); h->w.action = h->action.data();
+    h->bound = true;
+    return PZ_OK;
+}
+
+size_t pz_workspace_bytes(const pz_handle *h, int batch) {
+    if (!h || batch < 1) return 0;
+    return carve(h->cfg, batch, h->prefix_chunk, nullptr).total;
+}
+
+int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,
+                 size_t *layer_stride_elems) {
+    if (!h || batch < 1) return PZ_ERR_INVALID;
+    Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
+    if (k_offset) *k_offset = (size_t)((char *)ws.kcache - (char *)0x1000);
+    if (v_offset) *v_offset = (size_t)((char *)ws.vcache - (char *)0x1000);
+    if (layer_stride_elems)
+        *layer_stride_elems = (size_t)batch * (h->cfg.s_vlm + h->cfg.cond_steps) * h->cfg.head_dim;
+    return PZ_OK;
+}
+
+static int precheck(pz_handle *h, const void *ws, size_t ws_bytes, int B) {
+    if (!h) return PZ_ERR_INVALID;
+    if (!h->bound) return fail(h, PZ_ERR_UNBOUND, "pz_bind_weights has not been called");
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, PZ_ERR_INVALID, "batch out of range (1..max_batch)");
+    if (!ws || ws_bytes < pz_workspace_bytes(h, B)) return fail(h, PZ_ERR_WORKSPACE, "workspace too small");
+    if (((uintptr_t)ws) & 1023) return fail(h, PZ_ERR_WORKSPACE, "workspace must be 1 KiB aligned");
+    return PZ_OK;
+}
+
+static int finish(pz_handle *h, int rc) {
+    g_launch_counter = nullptr;
+    if (rc) return rc;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, PZ_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    return PZ_OK;
+}
+
+int pz_embed_prefix(pz_handle *h, const int64_t *ids, const void *pixels, void *ws, size_t ws_bytes,
+                    int B, const pz_capture *cap, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!ids || !pixels) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_embed_prefix<bf16>(h, ids, pixels, ws, B, cap, st)
+                                     : run_embed_prefix<float>(h, ids, pixels, ws, B, cap, st);
+    return finish(h, rc);
+}
+
+int pz_prefill(pz_handle *h, const int32_t *valid_len, const float *proprio, void *ws, size_t ws_bytes,
+               int B, const pz_capture *cap, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!valid_len || !proprio) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_prefill<bf16>(h, valid_len, proprio, ws, B, cap, st)
+                                     : run_prefill<float>(h, valid_len, proprio, ws, B, cap, st);
+    return finish(h, rc);
+}
+
+int pz_denoise(pz_handle *h, const int32_t *valid_len, const float *noise, float *out, void *ws,
+               size_t ws_bytes, int B, const pz_capture *cap, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!valid_len || !noise || !out) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_denoise<bf16>(h, valid_len, noise, out, ws, B, cap, st)
+                                     : run_denoise<float>(h, valid_len, noise, out, ws, B, cap, st);
+    return finish(h, rc);
+}
+
+int pz_infer_action(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len,
+                    const float *proprio, const float *noise, float *out, void *ws, size_t ws_bytes,
+                    int B, const pz_capture *cap, void *stream) {
+    if (h) h->lc.n = 0;
+    PZ_TRY(pz_embed_prefix(h, ids, pixels, ws, ws_bytes, B, cap, stream));
+    PZ_TRY(pz_prefill(h, valid_len, proprio, ws, ws_bytes, B, cap, stream));
+    PZ_TRY(pz_denoise(h, valid_len, noise, out, ws, ws_bytes, B, cap, stream));
+    return PZ_OK;
+}
+
+int64_t pz_launch_count(const pz_handle *h) { return h ? h->lc.n : 0; }
+
+// ---- single-op entry points -------------------------------------------------
+int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const float *d_bias, void *d_c,
+                 int M, int N, int K, int lda, int ldc, int flags, float alpha, void *stream) {
+    LinearArgs a = lin(d_a, lda, d_w, d_bias, d_c, ldc, M, N, K, flags, alpha);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) {
+        if (dtype == PZ_BF16) launch_linear_simple<bf16>(a, st); else launch_linear_simple<float>(a, st);
+    } else if (impl == 1) {
+        if (dtype != PZ_BF16 || !gemm_tc_supported(a)) return PZ_ERR_INVALID;
+        const char *e = nullptr;
+        int rc = launch_linear_tc(a, st, &e);
+        if (rc) { g_create_error = e ? e : "tcgen05 gemm failed"; return rc; }
+    } else if (impl == 2) {
+        if (dtype != PZ_BF16 || !skinny_supported(a)) return PZ_ERR_INVALID;
+        int rc = launch_linear_skinny(a, st);
+        if (rc) return rc;
+    } else {
+        return PZ_ERR_INVALID;
+    }
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
+int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
+                    const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
+                    int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,
+                    int s_vlm, int n_fresh, int kv_heads, float scale, float softcap, void *stream) {
+    // Dense test layout: Q,O [B, q_rows, n_heads*hd]; K,V [B, s_cache, kv_heads*hd];
+    // K2,V2 [B, n_fresh, kv_heads*hd].
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    int qd = n_heads * head_dim, kd = kv_heads * head_dim;
+    a.Q = d_q; a.q_batch_stride = (long)q_rows * qd; a.q_row_stride = qd; a.q_head_stride = head_dim;
+    a.K = d_k; a.V = d_v; a.kv_batch_stride = (long)s_cache * kd; a.kv_row_stride = kd;
+    a.kv_head_stride = kv_heads == 1 ? 0 : head_dim;
+    a.K2 = d_k2; a.V2 = d_v2; a.kv2_batch_stride = (long)n_fresh * kd; a.kv2_row_stride = kd;
+    a.valid_len = d_valid_len;
+    a.O = d_out; a.o_batch_stride = (long)q_rows * qd; a.o_row_stride = qd; a.o_head_stride = head_dim;
+    a.batch = batch; a.n_heads = n_heads; a.head_dim = head_dim; a.q_rows = q_rows; a.q_row0 = q_row0;
+    a.s_cache = s_cache; a.s_vlm = s_vlm; a.n_fresh = n_fresh; a.scale = scale; a.softcap = softcap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) {
+        if (dtype == PZ_BF16) launch_attn_simple<bf16>(a, st); else launch_attn_simple<float>(a, st);
+    } else if (impl == 1) {
+        if (dtype != PZ_BF16 || !attn_mma_supported(a)) return PZ_ERR_INVALID;
+        int rc = launch_attn_mma(a, st);
+        if (rc) return rc;
+    } else {
+        return PZ_ERR_INVALID;
+    }
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
+}  // extern "C"

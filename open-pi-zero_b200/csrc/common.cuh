@@ -1,0 +1,104 @@
+// common.cuh -- shared device helpers and host-side launch bookkeeping.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pz_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define PZ_DEVINL __device__ __forceinline__
+
+// ---- scalar conversion -------------------------------------------------
+template <typename T> PZ_DEVINL float to_f32(T v);
+template <> PZ_DEVINL float to_f32<float>(float v) { return v; }
+template <> PZ_DEVINL float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> PZ_DEVINL T from_f32(float v);
+template <> PZ_DEVINL float from_f32<float>(float v) { return v; }
+template <> PZ_DEVINL bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+PZ_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+PZ_DEVINL float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+PZ_DEVINL float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// gelu(approximate="tanh"): paligemma/modules.py:94, siglip.py:190
+PZ_DEVINL float gelu_tanh(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    float u = k0 * (x + k1 * x * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
+PZ_DEVINL float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+PZ_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+PZ_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (scratch: 32 floats of shared memory)
+PZ_DEVINL float block_sum(float v, float *scratch) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    float r = (lane < nw) ? scratch[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+// ---- linear-layer argument block (all GEMM flavours share it) ------------
+enum : int {
+    LIN_GELU = 1,      // gelu_tanh(acc + bias)
+    LIN_OUT_F32 = 2,   // C is fp32 (else T)
+    LIN_ACCUM = 4,     // C(fp32) += alpha * (acc + bias)
+    LIN_GEGLU = 8,     // W rows are [128 gate | 128 up] blocks; C[M, N/2] = gelu(gate)*up
+    LIN_SILU = 16,     // silu(acc + bias)
+};
+
+struct LinearArgs {
+    const void *A;      // [M, K] T, row stride lda
+    const void *W;      // [N, K] T, row stride K
+    const float *bias;  // [N] or nullptr
+    void *C;            // [M, N] (T or fp32), row stride ldc
+    int M, N, K, lda, ldc;
+    float alpha;
+    int flags;
+};
+
+// ---- attention argument block ------------------------------------------
+// Query rows are (sample b, query token r, head h).  Keys come in two
+// segments: a cache segment of s_cache rows (first s_vlm of them are image/text
+// positions, valid iff index < valid_len[b]; rows >= s_vlm, the proprio rows,
+// are always visible to rows that can see them) and an optional fresh segment
+// of n_fresh rows (the action tokens of the current Euler step).
+// Row r (global token index q_row0 + r in [vlm | proprio | action] order) sees:
+//   r <  s_vlm            : cache keys j < valid_len  (and is itself skipped if r >= valid_len)
+//   s_vlm <= r < s_cache  : cache keys j < valid_len or s_vlm <= j < s_cache
+//   r >= s_cache          : the above plus every fresh key
+// (block mask of pizero.py:271-310).  valid_len == nullptr => everything visible
+// (SigLIP, siglip.py:133-152).
+struct AttnArgs {
+    const void *Q; long q_batch_stride; int q_row_stride, q_head_stride;
+    const void *K, *V; long kv_batch_stride; int kv_row_stride, kv_head_stride;
+    const void *K2, *V2; long kv2_batch_stride; int kv2_row_stride;
+    const int32_t *valid_len;
+    void *O; long o_batch_stride; int o_row_stride, o_head_stride;
+    int batch, n_heads, head_dim, q_rows, q_row0, s_cache, s_vlm, n_fresh;
+    float scale, softcap;
+};
+
+// host-side: every launch goes through this counter (bench.py: gpu_launches)
+struct LaunchCounter { long long n = 0; };
+extern thread_local LaunchCounter *g_launch_counter;
+static inline void count_launch() { if (g_launch_counter) g_launch_counter->n++; }

@@ -1,0 +1,291 @@
+// elementwise.cu -- normalisation, layout and sampler kernels (HBM-bound; all
+// global access is coalesced and, where alignment allows, 16-byte vectorised).
+#include "common.cuh"
+#include "kernels.h"
+
+// ---- im2col for the 14x14/14 patch conv (siglip.py:69) ---------------------
+// patches[img*P + py*G + px][c*ps*ps + ky*ps + kx] = pix[img][c][py*ps+ky][px*ps+kx]
+template <typename T>
+__global__ void im2col_kernel(const T *__restrict__ pix, T *__restrict__ patches, int image,
+                              int patch, int k_pad, long total) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int k = i % k_pad;
+    long row = i / k_pad;
+    int G = image / patch, P = G * G;
+    int img = row / P, p = row % P;
+    int py = p / G, px = p % G;
+    int kk = patch * patch;
+    T v = from_f32<T>(0.f);
+    if (k < 3 * kk) {
+        int c = k / kk, r = k % kk, ky = r / patch, kx = r % patch;
+        v = pix[(((long)img * 3 + c) * image + (py * patch + ky)) * image + px * patch + kx];
+    }
+    patches[i] = v;
+}
+template <typename T>
+void launch_im2col(const T *pix, T *patches, int n_images, int image, int patch, int k_pad,
+                   cudaStream_t st) {
+    int G = image / patch;
+    long total = (long)n_images * G * G * k_pad;
+    im2col_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pix, patches, image, patch,
+                                                                     k_pad, total);
+    count_launch();
+}
+template void launch_im2col<float>(const float *, float *, int, int, int, int, cudaStream_t);
+template void launch_im2col<bf16>(const bf16 *, bf16 *, int, int, int, int, cudaStream_t);
+
+// x[r][c] = table[r % period][c]   (position embedding broadcast, siglip.py:76)
+__global__ void bcast_rows_kernel(float *__restrict__ x, const float *__restrict__ table,
+                                  long total, int cols, int period) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long r = i / cols;
+    int c = i % cols;
+    x[i] = table[(r % period) * cols + c];
+}
+void launch_bcast_rows(float *x, const float *table, long rows, int cols, int period,
+                       cudaStream_t st) {
+    long total = rows * cols;
+    bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, table, total, cols,
+                                                                      period);
+    count_launch();
+}
+
+// ---- LayerNorm (siglip.py:211,217,298): one warp per row, fp32 statistics ----
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x,
+                                                        const float *__restrict__ w,
+                                                        const float *__restrict__ b,
+                                                        T *__restrict__ out, long rows, int cols,
+                                                        float eps) {
+    long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float *xr = x + row * cols;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += xr[c];
+    float mean = warp_sum(s) / cols;
+    float v = 0.f;
+    for (int c = lane; c < cols; c += 32) { float d = xr[c] - mean; v += d * d; }
+    float rstd = rsqrtf(warp_sum(v) / cols + eps);
+    T *o = out + row * cols;
+    for (int c = lane; c < cols; c += 32) o[c] = from_f32<T>((xr[c] - mean) * rstd * w[c] + b[c]);
+}
+template <typename T>
+void launch_layernorm(const float *x, const float *w, const float *b, T *out, long rows, int cols,
+                      float eps, cudaStream_t st) {
+    layernorm_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, b, out, rows, cols, eps);
+    count_launch();
+}
+template void launch_layernorm<float>(const float *, const float *, const float *, float *, long,
+                                      int, float, cudaStream_t);
+template void launch_layernorm<bf16>(const float *, const float *, const float *, bf16 *, long,
+                                     int, float, cudaStream_t);
+
+// ---- Gemma RMSNorm (paligemma/modules.py:13-21): x*rsqrt(mean x^2+eps)*(1+w) --
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float *__restrict__ x,
+                                                      const float *__restrict__ w,
+                                                      T *__restrict__ out, long rows, int cols,
+                                                      float eps) {
+    long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * cols);
+    int n4 = cols >> 2;
+    float s = 0.f;
+    for (int c = lane; c < n4; c += 32) {
+        float4 v = xr[c];
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    float r = rsqrtf(warp_sum(s) / cols + eps);
+    const float4 *wr = reinterpret_cast<const float4 *>(w);
+    T *o = out + row * cols;
+    for (int c = lane; c < n4; c += 32) {
+        float4 v = xr[c], g = wr[c];
+        o[4 * c + 0] = from_f32<T>(v.x * r * (1.f + g.x));
+        o[4 * c + 1] = from_f32<T>(v.y * r * (1.f + g.y));
+        o[4 * c + 2] = from_f32<T>(v.z * r * (1.f + g.z));
+        o[4 * c + 3] = from_f32<T>(v.w * r * (1.f + g.w));
+    }
+}
+template <typename T>
+void launch_rmsnorm(const float *x, const float *w, T *out, long rows, int cols, float eps,
+                    cudaStream_t st) {
+    rmsnorm_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, out, rows, cols, eps);
+    count_launch();
+}
+template void launch_rmsnorm<float>(const float *, const float *, float *, long, int, float,
+                                    cudaStream_t);
+template void launch_rmsnorm<bf16>(const float *, const float *, bf16 *, long, int, float,
+                                   cudaStream_t);
+
+// ---- embedding merge (pizero.py:385-413 + joint_model.py:348-355) -------------
+// x[b][s] = feats[b][rank of s among image tokens]            if ids == image token
+//         = 0                                                  if ids == pad
+//         = embed[ids] * sqrt(hidden)                          otherwise
+// feats is the projector output; the reference divides it by sqrt(hidden) and
+// the joint model multiplies every row by sqrt(hidden) again, so image rows
+// enter layer 0 unscaled.
+template <typename T>
+__global__ void __launch_bounds__(256) embed_merge_kernel(
+    const int64_t *__restrict__ ids, const T *__restrict__ embed, const float *__restrict__ feats,
+    float *__restrict__ x, int s_vlm, int hidden, int n_feat_rows, int image_token, int pad_token,
+    float text_scale) {
+    int b = blockIdx.y, s = blockIdx.x;
+    const int64_t *row_ids = ids + (long)b * s_vlm;
+    long id = row_ids[s];
+    float *xr = x + ((long)b * s_vlm + s) * hidden;
+    __shared__ int rank_sh;
+    if (id == image_token) {
+        // rank = number of image tokens before s (block-wide count)
+        int cnt = 0;
+        for (int j = threadIdx.x; j < s; j += blockDim.x) cnt += (row_ids[j] == image_token);
+        __shared__ float scratch[32];
+        int rank = (int)(block_sum((float)cnt, scratch) + 0.5f);
+        if (threadIdx.x == 0) rank_sh = rank;
+        __syncthreads();
+        rank = rank_sh;
+        if (rank < n_feat_rows) {
+            const float *f = feats + ((long)b * n_feat_rows + rank) * hidden;
+            for (int c = threadIdx.x; c < hidden; c += blockDim.x) xr[c] = f[c];
+        } else {
+            for (int c = threadIdx.x; c < hidden; c += blockDim.x) xr[c] = 0.f;
+        }
+    } else if (id == pad_token) {
+        for (int c = threadIdx.x; c < hidden; c += blockDim.x) xr[c] = 0.f;
+    } else {
+        const T *e = embed + id * hidden;
+        for (int c = threadIdx.x; c < hidden; c += blockDim.x) xr[c] = to_f32<T>(e[c]) * text_scale;
+    }
+}
+template <typename T>
+void launch_embed_merge(const int64_t *ids, const T *embed, const float *feats, float *x,
+                        int batch, int s_vlm, int hidden, int n_feat_rows, int image_token,
+                        int pad_token, float text_scale, cudaStream_t st) {
+    dim3 grid(s_vlm, batch);
+    embed_merge_kernel<T><<<grid, 256, 0, st>>>(ids, embed, feats, x, s_vlm, hidden, n_feat_rows,
+                                               image_token, pad_token, text_scale);
+    count_launch();
+}
+template void launch_embed_merge<float>(const int64_t *, const float *, const float *, float *,
+                                        int, int, int, int, int, int, float, cudaStream_t);
+template void launch_embed_merge<bf16>(const int64_t *, const bf16 *, const float *, float *, int,
+                                       int, int, int, int, int, float, cudaStream_t);
+
+// ---- RoPE + Q/K/V split (mixture.py:187-235, model/utils.py:4-16) ------------
+// qkv row = [q (nh*hd) | k (hd) | v (hd)] (one KV head).  Half-split rotation:
+// out[i] = x[i]*cos[i] - x[i+hd/2]*sin[i],  out[i+hd/2] = x[i+hd/2]*cos[i] + x[i]*sin[i].
+// One block per token row; thread t handles pair index t of each head.
+template <typename T>
+__global__ void rope_split_kernel(const T *__restrict__ qkv, int qkv_ld, T *__restrict__ q_out,
+                                  long q_batch_stride, T *__restrict__ k_out,
+                                  T *__restrict__ v_out, long kv_batch_stride,
+                                  const float *__restrict__ cos_t, const float *__restrict__ sin_t,
+                                  int s_x, int pos0, int n_heads, int head_dim) {
+    int row = blockIdx.x;
+    int b = row / s_x, s = row % s_x;
+    int half = head_dim >> 1;
+    const T *in = qkv + (long)row * qkv_ld;
+    const float *cs = cos_t + (long)(pos0 + s) * half;
+    const float *sn = sin_t + (long)(pos0 + s) * half;
+    T *qo = q_out + b * q_batch_stride + (long)s * n_heads * head_dim;
+    T *ko = k_out + b * kv_batch_stride + (long)s * head_dim;
+    T *vo = v_out + b * kv_batch_stride + (long)s * head_dim;
+    for (int i = threadIdx.x; i < (n_heads + 1) * half; i += blockDim.x) {
+        int h = i / half, p = i % half;
+        float c = cs[p], sv = sn[p];
+        float x1 = to_f32<T>(in[h * head_dim + p]), x2 = to_f32<T>(in[h * head_dim + p + half]);
+        float o1 = x1 * c - x2 * sv, o2 = x2 * c + x1 * sv;
+        T *dst = (h < n_heads) ? qo + h * head_dim : ko;
+        dst[p] = from_f32<T>(o1);
+        dst[p + half] = from_f32<T>(o2);
+    }
+    const T *vin = in + (n_heads + 1) * head_dim;
+    for (int i = threadIdx.x; i < head_dim; i += blockDim.x) vo[i] = vin[i];
+}
+template <typename T>
+void launch_rope_split(const T *qkv, int qkv_ld, T *q_out, long q_batch_stride, T *k_out,
+                       T *v_out, long kv_batch_stride, const float *cos_t, const float *sin_t,
+                       int batch, int s_x, int pos0, int n_heads, int head_dim,
+                       cudaStream_t st) {
+    rope_split_kernel<T><<<batch * s_x, 256, 0, st>>>(qkv, qkv_ld, q_out, q_batch_stride, k_out,
+                                                      v_out, kv_batch_stride, cos_t, sin_t, s_x,
+                                                      pos0, n_heads, head_dim);
+    count_launch();
+}
+template void launch_rope_split<float>(const float *, int, float *, long, float *, float *, long,
+                                       const float *, const float *, int, int, int, int, int,
+                                       cudaStream_t);
+template void launch_rope_split<bf16>(const bf16 *, int, bf16 *, long, bf16 *, bf16 *, long,
+                                      const float *, const float *, int, int, int, int, int,
+                                      cudaStream_t);
+
+// ---- small casts --------------------------------------------------------------
+template <typename T>
+__global__ void cast_pad_kernel(const float *__restrict__ src, T *__restrict__ dst, long total,
+                                int cols, int cols_pad) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long r = i / cols_pad;
+    int c = i % cols_pad;
+    dst[i] = from_f32<T>(c < cols ? src[r * cols + c] : 0.f);
+}
+template <typename T>
+void launch_cast_pad(const float *src, T *dst, long rows, int cols, int cols_pad,
+                     cudaStream_t st) {
+    long total = rows * cols_pad;
+    cast_pad_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, total, cols,
+                                                                       cols_pad);
+    count_launch();
+}
+template void launch_cast_pad<float>(const float *, float *, long, int, int, cudaStream_t);
+template void launch_cast_pad<bf16>(const float *, bf16 *, long, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void to_f32_kernel(const T *__restrict__ src, float *__restrict__ dst, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = to_f32<T>(src[i]);
+}
+template <typename T>
+void launch_to_f32(const T *src, float *dst, long n, cudaStream_t st) {
+    to_f32_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    count_launch();
+}
+template void launch_to_f32<float>(const float *, float *, long, cudaStream_t);
+template void launch_to_f32<bf16>(const bf16 *, float *, long, cudaStream_t);
+
+// ---- Euler update (pizero.py:479-481): action += dt * velocity ---------------
+__global__ void euler_kernel(float *__restrict__ action, const float *__restrict__ vel,
+                             int vel_ld, float dt, long total, int adim,
+                             float *__restrict__ vel_capture) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long r = i / adim;
+    int c = i % adim;
+    float v = vel[r * vel_ld + c];
+    if (vel_capture) vel_capture[i] = v;
+    action[i] += dt * v;
+}
+void launch_euler(float *action, const float *vel, int vel_ld, float dt, long rows, int adim,
+                  float *vel_capture, cudaStream_t st) {
+    long total = rows * adim;
+    euler_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(action, vel, vel_ld, dt, total,
+                                                                 adim, vel_capture);
+    count_launch();
+}
+
+// final clamp (pizero.py:484-489); clip < 0 => copy only
+__global__ void clamp_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, long n,
+                                  float clip) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = src[i];
+    if (clip >= 0.f) v = fminf(fmaxf(v, -clip), clip);
+    dst[i] = v;
+}
+void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStream_t st) {
+    clamp_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, clip);
+    count_launch();
+}

@@ -1,0 +1,48 @@
+// kernels.h -- host-callable launchers (one per kernel family).
+#pragma once
+#include "common.cuh"
+
+// simple.cu
+template <typename T> void launch_linear_simple(const LinearArgs &a, cudaStream_t st);
+template <typename T> void launch_attn_simple(const AttnArgs &a, cudaStream_t st);
+
+// elementwise.cu
+template <typename T>
+void launch_im2col(const T *pix, T *patches, int n_images, int image, int patch, int k_pad,
+                   cudaStream_t st);
+void launch_bcast_rows(float *x, const float *table, long rows, int cols, int period,
+                       cudaStream_t st);
+template <typename T>
+void launch_layernorm(const float *x, const float *w, const float *b, T *out, long rows, int cols,
+                      float eps, cudaStream_t st);
+template <typename T>
+void launch_rmsnorm(const float *x, const float *w, T *out, long rows, int cols, float eps,
+                    cudaStream_t st);
+template <typename T>
+void launch_embed_merge(const int64_t *ids, const T *embed, const float *feats, float *x,
+                        int batch, int s_vlm, int hidden, int n_feat_rows, int image_token,
+                        int pad_token, float text_scale, cudaStream_t st);
+template <typename T>
+void launch_rope_split(const T *qkv, int qkv_ld, T *q_out, long q_batch_stride, T *k_out,
+                       T *v_out, long kv_batch_stride, const float *cos_t, const float *sin_t,
+                       int batch, int s_x, int pos0, int n_heads, int head_dim,
+                       cudaStream_t st);
+template <typename T>
+void launch_cast_pad(const float *src, T *dst, long rows, int cols, int cols_pad, cudaStream_t st);
+template <typename T>
+void launch_to_f32(const T *src, float *dst, long n, cudaStream_t st);
+void launch_euler(float *action, const float *vel, int vel_ld, float dt, long rows, int adim,
+                  float *vel_capture, cudaStream_t st);
+void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStream_t st);
+
+// gemm_tc.cu (tcgen05 + TMA, bf16)
+int gemm_tc_supported(const LinearArgs &a);
+int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err);
+
+// skinny.cu (weight streaming for M <= 64, bf16)
+int skinny_supported(const LinearArgs &a);
+int launch_linear_skinny(const LinearArgs &a, cudaStream_t st);
+
+// attn_mma.cu (tensor-core attention, bf16)
+int attn_mma_supported(const AttnArgs &a);
+int launch_attn_mma(const AttnArgs &a, cudaStream_t st);

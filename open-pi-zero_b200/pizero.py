@@ -1,0 +1,541 @@
+"""Drop-in `PiZero` / `PiZeroInference` for the `infer_action` path.
+
+Same constructor contract, method names, keyword arguments and `state_dict()`
+keys as the reference's `src/model/vla/pizero.py` (class `PiZero` :28,
+`infer_action` :416, `build_causal_mask_and_position_ids` :271,
+`split_full_mask_into_submasks` :326, `tie_action_proprio_weights` :262,
+`PiZeroInference` :664), so a reference checkpoint loads with
+`load_state_dict(strict=True)` and `EvalAgent` (`src/agent/eval.py:32-125`) can
+call `self.model(**inputs)` unchanged.
+
+What is different underneath: the modules below only *hold parameters* under
+the reference's names.  All arithmetic of `infer_action` runs in the
+hand-written sm_100a kernels of `libpz_b200.so` (C ABI: `include/pz_b200.h`),
+fed from packed weight buffers built once per (weights, dtype, device).  There
+is no PyTorch/CPU fallback: without the CUDA library or a CUDA device the call
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import AttrDict, cfg_from_dims, dims_from_cfg
+from .synth import state_dict_spec
+
+
+class PzError(RuntimeError):
+    pass
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Holder(nn.Module):
+    """Parameter container: nested modules named after the reference's
+    attribute paths so that state_dict() reproduces its 938 keys."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise PzError("this module only holds parameters; call PiZero.infer_action")
+
+
+def _attach(root: nn.Module, key: str, tensor: torch.Tensor) -> None:
+    parts = key.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Holder())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class KVCache:
+    """Read-only view of one mixture's prefix KV inside the workspace, with the
+    reference's `KVCache` accessors (`src/model/kv_cache.py:6-46`).  The
+    storage is one `[layers, B, S_cache, head_dim]` tensor per K and V
+    (K post-RoPE, V raw, pad positions included) instead of Python lists that
+    grow by `torch.cat`."""
+
+    def __init__(self, k: torch.Tensor, v: torch.Tensor, lo: int, hi: int, filled: int):
+        self._k, self._v, self._lo, self._hi, self._filled = k, v, lo, hi, filled
+
+    def has_item(self, layer_idx) -> bool:
+        return layer_idx < self._filled
+
+    def num_items(self) -> int:
+        return 0 if self._filled == 0 else self._hi - self._lo
+
+    def get(self, layer_idx) -> Tuple[torch.Tensor, torch.Tensor]:
+        # [B, num_kv_heads = 1, S, head_dim], as the reference returns
+        return (self._k[layer_idx, :, self._lo:self._hi].unsqueeze(1),
+                self._v[layer_idx, :, self._lo:self._hi].unsqueeze(1))
+
+    def update(self, key_states, value_states, layer_idx):
+        raise PzError("the prefix KV cache is written by the prefill kernels, not from Python")
+
+
+class JointModel(_Holder):
+    """Holds `mixtures.{vlm,proprio,action}` parameters; mirrors the attributes
+    callers read on the reference's `JointModel` (`joint_model.py:308-326`)."""
+
+    def __init__(self, dims: dict):
+        super().__init__()
+        self.num_hidden_layers = dims["num_layers"]
+        self.mixture_names = ["vlm", "proprio", "action"]
+        self.cache_names = ["vlm", "proprio"]
+        self.num_mixture = 3
+
+
+class PiZero(nn.Module):
+    def __init__(self, cfg, use_ddp: bool = False, *, device=None, dtype=None,
+                 init: str = "reference", max_batch: int = 64):
+        """`cfg`: the reference's config tree (OmegaConf DictConfig, AttrDict or
+        dict with the fields of config/train/bridge.yaml:85-181) or the flat
+        dims dict of `open-pi-zero_b200/config.py`.
+
+        Extra keyword-only arguments (not in the reference): `device`/`dtype`
+        to create parameters in place, `init` in {"reference", "empty"},
+        `max_batch` (workspace sizing; grows on demand)."""
+        super().__init__()
+        self.dims = dims_from_cfg(cfg)
+        self.cfg = cfg if not isinstance(cfg, dict) or "mixture" in cfg else cfg_from_dims(self.dims)
+        self.use_ddp = use_ddp
+        d = self.dims
+        self.vocab_size = d["vocab_size"]
+        self.pad_token_id = d["pad_token_id"]
+        self.image_token_index = d["image_token_index"]
+        self.max_image_text_tokens = d["max_image_text_tokens"]
+        self.num_proprio_tokens = d["cond_steps"]
+        self.num_action_tokens = d["horizon_steps"]
+        self.total_num_tokens = (self.max_image_text_tokens + self.num_proprio_tokens
+                                 + self.num_action_tokens)
+        self.image_text_hidden_size = d["vlm_hidden"]
+        self.proprio_hidden_size = d["act_hidden"]
+        self.action_hidden_size = d["act_hidden"]
+        self.num_inference_steps = d["num_inference_steps"]
+        self.horizon_steps = d["horizon_steps"]
+        self.action_dim = d["action_dim"]
+        self.proprio_dim = d["proprio_dim"]
+        self.final_action_clip_value = d["final_action_clip_value"]
+
+        self.joint_model = JointModel(d)
+        dtype = dtype or torch.float32
+        if init == "reference":
+            from .synth import init_state_dict
+            sd = init_state_dict(d, seed=int(torch.initial_seed() % (2 ** 31)), tie_proprio=False)
+            for k, t in sd.items():
+                _attach(self, k, t.to(device=device, dtype=dtype))
+        elif init == "empty":
+            for k, shape, _, _ in state_dict_spec(d):
+                _attach(self, k, torch.empty(shape, device=device, dtype=dtype))
+        else:
+            raise ValueError(f"init must be 'reference' or 'empty', got {init!r}")
+        self._tied = False
+        self._max_batch = max_batch
+        self._handle = None
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+        self._ws_batch = 0
+        self._flags = _lib.PZ_FLAG_SIMPLE_KERNELS if os.environ.get("PZ_SIMPLE_KERNELS") == "1" else 0
+        self.last_launch_count = 0
+        self.eval()
+
+    # ------------------------------------------------------------------ misc
+    def no_sync(self):   # NoSyncBase parity (src/utils/decorator.py:14-28); inert at inference
+        import contextlib
+        return contextlib.nullcontext()
+
+    def freeze_all_weights(self):
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def tie_action_proprio_weights(self):
+        """pizero.py:262-264: proprio uses the action expert's weights."""
+        self.joint_model.mixtures._modules["proprio"] = self.joint_model.mixtures._modules["action"]
+        self._tied = True
+        self._packed_key = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        # checkpoints written from a torch.compile'd model carry "_orig_mod." (eval.py:184-188)
+        sd = {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
+        out = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._packed_key = None
+        return out
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._packed_key = None
+        return out
+
+    # ------------------------------------------------------ input preparation
+    def build_causal_mask_and_position_ids(self, attention_mask: torch.Tensor, dtype: torch.dtype):
+        """Same outputs as pizero.py:271-324 (block mask with finfo.min, position
+        ids starting at 1), built without the per-sample Python loop."""
+        bsz = attention_mask.size(0)
+        dev = attention_mask.device
+        Sv, Sp, H = self.max_image_text_tokens, self.num_proprio_tokens, self.num_action_tokens
+        S = self.total_num_tokens
+        cnt = attention_mask.sum(dim=1).view(bsz, 1, 1)
+        idx = torch.arange(S, device=dev)
+        row, col = idx.view(1, S, 1), idx.view(1, 1, S)
+        col_valid = col < cnt
+        vis = (row < cnt) & col_valid                                   # image/text block
+        vis = vis | ((row >= Sv) & col_valid)                           # proprio/action -> image/text
+        vis = vis | ((row >= Sv) & (row < Sv + Sp) & (col >= Sv) & (col < Sv + Sp))
+        vis = vis | ((row >= Sv + Sp) & (col >= Sv))
+        mask = torch.full((bsz, S, S), torch.finfo(dtype).min, dtype=dtype, device=dev)
+        mask = mask.masked_fill(vis, 0).unsqueeze(1)
+        vlm_pos = torch.arange(1, Sv + 1, device=dev).repeat(bsz, 1)
+        proprio_pos = torch.arange(1, Sp + 1, device=dev).repeat(bsz, 1)
+        action_pos = torch.arange(Sp + 1, Sp + H + 1, device=dev).repeat(bsz, 1)
+        return mask, vlm_pos, proprio_pos, action_pos
+
+    def split_full_mask_into_submasks(self, causal_mask: torch.Tensor):
+        """pizero.py:326-336."""
+        n = self.max_image_text_tokens + self.num_proprio_tokens
+        return causal_mask[..., :n, :n], causal_mask[..., -self.num_action_tokens:, :]
+
+    # ---------------------------------------------------------------- packing
+    def _param_key(self):
+        ps = list(self.parameters())
+        return (ps[0].dtype, ps[0].device, sum(p._version for p in ps), ps[0].data_ptr(), self._tied,
+                self._flags)
+
+    @torch.no_grad()
+    def pack(self, force: bool = False):
+        """Build the kernel-side weight buffers (fused QKV, interleaved gate|up,
+        padded small matrices, fp32 vectors, RoPE and time tables) and bind them."""
+        key = self._param_key()
+        if not force and self._packed_key == key and self._handle is not None:
+            return
+        sd = dict(self.state_dict())
+        p0 = sd["embed_tokens.weight"]
+        if p0.device.type != "cuda":
+            raise PzError("PiZero.infer_action needs the model on a CUDA device (no CPU path)")
+        if p0.dtype not in (torch.float32, torch.bfloat16):
+            raise PzError(f"unsupported parameter dtype {p0.dtype}")
+        lib = _lib.load()
+        d, dev, T = self.dims, p0.device, p0.dtype
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()   # noqa: E731
+        mat = lambda t: t.detach().to(T).contiguous()               # noqa: E731
+        keep = []   # owns every packed tensor
+
+        def own(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        A, H = d["act_hidden"], d["vlm_hidden"]
+        V, ps = d["vit_hidden"], d["patch_size"]
+        kp = _round_up(3 * ps * ps, 64)
+        skp = _round_up(max(d["action_dim"], d["proprio_dim"]), 8)
+        w = _lib.PzWeights()
+        w.embed = own(mat(sd["embed_tokens.weight"]))
+        vpfx = "vision_tower.vision_model."
+        pw = torch.zeros((V, kp), dtype=T, device=dev)
+        pw[:, :3 * ps * ps] = sd[vpfx + "embeddings.patch_embedding.weight"].reshape(V, -1).to(T)
+        w.patch_w = own(pw)
+        w.patch_b = own(f32(sd[vpfx + "embeddings.patch_embedding.bias"]))
+        w.pos_emb = own(f32(sd[vpfx + "embeddings.position_embedding.weight"]))
+        vit = (_lib.PzVitLayer * d["vit_layers"])()
+        for i in range(d["vit_layers"]):
+            q = vpfx + f"encoder.layers.{i}."
+            L = vit[i]
+            L.ln1_w, L.ln1_b = own(f32(sd[q + "layer_norm1.weight"])), own(f32(sd[q + "layer_norm1.bias"]))
+            L.w_qkv = own(mat(torch.cat([sd[q + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0)))
+            L.b_qkv = own(f32(torch.cat([sd[q + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0)))
+            L.w_o, L.b_o = own(mat(sd[q + "self_attn.out_proj.weight"])), own(f32(sd[q + "self_attn.out_proj.bias"]))
+            L.ln2_w, L.ln2_b = own(f32(sd[q + "layer_norm2.weight"])), own(f32(sd[q + "layer_norm2.bias"]))
+            L.w_fc1, L.b_fc1 = own(mat(sd[q + "mlp.fc1.weight"])), own(f32(sd[q + "mlp.fc1.bias"]))
+            L.w_fc2, L.b_fc2 = own(mat(sd[q + "mlp.fc2.weight"])), own(f32(sd[q + "mlp.fc2.bias"]))
+        keep.append(vit)
+        w.vit = C.cast(vit, C.POINTER(_lib.PzVitLayer))
+        w.post_ln_w, w.post_ln_b = own(f32(sd[vpfx + "post_layernorm.weight"])), own(f32(sd[vpfx + "post_layernorm.bias"]))
+        w.proj_w = own(mat(sd["multi_modal_projector.linear.weight"]))
+        w.proj_b = own(f32(sd["multi_modal_projector.linear.bias"]))
+
+        GU = 128
+
+        def pack_mixture(name):
+            arr = (_lib.PzMixLayer * d["num_layers"])()
+            for i in range(d["num_layers"]):
+                p = f"joint_model.mixtures.{name}.layers.{i}."
+                L = arr[i]
+                L.norm_in = own(f32(sd[p + "input_layernorm.weight"]))
+                L.w_qkv = own(mat(torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0)))
+                L.w_o = own(mat(sd[p + "self_attn.o_proj.weight"]))
+                L.norm_post = own(f32(sd[p + "post_attention_layernorm.weight"]))
+                g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+                inter, hid = g.shape
+                gu = torch.stack([g.reshape(inter // GU, GU, hid), u.reshape(inter // GU, GU, hid)], 1)
+                L.w_gate_up = own(mat(gu.reshape(2 * inter, hid)))
+                L.w_down = own(mat(sd[p + "mlp.down_proj.weight"]))
+            keep.append(arr)
+            return arr
+
+        vlm = pack_mixture("vlm")
+        action = pack_mixture("action")
+        same = self._tied or all(
+            torch.equal(sd[k], sd[k.replace(".proprio.", ".action.", 1)])
+            for k in sd if k.startswith("joint_model.mixtures.proprio."))
+        proprio = action if same else pack_mixture("proprio")   # alias only if bit-equal (SURVEY 8a note 4)
+        w.vlm = C.cast(vlm, C.POINTER(_lib.PzMixLayer))
+        w.action = C.cast(action, C.POINTER(_lib.PzMixLayer))
+        w.proprio = C.cast(proprio, C.POINTER(_lib.PzMixLayer))
+        w.action_final_norm = own(f32(sd["joint_model.mixtures.action.norm.weight"]))
+
+        def pad_k(t, k):
+            out = torch.zeros((t.shape[0], k), dtype=T, device=dev)
+            out[:, :t.shape[1]] = t.to(T)
+            return out
+
+        w.enc_w1 = own(pad_k(sd["action_encoder.linear_1.weight"], skp))
+        w.enc_b1 = own(f32(sd["action_encoder.linear_1.bias"]))
+        w2 = sd["action_encoder.linear_2.weight"]
+        w.enc_w2a = own(mat(w2[:, A:]))
+        # time conditioning is a per-step constant: t_i accumulates
+        # dt in fp32 exactly as pizero.py:460-481 does in an fp32 run; the embedding
+        # follows vla/modules.py:15-22.
+        n_steps = d["num_inference_steps"]
+        half = A // 2
+        freq = torch.exp(torch.arange(half, device=dev, dtype=torch.float32)
+                         * -(math.log(d["time_max_period"]) / (half - 1)))
+        t = torch.zeros(1, device=dev, dtype=torch.float32)
+        tb = []
+        for _ in range(n_steps):
+            e = t[:, None] * freq[None, :]
+            temb = torch.cat((e.sin(), e.cos()), dim=-1)[0]
+            tb.append(w2[:, :A].float() @ temb + sd["action_encoder.linear_2.bias"].float())
+            t = t + 1.0 / n_steps
+        w.enc_time_bias = own(torch.stack(tb).contiguous())
+        w.enc_w3 = own(mat(sd["action_encoder.linear_3.weight"]))
+        w.enc_b3 = own(f32(sd["action_encoder.linear_3.bias"]))
+        w.prop_w = own(pad_k(sd["proprio_encoder.weight"], skp))
+        w.prop_b = own(f32(sd["proprio_encoder.bias"]))
+        dw = torch.zeros((8, A), dtype=T, device=dev)
+        dw[:d["action_dim"]] = sd["action_decoder.weight"].to(T)
+        w.dec_w = own(dw)
+        db = torch.zeros(8, dtype=torch.float32, device=dev)
+        db[:d["action_dim"]] = sd["action_decoder.bias"].float()
+        w.dec_b = own(db)
+
+        def rope(theta, n_pos):   # paligemma/modules.py:36-67, positions start at 1
+            hd = d["head_dim"]
+            inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+            fr = torch.arange(1, n_pos + 1, dtype=torch.float32)[:, None] * inv[None, :]
+            return fr.cos().to(dev).contiguous(), fr.sin().to(dev).contiguous()
+
+        c1, s1 = rope(d["vlm_rope_theta"], d["max_image_text_tokens"])
+        c2, s2 = rope(d["act_rope_theta"], d["cond_steps"] + d["horizon_steps"])
+        w.rope_vlm_cos, w.rope_vlm_sin = own(c1), own(s1)
+        w.rope_act_cos, w.rope_act_sin = own(c2), own(s2)
+        w.small_k_pad = skp
+
+        cfg = _lib.PzConfig()
+        cfg.dtype = _lib.PZ_BF16 if T == torch.bfloat16 else _lib.PZ_F32
+        cfg.vocab_size, cfg.pad_token_id = d["vocab_size"], d["pad_token_id"]
+        cfg.image_token_index = d["image_token_index"]
+        cfg.s_vlm, cfg.n_img_tokens, cfg.n_images = d["max_image_text_tokens"], d["num_image_tokens"], d.get("num_images", 1)
+        cfg.cond_steps, cfg.horizon = d["cond_steps"], d["horizon_steps"]
+        cfg.action_dim, cfg.proprio_dim, cfg.n_steps = d["action_dim"], d["proprio_dim"], n_steps
+        clip = d["final_action_clip_value"]
+        cfg.clip = -1.0 if clip is None else float(clip)
+        cfg.n_layers, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim = d["num_layers"], d["num_heads"], d["num_kv_heads"], d["head_dim"]
+        cfg.vlm_hidden, cfg.vlm_inter, cfg.act_hidden, cfg.act_inter = H, d["vlm_inter"], A, d["act_inter"]
+        cfg.vit_hidden, cfg.vit_inter, cfg.vit_layers, cfg.vit_heads = V, d["vit_inter"], d["vit_layers"], d["vit_heads"]
+        cfg.image_size, cfg.patch_size, cfg.patch_k_pad = d["image_size"], ps, kp
+        cfg.max_batch = 1 << 20
+        cfg.flags = self._flags
+        self._destroy_handle()
+        hnd = C.c_void_p()
+        rc = lib.pz_create(C.byref(cfg), C.byref(hnd))
+        if rc != 0:
+            raise PzError(f"pz_create failed ({rc}): {lib.pz_last_error(None).decode()}")
+        rc = lib.pz_bind_weights(hnd, C.byref(w))
+        if rc != 0:
+            msg = lib.pz_last_error(hnd).decode()
+            lib.pz_destroy(hnd)
+            raise PzError(f"pz_bind_weights failed ({rc}): {msg}")
+        self._handle, self._packed, self._packed_key = hnd, (keep, w), key
+        self._T = T
+        self._workspace, self._ws_batch = None, 0
+
+    def _destroy_handle(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().pz_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy_handle()
+        except Exception:
+            pass
+
+    def release_unpacked_parameters(self):
+        """Free the reference-layout parameters after packing (inference-only
+        deployments: halves the resident weight memory).  state_dict() is empty
+        afterwards."""
+        self.pack()
+        for mod in self.modules():
+            for name in list(mod._parameters):
+                mod._parameters[name] = nn.Parameter(torch.empty(0, device="cpu"), requires_grad=False)
+        self._packed_key = self._param_key()
+
+    def _ensure_workspace(self, batch: int):
+        lib = _lib.load()
+        if self._workspace is None or batch > self._ws_batch:
+            cap = batch
+            nbytes = lib.pz_workspace_bytes(self._handle, cap)
+            dev = self._packed[0][0].device
+            self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            self._ws_batch = cap
+            self._ws_bytes = nbytes
+        # every call uses the layout of its own batch size (a prefix of the buffer)
+        base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+        return base, lib.pz_workspace_bytes(self._handle, batch)
+
+    # -------------------------------------------------------------- inference
+    def _valid_len(self, image_text_proprio_mask, input_ids, valid_len):
+        if valid_len is not None:
+            return valid_len.to(device=input_ids.device, dtype=torch.int32).contiguous()
+        if image_text_proprio_mask is not None:
+            # row 0 is an image token: its visible columns are exactly the valid image/text
+            # positions (pizero.py:296-300)
+            Sv = self.max_image_text_tokens
+            return (image_text_proprio_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).contiguous()
+        return (input_ids != self.pad_token_id).sum(-1, dtype=torch.int32).contiguous()
+
+    @torch.no_grad()
+    def infer_action(
+        self,
+        input_ids: torch.LongTensor,
+        pixel_values: torch.FloatTensor,
+        image_text_proprio_mask: Optional[torch.FloatTensor] = None,
+        action_mask: Optional[torch.FloatTensor] = None,
+        vlm_position_ids: Optional[torch.LongTensor] = None,
+        proprio_position_ids: Optional[torch.LongTensor] = None,
+        action_position_ids: Optional[torch.LongTensor] = None,
+        proprios: Optional[torch.FloatTensor] = None,
+        *,
+        noise: Optional[torch.Tensor] = None,
+        valid_len: Optional[torch.Tensor] = None,
+        capture: Optional[dict] = None,
+    ) -> torch.FloatTensor:
+        """pizero.py:416-490.  The eight reference arguments keep their names and
+        meaning.  The dense masks are only used to read the per-sample valid
+        length (the block structure is applied inside the attention kernels,
+        SURVEY.md F8); position ids are the canonical ones
+        `build_causal_mask_and_position_ids` returns (checked when
+        PZ_CHECK_INPUTS=1).  Extras: `noise` ([B,H,A]; default: torch.randn as
+        the reference), `valid_len` (int32 [B], skips the masks entirely),
+        `capture` (dict filled with per-layer tensors for parity tests).
+        Returns fp32 `[B, horizon, action_dim]`."""
+        if proprios is None:
+            raise TypeError("infer_action() missing required argument: 'proprios'")
+        self.pack()
+        lib = _lib.load()
+        d = self.dims
+        dev = self._packed[0][0].device
+        B = input_ids.shape[0]
+        Sv, H, Adim = self.max_image_text_tokens, self.horizon_steps, self.action_dim
+        if input_ids.shape != (B, Sv):
+            raise ValueError(f"input_ids must be [B, {Sv}], got {tuple(input_ids.shape)}")
+        n_img = d.get("num_images", 1)
+        pix_elems = n_img * 3 * d["image_size"] ** 2
+        if pixel_values.shape[0] != B or pixel_values[0].numel() != pix_elems:
+            raise ValueError(f"pixel_values must be [B, {'%d, ' % n_img if n_img > 1 else ''}3, "
+                             f"{d['image_size']}, {d['image_size']}], got {tuple(pixel_values.shape)}")
+        if proprios.shape != (B, self.num_proprio_tokens, self.proprio_dim):
+            raise ValueError(f"proprios must be [B, {self.num_proprio_tokens}, {self.proprio_dim}]")
+        if os.environ.get("PZ_CHECK_INPUTS") == "1":
+            _, vp_, pp_, ap_ = self.build_causal_mask_and_position_ids(
+                torch.ones((B, Sv), dtype=torch.int64, device=dev), torch.float32)
+            for got, want, nm in ((vlm_position_ids, vp_, "vlm"), (proprio_position_ids, pp_, "proprio"),
+                                  (action_position_ids, ap_, "action")):
+                if got is not None and not torch.equal(got.to(dev), want):
+                    raise ValueError(f"{nm}_position_ids differ from build_causal_mask_and_position_ids")
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        pix = pixel_values.to(device=dev, dtype=self._T).contiguous()
+        prop = proprios.to(device=dev, dtype=torch.float32).contiguous()
+        vlen = self._valid_len(image_text_proprio_mask, ids, valid_len)
+        if noise is None:   # pizero.py:454-456
+            noise = torch.randn((B, H, Adim), device=dev, dtype=pixel_values.dtype)
+        nz = noise.to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty((B, H, Adim), device=dev, dtype=torch.float32)
+        ws, ws_bytes = self._ensure_workspace(B)
+        cap_struct, cap_bufs = None, None
+        if capture is not None:
+            cap_struct, cap_bufs = self._make_capture(B, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
+                                 prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
+                                 C.byref(cap_struct) if cap_struct is not None else None, stream)
+        if rc != 0:
+            raise PzError(f"pz_infer_action failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
+        self.last_launch_count = int(lib.pz_launch_count(self._handle))
+        if capture is not None:
+            capture.update(cap_bufs)
+            capture["action"] = out
+            capture["kv"] = self.kv_caches(B)
+        # keep the inputs alive until the stream has consumed them
+        self._inflight = (ids, pix, prop, vlen, nz)
+        return out
+
+    def _make_capture(self, B, dev):
+        d = self.dims
+        L, T_, Sv, Sp, Hz = d["num_layers"], d["num_inference_steps"], d["max_image_text_tokens"], d["cond_steps"], d["horizon_steps"]
+        Mv = B * d.get("num_images", 1) * d["num_image_tokens"]
+        z = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)   # noqa: E731
+        bufs = dict(
+            vit_out=z(Mv, d["vit_hidden"]), image_features=z(Mv, d["vlm_hidden"]),
+            prefix_embeds=z(B, Sv, d["vlm_hidden"]), prefix_vlm=z(max(L - 1, 1), B, Sv, d["vlm_hidden"]),
+            prefix_proprio=z(max(L - 1, 1), B, Sp, d["act_hidden"]),
+            denoise_action=z(T_, L, B, Hz, d["act_hidden"]), velocities=z(T_, B, Hz, d["action_dim"]),
+            action_preclip=z(B, Hz, d["action_dim"]))
+        cs = _lib.PzCapture()
+        for k, t in bufs.items():
+            setattr(cs, k, t.data_ptr())
+        return cs, bufs
+
+    def kv_caches(self, batch: int) -> dict:
+        """The prefix KV of the last call as reference-style caches
+        (`joint_model.build_mixture_caches`, joint_model.py:325)."""
+        lib = _lib.load()
+        d = self.dims
+        ko, vo, ls = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        lib.pz_kv_layout(self._handle, batch, C.byref(ko), C.byref(vo), C.byref(ls))
+        base = (self._workspace.data_ptr() + 1023) // 1024 * 1024 - self._workspace.data_ptr()
+        es = 2 if self._T == torch.bfloat16 else 4
+        Sc = d["max_image_text_tokens"] + d["cond_steps"]
+        n = d["num_layers"] * batch * Sc * d["head_dim"]
+
+        def view(off):
+            raw = self._workspace[base + off: base + off + n * es]
+            return raw.view(self._T).view(d["num_layers"], batch, Sc, d["head_dim"])
+
+        k, v = view(ko.value), view(vo.value)
+        Sv = d["max_image_text_tokens"]
+        return {"vlm": KVCache(k, v, 0, Sv, d["num_layers"]),
+                "proprio": KVCache(k, v, Sv, Sc, d["num_layers"])}
+
+    def forward(self, *args, **kwargs):
+        raise PzError("PiZero.forward (flow-matching training loss, pizero.py:607-661) is outside "
+                      "this library's scope; use infer_action / PiZeroInference")
+
+
+class PiZeroInference(PiZero):
+    """pizero.py:664-686: `forward` is `infer_action`, so `model(**inputs)` works."""
+
+    def forward(self, input_ids, pixel_values, image_text_proprio_mask=None, action_mask=None,
+                vlm_position_ids=None, proprio_position_ids=None, action_position_ids=None,
+                proprios=None, **extra):
+        return super().infer_action(input_ids, pixel_values, image_text_proprio_mask, action_mask,
+                                    vlm_position_ids, proprio_position_ids, action_position_ids,
+                                    proprios, **extra)
