@@ -1,0 +1,115 @@
+"""CPU: host-side logic of the drop-in boundary and the C-ABI library surface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT, SMALL, pz
+from oracle import pizero_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from open_pi_zero_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "pz_b200.h")).read()
+    declared = set(re.findall(r"\b(pz_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pz_abi_version() == _lib.PZ_ABI_VERSION
+
+
+def test_create_rejects_bad_config_without_gpu():
+    from open_pi_zero_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.PzConfig()
+    h = ctypes.c_void_p()
+    assert lib.pz_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"" != lib.pz_last_error(None)
+    assert lib.pz_workspace_bytes(None, 4) == 0
+
+
+def test_state_dict_contract_938_keys():
+    from open_pi_zero_b200.pizero import PiZero
+    m = PiZero(pz.cfg_from_dims(pz.make_dims()), init="empty", device="meta")
+    sd = m.state_dict()
+    assert len(sd) == 938
+    assert sd["embed_tokens.weight"].shape == (257216, 2048)
+    assert sd["vision_tower.vision_model.embeddings.patch_embedding.weight"].shape == (1152, 3, 14, 14)
+    assert sd["joint_model.mixtures.vlm.layers.17.mlp.down_proj.weight"].shape == (2048, 16384)
+    assert sd["joint_model.mixtures.action.layers.0.self_attn.q_proj.weight"].shape == (2048, 1024)
+    assert sd["joint_model.mixtures.proprio.norm.weight"].shape == (1024,)
+    assert "joint_model.mixtures.vlm.norm.weight" not in sd
+    assert sd["action_encoder.linear_2.weight"].shape == (1024, 2048)
+    assert sd["action_decoder.weight"].shape == (7, 1024)
+    n = sum(v.numel() for k, v in sd.items() if ".proprio." not in k)
+    assert abs(n - 3.238e9) < 2e6    # 3.238 B unique parameters
+
+
+def test_load_state_dict_strict_and_orig_mod_prefix():
+    from open_pi_zero_b200.pizero import PiZero
+    sd = pz.init_state_dict(SMALL, seed=0)
+    m = PiZero(SMALL, init="empty")
+    m.load_state_dict({"_orig_mod." + k: v for k, v in sd.items()}, strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+    bad = dict(sd)
+    bad.pop("action_decoder.bias")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    m.tie_action_proprio_weights()
+    assert len(m.state_dict()) == len(sd)     # tied: both prefixes are still emitted
+
+
+def test_mask_and_position_builder_matches_reference_semantics():
+    from open_pi_zero_b200.pizero import PiZero
+    m = PiZero(SMALL, init="empty", device="meta")
+    inp = pz.make_inputs(SMALL, 7, seed=3, min_text=0)
+    for dtype in (torch.float32, torch.bfloat16):
+        mask, vp, pp, ap = m.build_causal_mask_and_position_ids(inp["attention_mask"], dtype)
+        full, pm, am, pos = O.build_masks_and_positions(SMALL, inp["attention_mask"], dtype)
+        assert torch.equal(mask, full)
+        assert torch.equal(vp, pos["vlm"]) and torch.equal(pp, pos["proprio"]) and torch.equal(ap, pos["action"])
+        a, b = m.split_full_mask_into_submasks(mask)
+        assert torch.equal(a, pm) and torch.equal(b, am)
+    vl = m._valid_len(pm, inp["input_ids"], None)
+    assert torch.equal(vl.to(torch.int64), inp["attention_mask"].sum(1))
+
+
+def test_config_round_trip_and_scope_guards():
+    d = pz.make_dims()
+    assert pz.dims_from_cfg(pz.cfg_from_dims(d)) == d
+    cfg = pz.cfg_from_dims(d)
+    cfg.mixture.vlm.use_lora = True
+    with pytest.raises(NotImplementedError):
+        pz.dims_from_cfg(cfg)
+    cfg = pz.cfg_from_dims(d)
+    cfg.action_expert_adaptive_mode = "adaLN"
+    with pytest.raises(NotImplementedError):
+        pz.dims_from_cfg(cfg)
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA -- never route through the oracle."""
+    from open_pi_zero_b200.pizero import PiZero, PzError
+    m = PiZero(SMALL, init="empty")
+    inp = pz.make_inputs(SMALL, 1)
+    with pytest.raises(PzError):
+        m.infer_action(inp["input_ids"], inp["pixel_values"], proprios=inp["proprios"])
+    import open_pi_zero_b200.pizero as mod
+    src = open(mod.__file__).read()
+    assert "oracle" not in src.replace("oracle/", "")
+
+
+def test_synthetic_inputs_follow_processor_layout():
+    d = pz.make_dims()
+    inp = pz.make_inputs(d, 8, seed=0)
+    ids = inp["input_ids"]
+    assert ids.shape == (8, 276) and (ids[:, :256] == 257152).all() and (ids[:, 256] == 2).all()
+    assert inp["pixel_values"].abs().max() <= 1.0
+    vl = inp["valid_len"]
+    assert vl.min() >= 257 + 4 and vl.max() <= 276 and len(set(vl.tolist())) > 1
+    for b in range(8):
+        assert (ids[b, int(vl[b]):] == 0).all() and (ids[b, : int(vl[b])] != 0).all()
