@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- `PiZero.infer_action` throughput / latency on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One step = one `infer_action` call (SigLIP + Gemma prefix + 10 Euler steps) over
+one batch of synthetic observations of the bridge shape (BASELINE.json
+configs[1]): 224 px image, 276 image+text tokens, 1 proprio token, chunk 4.
+Per-GPU batch 64, one full replica per GPU, batch-sharded, no collective
+(weak scaling).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import open_pi_zero_b200 as pz  # noqa: E402
+
+METRIC = "action chunks/s per box (bridge-shape infer_action, bf16); p50 infer_action latency at bs=1"
+UNIT = "action_chunks/s"
+PER_GPU_BATCH = int(os.environ.get("PZ_BENCH_BATCH", "64"))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p["bf16_tflops"],
+                    tflops_sustained=p["bf16_tflops_sustained"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def build_model(dims, device, cpu_state_dict=None):
+    from open_pi_zero_b200.pizero import PiZeroInference
+    if cpu_state_dict is not None:
+        m = PiZeroInference(pz.cfg_from_dims(dims), init="empty")
+        m.load_state_dict(cpu_state_dict, strict=True)
+        m = m.to(torch.bfloat16).to(device)
+    else:
+        m = PiZeroInference(pz.cfg_from_dims(dims), init="empty", device=device, dtype=torch.bfloat16)
+        from open_pi_zero_b200.synth import fill_random_
+        fill_random_(m, dims, seed=42)
+    m.pack()
+    return m
+
+
+def device_inputs(m, inp, device):
+    return dict(input_ids=inp["input_ids"].to(device),
+                pixel_values=inp["pixel_values"].to(device=device, dtype=torch.bfloat16),
+                proprios=inp["proprios"].to(device), noise=inp["noise"].to(device),
+                valid_len=inp["valid_len"].to(device))
+
+
+def run_cpu_oracle(dims, sd, steps, warmup, batch=1):
+    """The reference's algorithm on the host cores (oracle port, fp32, all threads)."""
+    from oracle import pizero_oracle as O
+    inp = pz.make_inputs(dims, batch, seed=0)
+    times, out = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.infer_action(sd, dims, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                             inp["proprios"], inp["noise"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, out, inp
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    dims = pz.make_dims()
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = pz.init_state_dict(dims, seed=42)
+    times, _, _ = run_cpu_oracle(dims, sd, args.steps, max(args.warmup, 1))
+    total = sum(times)
+    value = len(times) / total
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="bridge infer_action: 224px image, 276 image+text tokens, 1 proprio, "
+                                     "chunk 4, 10 Euler steps; reference algorithm on host CPU, bs=1 per step",
+                            global_batch=1),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                                  sample=f"{len(times)} infer_action calls at bs=1, fp32, after "
+                                         f"{max(args.warmup, 1)} warm-up"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-latency", action="store_true", help="profiling runs only")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the infer_action path has no CPU fallback")
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    warmup = max(args.warmup, 3)
+    dims = pz.make_dims()
+    B = PER_GPU_BATCH
+    peaks = measured_peaks()
+
+    do_cpu = (world == 1 and not args.no_cpu_baseline)
+    sd = pz.init_state_dict(dims, seed=42) if do_cpu else None
+    model = build_model(dims, device, sd)
+    inp = pz.make_inputs(dims, B, seed=1000 + rank)
+    dev_in = device_inputs(model, inp, device)
+
+    def step():
+        return model(**dev_in)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    sync_all()
+    model.timing_begin(model.TAG_VLM_GATE_UP)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        sync_all()
+    clocks = clk.summary()
+    ms_total = e0.elapsed_time(e1)
+    gu_ms, gu_n = model.timing_end()
+    launches = model.last_launch_count * args.steps
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with host buffers ----------------
+    host = {k: v.pin_memory() for k, v in dict(
+        input_ids=inp["input_ids"], pixel_values=inp["pixel_values"].to(torch.bfloat16),
+        proprios=inp["proprios"], noise=inp["noise"], valid_len=inp["valid_len"]).items()}
+    out_host = torch.empty((B, dims["horizon_steps"], dims["action_dim"]), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step():
+        dv = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        out = model(**dv)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_s = float("nan")
+    if not args.skip_e2e:
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    # ---- bs=1 latency (p50) --------------------------------------------------
+    lat = None
+    if rank == 0 and not args.skip_latency:
+        one = {k: v[:1].contiguous() for k, v in dev_in.items()}
+        for _ in range(10):
+            model(**one)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(50):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model(**one)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        lat = dict(p50_ms=statistics.median(ts), min_ms=min(ts), launches=model.last_launch_count)
+    sync_all()
+
+    # ---- roofline of the dominant kernel (VLM gate|up GEMM, tensor-bound) -----
+    Mchunk = min(B, 64) * dims["max_image_text_tokens"]
+    flops_per_launch = 2.0 * Mchunk * (2 * dims["vlm_inter"]) * dims["vlm_hidden"]
+    roof = None
+    if gu_n > 0:
+        avg_ms = gu_ms / gu_n
+        achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="gemm_tc_kernel<256> (VLM gate|up + GeGLU)", achieved=achieved,
+                    peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
+                    traffic=None, avg_launch_ms=avg_ms, launches_timed=gu_n,
+                    share_of_step=gu_ms / ms_total, peak_source=peaks["source"] + ", sustained figure")
+
+    cpu = None
+    if do_cpu and rank == 0:
+        torch.set_num_threads(os.cpu_count() or 1)
+        times, want, cinp = run_cpu_oracle(dims, sd, steps=3, warmup=1)
+        got = model(input_ids=cinp["input_ids"].to(device), pixel_values=cinp["pixel_values"].to(device),
+                    proprios=cinp["proprios"].to(device), noise=cinp["noise"].to(device),
+                    valid_len=cinp["valid_len"].to(device)).cpu()
+        cpu = dict(value=len(times) / sum(times), unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                   sample="3 infer_action calls at bs=1 (fp32 oracle port of the reference, all host "
+                          "threads) after 1 warm-up",
+                   max_abs_gpu_vs_cpu=float((got - want).abs().max()))
+
+    if rank == 0:
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup,
+            ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="bf16", data="synthetic",
+            config=dict(workload=f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
+                                 "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
+                                 "3.24B-parameter model", global_batch=world * B, per_gpu_batch=B,
+                        parallelism=f"replica x{world}, batch-sharded, no collective",
+                        l2="working set per step (6.5 GB bf16 weights + activations) >> 126 MB L2; no flush"),
+            clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+            gpu_launches=launches, latency_bs1=lat, roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,14 @@ int pz_denoise(pz_handle *h, const int32_t *d_valid_len, const float *d_noise,
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);
 
+/* CUDA-event timing of one kernel family inside real calls (bench.py's roofline
+ * object).  tag: 1 = VLM gate|up GEMM, 2 = VLM down GEMM, 3 = action gate|up.
+ * pz_timing_begin arms it; every tagged launch of the following calls is
+ * bracketed by events on the launching stream; pz_timing_end synchronises on
+ * those events and returns the summed duration and the number of launches. */
+int pz_timing_begin(pz_handle *h, int tag);
+int pz_timing_end(pz_handle *h, double *total_ms, int64_t *launches);
+
 /* ---- single-op entry points (unit tests of the hand-written kernels) ---- */
 
 /* C = alpha * epilogue(A[M,K] . W[N,K]^T + bias[N]).  impl: 0 = SIMT reference

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -26,7 +27,23 @@ struct pz_handle {
     std::string err;
     LaunchCounter lc;
     int prefix_chunk = 64;
+    // optional CUDA-event timing of one tagged kernel family (bench.py roofline)
+    int timing_tag = 0;                       // 0 = off
+    std::vector<cudaEvent_t> ev;              // pairs (start, stop)
+    size_t ev_used = 0;
 };
+
+enum { TAG_VLM_GATE_UP = 1, TAG_VLM_DOWN = 2, TAG_ACT_GATE_UP = 3, TAG_VIT_FC1 = 4 };
+
+static void tick(pz_handle *h, int tag, cudaStream_t st) {
+    if (h->timing_tag != tag) return;
+    if (h->ev_used == h->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev.push_back(e);
+    }
+    cudaEventRecord(h->ev[h->ev_used++], st);
+}
 
 static int fail(pz_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg; else g_create_error = msg;
@@ -233,10 +250,15 @@ static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *h
     PZ_TRY(Ops<T>::linear(h, lin(att, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
                                  LIN_OUT_F32 | LIN_ACCUM), st));
     launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
+    int tag_gu = hidden == c.vlm_hidden ? TAG_VLM_GATE_UP : TAG_ACT_GATE_UP;
+    tick(h, tag_gu, st);
     PZ_TRY(Ops<T>::linear(h, lin(hbuf, hidden, L.w_gate_up, nullptr, mlp, inter, M, 2 * inter, hidden,
                                  LIN_GEGLU), st));
+    tick(h, tag_gu, st);
+    if (hidden == c.vlm_hidden) tick(h, TAG_VLM_DOWN, st);
     PZ_TRY(Ops<T>::linear(h, lin(mlp, inter, L.w_down, nullptr, x, hidden, M, hidden, inter,
                                  LIN_OUT_F32 | LIN_ACCUM), st));
+    if (hidden == c.vlm_hidden) tick(h, TAG_VLM_DOWN, st);
     return 0;
 }
 
@@ -266,9 +288,17 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
             T *Vc = (T *)ws.vcache + ((size_t)l * B + b0) * kv_bs;
             // vlm block: norm -> fused QKV projection -> RoPE; K (post-RoPE) and V go to the cache
             launch_rmsnorm<T>(x, h->vlm[l].norm_in, (T *)ws.h, M, H, 1e-6f, st);
-            PZ_TRY(Ops<T>::linear(h, lin(ws.h, H, h->vlm[l].w_qkv, nullptr, ws.qkv, qkvd, M, qkvd, H), st));
-            launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)S_v * qd, Kc, Vc, kv_bs,
-                                 w.rope_vlm_cos, w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
+            if (std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 && H % 8 == 0) {
+                // one kernel: tcgen05 GEMM with RoPE, Q/K/V split and the cache write in its epilogue
+                const char *e = nullptr;
+                int rc = launch_qkv_rope_tc(ws.h, H, h->vlm[l].w_qkv, ws.q, Kc, Vc, kv_bs, w.rope_vlm_cos,
+                                            w.rope_vlm_sin, M, H, nh, S_v, st, &e);
+                if (rc) return fail(h, rc, e ? e : "fused qkv+rope launch failed");
+            } else {
+                PZ_TRY(Ops<T>::linear(h, lin(ws.h, H, h->vlm[l].w_qkv, nullptr, ws.qkv, qkvd, M, qkvd, H), st));
+                launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)S_v * qd, Kc, Vc, kv_bs,
+                                     w.rope_vlm_cos, w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
+            }
             // proprio block through the action-expert-shaped weights
             launch_rmsnorm<T>(ws.xp, h->proprio[l].norm_in, (T *)ws.hp, Mp, A, 1e-6f, st);
             PZ_TRY(Ops<T>::linear(h, lin(ws.hp, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), st));
@@ -396,7 +426,11 @@ int pz_create(const pz_config *cfg, pz_handle **out) {
     return PZ_OK;
 }
 
-void pz_destroy(pz_handle *h) { delete h; }
+void pz_destroy(pz_handle *h) {
+    if (!h) return;
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    delete h;
+}
 
 int pz_bind_weights(pz_handle *h, const pz_weights *w) {
     if (!h || !w) return PZ_ERR_INVALID;
@@ -494,6 +528,29 @@ int pz_infer_action(pz_handle *h, const int64_t *ids, const void *pixels, const 
 }
 
 int64_t pz_launch_count(const pz_handle *h) { return h ? h->lc.n : 0; }
+
+int pz_timing_begin(pz_handle *h, int tag) {
+    if (!h) return PZ_ERR_INVALID;
+    h->timing_tag = tag;
+    h->ev_used = 0;
+    return PZ_OK;
+}
+
+int pz_timing_end(pz_handle *h, double *total_ms, int64_t *launches) {
+    if (!h) return PZ_ERR_INVALID;
+    double ms = 0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        if (cudaEventSynchronize(h->ev[i + 1]) != cudaSuccess) return fail(h, PZ_ERR_CUDA, "event sync failed");
+        float t = 0;
+        cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)(h->ev_used / 2);
+    h->timing_tag = 0;
+    h->ev_used = 0;
+    return PZ_OK;
+}
 
 // ---- single-op entry points -------------------------------------------------
 int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const float *d_bias, void *d_c,

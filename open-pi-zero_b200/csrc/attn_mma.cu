@@ -1,4 +1,279 @@
+// attn_mma.cu -- fused block-masked attention on tensor cores (bf16 in, fp32
+// softmax and accumulation), flash-style: the score matrix never touches HBM.
+//
+// Replaces the reference's materialised attention
+//   joint_model.py:243-282  (repeat_kv, cat, QK^T/sqrt(d), tanh soft-cap 50, +mask, fp32 softmax, PV)
+//   siglip.py:133-152       (QK^T * d^-0.5, fp32 softmax, PV; no mask)
+// The block mask of pizero.py:271-310 is applied in registers from the per-sample
+// valid length; the dense [B,1,S,S] mask is never read.  MQA
+// (one KV head) is folded: (head, token) pairs are just more query rows against
+// the same K/V tile (SURVEY.md 8a note 6), so each CTA streams the cached K/V once.
+//
+// CTA = 4 warps x 16 query rows; keys in tiles of 64; cp.async staging, ldmatrix
+// fragments, mma.sync.m16n8k16.  (<1 % of the path's FLOPs: 11.3 of 1268 GFLOP.)
 #include "common.cuh"
 #include "kernels.h"
-int attn_mma_supported(const AttnArgs &) { return 0; }
-int launch_attn_mma(const AttnArgs &, cudaStream_t) { return PZ_ERR_INVALID; }
+
+namespace {
+
+constexpr int ROWS_PER_CTA = 64, KEY_TILE = 64, NTHREADS = 128;
+
+PZ_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PZ_DEVINL void cp_async16(void *dst, const void *src, bool valid) {
+    int sz = valid ? 16 : 0;   // src-size 0 => destination is zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz)
+                 : "memory");
+}
+PZ_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PZ_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+PZ_DEVINL void ldsm_x4(uint32_t (&r)[4], const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+PZ_DEVINL void ldsm_x4_t(uint32_t (&r)[4], const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+PZ_DEVINL void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// visibility classes of a launch (all of its query rows share one)
+enum { CLS_ALL = 0, CLS_VLM = 1, CLS_PROPRIO = 2, CLS_ACTION = 3 };
+
+template <int HD>   // true head_dim; HDP = padded to a multiple of 16
+__global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int cls, int mqa) {
+    constexpr int HDP = (HD + 15) / 16 * 16;
+    constexpr int LDS = HDP + 8;            // +16 B per row: conflict-free ldmatrix
+    constexpr int CHUNKS = HD / 8;          // 16-byte chunks of real data per row
+    constexpr int PCHUNKS = HDP / 8;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    bf16 *sQ = (bf16 *)smem_raw;
+    bf16 *sK = sQ + ROWS_PER_CTA * LDS;
+    bf16 *sV = sK + KEY_TILE * LDS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.z;
+    const int head_y = blockIdx.y;                       // only used when !mqa
+    const int rows_total = mqa ? a.n_heads * a.q_rows : a.q_rows;
+    const int row0 = blockIdx.x * ROWS_PER_CTA;
+    const int vlen = a.valid_len ? a.valid_len[b] : a.s_cache;
+
+    int n_keys;   // keys [0, n_keys) are iterated; the pad gap [vlen, s_vlm) is masked
+    if (cls == CLS_ALL) n_keys = a.s_cache;
+    else if (cls == CLS_VLM) n_keys = vlen;
+    else if (cls == CLS_PROPRIO) n_keys = a.s_cache;
+    else n_keys = a.s_cache + a.n_fresh;
+    const int n_tiles = (n_keys + KEY_TILE - 1) / KEY_TILE;
+
+    const bf16 *Qb = (const bf16 *)a.Q + b * a.q_batch_stride;
+    const bf16 *Kb = (const bf16 *)a.K + b * a.kv_batch_stride + (mqa ? 0 : head_y * a.kv_head_stride);
+    const bf16 *Vb = (const bf16 *)a.V + b * a.kv_batch_stride + (mqa ? 0 : head_y * a.kv_head_stride);
+    const bf16 *K2b = a.K2 ? (const bf16 *)a.K2 + b * a.kv2_batch_stride : nullptr;
+    const bf16 *V2b = a.V2 ? (const bf16 *)a.V2 + b * a.kv2_batch_stride : nullptr;
+
+    // ---- stage Q (once) and the first K tile -----------------------------
+    for (int i = tid; i < ROWS_PER_CTA * PCHUNKS; i += NTHREADS) {
+        int r = i / PCHUNKS, c = i % PCHUNKS;
+        int row = row0 + r;
+        bool ok = row < rows_total && c < CHUNKS;
+        int h = mqa ? row / a.q_rows : head_y;
+        int tok = mqa ? row % a.q_rows : row;
+        const bf16 *src = ok ? Qb + (long)tok * a.q_row_stride + h * a.q_head_stride + c * 8 : Qb;
+        cp_async16(sQ + r * LDS + c * 8, src, ok);
+    }
+    auto load_kv = [&](bf16 *dst, const bf16 *base, const bf16 *base2, int tile) {
+        for (int i = tid; i < KEY_TILE * PCHUNKS; i += NTHREADS) {
+            int r = i / PCHUNKS, c = i % PCHUNKS;
+            int j = tile * KEY_TILE + r;
+            bool ok = j < n_keys && c < CHUNKS;
+            const bf16 *src = base;
+            if (ok) src = (j < a.s_cache) ? base + (long)j * a.kv_row_stride + c * 8
+                                          : base2 + (long)(j - a.s_cache) * a.kv2_row_stride + c * 8;
+            cp_async16(dst + r * LDS + c * 8, src, ok);
+        }
+    };
+    load_kv(sK, Kb, K2b, 0);
+    cp_async_commit();
+
+    float o[HDP / 8][4];
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    const float scale = a.scale, cap = a.softcap, inv_cap = cap > 0.f ? 1.f / cap : 0.f;
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        load_kv(sV, Vb, V2b, tile);
+        cp_async_commit();
+        cp_async_wait<1>();          // Q and K(tile) have landed
+        __syncthreads();
+
+        // ---- S = Q K^T for this warp's 16 rows x 64 keys ------------------
+        float s[KEY_TILE / 8][4];
+#pragma unroll
+        for (int i = 0; i < KEY_TILE / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < HDP / 16; ++ks) {
+            uint32_t qa[4];
+            ldsm_x4(qa, sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+            for (int nt2 = 0; nt2 < KEY_TILE / 16; ++nt2) {
+                // 16 keys x 16 d: matrices (keys 0-7,d 0-7), (keys 0-7,d 8-15), (keys 8-15,d 0-7), (keys 8-15,d 8-15)
+                uint32_t kb[4];
+                ldsm_x4(kb, sK + (nt2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+                mma_bf16(s[2 * nt2], qa, kb[0], kb[1]);
+                mma_bf16(s[2 * nt2 + 1], qa, kb[2], kb[3]);
+            }
+        }
+        __syncthreads();             // every warp is done reading sK
+        if (tile + 1 < n_tiles) load_kv(sK, Kb, K2b, tile + 1);
+        cp_async_commit();
+
+        // ---- scale, soft-cap, mask, online softmax --------------------------
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < KEY_TILE / 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int j = tile * KEY_TILE + nt * 8 + 2 * t + (e & 1);
+                bool vis;
+                if (cls == CLS_ALL) vis = j < n_keys;
+                else if (cls == CLS_VLM) vis = j < vlen;
+                else vis = (j < vlen) || (j >= a.s_vlm && j < n_keys);
+                float v = s[nt][e] * scale;
+                if (cap > 0.f) v = tanhf(v * inv_cap) * cap;
+                v = vis ? v : -INFINITY;
+                s[nt][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+        }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            float m_new = fmaxf(m_run[r], mx[r]);
+            float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+            corr[r] = __expf(m_run[r] - m_safe);     // m_run = -inf -> 0
+            m_run[r] = m_new;
+            mx[r] = m_safe;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pa[KEY_TILE / 16][4];
+#pragma unroll
+        for (int nt = 0; nt < KEY_TILE / 8; ++nt) {
+            float p0 = __expf(s[nt][0] - mx[0]), p1 = __expf(s[nt][1] - mx[0]);
+            float p2 = __expf(s[nt][2] - mx[1]), p3 = __expf(s[nt][3] - mx[1]);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            // C fragments of two adjacent 8-key tiles form one 16-key A fragment
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int i = 0; i < HDP / 8; ++i) {
+            o[i][0] *= corr[0]; o[i][1] *= corr[0];
+            o[i][2] *= corr[1]; o[i][3] *= corr[1];
+        }
+
+        cp_async_wait<1>();          // V(tile) has landed (K(tile+1) may still be in flight)
+        __syncthreads();
+        // ---- O += P V -------------------------------------------------------
+#pragma unroll
+        for (int kk = 0; kk < KEY_TILE / 16; ++kk) {
+#pragma unroll
+            for (int dt2 = 0; dt2 < HDP / 16; ++dt2) {
+                // 16 keys x 16 d, transposed on load: (keys 0-7,d 0-7), (keys 8-15,d 0-7), (keys 0-7,d 8-15), (keys 8-15,d 8-15)
+                uint32_t vb[4];
+                ldsm_x4_t(vb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dt2 * 16 + (lane >> 4) * 8);
+                mma_bf16(o[2 * dt2], pa[kk], vb[0], vb[1]);
+                mma_bf16(o[2 * dt2 + 1], pa[kk], vb[2], vb[3]);
+            }
+        }
+        __syncthreads();             // every warp is done reading sV
+    }
+    cp_async_wait<0>();
+
+    // ---- normalise and store ------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float l = l_run[r];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        l_run[r] = l > 0.f ? 1.f / l : 0.f;
+    }
+    bf16 *Ob = (bf16 *)a.O + b * a.o_batch_stride;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int row = row0 + warp * 16 + g + r * 8;
+        if (row >= rows_total) continue;
+        int h = mqa ? row / a.q_rows : head_y;
+        int tok = mqa ? row % a.q_rows : row;
+        bf16 *dst = Ob + (long)tok * a.o_row_stride + h * a.o_head_stride;
+        // pad rows (token >= valid_len) are never read by a valid row: write zeros
+        const float nrm = (cls == CLS_VLM && a.q_row0 + tok >= vlen) ? 0.f : l_run[r];
+#pragma unroll
+        for (int i = 0; i < HDP / 8; ++i) {
+            int d = i * 8 + 2 * t;
+            if (d < HD)
+                *reinterpret_cast<uint32_t *>(dst + d) = pack_bf16x2(o[i][2 * r] * nrm, o[i][2 * r + 1] * nrm);
+        }
+    }
+}
+
+template <int HD>
+int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
+    constexpr int HDP = (HD + 15) / 16 * 16;
+    constexpr int LDS = HDP + 8;
+    size_t smem = (size_t)(ROWS_PER_CTA + 2 * KEY_TILE) * LDS * sizeof(bf16);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return PZ_ERR_CUDA;
+        attr_set = true;
+    }
+    int rows_total = mqa ? a.n_heads * a.q_rows : a.q_rows;
+    dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
+    attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa);
+    count_launch();
+    return 0;
+}
+
+int classify(const AttnArgs &a) {
+    if (!a.valid_len) return (a.n_fresh == 0 && a.s_vlm == a.s_cache) ? CLS_ALL : -1;
+    int lo = a.q_row0, hi = a.q_row0 + a.q_rows;
+    if (hi <= a.s_vlm) return a.n_fresh == 0 ? CLS_VLM : -1;
+    if (lo >= a.s_vlm && hi <= a.s_cache) return a.n_fresh == 0 ? CLS_PROPRIO : -1;
+    if (lo >= a.s_cache) return CLS_ACTION;
+    return -1;
+}
+
+}  // namespace
+
+int attn_mma_supported(const AttnArgs &a) {
+    if (a.head_dim != 72 && a.head_dim != 256) return 0;
+    if (classify(a) < 0) return 0;
+    // 16-byte cp.async granularity
+    if (a.q_row_stride % 8 || a.q_head_stride % 8 || a.kv_row_stride % 8 || a.kv_head_stride % 8) return 0;
+    if (a.q_batch_stride % 8 || a.kv_batch_stride % 8 || a.o_row_stride % 2 || a.o_head_stride % 2) return 0;
+    if (a.n_fresh && (a.kv2_row_stride % 8 || a.kv2_batch_stride % 8 || !a.K2 || !a.V2)) return 0;
+    if (((uintptr_t)a.Q | (uintptr_t)a.K | (uintptr_t)a.V | (uintptr_t)a.K2 | (uintptr_t)a.V2) & 15) return 0;
+    if ((uintptr_t)a.O & 3) return 0;
+    return 1;
+}
+
+int launch_attn_mma(const AttnArgs &a, cudaStream_t st) {
+    int cls = classify(a);
+    int mqa = a.kv_head_stride == 0;
+    if (a.head_dim == 72) return launch<72>(a, cls, mqa, st);
+    return launch<256>(a, cls, mqa, st);
+}

@@ -20,6 +20,7 @@
 // pass (reference call sites: siglip.py:115-119,164,188-192; mixture.py:187-218;
 // paligemma/modules.py:86-95), and for the denoise layers when B*horizon > 64.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -107,7 +108,7 @@ PZ_DEVINL uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 // Instruction descriptor: D fp32, A/B bf16, both K-major, M x N.
-constexpr uint32_t umma_idesc(int M, int N) {
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -118,7 +119,18 @@ struct TcParams {
     float alpha;
     int flags;
     int tiles_m, tiles_n;
+    // fused RoPE + Q/K/V split (LIN_ROPE): BN = 256 = head_dim, one N tile per head
+    const float *rope_cos, *rope_sin;   // [s_x, 128] fp32
+    bf16 *k_out, *v_out;                // cache rows: base + b*kv_batch_stride + s*256
+    long kv_batch_stride;
+    int s_x, n_q_tiles;
 };
+
+constexpr int LIN_ROPE = 1 << 10;       // internal flag of this file
+
+constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant
+constexpr int NUM_THREADS2 = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = BN == 256 ? 4 : 6;
@@ -126,17 +138,49 @@ template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two: 256 / 512)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+PZ_DEVINL float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// gelu-tanh with the hardware tanh (rel. error 2^-11, far below the bf16 rounding of the output)
+PZ_DEVINL float gelu_fast(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    return 0.5f * x * (1.0f + tanh_fast(k0 * (x + k1 * x * x * x)));
+}
+
+PZ_DEVINL void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+PZ_DEVINL void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+PZ_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+PZ_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PZ_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+PZ_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap map_c, const TcParams p) {
     using cfg = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = (uint64_t *)(smem + cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t *full_bar = (uint64_t *)(smem + cfg::BAR_OFF);
     uint64_t *empty_bar = full_bar + cfg::STAGES;
     uint64_t *tfull_bar = empty_bar + cfg::STAGES;
     uint64_t *tempty_bar = tfull_bar + 2;
@@ -149,10 +193,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -216,66 +261,161 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= EPI_WARP0) {
         // ---------------------------------------------------- epilogue ----
-        const int q = warp & 3;   // TMEM lane quadrant this warp may read
+        // Warp pair (q, half): TMEM lanes [32q, 32q+32) = tile rows, column half `half`.
+        // Results are staged in a per-warp 32 x 128 B swizzled buffer and leave through
+        // TMA (plain store, or fp32 reduce-add into the residual stream), so HBM/L2 sees
+        // full 128-byte lines and out-of-range rows/columns are clipped by the hardware.
+        const int q = warp & 3;
+        const int half = (warp - EPI_WARP0) >> 2;
+        uint8_t *stg = smem + cfg::STG_OFF + (warp - EPI_WARP0) * STG_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool geglu = p.flags & LIN_GEGLU;
         const bool out_f32 = p.flags & LIN_OUT_F32;
+        const bool accum = p.flags & LIN_ACCUM;
+        const bool rope = p.flags & LIN_ROPE;
+        const int n_out = geglu ? p.N / 2 : p.N;
+        const int sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
+        uint8_t *stg_row = stg + lane * 128;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int tm = t % p.tiles_m, tn = t / p.tiles_m;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = tm * BM + q * 32 + lane;
+            const int row0 = tm * BM + q * 32;       // first row of this warp
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-            const int n_chunks = geglu ? BN / 64 : BN / 32;
-            for (int c = 0; c < n_chunks; ++c) {
-                uint32_t r[32];
-                float v[32];
-                tc_ld32(taddr + c * 32, r);
-                int col0;   // first output column of this chunk
-                if (geglu) {
-                    uint32_t u[32];
-                    tc_ld32(taddr + BN / 2 + c * 32, u);
-                    tc_ld_wait();
+            if (rope) {
+                if constexpr (BN == 256) {
+                    // ---- fused RoPE (half-split rotation, model/utils.py:4-16) + Q/K/V split ----
+                    const int row = row0 + lane;
+                    const int bb = row / p.s_x, ss = row % p.s_x;
+                    if (tn <= p.n_q_tiles) {
+                        const float *cs = p.rope_cos + (long)ss * 128;
+                        const float *sn = p.rope_sin + (long)ss * 128;
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int c = half * 2 + cc;        // pair index: cols [32c,32c+32) with +128
+                            uint32_t r1[32], r2[32];
+                            tc_ld32(taddr + c * 32, r1);
+                            tc_ld32(taddr + 128 + c * 32, r2);
+                            tc_ld_wait();
+                            uint32_t o1[16], o2[16];
+                            if (row < p.M) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        v[i] = gelu_tanh(__uint_as_float(r[i])) * __uint_as_float(u[i]) * p.alpha;
-                    col0 = tn * (BN / 2) + c * 32;
-                } else {
-                    tc_ld_wait();
-                    col0 = tn * BN + c * 32;
+                                for (int i = 0; i < 32; i += 4) {
+                                    float4 cv = __ldg(reinterpret_cast<const float4 *>(cs + c * 32 + i));
+                                    float4 sv = __ldg(reinterpret_cast<const float4 *>(sn + c * 32 + i));
+                                    float cf[4] = {cv.x, cv.y, cv.z, cv.w}, sf[4] = {sv.x, sv.y, sv.z, sv.w};
+                                    float a1[4], a2[4];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]);
-                        if (p.bias && col0 + i < p.N) x += __ldg(p.bias + col0 + i);
-                        if (p.flags & LIN_GELU) x = gelu_tanh(x);
-                        if (p.flags & LIN_SILU) x = silu(x);
-                        v[i] = x * p.alpha;
-                    }
-                }
-                const int n_out = geglu ? p.N / 2 : p.N;
-                if (row < p.M && col0 < n_out) {
-                    int nvalid = n_out - col0 < 32 ? n_out - col0 : 32;   // multiple of 8 (checked on host)
-                    if (out_f32) {
-                        float *dst = (float *)p.C + (long)row * p.ldc + col0;
-                        for (int i = 0; i < nvalid; i += 4) {
-                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            if (p.flags & LIN_ACCUM) {
-                                float4 old = *reinterpret_cast<float4 *>(dst + i);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                    for (int j = 0; j < 4; ++j) {
+                                        float x1 = __uint_as_float(r1[i + j]), x2 = __uint_as_float(r2[i + j]);
+                                        a1[j] = x1 * cf[j] - x2 * sf[j];
+                                        a2[j] = x2 * cf[j] + x1 * sf[j];
+                                    }
+                                    o1[i / 2] = pack_bf16x2(a1[0], a1[1]); o1[i / 2 + 1] = pack_bf16x2(a1[2], a1[3]);
+                                    o2[i / 2] = pack_bf16x2(a2[0], a2[1]); o2[i / 2 + 1] = pack_bf16x2(a2[2], a2[3]);
+                                }
+                                bf16 *dst;
+                                if (tn < p.n_q_tiles) dst = (bf16 *)p.C + (long)row * p.ldc + tn * 256;
+                                else dst = p.k_out + bb * p.kv_batch_stride + (long)ss * 256;
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    *reinterpret_cast<uint4 *>(dst + c * 32 + 2 * i) = make_uint4(o1[i], o1[i + 1], o1[i + 2], o1[i + 3]);
+                                    *reinterpret_cast<uint4 *>(dst + 128 + c * 32 + 2 * i) = make_uint4(o2[i], o2[i + 1], o2[i + 2], o2[i + 3]);
+                                }
                             }
-                            *reinterpret_cast<float4 *>(dst + i) = o;
                         }
                     } else {
-                        bf16 *dst = (bf16 *)p.C + (long)row * p.ldc + col0;
-                        for (int i = 0; i < nvalid; i += 8) {
-                            uint4 o;
-                            o.x = pack_bf16x2(v[i], v[i + 1]);
-                            o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                            o.z = pack_bf16x2(v[i + 4], v[i + 5]);
-                            o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                            *reinterpret_cast<uint4 *>(dst + i) = o;
+                        // V tile: plain copy into the cache
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int c = half * 4 + cc;
+                            uint32_t r1[32];
+                            tc_ld32(taddr + c * 32, r1);
+                            tc_ld_wait();
+                            if (row < p.M) {
+                                bf16 *dst = p.v_out + bb * p.kv_batch_stride + (long)ss * 256 + c * 32;
+#pragma unroll
+                                for (int i = 0; i < 32; i += 8) {
+                                    uint4 o;
+                                    o.x = pack_bf16x2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+                                    o.y = pack_bf16x2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
+                                    o.z = pack_bf16x2(__uint_as_float(r1[i + 4]), __uint_as_float(r1[i + 5]));
+                                    o.w = pack_bf16x2(__uint_as_float(r1[i + 6]), __uint_as_float(r1[i + 7]));
+                                    *reinterpret_cast<uint4 *>(dst + i) = o;
+                                }
+                            }
                         }
+                    }
+                }
+            } else {
+                // output columns of this warp inside the tile
+                const int cols_out_tile = geglu ? BN / 2 : BN;
+                const int per_store = out_f32 ? 32 : 64;                 // output columns per 128-byte staging row
+                const int my_cols0 = half * (cols_out_tile / 2);
+                for (int oc = 0; oc < cols_out_tile / 2; oc += per_store) {
+                    const int col_tile = my_cols0 + oc;                   // first output column (tile-local)
+                    const int col_glob = tn * cols_out_tile + col_tile;
+                    if (col_glob >= n_out) break;
+                    // make sure the previous TMA store has finished reading the staging buffer
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                    const int n_sub = out_f32 ? 1 : 2;                    // 32-column TMEM chunks per staging row
+                    for (int sb = 0; sb < n_sub; ++sb) {
+                        const int ct = col_tile + sb * 32;                // tile-local output column of this chunk
+                        uint32_t r[32];
+                        float v[32];
+                        if (geglu) {
+                            uint32_t u[32];
+                            tc_ld32(taddr + ct, r);
+                            tc_ld32(taddr + BN / 2 + ct, u);
+                            tc_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                v[i] = gelu_fast(__uint_as_float(r[i])) * __uint_as_float(u[i]) * p.alpha;
+                        } else {
+                            tc_ld32(taddr + ct, r);
+                            tc_ld_wait();
+                            const int cg = tn * BN + ct;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                                if (p.bias) {
+                                    if (cg + i + 3 < p.N) {
+                                        float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + cg + i));
+                                        b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) if (cg + i + j < p.N) b4[j] = __ldg(p.bias + cg + i + j);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float x = __uint_as_float(r[i + j]) + b4[j];
+                                    if (p.flags & LIN_GELU) x = out_f32 ? gelu_tanh(x) : gelu_fast(x);
+                                    if (p.flags & LIN_SILU) x = silu(x);
+                                    v[i + j] = x * p.alpha;
+                                }
+                            }
+                        }
+                        // stage: 16-byte chunk index XOR (row & 7) = TMA SWIZZLE_128B
+                        if (out_f32) {
+#pragma unroll
+                            for (int ch = 0; ch < 8; ++ch)
+                                st_shared_v4(stg_row + ((ch ^ sw) << 4), __float_as_uint(v[4 * ch]), __float_as_uint(v[4 * ch + 1]),
+                                             __float_as_uint(v[4 * ch + 2]), __float_as_uint(v[4 * ch + 3]));
+                        } else {
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch)
+                                st_shared_v4(stg_row + (((sb * 4 + ch) ^ sw) << 4), pack_bf16x2(v[8 * ch], v[8 * ch + 1]),
+                                             pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]), pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]),
+                                             pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (accum) tma_reduce_add_2d(&map_c, stg, col_glob, row0);
+                        else tma_store_2d(&map_c, stg, col_glob, row0);
+                        bulk_commit();
                     }
                 }
             }
@@ -284,6 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait0();     // all stores of this warp are complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -315,24 +456,25 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2D bf16 tensor [rows, cols] with row stride ld (elements); box = 64 cols x box_rows, 128B swizzle
-bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows) {
+// 2D tensor [rows, cols] with row stride ld (elements); box = (128 bytes of columns) x box_rows, 128B swizzle
+bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows, bool f32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 int g_num_sms = 0;
 
 template <int BN>
-int launch(const LinearArgs &a, cudaStream_t st, const char **err) {
+int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
     using cfg = Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -348,19 +490,23 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    CUtensorMap ma, mw;
-    if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.K, BN)) {
+    CUtensorMap ma, mw, mc;
+    const bool f32out = a.flags & LIN_OUT_F32;
+    const int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
+    if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.K, BN) ||
+        !make_map(&mc, a.C, a.M, n_out, a.ldc, 32, f32out)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return PZ_ERR_CUDA;
     }
     TcParams p;
+    if (extra) p = *extra; else memset(&p, 0, sizeof(p));
     p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc; p.bias = a.bias; p.C = a.C;
-    p.alpha = a.alpha; p.flags = a.flags;
+    p.alpha = a.alpha; p.flags = a.flags | (extra ? LIN_ROPE : 0);
     p.tiles_m = (a.M + BM - 1) / BM;
     p.tiles_n = (a.N + BN - 1) / BN;
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, st>>>(ma, mw, p);
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS2, cfg::SMEM_BYTES, st>>>(ma, mw, mc, p);
     count_launch();
     return 0;
 }
@@ -371,7 +517,7 @@ int gemm_tc_supported(const LinearArgs &a) {
     if (a.M < 1 || a.K % 8 || a.lda % 8) return 0;          // TMA: 16-byte global strides
     if (((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.C) & 15) return 0;
     int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
-    if (n_out % 8 || a.ldc % 8) return 0;                    // vector stores
+    if (n_out % 8 || a.ldc % 8) return 0;                    // TMA store: 16-byte global strides
     if ((a.flags & LIN_GEGLU) && (a.N % 256)) return 0;      // gate|up blocks of 128 pair up inside one 256-wide tile
     if ((a.flags & LIN_ACCUM) && !(a.flags & LIN_OUT_F32)) return 0;
     return 1;
@@ -384,4 +530,22 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err) {
     long tiles256 = (long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
     bool use256 = geglu || (a.N >= 256 && tiles256 >= 120);
     return use256 ? launch<256>(a, st, err) : launch<128>(a, st, err);
+}
+
+// Fused QKV projection + RoPE + cache write for the prefix pass (head_dim 256):
+// q (post-RoPE) -> q_out [M, n_heads*256]; K (post-RoPE), V -> cache rows
+// (b, s) = (m / s_x, m % s_x) at k_out/v_out + b*kv_batch_stride + s*256.
+// Replaces mixture.py:187-235 + the kv_cache.update of joint_model.py:195-219.
+int launch_qkv_rope_tc(const void *A, int lda, const void *W, void *q_out, void *k_out, void *v_out,
+                       long kv_batch_stride, const float *cos_t, const float *sin_t, int M, int K,
+                       int n_heads, int s_x, cudaStream_t st, const char **err) {
+    LinearArgs a;
+    a.A = A; a.W = W; a.bias = nullptr; a.C = q_out;
+    a.M = M; a.N = (n_heads + 2) * 256; a.K = K; a.lda = lda; a.ldc = n_heads * 256;
+    a.alpha = 1.f; a.flags = 0;
+    TcParams ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.rope_cos = cos_t; ex.rope_sin = sin_t; ex.k_out = (bf16 *)k_out; ex.v_out = (bf16 *)v_out;
+    ex.kv_batch_stride = kv_batch_stride; ex.s_x = s_x; ex.n_q_tiles = n_heads;
+    return launch<256>(a, st, err, &ex);
 }

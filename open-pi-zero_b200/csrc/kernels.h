@@ -38,6 +38,9 @@ void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStr
 // gemm_tc.cu (tcgen05 + TMA, bf16)
 int gemm_tc_supported(const LinearArgs &a);
 int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err);
+int launch_qkv_rope_tc(const void *A, int lda, const void *W, void *q_out, void *k_out, void *v_out,
+                       long kv_batch_stride, const float *cos_t, const float *sin_t, int M, int K,
+                       int n_heads, int s_x, cudaStream_t st, const char **err);
 
 // skinny.cu (weight streaming for M <= 64, bf16)
 int skinny_supported(const LinearArgs &a);

@@ -525,6 +525,20 @@ class PiZero(nn.Module):
         return {"vlm": KVCache(k, v, 0, Sv, d["num_layers"]),
                 "proprio": KVCache(k, v, Sv, Sc, d["num_layers"])}
 
+    # kernel-family timing taps (bench.py roofline object)
+    TAG_VLM_GATE_UP, TAG_VLM_DOWN, TAG_ACT_GATE_UP = 1, 2, 3
+
+    def timing_begin(self, tag: int):
+        self.pack()
+        _lib.load().pz_timing_begin(self._handle, tag)
+
+    def timing_end(self):
+        ms, n = C.c_double(), C.c_int64()
+        rc = _lib.load().pz_timing_end(self._handle, C.byref(ms), C.byref(n))
+        if rc != 0:
+            raise PzError("pz_timing_end failed")
+        return ms.value, n.value
+
     def forward(self, *args, **kwargs):
         raise PzError("PiZero.forward (flow-matching training loss, pizero.py:607-661) is outside "
                       "this library's scope; use infer_action / PiZeroInference")
