@@ -194,12 +194,15 @@ int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const fl
                  void *d_c, int M, int N, int K, int lda, int ldc, int flags, float alpha,
                  void *stream);
 
-/* Block-masked attention over [cache | fresh] keys; see csrc/attention.cuh. */
+/* Block-masked attention over [cache | fresh] keys (csrc/common.cuh: AttnArgs).
+ * Dense test layout: Q,O [B, q_rows, n_heads*hd]; K,V [B, s_cache, kv_heads*hd];
+ * K2,V2 [B, n_fresh, kv_heads*hd].  impl: 0 = SIMT reference, 1 = tensor-core
+ * kernel (bf16).  d_scratch (optional fp32) enables the split-key decode path. */
 int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
                     const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
                     int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,
                     int s_vlm, int n_fresh, int kv_heads, float scale, float softcap,
-                    void *stream);
+                    void *d_scratch, size_t scratch_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -104,7 +104,7 @@ def load(build_if_needed: bool = True):
     lib.pz_op_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_float, vp]
     lib.pz_op_attention.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp] + \
-        [C.c_int] * 9 + [C.c_float, C.c_float, vp]
+        [C.c_int] * 9 + [C.c_float, C.c_float, vp, C.c_size_t, vp]
     if lib.pz_abi_version() != PZ_ABI_VERSION:
         raise RuntimeError("libpz_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -74,7 +74,8 @@ struct Workspace {
     float *xp;
     // denoise scratch (whole batch)
     void *a_in, *e1, *z, *ha, *qkva, *qa, *ka, *va, *atta, *mlpa;
-    float *act, *xa, *vel;
+    float *act, *xa, *vel, *att_scratch;
+    size_t att_scratch_bytes;
     size_t total;
 };
 
@@ -125,6 +126,12 @@ static Workspace carve(const pz_config &c, int B, int chunk, void *base) {
     w.atta = b.take<void>(Ma * qd * es);
     w.mlpa = b.take<void>(Ma * c.act_inter * es);
     w.vel = b.take<float>(Ma * 8 * 4);
+    {   // split-key attention partials (decode): [B][key tiles][heads*rows][hd + 2] fp32
+        size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
+        size_t tiles = (S_c + c.horizon + 63) / 64;
+        w.att_scratch_bytes = rows <= 64 ? (size_t)B * tiles * rows * (c.head_dim + 2) * 4 : 0;
+        w.att_scratch = b.take<float>(w.att_scratch_bytes);
+    }
     w.total = (b.off + 1023) & ~(size_t)1023;
     return w;
 }
@@ -319,6 +326,7 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
             av.Q = ws.q; av.q_batch_stride = (long)S_v * qd; av.O = ws.att; av.o_batch_stride = (long)S_v * qd;
             av.q_rows = S_v; av.q_row0 = 0;
             PZ_TRY(Ops<T>::attention(h, av, st));
+            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
             AttnArgs ap = a;   // proprio rows
             ap.Q = ws.qp; ap.q_batch_stride = (long)S_p * qd; ap.O = ws.attp; ap.o_batch_stride = (long)S_p * qd;
             ap.q_rows = S_p; ap.q_row0 = S_v;
@@ -376,6 +384,7 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
             a.batch = B; a.n_heads = nh; a.head_dim = hd; a.q_rows = Hz; a.q_row0 = S_c;
             a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = Hz;
             a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
             PZ_TRY(Ops<T>::attention(h, a, st));
             PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st));
             if (cap && cap->denoise_action)
@@ -577,7 +586,8 @@ int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const fl
 int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
                     const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
                     int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,
-                    int s_vlm, int n_fresh, int kv_heads, float scale, float softcap, void *stream) {
+                    int s_vlm, int n_fresh, int kv_heads, float scale, float softcap, void *d_scratch,
+                    size_t scratch_bytes, void *stream) {
     // Dense test layout: Q,O [B, q_rows, n_heads*hd]; K,V [B, s_cache, kv_heads*hd];
     // K2,V2 [B, n_fresh, kv_heads*hd].
     AttnArgs a;
@@ -591,6 +601,7 @@ int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const
     a.O = d_out; a.o_batch_stride = (long)q_rows * qd; a.o_row_stride = qd; a.o_head_stride = head_dim;
     a.batch = batch; a.n_heads = n_heads; a.head_dim = head_dim; a.q_rows = q_rows; a.q_row0 = q_row0;
     a.s_cache = s_cache; a.s_vlm = s_vlm; a.n_fresh = n_fresh; a.scale = scale; a.softcap = softcap;
+    a.scratch = (float *)d_scratch; a.scratch_bytes = scratch_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 0) {
         if (dtype == PZ_BF16) launch_attn_simple<bf16>(a, st); else launch_attn_simple<float>(a, st);

@@ -48,7 +48,7 @@ PZ_DEVINL void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint
 enum { CLS_ALL = 0, CLS_VLM = 1, CLS_PROPRIO = 2, CLS_ACTION = 3 };
 
 template <int HD>   // true head_dim; HDP = padded to a multiple of 16
-__global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int cls, int mqa) {
+__global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int cls, int mqa, int split) {
     constexpr int HDP = (HD + 15) / 16 * 16;
     constexpr int LDS = HDP + 8;            // +16 B per row: conflict-free ldmatrix
     constexpr int CHUNKS = HD / 8;          // 16-byte chunks of real data per row
@@ -71,7 +71,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     else if (cls == CLS_VLM) n_keys = vlen;
     else if (cls == CLS_PROPRIO) n_keys = a.s_cache;
     else n_keys = a.s_cache + a.n_fresh;
-    const int n_tiles = (n_keys + KEY_TILE - 1) / KEY_TILE;
+    const int n_tiles_all = (n_keys + KEY_TILE - 1) / KEY_TILE;
+    // split-key mode (decode): this CTA owns exactly one key tile and writes an
+    // unnormalised partial (o, m, l); a second kernel combines the partials
+    const int tile_lo = split ? blockIdx.y : 0;
+    const int n_tiles = split ? min(n_tiles_all, tile_lo + 1) : n_tiles_all;
 
     const bf16 *Qb = (const bf16 *)a.Q + b * a.q_batch_stride;
     const bf16 *Kb = (const bf16 *)a.K + b * a.kv_batch_stride + (mqa ? 0 : head_y * a.kv_head_stride);
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
             cp_async16(dst + r * LDS + c * 8, src, ok);
         }
     };
-    load_kv(sK, Kb, K2b, 0);
+    load_kv(sK, Kb, K2b, tile_lo);
     cp_async_commit();
 
     float o[HDP / 8][4];
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     const float scale = a.scale, cap = a.softcap, inv_cap = cap > 0.f ? 1.f / cap : 0.f;
 
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    for (int tile = tile_lo; tile < n_tiles; ++tile) {
         load_kv(sV, Vb, V2b, tile);
         cp_async_commit();
         cp_async_wait<1>();          // Q and K(tile) have landed
@@ -209,8 +213,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
         float l = l_run[r];
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
-        l_run[r] = l > 0.f ? 1.f / l : 0.f;
+        l_run[r] = l;
     }
+    if (split) {
+        // partial layout: [b][tile][row][HD + 2] = o[HD] (unnormalised), m, l
+        float *base = a.scratch + (((long)b * gridDim.y + blockIdx.y) * rows_total) * (HD + 2);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int row = row0 + warp * 16 + g + r * 8;
+            if (row >= rows_total) continue;
+            float *dst = base + (long)row * (HD + 2);
+#pragma unroll
+            for (int i = 0; i < HDP / 8; ++i) {
+                int d = i * 8 + 2 * t;
+                if (d < HD) *reinterpret_cast<float2 *>(dst + d) = make_float2(o[i][2 * r], o[i][2 * r + 1]);
+            }
+            if (t == 0) { dst[HD] = m_run[r]; dst[HD + 1] = l_run[r]; }
+        }
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
     bf16 *Ob = (bf16 *)a.O + b * a.o_batch_stride;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -230,6 +253,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     }
 }
 
+// combine the split-key partials: one warp per (sample, query row)
+template <int HD>
+__global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a, int n_splits) {
+    const int lane = threadIdx.x & 31;
+    const int rows_total = a.n_heads * a.q_rows;
+    long wid = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wid >= (long)a.batch * rows_total) return;
+    int b = wid / rows_total, row = wid % rows_total;
+    const float *base = a.scratch + ((long)b * n_splits * rows_total + row) * (HD + 2);
+    const long sstride = (long)rows_total * (HD + 2);
+    float mx = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) mx = fmaxf(mx, base[s * sstride + HD]);
+    float acc[HD / 32];
+#pragma unroll
+    for (int i = 0; i < HD / 32; ++i) acc[i] = 0.f;
+    float l = 0.f;
+    for (int s = 0; s < n_splits; ++s) {
+        const float *p = base + s * sstride;
+        float m = p[HD];
+        float w = (m == -INFINITY) ? 0.f : __expf(m - mx);
+        l += p[HD + 1] * w;
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) acc[i] += p[i * 32 + lane] * w;
+    }
+    float inv = l > 0.f ? 1.f / l : 0.f;
+    int h = row / a.q_rows, tok = row % a.q_rows;
+    bf16 *dst = (bf16 *)a.O + b * a.o_batch_stride + (long)tok * a.o_row_stride + h * a.o_head_stride;
+#pragma unroll
+    for (int i = 0; i < HD / 32; ++i) dst[i * 32 + lane] = __float2bfloat16_rn(acc[i] * inv);
+}
+
 template <int HD>
 int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
     constexpr int HDP = (HD + 15) / 16 * 16;
@@ -242,8 +296,25 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
         attr_set = true;
     }
     int rows_total = mqa ? a.n_heads * a.q_rows : a.q_rows;
+    if constexpr (HD % 32 == 0) {
+        // decode (action / proprio rows, MQA): too few query rows to fill the machine by rows, so
+        // split the keys across CTAs (flash-decoding) and combine
+        int n_keys = a.s_cache + (cls == CLS_ACTION ? a.n_fresh : 0);
+        int n_splits = (n_keys + KEY_TILE - 1) / KEY_TILE;
+        size_t need = (size_t)a.batch * n_splits * rows_total * (HD + 2) * sizeof(float);
+        if (mqa && (cls == CLS_ACTION || cls == CLS_PROPRIO) && rows_total <= ROWS_PER_CTA && n_splits > 1 &&
+            a.scratch && a.scratch_bytes >= need) {
+            dim3 grid(1, n_splits, a.batch);
+            attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa, 1);
+            count_launch();
+            long warps = (long)a.batch * rows_total;
+            attn_combine_kernel<HD><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a, n_splits);
+            count_launch();
+            return 0;
+        }
+    }
     dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
-    attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa);
+    attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa, 0);
     count_launch();
     return 0;
 }

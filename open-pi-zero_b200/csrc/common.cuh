@@ -96,6 +96,9 @@ struct AttnArgs {
     void *O; long o_batch_stride; int o_row_stride, o_head_stride;
     int batch, n_heads, head_dim, q_rows, q_row0, s_cache, s_vlm, n_fresh;
     float scale, softcap;
+    // optional fp32 scratch for the split-key (flash-decoding) path:
+    // batch * key_tiles * n_heads*q_rows * (head_dim + 2) floats
+    float *scratch; size_t scratch_bytes;
 };
 
 // host-side: every launch goes through this counter (bench.py: gpu_launches)

@@ -119,6 +119,7 @@ struct TcParams {
     float alpha;
     int flags;
     int tiles_m, tiles_n;
+    int ksplit, kb_per_split;           // split-K (fp32 reduce-add outputs only)
     // fused RoPE + Q/K/V split (LIN_ROPE): BN = 256 = head_dim, one N tile per head
     const float *rope_cos, *rope_sin;   // [s_x, 128] fp32
     bf16 *k_out, *v_out;                // cache rows: base + b*kv_batch_stride + s*256
@@ -188,7 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_mn * p.ksplit;   // tile t -> (t % tiles_mn, k-split t / tiles_mn)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -218,8 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int tm = t % p.tiles_m, tn = t / p.tiles_m;   // m fastest: concurrent CTAs share the W tile in L2
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int tmn = t % tiles_mn, ks = t / tiles_mn;
+                int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;   // m fastest: concurrent CTAs share the W tile in L2
+                int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sa = smem + stage * cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
@@ -241,7 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int ks = t / tiles_mn;
+                int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
@@ -250,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in 16 B units
-                        tc_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        tc_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     }
                     tc_commit(&empty_bar[stage]);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -278,7 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
         uint8_t *stg_row = stg + lane * 128;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            int tm = t % p.tiles_m, tn = t / p.tiles_m;
+            int tmn = t % tiles_mn, ksp = t / tiles_mn;
+            int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = tm * BM + q * 32;       // first row of this warp
@@ -378,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
                                 float b4[4] = {0.f, 0.f, 0.f, 0.f};
-                                if (p.bias) {
+                                if (p.bias && ksp == 0) {
                                     if (cg + i + 3 < p.N) {
                                         float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + cg + i));
                                         b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
@@ -504,7 +511,17 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     p.alpha = a.alpha; p.flags = a.flags | (extra ? LIN_ROPE : 0);
     p.tiles_m = (a.M + BM - 1) / BM;
     p.tiles_n = (a.N + BN - 1) / BN;
-    int tiles = p.tiles_m * p.tiles_n;
+    // split K when the output grid cannot fill the machine and the epilogue is a pure fp32
+    // accumulate (TMA reduce-add makes the combine free): o_proj / down_proj at small M
+    int num_kb = (a.K + BK - 1) / BK;
+    p.ksplit = 1;
+    if ((a.flags & LIN_ACCUM) && !(a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU)) && !extra) {
+        int mn = p.tiles_m * p.tiles_n;
+        while (mn * p.ksplit * 2 <= g_num_sms && num_kb / (p.ksplit * 2) >= 4) p.ksplit *= 2;
+    }
+    p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    int tiles = p.tiles_m * p.tiles_n * p.ksplit;
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
     gemm_tc_kernel<BN><<<grid, NUM_THREADS2, cfg::SMEM_BYTES, st>>>(ma, mw, mc, p);
     count_launch();

@@ -145,6 +145,9 @@ class PiZero(nn.Module):
         self._workspace = None
         self._ws_batch = 0
         self._flags = _lib.PZ_FLAG_SIMPLE_KERNELS if os.environ.get("PZ_SIMPLE_KERNELS") == "1" else 0
+        self.use_cuda_graph = os.environ.get("PZ_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._timing_armed = False
         self.last_launch_count = 0
         self.eval()
 
@@ -366,6 +369,7 @@ class PiZero(nn.Module):
         self._handle, self._packed, self._packed_key = hnd, (keep, w), key
         self._T = T
         self._workspace, self._ws_batch = None, 0
+        self._graphs = {}
 
     def _destroy_handle(self):
         if getattr(self, "_handle", None) is not None:
@@ -468,18 +472,14 @@ class PiZero(nn.Module):
         if noise is None:   # pizero.py:454-456
             noise = torch.randn((B, H, Adim), device=dev, dtype=pixel_values.dtype)
         nz = noise.to(device=dev, dtype=torch.float32).contiguous()
+        if capture is None and self.use_cuda_graph and not self._timing_armed:
+            return self._replay_graph(B, ids, pix, vlen, prop, nz)
         out = torch.empty((B, H, Adim), device=dev, dtype=torch.float32)
         ws, ws_bytes = self._ensure_workspace(B)
         cap_struct, cap_bufs = None, None
         if capture is not None:
             cap_struct, cap_bufs = self._make_capture(B, dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
-                                 prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
-                                 C.byref(cap_struct) if cap_struct is not None else None, stream)
-        if rc != 0:
-            raise PzError(f"pz_infer_action failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
-        self.last_launch_count = int(lib.pz_launch_count(self._handle))
+        self._launch(ids, pix, vlen, prop, nz, out, ws, ws_bytes, B, cap_struct)
         if capture is not None:
             capture.update(cap_bufs)
             capture["action"] = out
@@ -487,6 +487,57 @@ class PiZero(nn.Module):
         # keep the inputs alive until the stream has consumed them
         self._inflight = (ids, pix, prop, vlen, nz)
         return out
+
+    def _launch(self, ids, pix, vlen, prop, nz, out, ws, ws_bytes, B, cap_struct=None):
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
+                                 prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
+                                 C.byref(cap_struct) if cap_struct is not None else None, stream)
+        if rc != 0:
+            raise PzError(f"pz_infer_action failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
+        self.last_launch_count = int(lib.pz_launch_count(self._handle))
+
+    # ------------------------------------------------------------- CUDA graphs
+    def _replay_graph(self, B, ids, pix, vlen, prop, nz):
+        """The whole call (~2k kernel launches at bs=1) is captured once per batch
+        size into a CUDA graph over static buffers and replayed: launch overhead
+        leaves the critical path (eager dispatch is launch-bound)."""
+        g = self._graphs.get(B)
+        if g is None:
+            lib = _lib.load()
+            dev = ids.device
+            st = dict(ids=torch.empty_like(ids), pix=torch.empty_like(pix), vlen=torch.empty_like(vlen),
+                      prop=torch.empty_like(prop), nz=torch.empty_like(nz),
+                      out=torch.empty((B, self.horizon_steps, self.action_dim), device=dev, dtype=torch.float32))
+            nbytes = lib.pz_workspace_bytes(self._handle, B)
+            st["ws_t"] = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            st["ws"] = (st["ws_t"].data_ptr() + 1023) // 1024 * 1024
+            st["ws_bytes"] = nbytes
+            for k, v in (("ids", ids), ("pix", pix), ("vlen", vlen), ("prop", prop), ("nz", nz)):
+                st[k].copy_(v)
+            # one eager run first: one-time function attributes / lazy module loading must not
+            # happen inside a capture
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._launch(st["ids"], st["pix"], st["vlen"], st["prop"], st["nz"], st["out"], st["ws"],
+                             st["ws_bytes"], B)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._launch(st["ids"], st["pix"], st["vlen"], st["prop"], st["nz"], st["out"], st["ws"],
+                             st["ws_bytes"], B)
+            st["graph"] = graph
+            st["launches"] = self.last_launch_count
+            self._graphs[B] = g = st
+        for k, v in (("ids", ids), ("pix", pix), ("vlen", vlen), ("prop", prop), ("nz", nz)):
+            g[k].copy_(v, non_blocking=True)
+        g["graph"].replay()
+        self.last_launch_count = g["launches"]
+        self._last_graph_B = B
+        return g["out"].clone()
 
     def _make_capture(self, B, dev):
         d = self.dims
@@ -529,12 +580,16 @@ class PiZero(nn.Module):
     TAG_VLM_GATE_UP, TAG_VLM_DOWN, TAG_ACT_GATE_UP = 1, 2, 3
 
     def timing_begin(self, tag: int):
+        """Arms event timing of one kernel family; calls run eagerly (not from a
+        captured graph) until timing_end()."""
         self.pack()
+        self._timing_armed = True
         _lib.load().pz_timing_begin(self._handle, tag)
 
     def timing_end(self):
         ms, n = C.c_double(), C.c_int64()
         rc = _lib.load().pz_timing_end(self._handle, C.byref(ms), C.byref(n))
+        self._timing_armed = False
         if rc != 0:
             raise PzError("pz_timing_end failed")
         return ms.value, n.value

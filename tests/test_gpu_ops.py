@@ -135,7 +135,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])   # 2 = tensor-core kernel with the split-key scratch
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
 def test_attention(impl, case):
     name, B, nh, hd, R, q0, s_cache, s_vlm, n_fresh, kvh, softcap, use_len = case
@@ -150,12 +150,17 @@ def test_attention(impl, case):
     vlen = torch.tensor([258, 276, 267][:B], device="cuda", dtype=torch.int32) if use_len else None
     out = torch.full((B, R, nh, hd), 7.0, device="cuda", dtype=bf)
     scale = hd ** -0.5
-    rc = lib.pz_op_attention(impl, 1, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+    scratch = torch.empty(B * 8 * nh * R * (hd + 2), device="cuda") if impl == 2 else None
+    if impl == 2 and R * nh > 64:
+        pytest.skip("split-key path is for decode-sized query blocks")
+    rc = lib.pz_op_attention(min(impl, 1), 1, q.data_ptr(), k.data_ptr(), v.data_ptr(),
                              k2.data_ptr() if n_fresh else None, v2.data_ptr() if n_fresh else None,
                              vlen.data_ptr() if use_len else None, out.data_ptr(), B, nh, hd, R, q0,
                              s_cache, s_vlm, n_fresh, kvh, scale, softcap,
+                             scratch.data_ptr() if scratch is not None else None,
+                             scratch.numel() * 4 if scratch is not None else 0,
                              torch.cuda.current_stream().cuda_stream)
-    if impl == 1 and rc == -1:
+    if impl >= 1 and rc == -1:
         pytest.skip("tensor-core attention does not cover this shape")
     assert rc == 0, rc
     torch.cuda.synchronize()
