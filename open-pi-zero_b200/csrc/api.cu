@@ -6,6 +6,7 @@
 // no allocation, no synchronisation, no hidden state besides the handle.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -16,6 +17,7 @@
 #include "kernels.h"
 
 thread_local LaunchCounter *g_launch_counter = nullptr;
+int g_pdl_enabled = [] { const char *e = getenv("PZ_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 static thread_local std::string g_create_error;
 
 struct pz_handle {
@@ -177,11 +179,26 @@ static LinearArgs lin(const void *A, int lda, const void *W, const float *bias, 
     LinearArgs a;
     a.A = A; a.W = W; a.bias = bias; a.C = C;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldc = ldc;
-    a.alpha = alpha; a.flags = flags;
+    a.alpha = alpha; a.flags = flags; a.norm_w = nullptr;
     return a;
 }
 
 #define PZ_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+// y = linear(rmsnorm(x)): one kernel when the skinny path can normalise while it loads the
+// activations (small M), otherwise the norm kernel writes `hbuf` and the GEMM reads it.
+template <typename T>
+static int norm_linear(pz_handle *h, const float *x, const float *norm_w, void *hbuf, LinearArgs a,
+                       int hidden, cudaStream_t st) {
+    if (std::is_same<T, bf16>::value && !(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS)) {
+        LinearArgs f = a;
+        f.A = x; f.lda = hidden; f.flags |= LIN_NORM_A; f.norm_w = norm_w;
+        if (skinny_supported(f)) return launch_linear_skinny(f, st);
+    }
+    launch_rmsnorm<T>(x, norm_w, (T *)hbuf, a.M, hidden, 1e-6f, st);
+    a.A = hbuf; a.lda = hidden;
+    return Ops<T>::linear(h, a, st);
+}
 
 static void copy_f32(float *dst, const float *src, size_t n, cudaStream_t st) {
     cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -256,11 +273,16 @@ static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *h
     int qd = c.n_heads * c.head_dim;
     PZ_TRY(Ops<T>::linear(h, lin(att, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
                                  LIN_OUT_F32 | LIN_ACCUM), st));
-    launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
     int tag_gu = hidden == c.vlm_hidden ? TAG_VLM_GATE_UP : TAG_ACT_GATE_UP;
+    if (M > 64) launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
     tick(h, tag_gu, st);
-    PZ_TRY(Ops<T>::linear(h, lin(hbuf, hidden, L.w_gate_up, nullptr, mlp, inter, M, 2 * inter, hidden,
-                                 LIN_GEGLU), st));
+    if (M > 64) {
+        PZ_TRY(Ops<T>::linear(h, lin(hbuf, hidden, L.w_gate_up, nullptr, mlp, inter, M, 2 * inter, hidden,
+                                     LIN_GEGLU), st));
+    } else {
+        PZ_TRY(norm_linear<T>(h, x, L.norm_post, hbuf, lin(nullptr, hidden, L.w_gate_up, nullptr, mlp, inter, M,
+                                                            2 * inter, hidden, LIN_GEGLU), hidden, st));
+    }
     tick(h, tag_gu, st);
     if (hidden == c.vlm_hidden) tick(h, TAG_VLM_DOWN, st);
     PZ_TRY(Ops<T>::linear(h, lin(mlp, inter, L.w_down, nullptr, x, hidden, M, hidden, inter,
@@ -307,8 +329,8 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
                                      w.rope_vlm_cos, w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
             }
             // proprio block through the action-expert-shaped weights
-            launch_rmsnorm<T>(ws.xp, h->proprio[l].norm_in, (T *)ws.hp, Mp, A, 1e-6f, st);
-            PZ_TRY(Ops<T>::linear(h, lin(ws.hp, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), st));
+            PZ_TRY(norm_linear<T>(h, ws.xp, h->proprio[l].norm_in, ws.hp,
+                                  lin(nullptr, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), A, st));
             launch_rope_split<T>((const T *)ws.qkvp, qkvd, (T *)ws.qp, (long)S_p * qd, Kc + (size_t)S_v * hd,
                                  Vc + (size_t)S_v * hd, kv_bs, w.rope_act_cos, w.rope_act_sin, nb, S_p,
                                  0, nh, hd, st);
@@ -368,21 +390,31 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
                                      sqrtf((float)A)), st));
         for (int l = 0; l < c.n_layers; ++l) {
             const pz_mix_layer &L = h->action[l];
-            launch_rmsnorm<T>(ws.xa, L.norm_in, (T *)ws.ha, Ma, A, 1e-6f, st);
-            PZ_TRY(Ops<T>::linear(h, lin(ws.ha, A, L.w_qkv, nullptr, ws.qkva, qkvd, Ma, qkvd, A), st));
-            launch_rope_split<T>((const T *)ws.qkva, qkvd, (T *)ws.qa, (long)Hz * qd, (T *)ws.ka,
-                                 (T *)ws.va, (long)Hz * hd, w.rope_act_cos, w.rope_act_sin, B, Hz, S_p,
-                                 nh, hd, st);
+            PZ_TRY(norm_linear<T>(h, ws.xa, L.norm_in, ws.ha, lin(nullptr, A, L.w_qkv, nullptr, ws.qkva, qkvd, Ma, qkvd, A),
+                                  A, st));
             AttnArgs a;
             memset(&a, 0, sizeof(a));
-            a.Q = ws.qa; a.q_batch_stride = (long)Hz * qd; a.q_row_stride = qd; a.q_head_stride = hd;
-            a.K = (T *)ws.kcache + (size_t)l * B * kv_bs; a.V = (T *)ws.vcache + (size_t)l * B * kv_bs;
-            a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
-            a.K2 = ws.ka; a.V2 = ws.va; a.kv2_batch_stride = (long)Hz * hd; a.kv2_row_stride = hd;
-            a.valid_len = valid_len;
-            a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
             a.batch = B; a.n_heads = nh; a.head_dim = hd; a.q_rows = Hz; a.q_row0 = S_c;
             a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = Hz;
+            a.K = (T *)ws.kcache + (size_t)l * B * kv_bs; a.V = (T *)ws.vcache + (size_t)l * B * kv_bs;
+            a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+            a.Q = ws.qkva; a.q_batch_stride = (long)Hz * qkvd; a.q_row_stride = qkvd; a.q_head_stride = hd;
+            a.K2 = (T *)ws.qkva + qd; a.V2 = (T *)ws.qkva + qd + hd;
+            a.kv2_batch_stride = (long)Hz * qkvd; a.kv2_row_stride = qkvd;
+            a.rope_cos = w.rope_act_cos; a.rope_sin = w.rope_act_sin; a.rope_pos0 = S_p;
+            a.valid_len = valid_len;
+            bool fused_rope = std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 &&
+                              attn_mma_supported(a);
+            if (!fused_rope) {
+                // separate RoPE + Q/K/V split kernel, attention on the rotated copies
+                launch_rope_split<T>((const T *)ws.qkva, qkvd, (T *)ws.qa, (long)Hz * qd, (T *)ws.ka,
+                                     (T *)ws.va, (long)Hz * hd, w.rope_act_cos, w.rope_act_sin, B, Hz, S_p,
+                                     nh, hd, st);
+                a.Q = ws.qa; a.q_batch_stride = (long)Hz * qd; a.q_row_stride = qd;
+                a.K2 = ws.ka; a.V2 = ws.va; a.kv2_batch_stride = (long)Hz * hd; a.kv2_row_stride = hd;
+                a.rope_cos = a.rope_sin = nullptr;
+            }
+            a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
             a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
             a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
             PZ_TRY(Ops<T>::attention(h, a, st));
@@ -392,12 +424,20 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
                          (size_t)Ma * A, st);
         }
         // final norm + decoder + Euler step (joint_model.py:375-380, pizero.py:479-481)
-        launch_rmsnorm<T>(ws.xa, w.action_final_norm, (T *)ws.ha, Ma, A, 1e-6f, st);
-        PZ_TRY(Ops<T>::linear(h, lin(ws.ha, A, w.dec_w, w.dec_b, ws.vel, 8, Ma, c.action_dim, A,
-                                     LIN_OUT_F32), st));
-        launch_euler(ws.act, ws.vel, 8, dt, Ma, c.action_dim,
-                     (cap && cap->velocities) ? cap->velocities + (size_t)step * Ma * c.action_dim : nullptr,
-                     st);
+        LinearArgs fused = lin(ws.xa, A, w.dec_w, w.dec_b, ws.act, c.action_dim, Ma, c.action_dim, A,
+                               LIN_OUT_F32 | LIN_ACCUM | LIN_NORM_A, dt);
+        fused.norm_w = w.action_final_norm;
+        if (std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && !(cap && cap->velocities) &&
+            skinny_supported(fused)) {
+            // one kernel: final norm, decoder, and the Euler update action += dt * (W h + b)
+            PZ_TRY(launch_linear_skinny(fused, st));
+        } else {
+            PZ_TRY(norm_linear<T>(h, ws.xa, w.action_final_norm, ws.ha,
+                                  lin(nullptr, A, w.dec_w, w.dec_b, ws.vel, 8, Ma, c.action_dim, A, LIN_OUT_F32), A, st));
+            launch_euler(ws.act, ws.vel, 8, dt, Ma, c.action_dim,
+                         (cap && cap->velocities) ? cap->velocities + (size_t)step * Ma * c.action_dim : nullptr,
+                         st);
+        }
     }
     if (cap && cap->action_preclip) copy_f32(cap->action_preclip, ws.act, (size_t)Ma * c.action_dim, st);
     launch_clamp_copy(ws.act, out, (long)Ma * c.action_dim, c.clip, st);

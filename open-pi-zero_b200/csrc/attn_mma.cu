@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     bf16 *sK = sQ + ROWS_PER_CTA * LDS;
     bf16 *sV = sK + KEY_TILE * LDS;
 
+    pdl_trigger();
+    pdl_wait();     // Q/K/V are produced by the preceding kernels
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.z;
@@ -84,20 +86,63 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     const bf16 *V2b = a.V2 ? (const bf16 *)a.V2 + b * a.kv2_batch_stride : nullptr;
 
     // ---- stage Q (once) and the first K tile -----------------------------
-    for (int i = tid; i < ROWS_PER_CTA * PCHUNKS; i += NTHREADS) {
-        int r = i / PCHUNKS, c = i % PCHUNKS;
-        int row = row0 + r;
-        bool ok = row < rows_total && c < CHUNKS;
-        int h = mqa ? row / a.q_rows : head_y;
-        int tok = mqa ? row % a.q_rows : row;
-        const bf16 *src = ok ? Qb + (long)tok * a.q_row_stride + h * a.q_head_stride + c * 8 : Qb;
-        cp_async16(sQ + r * LDS + c * 8, src, ok);
+    const bool rope = (HD == 256) && a.rope_cos != nullptr;
+    // half-split rotation (model/utils.py:4-16) of one 8-element chunk pair (d, d+128)
+    auto rope_pair = [&](bf16 *dst_row, const bf16 *src_row, int c, int pos) {
+        uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(src_row + c * 8));
+        uint4 r2 = __ldg(reinterpret_cast<const uint4 *>(src_row + 128 + c * 8));
+        const float4 *cs = reinterpret_cast<const float4 *>(a.rope_cos + (long)pos * 128 + c * 8);
+        const float4 *sn = reinterpret_cast<const float4 *>(a.rope_sin + (long)pos * 128 + c * 8);
+        float4 c0 = __ldg(cs), c1 = __ldg(cs + 1), s0 = __ldg(sn), s1 = __ldg(sn + 1);
+        float cf[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float sf[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t w1[4] = {r1.x, r1.y, r1.z, r1.w}, w2[4] = {r2.x, r2.y, r2.z, r2.w}, o1[4], o2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x1a = bf16lo(w1[j]), x1b = bf16hi(w1[j]), x2a = bf16lo(w2[j]), x2b = bf16hi(w2[j]);
+            o1[j] = pack_bf16x2(x1a * cf[2 * j] - x2a * sf[2 * j], x1b * cf[2 * j + 1] - x2b * sf[2 * j + 1]);
+            o2[j] = pack_bf16x2(x2a * cf[2 * j] + x1a * sf[2 * j], x2b * cf[2 * j + 1] + x1b * sf[2 * j + 1]);
+        }
+        *reinterpret_cast<uint4 *>(dst_row + c * 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+        *reinterpret_cast<uint4 *>(dst_row + 128 + c * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    };
+    if (rope) {
+        for (int i = tid; i < ROWS_PER_CTA * 16; i += NTHREADS) {
+            int r = i / 16, c = i % 16;
+            int row = row0 + r;
+            bf16 *dst = sQ + r * LDS;
+            if (row < rows_total) {
+                int h = mqa ? row / a.q_rows : head_y;
+                int tok = mqa ? row % a.q_rows : row;
+                rope_pair(dst, Qb + (long)tok * a.q_row_stride + h * a.q_head_stride, c, a.rope_pos0 + tok);
+            } else {
+                *reinterpret_cast<uint4 *>(dst + c * 8) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(dst + 128 + c * 8) = make_uint4(0, 0, 0, 0);
+            }
+        }
+    } else {
+        for (int i = tid; i < ROWS_PER_CTA * PCHUNKS; i += NTHREADS) {
+            int r = i / PCHUNKS, c = i % PCHUNKS;
+            int row = row0 + r;
+            bool ok = row < rows_total && c < CHUNKS;
+            int h = mqa ? row / a.q_rows : head_y;
+            int tok = mqa ? row % a.q_rows : row;
+            const bf16 *src = ok ? Qb + (long)tok * a.q_row_stride + h * a.q_head_stride + c * 8 : Qb;
+            cp_async16(sQ + r * LDS + c * 8, src, ok);
+        }
     }
     auto load_kv = [&](bf16 *dst, const bf16 *base, const bf16 *base2, int tile) {
+        const bool rope_k = rope && dst == sK;
         for (int i = tid; i < KEY_TILE * PCHUNKS; i += NTHREADS) {
             int r = i / PCHUNKS, c = i % PCHUNKS;
             int j = tile * KEY_TILE + r;
             bool ok = j < n_keys && c < CHUNKS;
+            if (rope_k && ok && j >= a.s_cache) {
+                // fresh (action) key: raw projection, rotate while staging
+                if (c < 16) rope_pair(dst + r * LDS, base2 + (long)(j - a.s_cache) * a.kv2_row_stride, c,
+                                      a.rope_pos0 + (j - a.s_cache));
+                continue;
+            }
             const bf16 *src = base;
             if (ok) src = (j < a.s_cache) ? base + (long)j * a.kv_row_stride + c * 8
                                           : base2 + (long)(j - a.s_cache) * a.kv2_row_stride + c * 8;
@@ -256,6 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
 // combine the split-key partials: one warp per (sample, query row)
 template <int HD>
 __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a, int n_splits) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int rows_total = a.n_heads * a.q_rows;
     long wid = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -305,17 +352,14 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
         if (mqa && (cls == CLS_ACTION || cls == CLS_PROPRIO) && rows_total <= ROWS_PER_CTA && n_splits > 1 &&
             a.scratch && a.scratch_bytes >= need) {
             dim3 grid(1, n_splits, a.batch);
-            attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa, 1);
-            count_launch();
-            long warps = (long)a.batch * rows_total;
-            attn_combine_kernel<HD><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a, n_splits);
-            count_launch();
-            return 0;
+            launch_k(attn_mma_kernel<HD>, dim3(grid), dim3(NTHREADS), smem, st, a, cls, mqa, 1);
+                    long warps = (long)a.batch * rows_total;
+            launch_k(attn_combine_kernel<HD>, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, st, a, n_splits);
+                    return 0;
         }
     }
     dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
-    attn_mma_kernel<HD><<<grid, NTHREADS, smem, st>>>(a, cls, mqa, 0);
-    count_launch();
+    launch_k(attn_mma_kernel<HD>, dim3(grid), dim3(NTHREADS), smem, st, a, cls, mqa, 0);
     return 0;
 }
 

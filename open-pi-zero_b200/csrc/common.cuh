@@ -64,6 +64,7 @@ enum : int {
     LIN_ACCUM = 4,     // C(fp32) += alpha * (acc + bias)
     LIN_GEGLU = 8,     // W rows are [128 gate | 128 up] blocks; C[M, N/2] = gelu(gate)*up
     LIN_SILU = 16,     // silu(acc + bias)
+    LIN_NORM_A = 32,   // A is the fp32 residual stream; apply Gemma RMSNorm (norm_w) while loading it
 };
 
 struct LinearArgs {
@@ -74,6 +75,7 @@ struct LinearArgs {
     int M, N, K, lda, ldc;
     float alpha;
     int flags;
+    const float *norm_w;   // LIN_NORM_A: RMSNorm scale (raw w; 1+w is applied), eps 1e-6
 };
 
 // ---- attention argument block ------------------------------------------
@@ -99,9 +101,35 @@ struct AttnArgs {
     // optional fp32 scratch for the split-key (flash-decoding) path:
     // batch * key_tiles * n_heads*q_rows * (head_dim + 2) floats
     float *scratch; size_t scratch_bytes;
+    // optional fused RoPE (tensor-core kernel, head_dim 256): Q rows and the fresh K2 rows are
+    // raw projections; rotate them while staging.  Table row = rope_pos0 + token index.
+    const float *rope_cos, *rope_sin; int rope_pos0;
 };
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------
+// Every kernel of this library is launched with programmatic stream serialisation:
+// it may start while its predecessor is still running, does whatever does not depend
+// on the predecessor (barrier / TMEM setup, descriptor prefetch, *weight* prefetch),
+// and only then waits.  Rule: pdl_wait() before the first access to any buffer a
+// previous kernel may read or write.  Without the launch attribute both are no-ops.
+PZ_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PZ_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // host-side: every launch goes through this counter (bench.py: gpu_launches)
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter *g_launch_counter;
+extern int g_pdl_enabled;
 static inline void count_launch() { if (g_launch_counter) g_launch_counter->n++; }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    count_launch();
+}

@@ -8,6 +8,8 @@
 template <typename T>
 __global__ void im2col_kernel(const T *__restrict__ pix, T *__restrict__ patches, int image,
                               int patch, int k_pad, long total) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int k = i % k_pad;
@@ -28,9 +30,8 @@ void launch_im2col(const T *pix, T *patches, int n_images, int image, int patch,
                    cudaStream_t st) {
     int G = image / patch;
     long total = (long)n_images * G * G * k_pad;
-    im2col_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pix, patches, image, patch,
+    launch_k(im2col_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pix, patches, image, patch,
                                                                      k_pad, total);
-    count_launch();
 }
 template void launch_im2col<float>(const float *, float *, int, int, int, int, cudaStream_t);
 template void launch_im2col<bf16>(const bf16 *, bf16 *, int, int, int, int, cudaStream_t);
@@ -38,6 +39,8 @@ template void launch_im2col<bf16>(const bf16 *, bf16 *, int, int, int, int, cuda
 // x[r][c] = table[r % period][c]   (position embedding broadcast, siglip.py:76)
 __global__ void bcast_rows_kernel(float *__restrict__ x, const float *__restrict__ table,
                                   long total, int cols, int period) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     long r = i / cols;
@@ -47,9 +50,8 @@ __global__ void bcast_rows_kernel(float *__restrict__ x, const float *__restrict
 void launch_bcast_rows(float *x, const float *table, long rows, int cols, int period,
                        cudaStream_t st) {
     long total = rows * cols;
-    bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, table, total, cols,
+    launch_k(bcast_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, table, total, cols,
                                                                       period);
-    count_launch();
 }
 
 // ---- LayerNorm (siglip.py:211,217,298): one warp per row, fp32 statistics ----
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
                                                         const float *__restrict__ b,
                                                         T *__restrict__ out, long rows, int cols,
                                                         float eps) {
+    pdl_trigger();
+    pdl_wait();
     long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -75,8 +79,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 template <typename T>
 void launch_layernorm(const float *x, const float *w, const float *b, T *out, long rows, int cols,
                       float eps, cudaStream_t st) {
-    layernorm_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, b, out, rows, cols, eps);
-    count_launch();
+    launch_k(layernorm_kernel<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, w, b, out, rows, cols, eps);
 }
 template void launch_layernorm<float>(const float *, const float *, const float *, float *, long,
                                       int, float, cudaStream_t);
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float *__restrict__ 
                                                       const float *__restrict__ w,
                                                       T *__restrict__ out, long rows, int cols,
                                                       float eps) {
+    pdl_trigger();
+    pdl_wait();
     long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -113,8 +118,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float *__restrict__ 
 template <typename T>
 void launch_rmsnorm(const float *x, const float *w, T *out, long rows, int cols, float eps,
                     cudaStream_t st) {
-    rmsnorm_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, out, rows, cols, eps);
-    count_launch();
+    launch_k(rmsnorm_kernel<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, w, out, rows, cols, eps);
 }
 template void launch_rmsnorm<float>(const float *, const float *, float *, long, int, float,
                                     cudaStream_t);
@@ -133,6 +137,8 @@ __global__ void __launch_bounds__(256) embed_merge_kernel(
     const int64_t *__restrict__ ids, const T *__restrict__ embed, const float *__restrict__ feats,
     float *__restrict__ x, int s_vlm, int hidden, int n_feat_rows, int image_token, int pad_token,
     float text_scale) {
+    pdl_trigger();
+    pdl_wait();
     int b = blockIdx.y, s = blockIdx.x;
     const int64_t *row_ids = ids + (long)b * s_vlm;
     long id = row_ids[s];
@@ -165,9 +171,8 @@ void launch_embed_merge(const int64_t *ids, const T *embed, const float *feats, 
                         int batch, int s_vlm, int hidden, int n_feat_rows, int image_token,
                         int pad_token, float text_scale, cudaStream_t st) {
     dim3 grid(s_vlm, batch);
-    embed_merge_kernel<T><<<grid, 256, 0, st>>>(ids, embed, feats, x, s_vlm, hidden, n_feat_rows,
+    launch_k(embed_merge_kernel<T>, dim3(grid), dim3(256), 0, st, ids, embed, feats, x, s_vlm, hidden, n_feat_rows,
                                                image_token, pad_token, text_scale);
-    count_launch();
 }
 template void launch_embed_merge<float>(const int64_t *, const float *, const float *, float *,
                                         int, int, int, int, int, int, float, cudaStream_t);
@@ -184,6 +189,8 @@ __global__ void rope_split_kernel(const T *__restrict__ qkv, int qkv_ld, T *__re
                                   T *__restrict__ v_out, long kv_batch_stride,
                                   const float *__restrict__ cos_t, const float *__restrict__ sin_t,
                                   int s_x, int pos0, int n_heads, int head_dim) {
+    pdl_trigger();
+    pdl_wait();
     int row = blockIdx.x;
     int b = row / s_x, s = row % s_x;
     int half = head_dim >> 1;
@@ -210,10 +217,9 @@ void launch_rope_split(const T *qkv, int qkv_ld, T *q_out, long q_batch_stride, 
                        T *v_out, long kv_batch_stride, const float *cos_t, const float *sin_t,
                        int batch, int s_x, int pos0, int n_heads, int head_dim,
                        cudaStream_t st) {
-    rope_split_kernel<T><<<batch * s_x, 256, 0, st>>>(qkv, qkv_ld, q_out, q_batch_stride, k_out,
+    launch_k(rope_split_kernel<T>, dim3(batch * s_x), dim3(256), 0, st, qkv, qkv_ld, q_out, q_batch_stride, k_out,
                                                       v_out, kv_batch_stride, cos_t, sin_t, s_x,
                                                       pos0, n_heads, head_dim);
-    count_launch();
 }
 template void launch_rope_split<float>(const float *, int, float *, long, float *, float *, long,
                                        const float *, const float *, int, int, int, int, int,
@@ -226,6 +232,8 @@ template void launch_rope_split<bf16>(const bf16 *, int, bf16 *, long, bf16 *, b
 template <typename T>
 __global__ void cast_pad_kernel(const float *__restrict__ src, T *__restrict__ dst, long total,
                                 int cols, int cols_pad) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     long r = i / cols_pad;
@@ -236,22 +244,22 @@ template <typename T>
 void launch_cast_pad(const float *src, T *dst, long rows, int cols, int cols_pad,
                      cudaStream_t st) {
     long total = rows * cols_pad;
-    cast_pad_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, total, cols,
+    launch_k(cast_pad_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, total, cols,
                                                                        cols_pad);
-    count_launch();
 }
 template void launch_cast_pad<float>(const float *, float *, long, int, int, cudaStream_t);
 template void launch_cast_pad<bf16>(const float *, bf16 *, long, int, int, cudaStream_t);
 
 template <typename T>
 __global__ void to_f32_kernel(const T *__restrict__ src, float *__restrict__ dst, long n) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = to_f32<T>(src[i]);
 }
 template <typename T>
 void launch_to_f32(const T *src, float *dst, long n, cudaStream_t st) {
-    to_f32_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
-    count_launch();
+    launch_k(to_f32_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, dst, n);
 }
 template void launch_to_f32<float>(const float *, float *, long, cudaStream_t);
 template void launch_to_f32<bf16>(const bf16 *, float *, long, cudaStream_t);
@@ -260,6 +268,8 @@ template void launch_to_f32<bf16>(const bf16 *, float *, long, cudaStream_t);
 __global__ void euler_kernel(float *__restrict__ action, const float *__restrict__ vel,
                              int vel_ld, float dt, long total, int adim,
                              float *__restrict__ vel_capture) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     long r = i / adim;
@@ -271,14 +281,15 @@ __global__ void euler_kernel(float *__restrict__ action, const float *__restrict
 void launch_euler(float *action, const float *vel, int vel_ld, float dt, long rows, int adim,
                   float *vel_capture, cudaStream_t st) {
     long total = rows * adim;
-    euler_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(action, vel, vel_ld, dt, total,
+    launch_k(euler_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, action, vel, vel_ld, dt, total,
                                                                  adim, vel_capture);
-    count_launch();
 }
 
 // final clamp (pizero.py:484-489); clip < 0 => copy only
 __global__ void clamp_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, long n,
                                   float clip) {
+    pdl_trigger();
+    pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = src[i];
@@ -286,6 +297,5 @@ __global__ void clamp_copy_kernel(const float *__restrict__ src, float *__restri
     dst[i] = v;
 }
 void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStream_t st) {
-    clamp_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, clip);
-    count_launch();
+    launch_k(clamp_copy_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, dst, n, clip);
 }

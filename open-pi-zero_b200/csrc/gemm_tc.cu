@@ -213,22 +213,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ----
         if (lane == 0) {
+            // PDL: the weight tiles of the first ring pass do not depend on the previous
+            // kernel -- issue them before waiting for it; activations (A) only after.
+            int pre = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                int t = blockIdx.x;
+                int tmn = t % tiles_mn, ks = t / tiles_mn;
+                int tn = tmn / p.tiles_m;
+                int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                pre = min(cfg::STAGES, kb1 - kb0);
+                for (int i = 0; i < pre; ++i) {
+                    uint8_t *sa = smem + i * cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[i], cfg::STAGE_BYTES);
+                    tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN);
+                }
+            }
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
+            int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
                 int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;   // m fastest: concurrent CTAs share the W tile in L2
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     uint8_t *sa = smem + stage * cfg::STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
+                    if (it >= pre) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
+                        tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN);
+                    }
                     tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM);
-                    tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -283,6 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n_out = geglu ? p.N / 2 : p.N;
         const int sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
         uint8_t *stg_row = stg + lane * 128;
+        pdl_wait();                              // C may still be read / written by the previous kernel
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int tmn = t % tiles_mn, ksp = t / tiles_mn;
             int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;
@@ -431,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) bulk_wait0();     // all stores of this warp are complete before exit
+        if (lane == 0) bulk_wait_read0();   // staging smem must outlive the store's read; completion = kernel end
     }
     tc_fence_before();
     __syncthreads();
@@ -523,14 +544,14 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
     int tiles = p.tiles_m * p.tiles_n * p.ksplit;
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS2, cfg::SMEM_BYTES, st>>>(ma, mw, mc, p);
-    count_launch();
+    launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS2), cfg::SMEM_BYTES, st, ma, mw, mc, p);
     return 0;
 }
 
 }  // namespace
 
 int gemm_tc_supported(const LinearArgs &a) {
+    if (a.flags & LIN_NORM_A) return 0;
     if (a.M < 1 || a.K % 8 || a.lda % 8) return 0;          // TMA: 16-byte global strides
     if (((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.C) & 15) return 0;
     int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
@@ -559,7 +580,7 @@ int launch_qkv_rope_tc(const void *A, int lda, const void *W, void *q_out, void 
     LinearArgs a;
     a.A = A; a.W = W; a.bias = nullptr; a.C = q_out;
     a.M = M; a.N = (n_heads + 2) * 256; a.K = K; a.lda = lda; a.ldc = n_heads * 256;
-    a.alpha = 1.f; a.flags = 0;
+    a.alpha = 1.f; a.flags = 0; a.norm_w = nullptr;
     TcParams ex;
     memset(&ex, 0, sizeof(ex));
     ex.rope_cos = cos_t; ex.rope_sin = sin_t; ex.k_out = (bf16 *)k_out; ex.v_out = (bf16 *)v_out;

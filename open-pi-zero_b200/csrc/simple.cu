@@ -11,6 +11,8 @@
 // 64x64 output tile, 16-wide K slab, 256 threads, 4x4 outputs per thread.
 template <typename T, bool GEGLU>
 __global__ void __launch_bounds__(256) linear_simple_kernel(LinearArgs a) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float sA[BK][BM + 1];
     __shared__ float sW[GEGLU ? 2 : 1][BK][BN + 1];
@@ -93,9 +95,8 @@ void launch_linear_simple(const LinearArgs &a, cudaStream_t st) {
     bool geglu = a.flags & LIN_GEGLU;
     int n_out = geglu ? a.N / 2 : a.N;
     dim3 grid((n_out + 63) / 64, (a.M + 63) / 64);
-    if (geglu) linear_simple_kernel<T, true><<<grid, 256, 0, st>>>(a);
-    else linear_simple_kernel<T, false><<<grid, 256, 0, st>>>(a);
-    count_launch();
+    if (geglu) launch_k(linear_simple_kernel<T, true>, dim3(grid), dim3(256), 0, st, a);
+    else launch_k(linear_simple_kernel<T, false>, dim3(grid), dim3(256), 0, st, a);
 }
 template void launch_linear_simple<float>(const LinearArgs &, cudaStream_t);
 template void launch_linear_simple<bf16>(const LinearArgs &, cudaStream_t);
@@ -107,6 +108,8 @@ template void launch_linear_simple<bf16>(const LinearArgs &, cudaStream_t);
 // fp32 softmax, PV) and siglip.py:133-152 (softcap = 0, no mask).
 template <typename T>
 __global__ void __launch_bounds__(128) attn_simple_kernel(AttnArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float smem[];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nk = a.s_cache + a.n_fresh;
@@ -181,8 +184,7 @@ void launch_attn_simple(const AttnArgs &a, cudaStream_t st) {
     long total = (long)a.batch * a.n_heads * a.q_rows;
     int nk = a.s_cache + a.n_fresh;
     size_t smem = 4 * (size_t)(a.head_dim + nk) * sizeof(float);
-    attn_simple_kernel<T><<<(unsigned)((total + 3) / 4), 128, smem, st>>>(a);
-    count_launch();
+    launch_k(attn_simple_kernel<T>, dim3((unsigned)((total + 3) / 4)), dim3(128), smem, st, a);
 }
 template void launch_attn_simple<float>(const AttnArgs &, cudaStream_t);
 template void launch_attn_simple<bf16>(const AttnArgs &, cudaStream_t);

@@ -41,8 +41,9 @@ PZ_DEVINL void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, ui
 }
 
 struct SkinnyParams {
-    const bf16 *A;   // x [M, K], row stride lda
+    const bf16 *A;   // x [M, K], row stride lda  (fp32 when LIN_NORM_A)
     const bf16 *W;   // [N, K]
+    const float *norm_w;
     const float *bias;
     void *C;
     int M, N, K, lda, ldc, flags, ksplit, n_mt;
@@ -50,8 +51,9 @@ struct SkinnyParams {
 };
 
 template <int MT>   // number of 8-row activation tiles (M <= 8*MT)
-__global__ void __launch_bounds__(NTHREADS) skinny_kernel(SkinnyParams p) {
+__global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(SkinnyParams p) {
     __shared__ float red[NWARPS][16][MT * 8 + 1];
+    __shared__ float s_rs[MT * 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const bool geglu = p.flags & LIN_GEGLU;
@@ -83,9 +85,9 @@ __global__ void __launch_bounds__(NTHREADS) skinny_kernel(SkinnyParams p) {
     for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    for (int k0 = kbeg; k0 < kend; k0 += 128) {
-        // up to 8 independent 16-byte weight loads in flight per thread
-        uint4 a[2][4];
+    // up to 8 independent 16-byte weight loads in flight per thread
+    uint4 a[2][4];
+    auto load_w = [&](int k0) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
 #pragma unroll
@@ -96,6 +98,31 @@ __global__ void __launch_bounds__(NTHREADS) skinny_kernel(SkinnyParams p) {
                 a[u][hk * 2 + 1] = ok ? ldg_stream(w1 + k) : zero4;
             }
         }
+    };
+    // Weights do not depend on the previous kernel: start streaming them, let the next
+    // kernel start its own prefetch, and only then wait for the activations (PDL).
+    load_w(kbeg);
+    pdl_trigger();
+    pdl_wait();
+    const bool norm_a = p.flags & LIN_NORM_A;
+    if (norm_a) {
+        // fused Gemma RMSNorm (paligemma/modules.py:13-21): every CTA recomputes the M row
+        // statistics of the fp32 residual (M*K*4 bytes from L2) instead of a separate kernel
+        const float *X = reinterpret_cast<const float *>(p.A);
+        for (int m = warp; m < p.M; m += NWARPS) {
+            const float4 *xr = reinterpret_cast<const float4 *>(X + (long)m * p.lda);
+            float ss = 0.f;
+            for (int c = lane; c < p.K / 4; c += 32) {
+                float4 v = __ldg(xr + c);
+                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) s_rs[m] = rsqrtf(ss / p.K + 1e-6f);
+        }
+        __syncthreads();
+    }
+    for (int k0 = kbeg; k0 < kend; k0 += 128) {
+        if (k0 > kbeg) load_w(k0);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
 #pragma unroll
@@ -106,7 +133,21 @@ __global__ void __launch_bounds__(NTHREADS) skinny_kernel(SkinnyParams p) {
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     int m = mt * 8 + g;
-                    uint4 x = (ok && m < p.M) ? __ldg(reinterpret_cast<const uint4 *>(p.A + (long)m * p.lda + k)) : zero4;
+                    uint4 x = zero4;
+                    if (ok && m < p.M) {
+                        if (norm_a) {
+                            const float *xp = reinterpret_cast<const float *>(p.A) + (long)m * p.lda + k;
+                            float4 x0 = __ldg(reinterpret_cast<const float4 *>(xp)), x1 = __ldg(reinterpret_cast<const float4 *>(xp + 4));
+                            float4 w0v = __ldg(reinterpret_cast<const float4 *>(p.norm_w + k)), w1v = __ldg(reinterpret_cast<const float4 *>(p.norm_w + k + 4));
+                            float r = s_rs[m];
+                            x.x = pack_bf16x2(x0.x * r * (1.f + w0v.x), x0.y * r * (1.f + w0v.y));
+                            x.y = pack_bf16x2(x0.z * r * (1.f + w0v.z), x0.w * r * (1.f + w0v.w));
+                            x.z = pack_bf16x2(x1.x * r * (1.f + w1v.x), x1.y * r * (1.f + w1v.y));
+                            x.w = pack_bf16x2(x1.z * r * (1.f + w1v.z), x1.w * r * (1.f + w1v.w));
+                        } else {
+                            x = __ldg(reinterpret_cast<const uint4 *>(p.A + (long)m * p.lda + k));
+                        }
+                    }
                     mma_bf16(acc[mt], ag.x, ag8.x, ag.y, ag8.y, x.x, x.y);
                     mma_bf16(acc[mt], ag.z, ag8.z, ag.w, ag8.w, x.z, x.w);
                 }
@@ -159,6 +200,7 @@ __global__ void __launch_bounds__(NTHREADS) skinny_kernel(SkinnyParams p) {
 int skinny_supported(const LinearArgs &a) {
     if (a.M < 1 || a.M > 8 * MAX_MT) return 0;
     if (a.K % 8 || a.lda % 8) return 0;
+    if ((a.flags & LIN_NORM_A) && (!a.norm_w || ((uintptr_t)a.norm_w & 15))) return 0;
     if (((uintptr_t)a.A | (uintptr_t)a.W) & 15) return 0;
     if ((a.flags & LIN_GEGLU) && (a.N % (2 * PZ_GU_BLOCK))) return 0;
     if ((a.flags & LIN_ACCUM) && !(a.flags & LIN_OUT_F32)) return 0;
@@ -167,25 +209,24 @@ int skinny_supported(const LinearArgs &a) {
 
 int launch_linear_skinny(const LinearArgs &a, cudaStream_t st) {
     SkinnyParams p;
-    p.A = (const bf16 *)a.A; p.W = (const bf16 *)a.W; p.bias = a.bias; p.C = a.C;
+    p.A = (const bf16 *)a.A; p.W = (const bf16 *)a.W; p.bias = a.bias; p.C = a.C; p.norm_w = a.norm_w;
     p.M = a.M; p.N = a.N; p.K = a.K; p.lda = a.lda; p.ldc = a.ldc; p.flags = a.flags; p.alpha = a.alpha;
     bool geglu = a.flags & LIN_GEGLU;
     int nblocks = geglu ? a.N / 16 : (a.N + 15) / 16;
     // split K across CTAs only where the epilogue is a pure fp32 accumulate (atomics)
     int ksplit = 1;
     if ((a.flags & LIN_ACCUM) && !(a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU))) {
-        while (nblocks * ksplit < 296 && a.K / (NWARPS * ksplit * 2) >= 64) ksplit *= 2;
+        while (nblocks * ksplit < 444 && a.K / (NWARPS * ksplit * 2) >= 64) ksplit *= 2;
     }
     p.ksplit = ksplit;
     int mt = (a.M + 7) / 8;
     p.n_mt = mt;
     dim3 grid(nblocks, ksplit);
     switch (mt) {
-        case 1: skinny_kernel<1><<<grid, NTHREADS, 0, st>>>(p); break;
-        case 2: skinny_kernel<2><<<grid, NTHREADS, 0, st>>>(p); break;
-        case 3: case 4: skinny_kernel<4><<<grid, NTHREADS, 0, st>>>(p); break;
-        default: skinny_kernel<8><<<grid, NTHREADS, 0, st>>>(p); break;
+        case 1: launch_k(skinny_kernel<1>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
+        case 2: launch_k(skinny_kernel<2>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
+        case 3: case 4: launch_k(skinny_kernel<4>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
+        default: launch_k(skinny_kernel<8>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
     }
-    count_launch();
     return 0;
 }
