@@ -133,6 +133,14 @@ def run_cpu_oracle(dims, sd, steps, warmup, batch=1):
     return times, out, inp
 
 
+def workload_config(world, B):
+    return dict(workload=f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
+                         "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
+                         "3.24B-parameter model", global_batch=world * B, per_gpu_batch=B,
+                parallelism=f"replica x{world}, batch-sharded, no collective",
+                l2="working set per step (6.5 GB bf16 weights + activations) >> 126 MB L2; no flush")
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
@@ -145,9 +153,9 @@ def reference_arm(args, rank):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="bridge infer_action: 224px image, 276 image+text tokens, 1 proprio, "
-                                     "chunk 4, 10 Euler steps; reference algorithm on host CPU, bs=1 per step",
-                            global_batch=1),
+                config=dict(workload_config(args.gpus, PER_GPU_BATCH),
+                            reference_sample="each step = one infer_action at bs=1 of the same workload, fp32, "
+                                             "reference algorithm (oracle port) on the host cores"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port",
                                   sample=f"{len(times)} infer_action calls at bs=1, fp32, after "
                                          f"{max(args.warmup, 1)} warm-up"),
@@ -310,11 +318,7 @@ def main():
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup,
             ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="bf16", data="synthetic",
-            config=dict(workload=f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
-                                 "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
-                                 "3.24B-parameter model", global_batch=world * B, per_gpu_batch=B,
-                        parallelism=f"replica x{world}, batch-sharded, no collective",
-                        l2="working set per step (6.5 GB bf16 weights + activations) >> 126 MB L2; no flush"),
+            config=workload_config(world, B),
             clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=launches, latency_bs1=lat, roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)

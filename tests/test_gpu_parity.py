@@ -148,6 +148,42 @@ def test_bridge_full_size_bf16_vs_reference_golden(golden_dir):
     _check_golden(_golden(golden_dir, "bridge"), torch.bfloat16, BF16_LAYER_TOL, BF16_ACTION_TOL, "bridge")
 
 
+def test_pi0_paper_shape_multi_image_chunk50():
+    """BASELINE configs[3] geometry: 3 images (768 image tokens), 48 text tokens, chunk 50 --
+    a capability the reference lacks; oracle = the reference's vision tower applied
+    per image + its unmodified joint model (oracle.embed_prefix, 5-D pixel_values)."""
+    d = pz.make_dims(pz.PI0_PAPER_DIMS, vocab_size=1024, image_token_index=1000, num_layers=2, vit_layers=2)
+    sd = pz.init_state_dict(d, seed=13, randomize_norms=True)
+    inp = pz.make_inputs(d, 2, seed=5, min_text=3)
+    ocap = {}
+    want = O.infer_action(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                          inp["proprios"], inp["noise"], capture=ocap)
+    for dtype, layer_tol, act_tol in ((torch.float32, FP32_LAYER_TOL, FP32_ACTION_TOL),
+                                      (torch.bfloat16, BF16_LAYER_TOL, BF16_ACTION_TOL)):
+        m = _model(d, sd, dtype)
+        out, cap = _run(m, d, inp)
+        report = {}
+        worst = _compare_all(d, inp, cap, ocap, layer_tol, report)
+        pre = max_abs(cap["action_preclip"], ocap["action_preclip"])
+        print(f"[pi0-shape {dtype}] worst layer rel {worst:.3e}; preclip max-abs {pre:.3e}")
+        assert pre < act_tol and max_abs(out, want) < act_tol
+        del m
+
+
+def test_cuda_graph_replay_matches_eager(monkeypatch):
+    """The production path (CUDA-graph replay, no capture taps) against the eager call."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=2, randomize_norms=True)
+    m = _model(d, sd, torch.bfloat16)
+    for seed in (1, 2):
+        inp = pz.make_inputs(d, 3, seed=seed)
+        eager, _ = _run(m, d, inp, capture=True)      # capture taps force the eager path
+        eager = eager.clone()
+        replay, _ = _run(m, d, inp, capture=False)    # graph (captured on first use, replayed after)
+        assert max_abs(eager, replay) < 2e-3           # fp32 atomics in the split-K GEMV: order may differ
+    assert 3 in m._graphs
+
+
 def test_batch_invariance_and_ragged_lengths():
     """Each sample's result must not depend on its neighbours or on pad content:
     run B=6 with ragged lengths, then each sample alone."""
