@@ -30,6 +30,9 @@ struct pz_handle {
     LaunchCounter lc;
     int prefix_chunk = 64;
     // optional CUDA-event timing of one tagged kernel family (bench.py roofline)
+    // fork/join side stream: the proprio token's chain of small kernels runs beside the VLM chain
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> sync_ev;
     int timing_tag = 0;                       // 0 = off
     std::vector<cudaEvent_t> ev;              // pairs (start, stop)
     size_t ev_used = 0;
@@ -180,6 +183,7 @@ static LinearArgs lin(const void *A, int lda, const void *W, const float *bias, 
     a.A = A; a.W = W; a.bias = bias; a.C = C;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldc = ldc;
     a.alpha = alpha; a.flags = flags; a.norm_w = nullptr;
+    a.cmb_splits = a.cmb_q_rows = a.cmb_heads = a.cmb_hd = 0;
     return a;
 }
 
@@ -268,11 +272,19 @@ static int run_embed_prefix(pz_handle *h, const int64_t *ids, const void *pixels
 // (joint_model.py:65-127, mixture.py:217-218, paligemma/modules.py:86-95)
 template <typename T>
 static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *hbuf, void *att,
-                          void *mlp, int M, int hidden, int inter, cudaStream_t st) {
+                          void *mlp, int M, int hidden, int inter, cudaStream_t st, int cmb_splits = 0,
+                          int cmb_q_rows = 0, const float *partials = nullptr) {
     const pz_config &c = h->cfg;
     int qd = c.n_heads * c.head_dim;
-    PZ_TRY(Ops<T>::linear(h, lin(att, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
-                                 LIN_OUT_F32 | LIN_ACCUM), st));
+    if (cmb_splits > 0) {
+        LinearArgs o = lin(partials, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
+                           LIN_OUT_F32 | LIN_ACCUM | LIN_COMBINE_A);
+        o.cmb_splits = cmb_splits; o.cmb_q_rows = cmb_q_rows; o.cmb_heads = c.n_heads; o.cmb_hd = c.head_dim;
+        PZ_TRY(launch_linear_skinny(o, st));
+    } else {
+        PZ_TRY(Ops<T>::linear(h, lin(att, qd, L.w_o, nullptr, x, hidden, M, hidden, qd,
+                                     LIN_OUT_F32 | LIN_ACCUM), st));
+    }
     int tag_gu = hidden == c.vlm_hidden ? TAG_VLM_GATE_UP : TAG_ACT_GATE_UP;
     if (M > 64) launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
     tick(h, tag_gu, st);
@@ -292,6 +304,22 @@ static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *h
 }
 
 // ------------------------------------------------ stage 2: prefix pass ------
+// Two dependency chains per layer (joint_model.py:24-127 over the mixtures vlm and proprio):
+//   VLM chain     : norm -> QKV+RoPE(+cache write) -> attention over keys < cnt -> o_proj -> norm -> MLP
+//   proprio chain : the same with the action-expert-shaped weights on 1 token per sample; its
+//                   attention additionally reads the VLM keys of the same layer.
+// VLM rows never attend to the proprio token (block mask, pizero.py:296-310), so the VLM chain does
+// not depend on the proprio chain at all: the latter runs on a forked side stream and only waits,
+// per layer, for the VLM K/V of that layer.
+static cudaEvent_t sync_event(pz_handle *h, size_t i) {
+    while (h->sync_ev.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        h->sync_ev.push_back(e);
+    }
+    return h->sync_ev[i];
+}
+
 template <typename T>
 static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *proprio, void *wsp,
                        int B, const pz_capture *cap, cudaStream_t st) {
@@ -302,20 +330,29 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
     const int S_v = c.s_vlm, S_p = c.cond_steps, S_c = S_v + S_p;
     const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
     const long kv_bs = (long)S_c * hd;
+    if (!h->side) {
+        if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(h, PZ_ERR_CUDA, "cannot create the side stream");
+    }
+    cudaStream_t sp = h->side;
+    size_t ev = 0;
+    cudaEvent_t e_fork = sync_event(h, ev++);
+    cudaEventRecord(e_fork, st);
+    cudaStreamWaitEvent(sp, e_fork, 0);
     for (int b0 = 0; b0 < B; b0 += h->prefix_chunk) {
         int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
         int M = nb * S_v, Mp = nb * S_p;
         float *x = ws.x + (size_t)b0 * S_v * H;
         // proprio encoder (pizero.py:436) and the sqrt(hidden) embed scale (joint_model.py:348-355)
         launch_cast_pad<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
-                           w.small_k_pad, st);
+                           w.small_k_pad, sp);
         PZ_TRY(Ops<T>::linear(h, lin(ws.pp, w.small_k_pad, w.prop_w, w.prop_b, ws.xp, A, Mp, A,
-                                     w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), st));
+                                     w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), sp));
         for (int l = 0; l < c.n_layers; ++l) {
             bool last = l == c.n_layers - 1;
             T *Kc = (T *)ws.kcache + ((size_t)l * B + b0) * kv_bs;
             T *Vc = (T *)ws.vcache + ((size_t)l * B + b0) * kv_bs;
-            // vlm block: norm -> fused QKV projection -> RoPE; K (post-RoPE) and V go to the cache
+            // ---- VLM chain (main stream): norm -> fused QKV projection + RoPE; K (post-RoPE), V -> cache
             launch_rmsnorm<T>(x, h->vlm[l].norm_in, (T *)ws.h, M, H, 1e-6f, st);
             if (std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 && H % 8 == 0) {
                 // one kernel: tcgen05 GEMM with RoPE, Q/K/V split and the cache write in its epilogue
@@ -328,12 +365,14 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
                 launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)S_v * qd, Kc, Vc, kv_bs,
                                      w.rope_vlm_cos, w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
             }
-            // proprio block through the action-expert-shaped weights
+            cudaEvent_t e_kv = sync_event(h, ev++);
+            cudaEventRecord(e_kv, st);
+            // ---- proprio chain (side stream)
             PZ_TRY(norm_linear<T>(h, ws.xp, h->proprio[l].norm_in, ws.hp,
-                                  lin(nullptr, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), A, st));
+                                  lin(nullptr, A, h->proprio[l].w_qkv, nullptr, ws.qkvp, qkvd, Mp, qkvd, A), A, sp));
             launch_rope_split<T>((const T *)ws.qkvp, qkvd, (T *)ws.qp, (long)S_p * qd, Kc + (size_t)S_v * hd,
                                  Vc + (size_t)S_v * hd, kv_bs, w.rope_act_cos, w.rope_act_sin, nb, S_p,
-                                 0, nh, hd, st);
+                                 0, nh, hd, sp);
             // last layer: the reference computes attention for vlm/proprio and drops it
             // (joint_model.py:297-299); only the K/V above are kept.
             if (last) break;
@@ -348,19 +387,24 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
             av.Q = ws.q; av.q_batch_stride = (long)S_v * qd; av.O = ws.att; av.o_batch_stride = (long)S_v * qd;
             av.q_rows = S_v; av.q_row0 = 0;
             PZ_TRY(Ops<T>::attention(h, av, st));
-            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
-            AttnArgs ap = a;   // proprio rows
-            ap.Q = ws.qp; ap.q_batch_stride = (long)S_p * qd; ap.O = ws.attp; ap.o_batch_stride = (long)S_p * qd;
-            ap.q_rows = S_p; ap.q_row0 = S_v;
-            PZ_TRY(Ops<T>::attention(h, ap, st));
             PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, M, H, c.vlm_inter, st));
-            PZ_TRY(post_attention<T>(h, h->proprio[l], ws.xp, ws.hp, ws.attp, ws.mlpp, Mp, A, c.act_inter, st));
             if (cap && cap->prefix_vlm)
                 copy_f32(cap->prefix_vlm + ((size_t)l * B + b0) * S_v * H, x, (size_t)M * H, st);
+            // proprio rows: need this layer's VLM keys
+            cudaStreamWaitEvent(sp, e_kv, 0);
+            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
+            AttnArgs ap = a;
+            ap.Q = ws.qp; ap.q_batch_stride = (long)S_p * qd; ap.O = ws.attp; ap.o_batch_stride = (long)S_p * qd;
+            ap.q_rows = S_p; ap.q_row0 = S_v;
+            PZ_TRY(Ops<T>::attention(h, ap, sp));
+            PZ_TRY(post_attention<T>(h, h->proprio[l], ws.xp, ws.hp, ws.attp, ws.mlpp, Mp, A, c.act_inter, sp));
             if (cap && cap->prefix_proprio)
-                copy_f32(cap->prefix_proprio + ((size_t)l * B + b0) * S_p * A, ws.xp, (size_t)Mp * A, st);
+                copy_f32(cap->prefix_proprio + ((size_t)l * B + b0) * S_p * A, ws.xp, (size_t)Mp * A, sp);
         }
     }
+    cudaEvent_t e_join = sync_event(h, ev++);
+    cudaEventRecord(e_join, sp);
+    cudaStreamWaitEvent(st, e_join, 0);
     return 0;
 }
 
@@ -417,8 +461,19 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
             a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
             a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
             a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
-            PZ_TRY(Ops<T>::attention(h, a, st));
-            PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st));
+            int n_splits = 0;
+            static const bool combine_in_oproj = getenv("PZ_COMBINE_IN_OPROJ") != nullptr;   // experimental
+            if (fused_rope && Ma <= 16 && combine_in_oproj) {
+                // small batch: leave the split-key partials uncombined; the o_proj GEMV combines them
+                // while it loads its activations (one kernel less on the latency-bound chain)
+                LinearArgs probe = lin(ws.att_scratch, qd, L.w_o, nullptr, ws.xa, A, Ma, A, qd,
+                                       LIN_OUT_F32 | LIN_ACCUM | LIN_COMBINE_A);
+                probe.cmb_splits = (S_c + Hz + 63) / 64; probe.cmb_q_rows = Hz; probe.cmb_heads = nh; probe.cmb_hd = hd;
+                if (skinny_supported(probe)) n_splits = launch_attn_mma_partials(a, st);
+            }
+            if (n_splits == 0) PZ_TRY(Ops<T>::attention(h, a, st));
+            PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st, n_splits, Hz,
+                                     ws.att_scratch));
             if (cap && cap->denoise_action)
                 copy_f32(cap->denoise_action + ((size_t)step * c.n_layers + l) * Ma * A, ws.xa,
                          (size_t)Ma * A, st);
@@ -478,6 +533,8 @@ int pz_create(const pz_config *cfg, pz_handle **out) {
 void pz_destroy(pz_handle *h) {
     if (!h) return;
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->sync_ev) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
 }
 

@@ -44,6 +44,13 @@ PZ_DEVINL void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// tanh(y) = 1 - 2 / (exp(2y) + 1) with ex2.approx / fast division: abs. error ~1e-7, i.e. < 1e-5 on
+// the soft-capped logit (cap 50) -- the libm tanhf costs more issue slots than the MMAs of a tile
+PZ_DEVINL float tanh_fast_acc(float y) {
+    float t = __expf(2.f * y);
+    return 1.f - __fdividef(2.f, t + 1.f);
+}
+
 // visibility classes of a launch (all of its query rows share one)
 enum { CLS_ALL = 0, CLS_VLM = 1, CLS_PROPRIO = 2, CLS_ACTION = 3 };
 
@@ -106,6 +113,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
         *reinterpret_cast<uint4 *>(dst_row + c * 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
         *reinterpret_cast<uint4 *>(dst_row + 128 + c * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
     };
+    auto load_kv = [&](bf16 *dst, const bf16 *base, const bf16 *base2, int tile) {
+        const bool rope_k = rope && dst == sK;
+        for (int i = tid; i < KEY_TILE * PCHUNKS; i += NTHREADS) {
+            int r = i / PCHUNKS, c = i % PCHUNKS;
+            int j = tile * KEY_TILE + r;
+            bool ok = j < n_keys && c < CHUNKS;
+            if (rope_k && ok && j >= a.s_cache) {
+                // fresh (action) key: raw projection, rotate while staging
+                if (c < 16) rope_pair(dst + r * LDS, base2 + (long)(j - a.s_cache) * a.kv2_row_stride, c,
+                                      a.rope_pos0 + (j - a.s_cache));
+                continue;
+            }
+            const bf16 *src = base;
+            if (ok) src = (j < a.s_cache) ? base + (long)j * a.kv_row_stride + c * 8
+                                          : base2 + (long)(j - a.s_cache) * a.kv2_row_stride + c * 8;
+            cp_async16(dst + r * LDS + c * 8, src, ok);
+        }
+    };
+    // K and V of the first tile first (their latency is the critical path); the Q staging
+    // work then overlaps with them
+    load_kv(sK, Kb, K2b, tile_lo);
+    cp_async_commit();
+    load_kv(sV, Vb, V2b, tile_lo);
+    cp_async_commit();
     if (rope) {
         for (int i = tid; i < ROWS_PER_CTA * 16; i += NTHREADS) {
             int r = i / 16, c = i % 16;
@@ -131,27 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
             cp_async16(sQ + r * LDS + c * 8, src, ok);
         }
     }
-    auto load_kv = [&](bf16 *dst, const bf16 *base, const bf16 *base2, int tile) {
-        const bool rope_k = rope && dst == sK;
-        for (int i = tid; i < KEY_TILE * PCHUNKS; i += NTHREADS) {
-            int r = i / PCHUNKS, c = i % PCHUNKS;
-            int j = tile * KEY_TILE + r;
-            bool ok = j < n_keys && c < CHUNKS;
-            if (rope_k && ok && j >= a.s_cache) {
-                // fresh (action) key: raw projection, rotate while staging
-                if (c < 16) rope_pair(dst + r * LDS, base2 + (long)(j - a.s_cache) * a.kv2_row_stride, c,
-                                      a.rope_pos0 + (j - a.s_cache));
-                continue;
-            }
-            const bf16 *src = base;
-            if (ok) src = (j < a.s_cache) ? base + (long)j * a.kv_row_stride + c * 8
-                                          : base2 + (long)(j - a.s_cache) * a.kv2_row_stride + c * 8;
-            cp_async16(dst + r * LDS + c * 8, src, ok);
-        }
-    };
-    load_kv(sK, Kb, K2b, tile_lo);
     cp_async_commit();
-
     float o[HDP / 8][4];
 #pragma unroll
     for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     const float scale = a.scale, cap = a.softcap, inv_cap = cap > 0.f ? 1.f / cap : 0.f;
 
     for (int tile = tile_lo; tile < n_tiles; ++tile) {
-        load_kv(sV, Vb, V2b, tile);
+        if (tile > tile_lo) load_kv(sV, Vb, V2b, tile);   // the first tile's V is already in flight
         cp_async_commit();
         cp_async_wait<1>();          // Q and K(tile) have landed
         __syncthreads();
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
                 else if (cls == CLS_VLM) vis = j < vlen;
                 else vis = (j < vlen) || (j >= a.s_vlm && j < n_keys);
                 float v = s[nt][e] * scale;
-                if (cap > 0.f) v = tanhf(v * inv_cap) * cap;
+                if (cap > 0.f) v = tanh_fast_acc(v * inv_cap) * cap;
                 v = vis ? v : -INFINITY;
                 s[nt][e] = v;
                 mx[e >> 1] = fmaxf(mx[e >> 1], v);
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(AttnArgs a, int n_spl
 }
 
 template <int HD>
-int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
+int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_only = 0) {
     constexpr int HDP = (HD + 15) / 16 * 16;
     constexpr int LDS = HDP + 8;
     size_t smem = (size_t)(ROWS_PER_CTA + 2 * KEY_TILE) * LDS * sizeof(bf16);
@@ -353,11 +364,13 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st) {
             a.scratch && a.scratch_bytes >= need) {
             dim3 grid(1, n_splits, a.batch);
             launch_k(attn_mma_kernel<HD>, dim3(grid), dim3(NTHREADS), smem, st, a, cls, mqa, 1);
-                    long warps = (long)a.batch * rows_total;
+            if (partials_only) return n_splits;   // the consumer (o_proj GEMV) combines
+            long warps = (long)a.batch * rows_total;
             launch_k(attn_combine_kernel<HD>, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, st, a, n_splits);
-                    return 0;
+            return 0;
         }
     }
+    if (partials_only) return 0;
     dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
     launch_k(attn_mma_kernel<HD>, dim3(grid), dim3(NTHREADS), smem, st, a, cls, mqa, 0);
     return 0;
@@ -391,4 +404,12 @@ int launch_attn_mma(const AttnArgs &a, cudaStream_t st) {
     int mqa = a.kv_head_stride == 0;
     if (a.head_dim == 72) return launch<72>(a, cls, mqa, st);
     return launch<256>(a, cls, mqa, st);
+}
+
+int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st) {
+    if (a.head_dim != 256 || a.kv_head_stride != 0) return 0;
+    int cls = classify(a);
+    if (cls < 0) return 0;
+    int r = launch<256>(a, cls, 1, st, 1);
+    return r > 0 ? r : 0;
 }

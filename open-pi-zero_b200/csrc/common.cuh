@@ -65,6 +65,7 @@ enum : int {
     LIN_GEGLU = 8,     // W rows are [128 gate | 128 up] blocks; C[M, N/2] = gelu(gate)*up
     LIN_SILU = 16,     // silu(acc + bias)
     LIN_NORM_A = 32,   // A is the fp32 residual stream; apply Gemma RMSNorm (norm_w) while loading it
+    LIN_COMBINE_A = 64, // A is the split-key attention partials; combine them while loading (skinny only)
 };
 
 struct LinearArgs {
@@ -76,6 +77,9 @@ struct LinearArgs {
     float alpha;
     int flags;
     const float *norm_w;   // LIN_NORM_A: RMSNorm scale (raw w; 1+w is applied), eps 1e-6
+    // LIN_COMBINE_A: A = partials [batch][n_splits][heads*q_rows][hd+2] fp32 (o, m, l) of attn_mma's
+    // split-key mode; logical A[m = b*q_rows + tok][k = h*hd + d]
+    int cmb_splits, cmb_q_rows, cmb_heads, cmb_hd;
 };
 
 // ---- attention argument block ------------------------------------------

@@ -120,6 +120,7 @@ struct TcParams {
     int flags;
     int tiles_m, tiles_n;
     int ksplit, kb_per_split;           // split-K (fp32 reduce-add outputs only)
+    int n_fastest;                      // tile raster: 1 = consecutive CTAs share the A tile (few N tiles, big A)
     // fused RoPE + Q/K/V split (LIN_ROPE): BN = 256 = head_dim, one N tile per head
     const float *rope_cos, *rope_sin;   // [s_x, 128] fp32
     bf16 *k_out, *v_out;                // cache rows: base + b*kv_batch_stride + s*256
@@ -224,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if ((int)blockIdx.x < num_tiles) {
                 int t = blockIdx.x;
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
-                int tn = tmn / p.tiles_m;
+                int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 pre = min(cfg::STAGES, kb1 - kb0);
                 for (int i = 0; i < pre; ++i) {
@@ -239,7 +240,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
-                int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;   // m fastest: concurrent CTAs share the W tile in L2
+                // raster: m fastest -> concurrent CTAs share the W tile in L2; n fastest -> they share the A tile
+                int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
+                int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     uint8_t *sa = smem + stage * cfg::STAGE_BYTES;
@@ -306,7 +309,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         pdl_wait();                              // C may still be read / written by the previous kernel
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int tmn = t % tiles_mn, ksp = t / tiles_mn;
-            int tm = tmn % p.tiles_m, tn = tmn / p.tiles_m;
+            int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
+            int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = tm * BM + q * 32;       // first row of this warp
@@ -540,6 +544,12 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
         int mn = p.tiles_m * p.tiles_n;
         while (mn * p.ksplit * 2 <= g_num_sms && num_kb / (p.ksplit * 2) >= 4) p.ksplit *= 2;
     }
+    // A bigger than what L2 keeps and only a few N tiles: let the CTAs that run together share the A
+    // tile (read from HBM once) instead of the W tile (which then stays L2 resident as a whole)
+    {
+        double a_bytes = (double)a.M * a.K * 2, w_bytes = (double)a.N * a.K * 2;
+        p.n_fastest = (!extra && a_bytes > 48e6 && w_bytes < 96e6 && p.tiles_n <= 32) ? 1 : 0;
+    }
     p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
     int tiles = p.tiles_m * p.tiles_n * p.ksplit;
@@ -551,7 +561,7 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
 }  // namespace
 
 int gemm_tc_supported(const LinearArgs &a) {
-    if (a.flags & LIN_NORM_A) return 0;
+    if (a.flags & (LIN_NORM_A | LIN_COMBINE_A)) return 0;
     if (a.M < 1 || a.K % 8 || a.lda % 8) return 0;          // TMA: 16-byte global strides
     if (((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.C) & 15) return 0;
     int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;

@@ -49,3 +49,6 @@ int launch_linear_skinny(const LinearArgs &a, cudaStream_t st);
 // attn_mma.cu (tensor-core attention, bf16)
 int attn_mma_supported(const AttnArgs &a);
 int launch_attn_mma(const AttnArgs &a, cudaStream_t st);
+// split-key decode only: returns the number of key splits (> 1) if the partials path applies and
+// launches just the partial kernel (no combine); 0 if it does not apply (nothing launched).
+int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st);

@@ -44,16 +44,25 @@ struct SkinnyParams {
     const bf16 *A;   // x [M, K], row stride lda  (fp32 when LIN_NORM_A)
     const bf16 *W;   // [N, K]
     const float *norm_w;
+    int cmb_splits, cmb_q_rows, cmb_heads, cmb_hd;
     const float *bias;
     void *C;
     int M, N, K, lda, ldc, flags, ksplit, n_mt;
     float alpha;
 };
 
-template <int MT>   // number of 8-row activation tiles (M <= 8*MT)
+template <int MT>   // number of 8-row activation tiles per CTA (rows per CTA <= 8*MT)
 __global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(SkinnyParams p) {
     __shared__ float red[NWARPS][16][MT * 8 + 1];
     __shared__ float s_rs[MT * 8];
+    __shared__ float s_cw[(MT <= 2) ? MT * 8 * 8 * 16 : 1];   // combine weights [m][head][split] (M<=16, <=8 heads, <=16 splits)
+    {   // blockIdx.z selects a chunk of 8*MT activation rows (M > 64 with a tiny N, e.g. the action decoder)
+        const int m0 = blockIdx.z * (8 * MT);
+        const size_t esz = (p.flags & LIN_NORM_A) ? 4 : 2;
+        p.A = reinterpret_cast<const bf16 *>(reinterpret_cast<const char *>(p.A) + (size_t)m0 * p.lda * esz);
+        p.C = reinterpret_cast<char *>(p.C) + (size_t)m0 * p.ldc * ((p.flags & LIN_OUT_F32) ? 4 : 2);
+        p.M = min(8 * MT, p.M - m0);
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const bool geglu = p.flags & LIN_GEGLU;
@@ -121,6 +130,30 @@ __global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(Skinn
         }
         __syncthreads();
     }
+    const bool cmb_a = p.flags & LIN_COMBINE_A;
+    if (cmb_a) {
+        // softmax-combine weights of the split-key attention partials: w_s = exp(m_s - max) / sum_s l_s exp(m_s - max)
+        const float *P = reinterpret_cast<const float *>(p.A);
+        const int rows_total = p.cmb_heads * p.cmb_q_rows, stride = p.cmb_hd + 2;
+        const int m_base = blockIdx.z * (8 * MT);
+        for (int i = threadIdx.x; i < p.M * p.cmb_heads; i += NTHREADS) {
+            int m = i / p.cmb_heads, hh = i % p.cmb_heads;
+            int gm = m_base + m, b = gm / p.cmb_q_rows, tok = gm % p.cmb_q_rows;
+            const float *base = P + ((long)b * p.cmb_splits * rows_total + (hh * p.cmb_q_rows + tok)) * stride;
+            float mx = -INFINITY;
+            for (int sp = 0; sp < p.cmb_splits; ++sp) mx = fmaxf(mx, base[(long)sp * rows_total * stride + p.cmb_hd]);
+            float l = 0.f;
+            for (int sp = 0; sp < p.cmb_splits; ++sp) {
+                const float *q = base + (long)sp * rows_total * stride;
+                float wgt = (q[p.cmb_hd] == -INFINITY) ? 0.f : __expf(q[p.cmb_hd] - mx);
+                s_cw[(m * 8 + hh) * 16 + sp] = wgt;
+                l += q[p.cmb_hd + 1] * wgt;
+            }
+            float inv = l > 0.f ? 1.f / l : 0.f;
+            for (int sp = 0; sp < p.cmb_splits; ++sp) s_cw[(m * 8 + hh) * 16 + sp] *= inv;
+        }
+        __syncthreads();
+    }
     for (int k0 = kbeg; k0 < kend; k0 += 128) {
         if (k0 > kbeg) load_w(k0);
 #pragma unroll
@@ -144,6 +177,24 @@ __global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(Skinn
                             x.y = pack_bf16x2(x0.z * r * (1.f + w0v.z), x0.w * r * (1.f + w0v.w));
                             x.z = pack_bf16x2(x1.x * r * (1.f + w1v.x), x1.y * r * (1.f + w1v.y));
                             x.w = pack_bf16x2(x1.z * r * (1.f + w1v.z), x1.w * r * (1.f + w1v.w));
+                        } else if (cmb_a) {
+                            const float *P = reinterpret_cast<const float *>(p.A);
+                            const int rows_total = p.cmb_heads * p.cmb_q_rows, stride = p.cmb_hd + 2;
+                            int gm = blockIdx.z * (8 * MT) + m, b = gm / p.cmb_q_rows, tok = gm % p.cmb_q_rows;
+                            int hh = k / p.cmb_hd, d = k % p.cmb_hd;
+                            const float *src = P + ((long)b * p.cmb_splits * rows_total + (hh * p.cmb_q_rows + tok)) * stride + d;
+                            float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            for (int sp = 0; sp < p.cmb_splits; ++sp) {
+                                const float2 *q = reinterpret_cast<const float2 *>(src + (long)sp * rows_total * stride);
+                                float wgt = s_cw[(m * 8 + hh) * 16 + sp];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 v = __ldg(q + j);
+                                    o8[2 * j] += v.x * wgt; o8[2 * j + 1] += v.y * wgt;
+                                }
+                            }
+                            x.x = pack_bf16x2(o8[0], o8[1]); x.y = pack_bf16x2(o8[2], o8[3]);
+                            x.z = pack_bf16x2(o8[4], o8[5]); x.w = pack_bf16x2(o8[6], o8[7]);
                         } else {
                             x = __ldg(reinterpret_cast<const uint4 *>(p.A + (long)m * p.lda + k));
                         }
@@ -198,9 +249,17 @@ __global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(Skinn
 }  // namespace
 
 int skinny_supported(const LinearArgs &a) {
-    if (a.M < 1 || a.M > 8 * MAX_MT) return 0;
+    // M <= 64: the weight-streaming regime.  Larger M only for tiny N (weights re-read per 64-row
+    // chunk stay in L2): the 7-wide action decoder.
+    if (a.M < 1 || (a.M > 8 * MAX_MT && a.N > 64)) return 0;
     if (a.K % 8 || a.lda % 8) return 0;
     if ((a.flags & LIN_NORM_A) && (!a.norm_w || ((uintptr_t)a.norm_w & 15))) return 0;
+    if (a.flags & LIN_COMBINE_A) {
+        if (a.M > 16 || a.cmb_heads > 8 || a.cmb_splits > 16 || a.cmb_hd % 8 || (a.flags & LIN_NORM_A)) return 0;
+        if (a.K != a.cmb_heads * a.cmb_hd) return 0;
+        if ((a.K % 8 || ((uintptr_t)a.W & 15))) return 0;
+        return 1;
+    }
     if (((uintptr_t)a.A | (uintptr_t)a.W) & 15) return 0;
     if ((a.flags & LIN_GEGLU) && (a.N % (2 * PZ_GU_BLOCK))) return 0;
     if ((a.flags & LIN_ACCUM) && !(a.flags & LIN_OUT_F32)) return 0;
@@ -210,6 +269,7 @@ int skinny_supported(const LinearArgs &a) {
 int launch_linear_skinny(const LinearArgs &a, cudaStream_t st) {
     SkinnyParams p;
     p.A = (const bf16 *)a.A; p.W = (const bf16 *)a.W; p.bias = a.bias; p.C = a.C; p.norm_w = a.norm_w;
+    p.cmb_splits = a.cmb_splits; p.cmb_q_rows = a.cmb_q_rows; p.cmb_heads = a.cmb_heads; p.cmb_hd = a.cmb_hd;
     p.M = a.M; p.N = a.N; p.K = a.K; p.lda = a.lda; p.ldc = a.ldc; p.flags = a.flags; p.alpha = a.alpha;
     bool geglu = a.flags & LIN_GEGLU;
     int nblocks = geglu ? a.N / 16 : (a.N + 15) / 16;
@@ -219,9 +279,9 @@ int launch_linear_skinny(const LinearArgs &a, cudaStream_t st) {
         while (nblocks * ksplit < 444 && a.K / (NWARPS * ksplit * 2) >= 64) ksplit *= 2;
     }
     p.ksplit = ksplit;
-    int mt = (a.M + 7) / 8;
+    int mt = a.M > 8 * MAX_MT ? MAX_MT : (a.M + 7) / 8;
     p.n_mt = mt;
-    dim3 grid(nblocks, ksplit);
+    dim3 grid(nblocks, ksplit, a.M > 8 * MAX_MT ? (a.M + 8 * MAX_MT - 1) / (8 * MAX_MT) : 1);
     switch (mt) {
         case 1: launch_k(skinny_kernel<1>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
         case 2: launch_k(skinny_kernel<2>, dim3(grid), dim3(NTHREADS), 0, st, p); break;
