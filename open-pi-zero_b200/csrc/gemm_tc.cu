@@ -156,9 +156,12 @@ PZ_DEVINL float gelu_fast(float x) {
     return 0.5f * x * (1.0f + tanh_fast(k0 * (x + k1 * x * x * x)));
 }
 
+// L2 policy for the output stream: the C tile is not re-read by this kernel, so it must not evict
+// the A / W tiles that the other CTAs are still streaming from L2 (evict-first)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 PZ_DEVINL void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(L2_EVICT_FIRST)
                  : "memory");
 }
 PZ_DEVINL void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
