@@ -172,6 +172,16 @@ int pz_denoise(pz_handle *h, const int32_t *d_valid_len, const float *d_noise,
                float *d_action_out, void *d_workspace, size_t workspace_bytes, int batch,
                const pz_capture *cap, void *stream);
 
+/* JointModel.forward (joint_model.py:328-383) for the two call patterns of the path, from
+ * caller-provided embeddings (fp32, already multiplied by sqrt(hidden) as joint_model.py:348-355 does):
+ *   pz_joint_prefix : vlm + proprio active, fills the workspace KV cache (return_caches=True)
+ *   pz_joint_action : action active, cache_mode="append_non_active"; writes the action hidden state
+ *                     after the mixture's final norm, fp32 [B, horizon, act_hidden]               */
+int pz_joint_prefix(pz_handle *h, const float *d_x_vlm, const float *d_x_proprio, const int32_t *d_valid_len,
+                    void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+int pz_joint_action(pz_handle *h, const float *d_x_action, const int32_t *d_valid_len, float *d_out_hidden,
+                    void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);
 

@@ -60,7 +60,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_kv_layout", "pz_infer_action", "pz_embed_prefix",
-           "pz_prefill", "pz_denoise", "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
+           "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
 _lib = None
 
@@ -97,6 +97,8 @@ def load(build_if_needed: bool = True):
     lib.pz_embed_prefix.argtypes = [hp, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PzCapture), vp]
     lib.pz_prefill.argtypes = [hp, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PzCapture), vp]
     lib.pz_denoise.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PzCapture), vp]
+    lib.pz_joint_prefix.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_joint_action.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_launch_count.argtypes = [hp]
     lib.pz_launch_count.restype = C.c_int64
     lib.pz_timing_begin.argtypes = [hp, C.c_int]

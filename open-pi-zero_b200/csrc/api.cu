@@ -322,7 +322,8 @@ static cudaEvent_t sync_event(pz_handle *h, size_t i) {
 
 template <typename T>
 static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *proprio, void *wsp,
-                       int B, const pz_capture *cap, cudaStream_t st) {
+                       int B, const pz_capture *cap, cudaStream_t st, const float *ext_x = nullptr,
+                       const float *ext_xp = nullptr) {
     const pz_config &c = h->cfg;
     const pz_weights &w = h->w;
     Workspace ws = carve(c, B, h->prefix_chunk, wsp);
@@ -336,6 +337,7 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
     }
     cudaStream_t sp = h->side;
     size_t ev = 0;
+    if (ext_x) copy_f32(ws.x, ext_x, (size_t)B * S_v * H, st);   // JointModel.forward entry: embeddings given
     cudaEvent_t e_fork = sync_event(h, ev++);
     cudaEventRecord(e_fork, st);
     cudaStreamWaitEvent(sp, e_fork, 0);
@@ -344,10 +346,14 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
         int M = nb * S_v, Mp = nb * S_p;
         float *x = ws.x + (size_t)b0 * S_v * H;
         // proprio encoder (pizero.py:436) and the sqrt(hidden) embed scale (joint_model.py:348-355)
-        launch_cast_pad<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
-                           w.small_k_pad, sp);
-        PZ_TRY(Ops<T>::linear(h, lin(ws.pp, w.small_k_pad, w.prop_w, w.prop_b, ws.xp, A, Mp, A,
-                                     w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), sp));
+        if (ext_xp) {
+            copy_f32(ws.xp, ext_xp + (size_t)b0 * S_p * A, (size_t)Mp * A, sp);
+        } else {
+            launch_cast_pad<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
+                               w.small_k_pad, sp);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.pp, w.small_k_pad, w.prop_w, w.prop_b, ws.xp, A, Mp, A,
+                                         w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), sp));
+        }
         for (int l = 0; l < c.n_layers; ++l) {
             bool last = l == c.n_layers - 1;
             T *Kc = (T *)ws.kcache + ((size_t)l * B + b0) * kv_bs;
@@ -408,6 +414,66 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
     return 0;
 }
 
+// ---------------------------------- the action expert's 18 layers over the cached prefix KV ----
+// (JointModel.forward with only "action" active, cache_mode="append_non_active":
+//  joint_model.py:164-168,358-373; keys = [cached vlm | cached proprio | fresh action])
+template <typename T>
+static int action_layers(pz_handle *h, Workspace &ws, const int32_t *valid_len, int B, float *cap_layers,
+                         cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    const int A = c.act_hidden, hd = c.head_dim, nh = c.n_heads, Hz = c.horizon;
+    const int S_v = c.s_vlm, S_p = c.cond_steps, S_c = S_v + S_p;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)S_c * hd;
+    const int Ma = B * Hz;
+        for (int l = 0; l < c.n_layers; ++l) {
+        const pz_mix_layer &L = h->action[l];
+        PZ_TRY(norm_linear<T>(h, ws.xa, L.norm_in, ws.ha, lin(nullptr, A, L.w_qkv, nullptr, ws.qkva, qkvd, Ma, qkvd, A),
+                              A, st));
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.batch = B; a.n_heads = nh; a.head_dim = hd; a.q_rows = Hz; a.q_row0 = S_c;
+        a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = Hz;
+        a.K = (T *)ws.kcache + (size_t)l * B * kv_bs; a.V = (T *)ws.vcache + (size_t)l * B * kv_bs;
+        a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+        a.Q = ws.qkva; a.q_batch_stride = (long)Hz * qkvd; a.q_row_stride = qkvd; a.q_head_stride = hd;
+        a.K2 = (T *)ws.qkva + qd; a.V2 = (T *)ws.qkva + qd + hd;
+        a.kv2_batch_stride = (long)Hz * qkvd; a.kv2_row_stride = qkvd;
+        a.rope_cos = w.rope_act_cos; a.rope_sin = w.rope_act_sin; a.rope_pos0 = S_p;
+        a.valid_len = valid_len;
+        bool fused_rope = std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 &&
+                          attn_mma_supported(a);
+        if (!fused_rope) {
+            // separate RoPE + Q/K/V split kernel, attention on the rotated copies
+            launch_rope_split<T>((const T *)ws.qkva, qkvd, (T *)ws.qa, (long)Hz * qd, (T *)ws.ka,
+                                 (T *)ws.va, (long)Hz * hd, w.rope_act_cos, w.rope_act_sin, B, Hz, S_p,
+                                 nh, hd, st);
+            a.Q = ws.qa; a.q_batch_stride = (long)Hz * qd; a.q_row_stride = qd;
+            a.K2 = ws.ka; a.V2 = ws.va; a.kv2_batch_stride = (long)Hz * hd; a.kv2_row_stride = hd;
+            a.rope_cos = a.rope_sin = nullptr;
+        }
+        a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
+        a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+        a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
+        int n_splits = 0;
+        static const bool combine_in_oproj = getenv("PZ_COMBINE_IN_OPROJ") != nullptr;   // experimental
+        if (fused_rope && Ma <= 16 && combine_in_oproj) {
+            // small batch: leave the split-key partials uncombined; the o_proj GEMV combines them
+            // while it loads its activations (one kernel less on the latency-bound chain)
+            LinearArgs probe = lin(ws.att_scratch, qd, L.w_o, nullptr, ws.xa, A, Ma, A, qd,
+                                   LIN_OUT_F32 | LIN_ACCUM | LIN_COMBINE_A);
+            probe.cmb_splits = (S_c + Hz + 63) / 64; probe.cmb_q_rows = Hz; probe.cmb_heads = nh; probe.cmb_hd = hd;
+            if (skinny_supported(probe)) n_splits = launch_attn_mma_partials(a, st);
+        }
+        if (n_splits == 0) PZ_TRY(Ops<T>::attention(h, a, st));
+        PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st, n_splits, Hz,
+                                 ws.att_scratch));
+        if (cap_layers) copy_f32(cap_layers + (size_t)l * Ma * A, ws.xa, (size_t)Ma * A, st);
+    }
+    return 0;
+}
+
 // ---------------------------------------------- stage 3: Euler sampler -------
 template <typename T>
 static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *noise, float *out,
@@ -432,52 +498,9 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
                                      Ma, A, A, LIN_SILU), st));
         PZ_TRY(Ops<T>::linear(h, lin(ws.z, A, w.enc_w3, w.enc_b3, ws.xa, A, Ma, A, A, LIN_OUT_F32,
                                      sqrtf((float)A)), st));
-        for (int l = 0; l < c.n_layers; ++l) {
-            const pz_mix_layer &L = h->action[l];
-            PZ_TRY(norm_linear<T>(h, ws.xa, L.norm_in, ws.ha, lin(nullptr, A, L.w_qkv, nullptr, ws.qkva, qkvd, Ma, qkvd, A),
-                                  A, st));
-            AttnArgs a;
-            memset(&a, 0, sizeof(a));
-            a.batch = B; a.n_heads = nh; a.head_dim = hd; a.q_rows = Hz; a.q_row0 = S_c;
-            a.s_cache = S_c; a.s_vlm = S_v; a.n_fresh = Hz;
-            a.K = (T *)ws.kcache + (size_t)l * B * kv_bs; a.V = (T *)ws.vcache + (size_t)l * B * kv_bs;
-            a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
-            a.Q = ws.qkva; a.q_batch_stride = (long)Hz * qkvd; a.q_row_stride = qkvd; a.q_head_stride = hd;
-            a.K2 = (T *)ws.qkva + qd; a.V2 = (T *)ws.qkva + qd + hd;
-            a.kv2_batch_stride = (long)Hz * qkvd; a.kv2_row_stride = qkvd;
-            a.rope_cos = w.rope_act_cos; a.rope_sin = w.rope_act_sin; a.rope_pos0 = S_p;
-            a.valid_len = valid_len;
-            bool fused_rope = std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 &&
-                              attn_mma_supported(a);
-            if (!fused_rope) {
-                // separate RoPE + Q/K/V split kernel, attention on the rotated copies
-                launch_rope_split<T>((const T *)ws.qkva, qkvd, (T *)ws.qa, (long)Hz * qd, (T *)ws.ka,
-                                     (T *)ws.va, (long)Hz * hd, w.rope_act_cos, w.rope_act_sin, B, Hz, S_p,
-                                     nh, hd, st);
-                a.Q = ws.qa; a.q_batch_stride = (long)Hz * qd; a.q_row_stride = qd;
-                a.K2 = ws.ka; a.V2 = ws.va; a.kv2_batch_stride = (long)Hz * hd; a.kv2_row_stride = hd;
-                a.rope_cos = a.rope_sin = nullptr;
-            }
-            a.O = ws.atta; a.o_batch_stride = (long)Hz * qd; a.o_row_stride = qd; a.o_head_stride = hd;
-            a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
-            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
-            int n_splits = 0;
-            static const bool combine_in_oproj = getenv("PZ_COMBINE_IN_OPROJ") != nullptr;   // experimental
-            if (fused_rope && Ma <= 16 && combine_in_oproj) {
-                // small batch: leave the split-key partials uncombined; the o_proj GEMV combines them
-                // while it loads its activations (one kernel less on the latency-bound chain)
-                LinearArgs probe = lin(ws.att_scratch, qd, L.w_o, nullptr, ws.xa, A, Ma, A, qd,
-                                       LIN_OUT_F32 | LIN_ACCUM | LIN_COMBINE_A);
-                probe.cmb_splits = (S_c + Hz + 63) / 64; probe.cmb_q_rows = Hz; probe.cmb_heads = nh; probe.cmb_hd = hd;
-                if (skinny_supported(probe)) n_splits = launch_attn_mma_partials(a, st);
-            }
-            if (n_splits == 0) PZ_TRY(Ops<T>::attention(h, a, st));
-            PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st, n_splits, Hz,
-                                     ws.att_scratch));
-            if (cap && cap->denoise_action)
-                copy_f32(cap->denoise_action + ((size_t)step * c.n_layers + l) * Ma * A, ws.xa,
-                         (size_t)Ma * A, st);
-        }
+        PZ_TRY(action_layers<T>(h, ws, valid_len, B,
+                                (cap && cap->denoise_action) ? cap->denoise_action + (size_t)step * c.n_layers * Ma * A : nullptr,
+                                st));
         // final norm + decoder + Euler step (joint_model.py:375-380, pizero.py:479-481)
         LinearArgs fused = lin(ws.xa, A, w.dec_w, w.dec_b, ws.act, c.action_dim, Ma, c.action_dim, A,
                                LIN_OUT_F32 | LIN_ACCUM | LIN_NORM_A, dt);
@@ -620,6 +643,33 @@ int pz_denoise(pz_handle *h, const int32_t *valid_len, const float *noise, float
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->cfg.dtype == PZ_BF16 ? run_denoise<bf16>(h, valid_len, noise, out, ws, B, cap, st)
                                      : run_denoise<float>(h, valid_len, noise, out, ws, B, cap, st);
+    return finish(h, rc);
+}
+
+int pz_joint_prefix(pz_handle *h, const float *x_vlm, const float *x_proprio, const int32_t *valid_len,
+                    void *ws, size_t ws_bytes, int B, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!x_vlm || !x_proprio || !valid_len) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_prefill<bf16>(h, valid_len, nullptr, ws, B, nullptr, st, x_vlm, x_proprio)
+                                     : run_prefill<float>(h, valid_len, nullptr, ws, B, nullptr, st, x_vlm, x_proprio);
+    return finish(h, rc);
+}
+
+int pz_joint_action(pz_handle *h, const float *x_action, const int32_t *valid_len, float *out_hidden, void *wsp,
+                    size_t ws_bytes, int B, void *stream) {
+    PZ_TRY(precheck(h, wsp, ws_bytes, B));
+    if (!x_action || !valid_len || !out_hidden) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve(h->cfg, B, h->prefix_chunk, wsp);
+    const size_t n = (size_t)B * h->cfg.horizon * h->cfg.act_hidden;
+    copy_f32(ws.xa, x_action, n, st);
+    int rc = h->cfg.dtype == PZ_BF16 ? action_layers<bf16>(h, ws, valid_len, B, nullptr, st)
+                                     : action_layers<float>(h, ws, valid_len, B, nullptr, st);
+    if (!rc) launch_rmsnorm<float>(ws.xa, h->w.action_final_norm, out_hidden, (long)B * h->cfg.horizon,
+                                   h->cfg.act_hidden, 1e-6f, st);   // Mixture.forward_norm, mixture.py:68-77
     return finish(h, rc);
 }
 

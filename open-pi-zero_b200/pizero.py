@@ -82,8 +82,9 @@ class KVCache:
 
 
 class JointModel(_Holder):
-    """Holds `mixtures.{vlm,proprio,action}` parameters; mirrors the attributes
-    callers read on the reference's `JointModel` (`joint_model.py:308-326`)."""
+    """Holds `mixtures.{vlm,proprio,action}` parameters and mirrors the reference's
+    `JointModel` surface (`joint_model.py:308-383`): attributes, `build_mixture_caches`
+    and `forward` for the two call patterns `infer_action` uses."""
 
     def __init__(self, dims: dict):
         super().__init__()
@@ -91,6 +92,61 @@ class JointModel(_Holder):
         self.mixture_names = ["vlm", "proprio", "action"]
         self.cache_names = ["vlm", "proprio"]
         self.num_mixture = 3
+        self._owner = None   # weakref to the PiZero that owns the packed weights / workspace
+
+    def build_mixture_caches(self):
+        """joint_model.py:325 -- empty caches; `forward(..., return_caches=True)` fills them."""
+        return {name: KVCache(None, None, 0, 0, 0) for name in self.cache_names}
+
+    @torch.no_grad()
+    def forward(self, attention_mask, position_ids_all, embeds_all, time_cond=None,
+                final_layer_post_attn_skip_names=("vlm", "proprio"), kv_caches={},
+                cache_mode="append_non_active", return_caches=False):
+        """joint_model.py:328-383 for (a) the prefix pass (vlm + proprio active, caches filled,
+        nothing returned for the skipped mixtures) and (b) the action pass over the cached prefix
+        (`cache_mode="append_non_active"`).  Other combinations (training forward with all three
+        active, "append"/"no_append" text generation) are outside this library's scope.
+        Like the reference, `embeds_all[*]` is scaled by sqrt(hidden) IN PLACE (joint_model.py:355)."""
+        assert cache_mode in ["no_append", "append", "append_non_active"], f"Invalid cache mode: {cache_mode}"
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise PzError("JointModel.forward needs the owning PiZero (construct it through PiZero)")
+        names = list(embeds_all.keys())
+        for n in names:
+            e = embeds_all[n]
+            e *= torch.tensor(e.shape[-1] ** 0.5, dtype=e.dtype, device=e.device)
+        owner.pack()
+        lib = _lib.load()
+        d = owner.dims
+        B = embeds_all[names[0]].shape[0]
+        Sv = d["max_image_text_tokens"]
+        vlen = (attention_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).contiguous()
+        ws, ws_bytes = owner._ensure_workspace(B)
+        stream = torch.cuda.current_stream(vlen.device).cuda_stream
+        f32 = lambda t: t.to(torch.float32).contiguous()   # noqa: E731
+        if names == ["vlm", "proprio"] and tuple(final_layer_post_attn_skip_names) == ("vlm", "proprio"):
+            xv, xp = f32(embeds_all["vlm"]), f32(embeds_all["proprio"])
+            rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
+                                     B, stream)
+            if rc != 0:
+                raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+            kv_caches.update(owner.kv_caches(B))
+            out = {}
+            return (out, kv_caches) if return_caches else out
+        if names == ["action"] and cache_mode == "append_non_active":
+            if not all(isinstance(kv_caches.get(n), KVCache) and kv_caches[n].has_item(0) for n in self.cache_names):
+                raise PzError("the action pass needs the caches a prefix JointModel.forward(return_caches=True) filled")
+            xa = f32(embeds_all["action"])
+            out = torch.empty_like(xa)
+            rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
+                                     B, stream)
+            if rc != 0:
+                raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+            res = {"action": out.to(embeds_all["action"].dtype)}
+            return (res, kv_caches) if return_caches else res
+        raise NotImplementedError(
+            f"JointModel.forward with active mixtures {names} / cache_mode {cache_mode!r} is outside the "
+            "infer_action path (training forward and text generation are not built)")
 
 
 class PiZero(nn.Module):
@@ -126,6 +182,8 @@ class PiZero(nn.Module):
         self.final_action_clip_value = d["final_action_clip_value"]
 
         self.joint_model = JointModel(d)
+        import weakref
+        self.joint_model._owner = weakref.ref(self)
         dtype = dtype or torch.float32
         if init == "reference":
             from .synth import init_state_dict

@@ -184,6 +184,53 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     assert 3 in m._graphs
 
 
+def test_joint_model_forward_api():
+    """The inner boundary: JointModel.forward for the prefix pass (fills the caches)
+    and the action pass over them, against the oracle's joint_forward on the same embeddings."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=17, randomize_norms=True)
+    m = _model(d, sd, torch.bfloat16)
+    jm = m.joint_model
+    B, Sv, Sp, Hz = 3, d["max_image_text_tokens"], d["cond_steps"], d["horizon_steps"]
+    g = torch.Generator().manual_seed(0)
+    ev = torch.randn(B, Sv, d["vlm_hidden"], generator=g) * 0.05
+    ep = torch.randn(B, Sp, d["act_hidden"], generator=g) * 0.05
+    ea = torch.randn(B, Hz, d["act_hidden"], generator=g) * 0.05
+    attn = torch.ones(B, Sv, dtype=torch.int64)
+    attn[0, 18:] = 0
+    attn[2, 21:] = 0
+    for b in range(B):
+        ev[b, int(attn[b].sum()):] = 0
+    _, pmask, amask, pos = O.build_masks_and_positions(d, attn, torch.float32)
+    okv = {"vlm": [], "proprio": []}
+    O.joint_forward(sd, d, pmask, {"vlm": pos["vlm"], "proprio": pos["proprio"]},
+                    {"vlm": ev.clone(), "proprio": ep.clone()}, okv)
+    want = O.joint_forward(sd, d, amask, {"action": pos["action"]}, {"action": ea.clone()}, okv)["action"]
+    caches = jm.build_mixture_caches()
+    assert not caches["vlm"].has_item(0)
+    ev_c, ep_c = ev.cuda(), ep.cuda()
+    out, caches = jm(attention_mask=pmask.cuda(), position_ids_all={"vlm": pos["vlm"].cuda(), "proprio": pos["proprio"].cuda()},
+                     embeds_all={"vlm": ev_c, "proprio": ep_c}, kv_caches=caches, return_caches=True)
+    assert out == {} and caches["vlm"].has_item(d["num_layers"] - 1) and caches["vlm"].num_items() == Sv
+    assert max_abs(ev_c, ev * d["vlm_hidden"] ** 0.5) < 1e-4          # scaled in place, like the reference
+    vl = attn.sum(1)
+    for l in range(d["num_layers"]):
+        k, v = caches["vlm"].get(l)
+        k2, v2 = okv["vlm"][l]
+        assert rel_err(valid_rows(k[:, 0].float(), vl), valid_rows(k2[:, 0], vl)) < BF16_LAYER_TOL
+        assert rel_err(valid_rows(v[:, 0].float(), vl), valid_rows(v2[:, 0], vl)) < BF16_LAYER_TOL
+    got = jm(attention_mask=amask.cuda(), position_ids_all={"action": pos["action"].cuda()},
+             embeds_all={"action": ea.cuda()}, kv_caches=caches, cache_mode="append_non_active")["action"]
+    torch.cuda.synchronize()
+    e = rel_err(got, want)
+    print(f"[JointModel.forward] action hidden rel err {e:.3e}")
+    assert e < BF16_LAYER_TOL
+    with pytest.raises(NotImplementedError):
+        jm(attention_mask=amask.cuda(), position_ids_all={}, embeds_all={"vlm": ev.cuda(), "action": ea.cuda()})
+    with pytest.raises(AssertionError):
+        jm(attention_mask=amask.cuda(), position_ids_all={}, embeds_all={"action": ea.cuda()}, cache_mode="bogus")
+
+
 def test_batch_invariance_and_ragged_lengths():
     """Each sample's result must not depend on its neighbours or on pad content:
     run B=6 with ragged lengths, then each sample alone."""
