@@ -143,6 +143,9 @@ size_t pz_workspace_bytes(const pz_handle *h, int batch);
 int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,
                  size_t *layer_stride_elems);
 
+/* Debug: workspace offset of the persistent sampler's barrier / phase-timestamp words. */
+size_t pz_debug_trace_offset(const pz_handle *h, int batch);
+
 /* PiZero.infer_action (pizero.py:416-490), whole call.
  *   d_input_ids  int64 [B, s_vlm]
  *   d_pixels     handle dtype [B*n_images, 3, image, image], already normalised

@@ -80,6 +80,7 @@ struct Workspace {
     // denoise scratch (whole batch)
     void *a_in, *e1, *z, *ha, *qkva, *qa, *ka, *va, *atta, *mlpa;
     float *act, *xa, *vel, *att_scratch;
+    unsigned int *mega_barrier;
     size_t att_scratch_bytes;
     size_t total;
 };
@@ -131,6 +132,7 @@ static Workspace carve(const pz_config &c, int B, int chunk, void *base) {
     w.atta = b.take<void>(Ma * qd * es);
     w.mlpa = b.take<void>(Ma * c.act_inter * es);
     w.vel = b.take<float>(Ma * 8 * 4);
+    w.mega_barrier = b.take<unsigned int>(128 * sizeof(unsigned int));
     {   // split-key attention partials (decode): [B][key tiles][heads*rows][hd + 2] fp32
         size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
         size_t tiles = (S_c + c.horizon + 63) / 64;
@@ -488,6 +490,18 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
     const int Ma = B * Hz;
     const float dt = (float)(1.0 / c.n_steps);
     copy_f32(ws.act, noise, (size_t)Ma * c.action_dim, st);
+    if (std::is_same<T, bf16>::value && denoise_mega_supported(c, B) &&
+        !(cap && (cap->denoise_action || cap->velocities || cap->action_preclip))) {
+        // small batch: the whole sampler as one persistent cooperative kernel (denoise_mega.cu)
+        MegaBuffers mb;
+        mb.kcache = ws.kcache; mb.vcache = ws.vcache; mb.batch_total = B; mb.valid_len = valid_len;
+        mb.act = ws.act; mb.xa = ws.xa; mb.partials = ws.att_scratch; mb.out = out;
+        mb.e1 = ws.e1; mb.z = ws.z; mb.qkv = ws.qkva; mb.mlp = ws.mlpa; mb.barrier = ws.mega_barrier;
+        const char *e = nullptr;
+        int rc = launch_denoise_mega(c, w, h->action.data(), mb, B, st, &e);
+        if (rc) return fail(h, rc, std::string("denoise_mega launch failed: ") + (e ? e : "?"));
+        return 0;
+    }
     for (int step = 0; step < c.n_steps; ++step) {
         // action encoder (vla/modules.py:39-53); the time half of linear_2 is the
         // per-step constant enc_time_bias[step]
@@ -580,6 +594,12 @@ int pz_bind_weights(pz_handle *h, const pz_weights *w) {
 size_t pz_workspace_bytes(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     return carve(h->cfg, batch, h->prefix_chunk, nullptr).total;
+}
+
+size_t pz_debug_trace_offset(const pz_handle *h, int batch) {
+    if (!h || batch < 1) return 0;
+    Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
+    return (size_t)((char *)ws.mega_barrier - (char *)0x1000);
 }
 
 int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,

@@ -52,3 +52,16 @@ int launch_attn_mma(const AttnArgs &a, cudaStream_t st);
 // split-key decode only: returns the number of key splits (> 1) if the partials path applies and
 // launches just the partial kernel (no combine); 0 if it does not apply (nothing launched).
 int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st);
+
+// denoise_mega.cu (persistent cooperative sampler for B * horizon <= 16)
+struct MegaBuffers {
+    const void *kcache, *vcache;   // [L][batch_total][S_c][256] bf16
+    int batch_total;
+    const int32_t *valid_len;
+    float *act, *xa, *partials, *out;
+    void *e1, *z, *qkv, *mlp;
+    unsigned int *barrier;         // 2 words
+};
+int denoise_mega_supported(const pz_config &c, int B);
+int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const MegaBuffers &bf,
+                        int B, cudaStream_t st, const char **err);

@@ -50,3 +50,13 @@ for i in range(3):
     tot += ms
     print(f"B={B} {names[i]:14s}: {ms:8.3f} ms  ({n1 - n0} launches, {1e3 * ms / max(n1 - n0, 1):.2f} us/launch)")
 print(f"B={B} total {tot:.3f} ms")
+
+# phase timestamps of the persistent sampler (CTA 0, step 1, layer 1)
+off = lib.pz_debug_trace_offset(m._handle, B)
+base = (ws - ws_t.data_ptr()) + off + 128
+raw = ws_t[base: base + 24 * 8].view(torch.int64).cpu().tolist()
+if raw[0] > 0:
+    names2 = ["QKV", "bar", "ATT", "bar", "O", "bar", "GU", "bar", "D", "bar"]
+    print("mega trace (us):", " ".join(f"{n}={(raw[i+1]-raw[i])/1e3:.2f}" for i, n in enumerate(names2)), f"layer={(raw[10]-raw[0])/1e3:.2f}")
+    print("GU items (us): stage->", f"{(raw[11]-raw[6])/1e3:.2f}", " ".join(
+        f"[wait={(raw[12+4*k]-raw[11+4*k])/1e3:.2f} gemv={(raw[13+4*k]-raw[12+4*k])/1e3:.2f} prefetch={(raw[14+4*k]-raw[13+4*k])/1e3:.2f}]" for k in range(2)))
