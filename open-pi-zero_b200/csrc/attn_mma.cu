@@ -54,7 +54,9 @@ PZ_DEVINL float tanh_fast_acc(float y) {
 // visibility classes of a launch (all of its query rows share one)
 enum { CLS_ALL = 0, CLS_VLM = 1, CLS_PROPRIO = 2, CLS_ACTION = 3 };
 
-template <int HD>   // true head_dim; HDP = padded to a multiple of 16
+// PRELOAD: all keys fit in shared memory (SigLIP: 256 keys x head_dim 72) -- K and V are staged once and
+// the tile loop runs without loads or block barriers.
+template <int HD, bool PRELOAD = false>   // true head_dim; HDP = padded to a multiple of 16
 __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int cls, int mqa, int split) {
     constexpr int HDP = (HD + 15) / 16 * 16;
     constexpr int LDS = HDP + 8;            // +16 B per row: conflict-free ldmatrix
@@ -62,8 +64,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     constexpr int PCHUNKS = HDP / 8;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     bf16 *sQ = (bf16 *)smem_raw;
-    bf16 *sK = sQ + ROWS_PER_CTA * LDS;
-    bf16 *sV = sK + KEY_TILE * LDS;
+    bf16 *sK0 = sQ + ROWS_PER_CTA * LDS;
+    const int kv_rows = PRELOAD ? (a.s_cache + a.n_fresh + KEY_TILE - 1) / KEY_TILE * KEY_TILE : KEY_TILE;
+    bf16 *sV0 = sK0 + kv_rows * LDS;
+    bf16 *sK = sK0, *sV = sV0;
 
     pdl_trigger();
     pdl_wait();     // Q/K/V are produced by the preceding kernels
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
         *reinterpret_cast<uint4 *>(dst_row + 128 + c * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
     };
     auto load_kv = [&](bf16 *dst, const bf16 *base, const bf16 *base2, int tile) {
-        const bool rope_k = rope && dst == sK;
+        const bool rope_k = rope && dst == sK0;
         for (int i = tid; i < KEY_TILE * PCHUNKS; i += NTHREADS) {
             int r = i / PCHUNKS, c = i % PCHUNKS;
             int j = tile * KEY_TILE + r;
@@ -133,10 +137,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     };
     // K and V of the first tile first (their latency is the critical path); the Q staging
     // work then overlaps with them
-    load_kv(sK, Kb, K2b, tile_lo);
-    cp_async_commit();
-    load_kv(sV, Vb, V2b, tile_lo);
-    cp_async_commit();
+    if (PRELOAD) {
+        for (int tl = 0; tl < n_tiles; ++tl) {
+            load_kv(sK0 + tl * KEY_TILE * LDS, Kb, K2b, tl);
+            load_kv(sV0 + tl * KEY_TILE * LDS, Vb, V2b, tl);
+        }
+        cp_async_commit();
+        cp_async_commit();
+    } else {
+        load_kv(sK, Kb, K2b, tile_lo);
+        cp_async_commit();
+        load_kv(sV, Vb, V2b, tile_lo);
+        cp_async_commit();
+    }
     if (rope) {
         for (int i = tid; i < ROWS_PER_CTA * 16; i += NTHREADS) {
             int r = i / 16, c = i % 16;
@@ -169,11 +182,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     const float scale = a.scale, cap = a.softcap, inv_cap = cap > 0.f ? 1.f / cap : 0.f;
 
+    if (PRELOAD) { cp_async_wait<0>(); __syncthreads(); }
     for (int tile = tile_lo; tile < n_tiles; ++tile) {
-        if (tile > tile_lo) load_kv(sV, Vb, V2b, tile);   // the first tile's V is already in flight
-        cp_async_commit();
-        cp_async_wait<1>();          // Q and K(tile) have landed
-        __syncthreads();
+        if (PRELOAD) {
+            sK = sK0 + tile * KEY_TILE * LDS;
+            sV = sV0 + tile * KEY_TILE * LDS;
+        } else {
+            if (tile > tile_lo) load_kv(sV, Vb, V2b, tile);   // the first tile's V is already in flight
+            cp_async_commit();
+            cp_async_wait<1>();          // Q and K(tile) have landed
+            __syncthreads();
+        }
 
         // ---- S = Q K^T for this warp's 16 rows x 64 keys ------------------
         float s[KEY_TILE / 8][4];
@@ -192,9 +211,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
                 mma_bf16(s[2 * nt2 + 1], qa, kb[2], kb[3]);
             }
         }
-        __syncthreads();             // every warp is done reading sK
-        if (tile + 1 < n_tiles) load_kv(sK, Kb, K2b, tile + 1);
-        cp_async_commit();
+        if (!PRELOAD) {
+            __syncthreads();             // every warp is done reading sK
+            if (tile + 1 < n_tiles) load_kv(sK, Kb, K2b, tile + 1);
+            cp_async_commit();
+        }
 
         // ---- scale, soft-cap, mask, online softmax --------------------------
         float mx[2] = {-INFINITY, -INFINITY};
@@ -245,8 +266,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
             o[i][2] *= corr[1]; o[i][3] *= corr[1];
         }
 
-        cp_async_wait<1>();          // V(tile) has landed (K(tile+1) may still be in flight)
-        __syncthreads();
+        if (!PRELOAD) {
+            cp_async_wait<1>();          // V(tile) has landed (K(tile+1) may still be in flight)
+            __syncthreads();
+        }
         // ---- O += P V -------------------------------------------------------
 #pragma unroll
         for (int kk = 0; kk < KEY_TILE / 16; ++kk) {
@@ -259,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
                 mma_bf16(o[2 * dt2 + 1], pa[kk], vb[2], vb[3]);
             }
         }
-        __syncthreads();             // every warp is done reading sV
+        if (!PRELOAD) __syncthreads();   // every warp is done reading sV
     }
     cp_async_wait<0>();
 
@@ -372,6 +395,20 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_on
     }
     if (partials_only) return 0;
     dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
+    if constexpr (HD <= 128) {
+        int kv_rows = (a.s_cache + a.n_fresh + KEY_TILE - 1) / KEY_TILE * KEY_TILE;
+        size_t smem_all = (size_t)(ROWS_PER_CTA + 2 * kv_rows) * LDS * sizeof(bf16);
+        if (cls == CLS_ALL && smem_all <= 110 * 1024) {
+            static bool attr2 = false;
+            if (!attr2) {
+                if (cudaFuncSetAttribute(attn_mma_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
+                    return PZ_ERR_CUDA;
+                attr2 = true;
+            }
+            launch_k(attn_mma_kernel<HD, true>, dim3(grid), dim3(NTHREADS), smem_all, st, a, cls, mqa, 0);
+            return 0;
+        }
+    }
     launch_k(attn_mma_kernel<HD>, dim3(grid), dim3(NTHREADS), smem, st, a, cls, mqa, 0);
     return 0;
 }

@@ -191,6 +191,30 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     assert 3 in m._graphs
 
 
+def test_prefix_chunking_matches_unchunked(monkeypatch):
+    """Large batches run the prefix pass in sub-batches (PZ_PREFIX_CHUNK, default 64) against one
+    KV cache; a ragged last chunk and the chunk boundaries must not change any sample."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=23, randomize_norms=True)
+    inp = pz.make_inputs(d, 7, seed=12, min_text=0)
+    whole = _model(d, sd, torch.bfloat16)
+    a, cap_a = _run(whole, d, inp)
+    monkeypatch.setenv("PZ_PREFIX_CHUNK", "3")      # 7 samples -> chunks of 3, 3, 1
+    chunked = _model(d, sd, torch.bfloat16)
+    b, cap_b = _run(chunked, d, inp)
+    vl = inp["valid_len"]
+    # tolerance: one bf16 ulp here and there (fp32 atomics in the split-K GEMV sum in arrival order)
+    assert rel_err(valid_rows(cap_a["prefix_vlm"][-1], vl), valid_rows(cap_b["prefix_vlm"][-1], vl)) < 5e-3
+    for l in range(d["num_layers"]):
+        ka, va = cap_a["kv"]["proprio"].get(l)
+        kb, vb = cap_b["kv"]["proprio"].get(l)
+        assert rel_err(ka.float(), kb.float()) < 5e-3 and rel_err(va.float(), vb.float()) < 5e-3
+    assert max_abs(a, b) < 2e-3
+    # production path (graph replay) with chunking
+    c, _ = _run(chunked, d, inp, capture=False)
+    assert max_abs(a, c) < 2e-3
+
+
 def test_joint_model_forward_api():
     """The inner boundary: JointModel.forward for the prefix pass (fills the caches)
     and the action pass over them, against the oracle's joint_forward on the same embeddings."""
