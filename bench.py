@@ -296,7 +296,7 @@ def main():
     if gu_n > 0:
         avg_ms = gu_ms / gu_n
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="gemm_tc_kernel<256> (VLM gate|up + GeGLU)", achieved=achieved,
+        roof = dict(bound="tensor", kernel="gemm_tc_kernel<256, cta_group::2> (VLM gate|up + GeGLU)", achieved=achieved,
                     peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
                     traffic=None, avg_launch_ms=avg_ms, launches_timed=gu_n,
                     share_of_step=gu_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps, peak_source=peaks["source"] + ", sustained figure")

@@ -20,6 +20,7 @@
 // pass (reference call sites: siglip.py:115-119,164,188-192; mixture.py:187-218;
 // paligemma/modules.py:86-95), and for the denoise layers when B*horizon > 64.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -93,6 +94,43 @@ PZ_DEVINL void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// ---- cta_group::2 (CTA pair) variants ---------------------------------------------------------
+PZ_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+PZ_DEVINL uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+PZ_DEVINL void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+PZ_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair load their own tiles; the transaction bytes are credited to the LEADER's
+// barrier (CTA rank bit cleared in the shared::cluster address)
+PZ_DEVINL void tma_load_2d_pair(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+PZ_DEVINL void tc_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+PZ_DEVINL void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
 PZ_DEVINL void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, bf16:
@@ -134,10 +172,13 @@ constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant
 constexpr int NUM_THREADS2 = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 
-template <int BN> struct Cfg {
-    static constexpr int STAGES = BN == 256 ? 4 : 6;
+// CG = 2: a CTA pair (cluster of 2, one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of the W tile, so a stage is 32 KB instead of 48 KB:
+// six stages fit, i.e. 50 % more K in flight per SM and a third less shared-memory / L2 traffic per FLOP.
+template <int BN, int CG = 1> struct Cfg {
+    static constexpr int STAGES = (CG == 2 || BN != 256) ? 6 : 4;
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two: 256 / 512)
     static constexpr int STG_OFF = STAGES * STAGE_BYTES;
@@ -178,11 +219,15 @@ PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_
                  : "memory");
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, CG>;
+    // CTA pair: `crank` 0 is the leader (issues the MMAs); `wid` / `nworkers` enumerate tile workers
+    // (single CTAs for CG = 1, CTA pairs for CG = 2)
+    const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const int wid = blockIdx.x / CG, nworkers = gridDim.x / CG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = (uint64_t *)(smem + cfg::BAR_OFF);
@@ -203,18 +248,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(tmem_slot)),
-                     "r"((uint32_t)cfg::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
@@ -225,23 +275,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // PDL: the weight tiles of the first ring pass do not depend on the previous
             // kernel -- issue them before waiting for it; activations (A) only after.
             int pre = 0;
-            if ((int)blockIdx.x < num_tiles) {
-                int t = blockIdx.x;
+            if (wid < num_tiles) {
+                int t = wid;
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
                 int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 pre = min(cfg::STAGES, kb1 - kb0);
                 for (int i = 0; i < pre; ++i) {
                     uint8_t *sa = smem + i * cfg::STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[i], cfg::STAGE_BYTES);
-                    tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN);
+                    if (crank == 0) mbar_expect_tx(&full_bar[i], cfg::STAGE_BYTES * CG);
+                    if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN + crank * (BN / 2));
+                    else tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN);
                 }
             }
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = wid; t < num_tiles; t += nworkers) {
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
                 // raster: m fastest -> concurrent CTAs share the W tile in L2; n fastest -> they share the A tile
                 int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
@@ -251,23 +302,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint8_t *sa = smem + stage * cfg::STAGE_BYTES;
                     if (it >= pre) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
-                        tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN);
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES * CG);
+                        if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN + crank * (BN / 2));
+                        else tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN);
                     }
-                    tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM);
+                    if (CG == 2) tma_load_2d_pair(&map_a, &full_bar[stage], sa, kb * BK, (tm * CG + crank) * BM);
+                    else tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------- MMA issuer ----
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM, BN);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = umma_idesc(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = wid; t < num_tiles; t += nworkers) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 uint32_t d_tmem = tmem_base + acc * BN;
@@ -282,12 +335,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in 16 B units
-                        tc_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        if (CG == 2) tc_mma_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        else tc_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     }
-                    tc_commit(&empty_bar[stage]);
+                    if (CG == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);
+                if (CG == 2) tc_commit_pair(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -310,13 +364,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
         uint8_t *stg_row = stg + lane * 128;
         pdl_wait();                              // C may still be read / written by the previous kernel
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
+        for (int t = wid; t < num_tiles; t += nworkers) {
             int tmn = t % tiles_mn, ksp = t / tiles_mn;
             int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
             int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row0 = tm * BM + q * 32;       // first row of this warp
+            const int row0 = (tm * CG + crank) * BM + q * 32;       // first row of this warp
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
             if (rope) {
                 if constexpr (BN == 256) {
@@ -456,18 +511,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_remote(tempty_leader0 + acc * 8);   // the leader's MMA thread owns the accumulators
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) bulk_wait_read0();   // staging smem must outlive the store's read; completion = kernel end
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // neither CTA may retire (or free TMEM) while the peer still uses it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)cfg::TMEM_COLS)
-                     : "memory");
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -508,12 +568,12 @@ bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld,
 
 int g_num_sms = 0;
 
-template <int BN>
+template <int BN, int CG>
 int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cfg::SMEM_BYTES) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(max dynamic smem) failed";
             return PZ_ERR_CUDA;
@@ -528,7 +588,7 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     CUtensorMap ma, mw, mc;
     const bool f32out = a.flags & LIN_OUT_F32;
     const int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
-    if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.K, BN) ||
+    if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.K, BN / CG) ||
         !make_map(&mc, a.C, a.M, n_out, a.ldc, 32, f32out)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return PZ_ERR_CUDA;
@@ -537,15 +597,16 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     if (extra) p = *extra; else memset(&p, 0, sizeof(p));
     p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc; p.bias = a.bias; p.C = a.C;
     p.alpha = a.alpha; p.flags = a.flags | (extra ? LIN_ROPE : 0);
-    p.tiles_m = (a.M + BM - 1) / BM;
+    p.tiles_m = (a.M + BM * CG - 1) / (BM * CG);   // tiles of the worker (CTA or CTA pair)
     p.tiles_n = (a.N + BN - 1) / BN;
     // split K when the output grid cannot fill the machine and the epilogue is a pure fp32
     // accumulate (TMA reduce-add makes the combine free): o_proj / down_proj at small M
     int num_kb = (a.K + BK - 1) / BK;
+    int workers_max = g_num_sms / CG;
     p.ksplit = 1;
     if ((a.flags & LIN_ACCUM) && !(a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU)) && !extra) {
         int mn = p.tiles_m * p.tiles_n;
-        while (mn * p.ksplit * 2 <= g_num_sms && num_kb / (p.ksplit * 2) >= 4) p.ksplit *= 2;
+        while (mn * p.ksplit * 2 <= workers_max && num_kb / (p.ksplit * 2) >= 4) p.ksplit *= 2;
     }
     // A bigger than what L2 keeps and only a few N tiles: let the CTAs that run together share the A
     // tile (read from HBM once) instead of the W tile (which then stays L2 resident as a whole)
@@ -556,9 +617,36 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
     int tiles = p.tiles_m * p.tiles_n * p.ksplit;
-    int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS2), cfg::SMEM_BYTES, st, ma, mw, mc, p);
+    int workers = tiles < workers_max ? tiles : workers_max;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(workers * CG); lc.blockDim = dim3(NUM_THREADS2); lc.dynamicSmemBytes = cfg::SMEM_BYTES; lc.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_pdl_enabled) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    lc.attrs = attr; lc.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&lc, gemm_tc_kernel<BN, CG>, ma, mw, mc, p);
+    count_launch();
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return PZ_ERR_CUDA;
+    }
     return 0;
+}
+
+// CTA pairs pay off when there are enough 256-row tiles to keep every pair busy
+bool use_pair(const LinearArgs &a) {
+    static const int mode = [] { const char *e = getenv("PZ_GEMM_CG"); return e ? atoi(e) : 0; }();
+    if (mode == 1) return false;
+    return a.M >= 2048 && a.N >= 256;
 }
 
 }  // namespace
@@ -580,7 +668,8 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err) {
     bool geglu = a.flags & LIN_GEGLU;
     long tiles256 = (long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
     bool use256 = geglu || (a.N >= 256 && tiles256 >= 120);
-    return use256 ? launch<256>(a, st, err) : launch<128>(a, st, err);
+    if (use256 && use_pair(a)) return launch<256, 2>(a, st, err);
+    return use256 ? launch<256, 1>(a, st, err) : launch<128, 1>(a, st, err);
 }
 
 // Fused QKV projection + RoPE + cache write for the prefix pass (head_dim 256):
@@ -598,5 +687,6 @@ int launch_qkv_rope_tc(const void *A, int lda, const void *W, void *q_out, void 
     memset(&ex, 0, sizeof(ex));
     ex.rope_cos = cos_t; ex.rope_sin = sin_t; ex.k_out = (bf16 *)k_out; ex.v_out = (bf16 *)v_out;
     ex.kv_batch_stride = kv_batch_stride; ex.s_x = s_x; ex.n_q_tiles = n_heads;
-    return launch<256>(a, st, err, &ex);
+    if (use_pair(a)) return launch<256, 2>(a, st, err, &ex);
+    return launch<256, 1>(a, st, err, &ex);
 }

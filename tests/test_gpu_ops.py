@@ -72,6 +72,11 @@ SHAPES = [
     (256, 1024, 1024, OUT_F32, True, 32.0),         # action encoder linear_3 * sqrt(hidden)
     (256, 1024, 1024, SILU, True, 1.0),
     (2048, 640, 640, OUT_F32 | ACCUM, True, 1.0),   # patch embedding (K padded 588 -> 640)
+    # M >= 2048: the cta_group::2 (CTA pair, 256 x 256 tiles) variant
+    (2208, 4096, 256, GEGLU, False, 1.0),
+    (2304, 4304, 1152, GELU, True, 1.0),
+    (2500, 2560, 2048, 0, False, 1.0),               # M tail inside a pair tile (2500 = 9*256 + 196)
+    (2049, 1152, 4304, OUT_F32 | ACCUM, True, 1.0),  # second CTA of the last pair almost empty
 ]
 
 

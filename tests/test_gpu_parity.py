@@ -191,6 +191,23 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     assert 3 in m._graphs
 
 
+def test_large_m_pair_gemm_and_fused_rope_vs_oracle():
+    """B = 9 at the real widths gives M = 2484 prefix rows: the CTA-pair (cta_group::2) GEMM variant,
+    including its fused RoPE / KV-cache epilogue, against the oracle."""
+    fx_dims = pz.make_dims(vocab_size=1024, image_token_index=1000, num_layers=2, vit_layers=2)
+    sd = pz.init_state_dict(fx_dims, seed=31, randomize_norms=True)
+    inp = pz.make_inputs(fx_dims, 9, seed=6)
+    ocap = {}
+    want = O.infer_action(sd, fx_dims, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                          inp["proprios"], inp["noise"], capture=ocap)
+    m = _model(fx_dims, sd, torch.bfloat16)
+    out, cap = _run(m, fx_dims, inp)
+    report = {}
+    worst = _compare_all(fx_dims, inp, cap, ocap, BF16_LAYER_TOL, report)
+    print(f"[pair-gemm width2 B=9] worst layer rel {worst:.3e}; clamped {max_abs(out, want):.3e}")
+    assert max_abs(out, want) < BF16_ACTION_TOL
+
+
 def test_prefix_chunking_matches_unchunked(monkeypatch):
     """Large batches run the prefix pass in sub-batches (PZ_PREFIX_CHUNK, default 64) against one
     KV cache; a ragged last chunk and the chunk boundaries must not change any sample."""
