@@ -288,9 +288,9 @@ static int post_attention(pz_handle *h, const pz_mix_layer &L, float *x, void *h
                                      LIN_OUT_F32 | LIN_ACCUM), st));
     }
     int tag_gu = hidden == c.vlm_hidden ? TAG_VLM_GATE_UP : TAG_ACT_GATE_UP;
-    if (M > 64) launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
+    if (M > 16) launch_rmsnorm<T>(x, L.norm_post, (T *)hbuf, M, hidden, 1e-6f, st);
     tick(h, tag_gu, st);
-    if (M > 64) {
+    if (M > 16) {
         PZ_TRY(Ops<T>::linear(h, lin(hbuf, hidden, L.w_gate_up, nullptr, mlp, inter, M, 2 * inter, hidden,
                                      LIN_GEGLU), st));
     } else {
@@ -468,7 +468,15 @@ static int action_layers(pz_handle *h, Workspace &ws, const int32_t *valid_len, 
             probe.cmb_splits = (S_c + Hz + 63) / 64; probe.cmb_q_rows = Hz; probe.cmb_heads = nh; probe.cmb_hd = hd;
             if (skinny_supported(probe)) n_splits = launch_attn_mma_partials(a, st);
         }
-        if (n_splits == 0) PZ_TRY(Ops<T>::attention(h, a, st));
+        if (n_splits == 0 && fused_rope && decode_attention_supported(c) &&
+            a.scratch_bytes >= (size_t)B * ((S_c + Hz + 63) / 64) * nh * Hz * (hd + 2) * sizeof(float)) {
+            // one CTA per (sample, key tile), all 8 warps busy, RoPE fused; then the combine kernel
+            int ns = launch_decode_attention(c, w, ws.qkva, ws.kcache, ws.vcache, B, valid_len, ws.att_scratch, l, B, st);
+            if (ns < 0) return fail(h, ns, "decode attention launch failed");
+            launch_attn_combine(a, ns, st);
+        } else if (n_splits == 0) {
+            PZ_TRY(Ops<T>::attention(h, a, st));
+        }
         PZ_TRY(post_attention<T>(h, L, ws.xa, ws.ha, ws.atta, ws.mlpa, Ma, A, c.act_inter, st, n_splits, Hz,
                                  ws.att_scratch));
         if (cap_layers) copy_f32(cap_layers + (size_t)l * Ma * A, ws.xa, (size_t)Ma * A, st);

@@ -219,20 +219,39 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int c
 
         // ---- scale, soft-cap, mask, online softmax --------------------------
         float mx[2] = {-INFINITY, -INFINITY};
+        // only a tile that straddles a visibility boundary needs the per-element mask (warp-uniform test)
+        const int j_lo = tile * KEY_TILE, j_hi = j_lo + KEY_TILE;
+        bool need_mask;
+        if (cls == CLS_ALL) need_mask = j_hi > n_keys;
+        else if (cls == CLS_VLM) need_mask = j_hi > vlen;
+        else need_mask = j_hi > vlen;                       // pad gap and the tail behind n_keys
+        if (!need_mask) {
 #pragma unroll
-        for (int nt = 0; nt < KEY_TILE / 8; ++nt) {
+            for (int nt = 0; nt < KEY_TILE / 8; ++nt) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int j = tile * KEY_TILE + nt * 8 + 2 * t + (e & 1);
-                bool vis;
-                if (cls == CLS_ALL) vis = j < n_keys;
-                else if (cls == CLS_VLM) vis = j < vlen;
-                else vis = (j < vlen) || (j >= a.s_vlm && j < n_keys);
-                float v = s[nt][e] * scale;
-                if (cap > 0.f) v = tanh_fast_acc(v * inv_cap) * cap;
-                v = vis ? v : -INFINITY;
-                s[nt][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                for (int e = 0; e < 4; ++e) {
+                    float v = s[nt][e] * scale;
+                    if (cap > 0.f) v = tanh_fast_acc(v * inv_cap) * cap;
+                    s[nt][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < KEY_TILE / 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int j = j_lo + nt * 8 + 2 * t + (e & 1);
+                    bool vis;
+                    if (cls == CLS_ALL) vis = j < n_keys;
+                    else if (cls == CLS_VLM) vis = j < vlen;
+                    else vis = (j < vlen) || (j >= a.s_vlm && j < n_keys);
+                    float v = s[nt][e] * scale;
+                    if (cap > 0.f) v = tanh_fast_acc(v * inv_cap) * cap;
+                    v = vis ? v : -INFINITY;
+                    s[nt][e] = v;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                }
             }
         }
         float corr[2];
@@ -449,4 +468,10 @@ int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st) {
     if (cls < 0) return 0;
     int r = launch<256>(a, cls, 1, st, 1);
     return r > 0 ? r : 0;
+}
+
+int launch_attn_combine(const AttnArgs &a, int n_splits, cudaStream_t st) {
+    long warps = (long)a.batch * a.n_heads * a.q_rows;
+    launch_k(attn_combine_kernel<256>, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, st, a, n_splits);
+    return 0;
 }

@@ -514,6 +514,18 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
     __syncthreads();
 }
 
+// ---- the attention item as a stand-alone kernel (decode attention for batches the persistent
+// kernel does not cover): grid = batch * key tiles, partials combined by attn_combine_kernel ----------
+__global__ void __launch_bounds__(NT, 2) decode_attn_kernel(const __grid_constant__ MegaParams p, int layer) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // attention_item addresses shared memory at SM_U + ...; rebase so that the union region starts at 0
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127) - SM_U;
+    pdl_trigger();
+    pdl_wait();
+    const int it = blockIdx.x;
+    attention_item(p, smem, layer, it / p.n_splits, it % p.n_splits);
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int MT>
 __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_constant__ MegaParams p) {
@@ -638,6 +650,34 @@ int denoise_mega_supported(const pz_config &c, int B) {
     if (c.n_layers > MAX_LAYERS || c.action_dim > 8) return 0;
     if ((c.s_vlm + c.cond_steps + c.horizon + KT - 1) / KT > 8) return 0;
     return 1;
+}
+
+int launch_decode_attention(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache,
+                            const void *vcache, int batch_total, const int32_t *valid_len, float *partials, int layer,
+                            int B, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr int smem = SM_ATT_END - SM_U + 256;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return PZ_ERR_CUDA;
+        attr_set = true;
+    }
+    MegaParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = c.horizon; p.M = B * c.horizon; p.nh = c.n_heads;
+    p.S_v = c.s_vlm; p.S_p = c.cond_steps; p.S_c = c.s_vlm + c.cond_steps;
+    p.n_splits = (p.S_c + p.H + KT - 1) / KT;
+    p.rope_cos = w.rope_act_cos; p.rope_sin = w.rope_act_sin;
+    p.kcache = (const bf16 *)kcache; p.vcache = (const bf16 *)vcache;
+    p.kv_batch_stride = (long)p.S_c * 256; p.kv_layer_stride = (long)batch_total * p.kv_batch_stride;
+    p.valid_len = valid_len; p.partials = partials; p.qkv = (bf16 *)const_cast<void *>(qkv);
+    launch_k(decode_attn_kernel, dim3(B * p.n_splits), dim3(NT), smem, st, p, layer);
+    return p.n_splits;
+}
+
+int decode_attention_supported(const pz_config &c) {
+    return c.dtype == PZ_BF16 && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && c.head_dim == 256 && c.n_kv_heads == 1 &&
+           c.n_heads * c.horizon <= QROWS && (c.s_vlm + c.cond_steps + c.horizon + KT - 1) / KT <= 8;
 }
 
 int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const MegaBuffers &bf,

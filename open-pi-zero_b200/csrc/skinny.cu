@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, MT <= 2 ? 3 : 1) skinny_kernel(Skinn
 int skinny_supported(const LinearArgs &a) {
     // M <= 64: the weight-streaming regime.  Larger M only for tiny N (weights re-read per 64-row
     // chunk stay in L2): the 7-wide action decoder.
-    if (a.M < 1 || (a.M > 8 * MAX_MT && a.N > 64)) return 0;
+    // (above ~16 rows the activation fragments no longer stay in registers / L1 cheaply and the
+    // tcgen05 GEMM wins even though its fixed cost is higher)
+    if (a.M < 1 || (a.M > 16 && a.N > 64)) return 0;
     if (a.K % 8 || a.lda % 8) return 0;
     if ((a.flags & LIN_NORM_A) && (!a.norm_w || ((uintptr_t)a.norm_w & 15))) return 0;
     if (a.flags & LIN_COMBINE_A) {
