@@ -145,6 +145,8 @@ int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offs
 
 /* Debug: workspace offset of the persistent sampler's barrier / phase-timestamp words. */
 size_t pz_debug_trace_offset(const pz_handle *h, int batch);
+/* Same for the flag-exchange sampler (denoise_mega2.cu): 128 globaltimer words. */
+size_t pz_debug_mega2_trace_offset(const pz_handle *h, int batch);
 
 /* PiZero.infer_action (pizero.py:416-490), whole call.
  *   d_input_ids  int64 [B, s_vlm]

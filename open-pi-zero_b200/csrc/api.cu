@@ -81,6 +81,8 @@ struct Workspace {
     void *a_in, *e1, *z, *ha, *qkva, *qa, *ka, *va, *atta, *mlpa;
     float *act, *xa, *vel, *att_scratch;
     unsigned int *mega_barrier;
+    void *mega_ll;
+    size_t mega_ll_bytes;
     size_t att_scratch_bytes;
     size_t total;
 };
@@ -133,6 +135,8 @@ static Workspace carve(const pz_config &c, int B, int chunk, void *base) {
     w.mlpa = b.take<void>(Ma * c.act_inter * es);
     w.vel = b.take<float>(Ma * 8 * 4);
     w.mega_barrier = b.take<unsigned int>(128 * sizeof(unsigned int));
+    w.mega_ll_bytes = denoise_mega2_ll_bytes(c, B < 2 ? B : 2);
+    w.mega_ll = b.take<void>(w.mega_ll_bytes);
     {   // split-key attention partials (decode): [B][key tiles][heads*rows][hd + 2] fp32
         size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
         size_t tiles = (S_c + c.horizon + 63) / 64;
@@ -498,8 +502,18 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
     const int Ma = B * Hz;
     const float dt = (float)(1.0 / c.n_steps);
     copy_f32(ws.act, noise, (size_t)Ma * c.action_dim, st);
-    if (std::is_same<T, bf16>::value && denoise_mega_supported(c, B) &&
-        !(cap && (cap->denoise_action || cap->velocities || cap->action_preclip))) {
+    const bool no_taps = !(cap && (cap->denoise_action || cap->velocities || cap->action_preclip));
+    if (std::is_same<T, bf16>::value && no_taps && denoise_mega2_supported(c, B)) {
+        // bs 1-2: barrier-free persistent sampler (denoise_mega2.cu)
+        Mega2Buffers mb;
+        mb.kcache = ws.kcache; mb.vcache = ws.vcache; mb.batch_total = B; mb.valid_len = valid_len;
+        mb.noise = ws.act; mb.out = out; mb.ll = ws.mega_ll; mb.ll_bytes = ws.mega_ll_bytes;
+        const char *e = nullptr;
+        int rc = launch_denoise_mega2(c, w, h->action.data(), mb, B, st, &e);
+        if (rc) return fail(h, rc, std::string("denoise_mega2 launch failed: ") + (e ? e : "?"));
+        return 0;
+    }
+    if (std::is_same<T, bf16>::value && denoise_mega_supported(c, B) && no_taps) {
         // small batch: the whole sampler as one persistent cooperative kernel (denoise_mega.cu)
         MegaBuffers mb;
         mb.kcache = ws.kcache; mb.vcache = ws.vcache; mb.batch_total = B; mb.valid_len = valid_len;
@@ -608,6 +622,12 @@ size_t pz_debug_trace_offset(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
     return (size_t)((char *)ws.mega_barrier - (char *)0x1000);
+}
+
+size_t pz_debug_mega2_trace_offset(const pz_handle *h, int batch) {
+    if (!h || batch < 1) return 0;
+    Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
+    return (size_t)((char *)ws.mega_ll - (char *)0x1000) + ws.mega_ll_bytes - 32768;
 }
 
 int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,

@@ -66,6 +66,21 @@ int denoise_mega_supported(const pz_config &c, int B);
 int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const MegaBuffers &bf,
                         int B, cudaStream_t st, const char **err);
 
+// denoise_mega2.cu (barrier-free persistent sampler for B * horizon <= 8: flagged 64-bit exchanges,
+// attention CTAs with shared-memory-resident KV, TMA bulk weight ring)
+struct Mega2Buffers {
+    const void *kcache, *vcache;   // [L][batch_total][S_c][256] bf16
+    int batch_total;
+    const int32_t *valid_len;
+    const float *noise;            // [B*horizon][action_dim] initial action
+    float *out;
+    void *ll; size_t ll_bytes;     // exchange buffers, >= denoise_mega2_ll_bytes()
+};
+size_t denoise_mega2_ll_bytes(const pz_config &c, int B);
+int denoise_mega2_supported(const pz_config &c, int B);
+int launch_denoise_mega2(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const Mega2Buffers &bf,
+                         int B, cudaStream_t st, const char **err);
+
 // stand-alone decode attention (one CTA per (sample, 64-key tile), RoPE fused, 8 warps): writes split-key
 // partials [B][splits][heads*horizon][258]; returns the number of splits (or < 0 on error)
 int decode_attention_supported(const pz_config &c);

@@ -90,8 +90,9 @@ def test_linear_tcgen05(M, N, K, flags, bias, alpha):
 @pytest.mark.parametrize("M,N,K,flags,bias,alpha", [
     (4, 2560, 1024, 0, False, 1.0), (4, 1024, 2048, OUT_F32 | ACCUM, False, 1.0),
     (4, 8192, 1024, GEGLU, False, 1.0), (4, 1024, 4096, OUT_F32 | ACCUM, False, 1.0),
-    (1, 2560, 1024, 0, False, 1.0), (20, 1024, 1024, SILU, True, 1.0), (64, 1024, 1024, OUT_F32, True, 32.0),
-    (8, 7, 1024, OUT_F32, True, 1.0), (12, 1024, 8, 0, True, 1.0)])
+    (1, 2560, 1024, 0, False, 1.0), (16, 1024, 1024, SILU, True, 1.0), (13, 1024, 1024, OUT_F32, True, 32.0),
+    (8, 7, 1024, OUT_F32, True, 1.0), (12, 1024, 8, 0, True, 1.0),
+    (256, 7, 1024, OUT_F32, True, 1.0)])   # M > 16 only for the tiny-N action decoder (skinny_supported)
 def test_linear_skinny(M, N, K, flags, bias, alpha):
     lib = _lib()
     e = _run_linear(2, M, N, K, flags, bias, alpha)
