@@ -32,6 +32,8 @@ import open_pi_zero_b200 as pz  # noqa: E402
 METRIC = "action chunks/s per box (bridge-shape infer_action, bf16); p50 infer_action latency at bs=1"
 UNIT = "action_chunks/s"
 PER_GPU_BATCH = int(os.environ.get("PZ_BENCH_BATCH", "64"))
+# DRAM bytes of one VLM gate|up GEMM launch at bs=64 (cta_group::2 kernel), from the committed ncu capture
+GATE_UP_DRAM_BYTES = 2.053190e9 + 571.228416e6
 
 
 def measured_peaks():
@@ -133,6 +135,148 @@ def run_cpu_oracle(dims, sd, steps, warmup, batch=1):
     return times, out, inp
 
 
+def run_cpu_reference(dims, sd, steps, warmup, batch=1):
+    """The UNMODIFIED reference (`baseline/_ref`, installed by `pip install --no-deps --target
+    baseline/_ref` from /root/reference) through its own `PiZero.infer_action`,
+    fp32, all host threads.  The three missing third-party imports (omegaconf, hydra,
+    bitsandbytes -- no arithmetic on this path) are the stand-ins of oracle/ref_shims.py.
+    Returns None when the install is not there (then the oracle port is timed instead)."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "src", "model", "vla")):
+        return None
+    from oracle import ref_shims
+    ref_shims.REFERENCE_ROOT = ref_root
+    try:
+        model = ref_shims.build_reference_model(dims)
+        model.load_state_dict(sd, strict=True)
+    except Exception as e:   # pragma: no cover - environment dependent
+        print(f"[bench] reference import failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+    inp = pz.make_inputs(dims, batch, seed=0)
+    cm, vpos, ppos, apos = model.build_causal_mask_and_position_ids(inp["attention_mask"], torch.float32)
+    pmask, amask = model.split_full_mask_into_submasks(cm)
+    orig_randn = torch.randn
+
+    def randn(*a, **kw):   # same initial noise as every other arm (pizero.py:454)
+        return inp["noise"].to(kw.get("dtype", torch.float32)).clone()
+
+    times, out = [], None
+    torch.randn = randn
+    try:
+        with torch.inference_mode():
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                out = model.infer_action(input_ids=inp["input_ids"], pixel_values=inp["pixel_values"],
+                                         image_text_proprio_mask=pmask, action_mask=amask, vlm_position_ids=vpos,
+                                         proprio_position_ids=ppos, action_position_ids=apos, proprios=inp["proprios"])
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+    finally:
+        torch.randn = orig_randn
+    return times, out.float(), inp
+
+
+def reference_on_gpu(dims, sd, device, B, steps=3):
+    """Extra (not the reference arm): the unmodified reference's eager PyTorch bf16 `infer_action` on this
+    same B200 (the honest same-box bar).  None if baseline/_ref is absent."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "src", "model", "vla")):
+        return None
+    from oracle import ref_shims
+    ref_shims.REFERENCE_ROOT = ref_root
+    try:
+        model = ref_shims.build_reference_model(dims)
+        model.load_state_dict(sd, strict=True)
+        model = model.to(torch.bfloat16).to(device)
+    except Exception as e:   # pragma: no cover
+        print(f"[bench] reference-on-GPU skipped ({type(e).__name__}: {e})", file=sys.stderr)
+        return None
+    res = {}
+    with torch.inference_mode():
+        for b, n in ((B, steps), (1, 10)):
+            inp = pz.make_inputs(dims, b, seed=0)
+            cm, vpos, ppos, apos = model.build_causal_mask_and_position_ids(inp["attention_mask"], torch.bfloat16)
+            pmask, amask = model.split_full_mask_into_submasks(cm)
+            kw = dict(input_ids=inp["input_ids"].to(device), pixel_values=inp["pixel_values"].to(device, torch.bfloat16),
+                      image_text_proprio_mask=pmask.to(device), action_mask=amask.to(device),
+                      vlm_position_ids=vpos.to(device), proprio_position_ids=ppos.to(device),
+                      action_position_ids=apos.to(device), proprios=inp["proprios"].to(device, torch.bfloat16))
+            for _ in range(2):
+                model.infer_action(**kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                model.infer_action(**kw)
+            e1.record()
+            torch.cuda.synchronize()
+            res[b] = e0.elapsed_time(e1) / n
+    del model
+    torch.cuda.empty_cache()
+    return dict(what="unmodified reference (baseline/_ref), eager PyTorch bf16 on this GPU, inputs resident",
+                batch=B, ms_per_step=res[B], value=B / (res[B] * 1e-3), unit=UNIT, latency_bs1_ms=res[1])
+
+
+def cpu_arm(dims, sd, steps, warmup):
+    """(times, action, inputs, kind): the reference itself when installed, else the oracle port."""
+    r = run_cpu_reference(dims, sd, steps, warmup)
+    if r is not None:
+        return r + ("reference",)
+    return run_cpu_oracle(dims, sd, steps, warmup) + ("port",)
+
+
+def denoise_bs1_roofline(model, dims, device, peaks):
+    """HBM roofline of the bs=1 sampler (the second regime BASELINE.json names): the 10 Euler steps as one
+    persistent kernel, captured in a CUDA graph and timed with CUDA events on the launching stream.
+    Algorithmic bytes per launch: 10 x (629.3 MB of action-expert weights + 5.11 MB prefix KV)."""
+    from open_pi_zero_b200 import _lib
+    lib = _lib.load()
+    inp = pz.make_inputs(dims, 1, seed=7)
+    ids = inp["input_ids"].to(device); pix = inp["pixel_values"].to(device, torch.bfloat16)
+    prop = inp["proprios"].to(device); nz = inp["noise"].to(device); vlen = inp["valid_len"].to(device)
+    out = torch.empty(1, dims["horizon_steps"], dims["action_dim"], device=device)
+    nbytes = lib.pz_workspace_bytes(model._handle, 1)
+    ws_t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    ws = (ws_t.data_ptr() + 1023) // 1024 * 1024
+
+    def st():
+        return torch.cuda.current_stream().cuda_stream
+
+    assert lib.pz_embed_prefix(model._handle, ids.data_ptr(), pix.data_ptr(), ws, nbytes, 1, None, st()) == 0
+    assert lib.pz_prefill(model._handle, vlen.data_ptr(), prop.data_ptr(), ws, nbytes, 1, None, st()) == 0
+
+    def den():
+        rc = lib.pz_denoise(model._handle, vlen.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, nbytes, 1, None, st())
+        assert rc == 0, lib.pz_last_error(model._handle)
+
+    n0 = lib.pz_launch_count(model._handle)
+    den()
+    n_launch = lib.pz_launch_count(model._handle) - n0
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        den()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    n_steps = dims["num_inference_steps"]
+    bytes_per_launch = n_steps * (629.3e6 + 5.11e6)
+    achieved = bytes_per_launch / (ms * 1e-3) / 1e9
+    return dict(bound="hbm", kernel="denoise_mega_kernel (10 Euler steps, persistent cooperative)", achieved=achieved,
+                peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+                avg_launch_ms=ms, launches_timed=reps, kernels_per_launch=int(n_launch),
+                peak_source=peaks["source"] + ", copy bandwidth")
+
+
 def workload_config(world, B):
     return dict(workload=f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
                          "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
@@ -147,7 +291,7 @@ def reference_arm(args, rank):
     dims = pz.make_dims()
     torch.set_num_threads(os.cpu_count() or 1)
     sd = pz.init_state_dict(dims, seed=42)
-    times, _, _ = run_cpu_oracle(dims, sd, args.steps, max(args.warmup, 1))
+    times, _, _, kind = cpu_arm(dims, sd, args.steps, max(args.warmup, 1))
     total = sum(times)
     value = len(times) / total
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
@@ -155,8 +299,9 @@ def reference_arm(args, rank):
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload_config(args.gpus, PER_GPU_BATCH),
                             reference_sample="each step = one infer_action at bs=1 of the same workload, fp32, "
-                                             "reference algorithm (oracle port) on the host cores"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                                             + ("the unmodified reference (baseline/_ref) " if kind == "reference"
+                                                else "reference algorithm (oracle port) ") + "on the host cores"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind=kind,
                                   sample=f"{len(times)} infer_action calls at bs=1, fp32, after "
                                          f"{max(args.warmup, 1)} warm-up"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -298,19 +443,28 @@ def main():
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm_tc_kernel<256, cta_group::2> (VLM gate|up + GeGLU)", achieved=achieved,
                     peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
-                    traffic=None, avg_launch_ms=avg_ms, launches_timed=gu_n,
+                    traffic=GATE_UP_DRAM_BYTES, traffic_source="profiles/r01_ncu_full_gemm_tc.txt (ncu --set full, "
+                    "dram__bytes_read.sum + dram__bytes_write.sum of one launch); algorithmic bytes 785 MB",
+                    avg_launch_ms=avg_ms, launches_timed=gu_n,
                     share_of_step=gu_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps, peak_source=peaks["source"] + ", sustained figure")
 
+    roof_denoise = None
+    if rank == 0 and not args.skip_latency:
+        roof_denoise = denoise_bs1_roofline(model, dims, device, peaks)
+    sync_all()
+
     cpu = None
+    ref_gpu = None
     if do_cpu and rank == 0:
         torch.set_num_threads(os.cpu_count() or 1)
-        times, want, cinp = run_cpu_oracle(dims, sd, steps=3, warmup=1)
+        times, want, cinp, kind = cpu_arm(dims, sd, steps=3, warmup=1)
         got = model(input_ids=cinp["input_ids"].to(device), pixel_values=cinp["pixel_values"].to(device),
                     proprios=cinp["proprios"].to(device), noise=cinp["noise"].to(device),
                     valid_len=cinp["valid_len"].to(device)).cpu()
-        cpu = dict(value=len(times) / sum(times), unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                   sample="3 infer_action calls at bs=1 (fp32 oracle port of the reference, all host "
-                          "threads) after 1 warm-up",
+        ref_gpu = reference_on_gpu(dims, sd, device, B)
+        cpu = dict(value=len(times) / sum(times), unit=UNIT, cores=torch.get_num_threads(), kind=kind,
+                   sample="3 infer_action calls at bs=1 (fp32, " + ("the unmodified reference from baseline/_ref"
+                          if kind == "reference" else "oracle port of the reference") + ", all host threads) after 1 warm-up",
                    max_abs_gpu_vs_cpu=float((got - want).abs().max()))
 
     if rank == 0:
@@ -320,7 +474,8 @@ def main():
             dtype="bf16", data="synthetic",
             config=workload_config(world, B),
             clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-            gpu_launches=launches, latency_bs1=lat, roofline=roof, cpu_baseline=cpu)
+            gpu_launches=launches, latency_bs1=lat, roofline=roof, roofline_denoise_bs1=roof_denoise,
+            cpu_baseline=cpu, reference_gpu_eager=ref_gpu)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

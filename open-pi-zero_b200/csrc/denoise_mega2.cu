@@ -1004,8 +1004,10 @@ size_t denoise_mega2_ll_bytes(const pz_config &c, int B) {
 }
 
 int denoise_mega2_supported(const pz_config &c, int B) {
-    const char *e = getenv("PZ_MEGA");   // 0: separate kernels, 1: denoise_mega.cu, 2 (default): this kernel
-    if (e && atoi(e) != 2) return 0;
+    // PZ_MEGA: 0 separate kernels, 1 (default) denoise_mega.cu, 2 this kernel.  Opt-in: measured on B200 it does
+    // not beat the grid-barrier kernel yet (6.05 vs 5.64 ms at bs=1 under graph replay)
+    const char *e = getenv("PZ_MEGA");
+    if (!e || atoi(e) != 2) return 0;
     if (c.dtype != PZ_BF16 || (c.flags & PZ_FLAG_SIMPLE_KERNELS)) return 0;
     if (B * c.horizon > MAXM || c.n_heads * c.horizon > QROWS || c.horizon > 4) return 0;
     if (c.head_dim != 256 || c.n_kv_heads != 1 || c.n_heads > 8) return 0;
