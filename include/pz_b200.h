@@ -137,6 +137,16 @@ int pz_bind_weights(pz_handle *h, const pz_weights *w);
 /* Bytes of scratch `pz_infer_action` needs for batch B (<= max_batch). */
 size_t pz_workspace_bytes(const pz_handle *h, int batch);
 
+/* Format of `d_pixel_values` for the following calls on this handle.
+ *   PZ_PIXELS_MODEL_DTYPE (default): normalised floats in the handle dtype, as the reference's
+ *                                    `pixel_values` argument (pizero.py:419)
+ *   PZ_PIXELS_U8: raw uint8 [B, (n_images,) 3, H, W] camera frames; the normalisation the reference's caller
+ *                 does on the host (VLAProcessor, src/model/vla/processing.py:27-58,108-113:
+ *                 x/255, then (x - 0.5)/0.5) is fused into the patch-gather kernel. */
+#define PZ_PIXELS_MODEL_DTYPE 0
+#define PZ_PIXELS_U8 1
+int pz_set_pixel_format(pz_handle *h, int format);
+
 /* Where the prefix KV cache lives inside the workspace (for parity tests):
  * K and V are each [n_layers][B][s_vlm+cond][head_dim] in the handle dtype
  * (replaces src/model/kv_cache.py: list-of-tensors growing by torch.cat). */
@@ -146,7 +156,7 @@ int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offs
 /* Debug: workspace offset of the persistent sampler's barrier / phase-timestamp words. */
 size_t pz_debug_trace_offset(const pz_handle *h, int batch);
 /* Same for the flag-exchange sampler (denoise_mega2.cu): 128 globaltimer words. */
-size_t pz_debug_mega2_trace_offset(const pz_handle *h, int batch);
+size_t pz_debug_ll_trace_offset(const pz_handle *h, int batch);
 
 /* PiZero.infer_action (pizero.py:416-490), whole call.
  *   d_input_ids  int64 [B, s_vlm]

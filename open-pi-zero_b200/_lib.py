@@ -59,7 +59,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
-           "pz_workspace_bytes", "pz_kv_layout", "pz_debug_trace_offset", "pz_debug_mega2_trace_offset", "pz_infer_action", "pz_embed_prefix",
+           "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_debug_ll_trace_offset", "pz_infer_action", "pz_embed_prefix",
            "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
 _lib = None
@@ -88,12 +88,13 @@ def load(build_if_needed: bool = True):
     lib.pz_last_error.argtypes = [hp]
     lib.pz_last_error.restype = C.c_char_p
     lib.pz_bind_weights.argtypes = [hp, C.POINTER(PzWeights)]
+    lib.pz_set_pixel_format.argtypes = [hp, C.c_int]
     lib.pz_workspace_bytes.argtypes = [hp, C.c_int]
     lib.pz_workspace_bytes.restype = C.c_size_t
     lib.pz_debug_trace_offset.argtypes = [hp, C.c_int]
     lib.pz_debug_trace_offset.restype = C.c_size_t
-    lib.pz_debug_mega2_trace_offset.argtypes = [hp, C.c_int]
-    lib.pz_debug_mega2_trace_offset.restype = C.c_size_t
+    lib.pz_debug_ll_trace_offset.argtypes = [hp, C.c_int]
+    lib.pz_debug_ll_trace_offset.restype = C.c_size_t
     lib.pz_kv_layout.argtypes = [hp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                  C.POINTER(C.c_size_t)]
     lib.pz_infer_action.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int,

@@ -29,6 +29,7 @@ struct pz_handle {
     std::string err;
     LaunchCounter lc;
     int prefix_chunk = 64;
+    int pixel_format = PZ_PIXELS_MODEL_DTYPE;   // pz_set_pixel_format
     // optional CUDA-event timing of one tagged kernel family (bench.py roofline)
     // fork/join side stream: the proprio token's chain of small kernels runs beside the VLM chain
     cudaStream_t side = nullptr;
@@ -228,9 +229,14 @@ static int run_embed_prefix(pz_handle *h, const int64_t *ids, const void *pixels
         int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
         int n_img = nb * c.n_images;
         int Mv = n_img * P;
-        const T *pix = (const T *)pixels + (size_t)b0 * c.n_images * img_elems;
         // patch embedding (siglip.py:59-78): conv as GEMM over im2col rows, + bias + position table
-        launch_im2col<T>(pix, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+        if (h->pixel_format == PZ_PIXELS_U8) {
+            const uint8_t *pix = (const uint8_t *)pixels + (size_t)b0 * c.n_images * img_elems;
+            launch_im2col_u8<T>(pix, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+        } else {
+            const T *pix = (const T *)pixels + (size_t)b0 * c.n_images * img_elems;
+            launch_im2col<T>(pix, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+        }
         launch_bcast_rows(ws.xv, w.pos_emb, Mv, V, P, st);
         PZ_TRY(Ops<T>::linear(h, lin(ws.patches, c.patch_k_pad, w.patch_w, w.patch_b, ws.xv, V, Mv, V,
                                      c.patch_k_pad, LIN_OUT_F32 | LIN_ACCUM), st));
@@ -613,6 +619,13 @@ int pz_bind_weights(pz_handle *h, const pz_weights *w) {
     return PZ_OK;
 }
 
+int pz_set_pixel_format(pz_handle *h, int format) {
+    if (!h) return PZ_ERR_INVALID;
+    if (format != PZ_PIXELS_MODEL_DTYPE && format != PZ_PIXELS_U8) return fail(h, PZ_ERR_INVALID, "unknown pixel format");
+    h->pixel_format = format;
+    return PZ_OK;
+}
+
 size_t pz_workspace_bytes(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     return carve(h->cfg, batch, h->prefix_chunk, nullptr).total;
@@ -624,7 +637,7 @@ size_t pz_debug_trace_offset(const pz_handle *h, int batch) {
     return (size_t)((char *)ws.mega_barrier - (char *)0x1000);
 }
 
-size_t pz_debug_mega2_trace_offset(const pz_handle *h, int batch) {
+size_t pz_debug_ll_trace_offset(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
     return (size_t)((char *)ws.mega_ll - (char *)0x1000) + ws.mega_ll_bytes - 32768;

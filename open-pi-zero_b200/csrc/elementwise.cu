@@ -33,6 +33,40 @@ void launch_im2col(const T *pix, T *patches, int n_images, int image, int patch,
     launch_k(im2col_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pix, patches, image, patch,
                                                                      k_pad, total);
 }
+// uint8 camera frames: the caller-side normalisation of VLAProcessor (processing.py:27-58,108-113:
+// x * (1/255) in fp32, then (x - 0.5) / 0.5) is applied while the patches are gathered, so the host never
+// materialises (or copies) float images
+template <typename T>
+__global__ void im2col_u8_kernel(const uint8_t *__restrict__ pix, T *__restrict__ patches, int image,
+                                 int patch, int k_pad, long total) {
+    pdl_trigger();
+    pdl_wait();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int k = i % k_pad;
+    long row = i / k_pad;
+    int G = image / patch, P = G * G;
+    int img = row / P, p = row % P;
+    int py = p / G, px = p % G;
+    int kk = patch * patch;
+    float v = 0.f;
+    if (k < 3 * kk) {
+        int c = k / kk, r = k % kk, ky = r / patch, kx = r % patch;
+        float u = (float)pix[(((long)img * 3 + c) * image + (py * patch + ky)) * image + px * patch + kx];
+        v = __fdiv_rn(__fsub_rn(__fmul_rn(u, (float)(1.0 / 255.0)), 0.5f), 0.5f);   // no FMA contraction: same roundings as torch
+    }
+    patches[i] = from_f32<T>(v);
+}
+template <typename T>
+void launch_im2col_u8(const uint8_t *pix, T *patches, int n_images, int image, int patch, int k_pad,
+                      cudaStream_t st) {
+    int G = image / patch;
+    long total = (long)n_images * G * G * k_pad;
+    launch_k(im2col_u8_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pix, patches, image, patch,
+                                                                        k_pad, total);
+}
+template void launch_im2col_u8<float>(const uint8_t *, float *, int, int, int, int, cudaStream_t);
+template void launch_im2col_u8<bf16>(const uint8_t *, bf16 *, int, int, int, int, cudaStream_t);
 template void launch_im2col<float>(const float *, float *, int, int, int, int, cudaStream_t);
 template void launch_im2col<bf16>(const bf16 *, bf16 *, int, int, int, int, cudaStream_t);
 

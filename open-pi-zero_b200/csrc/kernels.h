@@ -10,6 +10,9 @@ template <typename T> void launch_attn_simple(const AttnArgs &a, cudaStream_t st
 template <typename T>
 void launch_im2col(const T *pix, T *patches, int n_images, int image, int patch, int k_pad,
                    cudaStream_t st);
+template <typename T>
+void launch_im2col_u8(const uint8_t *pix, T *patches, int n_images, int image, int patch, int k_pad,
+                      cudaStream_t st);
 void launch_bcast_rows(float *x, const float *table, long rows, int cols, int period,
                        cudaStream_t st);
 template <typename T>

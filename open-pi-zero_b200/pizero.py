@@ -524,11 +524,14 @@ class PiZero(nn.Module):
                 if got is not None and not torch.equal(got.to(dev), want):
                     raise ValueError(f"{nm}_position_ids differ from build_causal_mask_and_position_ids")
         ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
-        pix = pixel_values.to(device=dev, dtype=self._T).contiguous()
+        # uint8 camera frames are normalised on the device while the patches are gathered
+        # (processing.py:27-58,108-113 fused into the im2col kernel); floats are the reference's argument
+        u8 = pixel_values.dtype == torch.uint8
+        pix = pixel_values.to(device=dev).contiguous() if u8 else pixel_values.to(device=dev, dtype=self._T).contiguous()
         prop = proprios.to(device=dev, dtype=torch.float32).contiguous()
         vlen = self._valid_len(image_text_proprio_mask, ids, valid_len)
         if noise is None:   # pizero.py:454-456
-            noise = torch.randn((B, H, Adim), device=dev, dtype=pixel_values.dtype)
+            noise = torch.randn((B, H, Adim), device=dev, dtype=self._T if u8 else pixel_values.dtype)
         nz = noise.to(device=dev, dtype=torch.float32).contiguous()
         if capture is None and self.use_cuda_graph and not self._timing_armed:
             return self._replay_graph(B, ids, pix, vlen, prop, nz)
@@ -546,9 +549,33 @@ class PiZero(nn.Module):
         self._inflight = (ids, pix, prop, vlen, nz)
         return out
 
+    @torch.no_grad()
+    def infer_action_naive(
+        self,
+        input_ids: torch.LongTensor,
+        pixel_values: torch.FloatTensor,
+        causal_mask: torch.FloatTensor,
+        vlm_position_ids: Optional[torch.LongTensor] = None,
+        proprio_position_ids: Optional[torch.LongTensor] = None,
+        action_position_ids: Optional[torch.LongTensor] = None,
+        proprios: Optional[torch.FloatTensor] = None,
+        *,
+        noise: Optional[torch.Tensor] = None,
+    ) -> torch.FloatTensor:
+        """pizero.py:492-550: the reference's second entry point (same seven arguments, the full
+        `[B,1,S,S]` mask instead of the two sub-masks).  The reference re-runs the VLM in every Euler step
+        there ("which is unnecessary", pizero.py:517); under the block mask the VLM / proprio rows do not
+        depend on the action rows, so the result is the cached path's (1.5e-7 apart in fp32) and
+        the same kernels serve it.  The valid length is read from row 0 of the mask."""
+        Sv = self.max_image_text_tokens
+        vlen = (causal_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).contiguous()
+        return self.infer_action(input_ids, pixel_values, None, None, vlm_position_ids, proprio_position_ids,
+                                 action_position_ids, proprios, noise=noise, valid_len=vlen)
+
     def _launch(self, ids, pix, vlen, prop, nz, out, ws, ws_bytes, B, cap_struct=None):
         lib = _lib.load()
         stream = torch.cuda.current_stream(out.device).cuda_stream
+        lib.pz_set_pixel_format(self._handle, 1 if pix.dtype == torch.uint8 else 0)
         rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
                                  prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
                                  C.byref(cap_struct) if cap_struct is not None else None, stream)
@@ -561,7 +588,8 @@ class PiZero(nn.Module):
         """The whole call (~2k kernel launches at bs=1) is captured once per batch
         size into a CUDA graph over static buffers and replayed: launch overhead
         leaves the critical path (eager dispatch is launch-bound)."""
-        g = self._graphs.get(B)
+        key = (B, pix.dtype)
+        g = self._graphs.get(key)
         if g is None:
             lib = _lib.load()
             dev = ids.device
@@ -589,7 +617,7 @@ class PiZero(nn.Module):
                              st["ws_bytes"], B)
             st["graph"] = graph
             st["launches"] = self.last_launch_count
-            self._graphs[B] = g = st
+            self._graphs[key] = g = st
         for k, v in (("ids", ids), ("pix", pix), ("vlen", vlen), ("prop", prop), ("nz", nz)):
             g[k].copy_(v, non_blocking=True)
         g["graph"].replay()

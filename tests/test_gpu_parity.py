@@ -188,7 +188,46 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
         eager = eager.clone()
         replay, _ = _run(m, d, inp, capture=False)    # graph (captured on first use, replayed after)
         assert max_abs(eager, replay) < 2e-3           # fp32 atomics in the split-K GEMV: order may differ
-    assert 3 in m._graphs
+    assert any(k[0] == 3 for k in m._graphs)
+
+
+def test_uint8_frames_match_host_normalisation():
+    """raw uint8 camera frames, normalised inside the patch-gather kernel, give exactly the
+    result of the reference's host-side VLAProcessor normalisation (processing.py:27-58,108-113) followed
+    by the float path.  The kernel applies the same fp32 operations in the same order (u * f32(1/255), - 0.5,
+    / 0.5, no FMA contraction), so the pixels are bit-identical; the comparison of the final actions still
+    needs a small tolerance because two runs of the path differ in the order of their fp32 reduce-adds."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=4, randomize_norms=True)
+    inp = pz.make_inputs(d, 3, seed=9)
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, tuple(inp["pixel_values"].shape), dtype=torch.uint8, generator=g)
+    host = (u8 * (1 / 255.0) - 0.5) / 0.5           # rescale() then normalize() of processing.py
+    for dtype in (torch.float32, torch.bfloat16):
+        m = _model(d, sd, dtype)
+        kw = dict(input_ids=inp["input_ids"].cuda(), proprios=inp["proprios"].cuda().to(dtype),
+                  noise=inp["noise"].cuda(), valid_len=inp["valid_len"].cuda())
+        for _ in range(2):                           # second call: CUDA-graph replay for both formats
+            want = m(pixel_values=host.cuda().to(dtype), **kw).clone()
+            got = m(pixel_values=u8.cuda(), **kw).clone()
+            torch.cuda.synchronize()
+            assert torch.isfinite(got).all()
+            assert max_abs(got, want) < 2e-3, max_abs(got, want)
+        del m
+
+
+def test_infer_action_naive_entry_point():
+    """pizero.py:492-550 (full-mask signature) against the oracle's own uncached implementation."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=6, randomize_norms=True)
+    inp = pz.make_inputs(d, 2, seed=12)
+    want = O.infer_action_naive(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                                inp["proprios"], inp["noise"])
+    m = _model(d, sd, torch.float32)
+    mask, vp, pp, ap = m.build_causal_mask_and_position_ids(inp["attention_mask"].cuda(), torch.float32)
+    got = m.infer_action_naive(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), mask, vp, pp, ap,
+                               inp["proprios"].cuda(), noise=inp["noise"].cuda())
+    assert max_abs(got, want) < FP32_ACTION_TOL
 
 
 def test_large_m_pair_gemm_and_fused_rope_vs_oracle():

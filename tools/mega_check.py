@@ -44,7 +44,7 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 2]:
         e1.record(); torch.cuda.synchronize()
         print(f"B={B} PZ_MEGA={ver}: {e0.elapsed_time(e1) / 20:.3f} ms per 10-step denoise; "
               f"max|out - separate kernels| = {float((out - outs['0']).abs().max()):.3e}; finite={bool(torch.isfinite(out).all())}")
-    off = lib.pz_debug_mega2_trace_offset(m._handle, B) + (ws - ws_t.data_ptr())
+    off = lib.pz_debug_ll_trace_offset(m._handle, B) + (ws - ws_t.data_ptr())
     raw = ws_t[off: off + 148 * 16 * 8].view(torch.int64).cpu().view(148, 16)
     G = 148 - 2 * B
     for errw in [int(x) & 0xFFFFFFFF for x in ws_t[off - 256: off - 256 + 20].view(torch.int32).cpu()]:

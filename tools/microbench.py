@@ -62,3 +62,10 @@ if __name__ == "__main__":
             bench_linear(2, M, 1024, 2048, OUT_F32 | ACCUM)
             bench_linear(2, M, 8192, 1024, GEGLU)
             bench_linear(2, M, 1024, 4096, OUT_F32 | ACCUM)
+    if which == "floor":
+        # fixed cost of one tcgen05 GEMM launch in a PDL chain: tiny K, then growing K / N
+        for (M, N, K) in ((128, 128, 64), (256, 1024, 64), (256, 2560, 64), (256, 2560, 256), (256, 2560, 512),
+                          (256, 2560, 1024), (256, 1024, 2048), (256, 1024, 4096)):
+            bench_linear(1, M, N, K, 0)
+        for (M, N, K) in ((256, 1024, 64), (256, 1024, 1024), (256, 1024, 2048), (256, 1024, 4096)):
+            bench_linear(1, M, N, K, OUT_F32 | ACCUM)
