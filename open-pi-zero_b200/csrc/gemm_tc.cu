@@ -176,13 +176,16 @@ constexpr int STG_BYTES = 4096;         // per-warp staging: 32 rows x 128 B
 // Each CTA stages its own 128 rows of A and HALF of the W tile, so a stage is 32 KB instead of 48 KB:
 // six stages fit, i.e. 50 % more K in flight per SM and a third less shared-memory / L2 traffic per FLOP.
 template <int BN, int CG = 1> struct Cfg {
-    static constexpr int STAGES = (CG == 2 || BN != 256) ? 6 : 4;
+    // CTA pairs (the big-M, compute-bound configuration) double-buffer the epilogue staging so that a warp never
+    // waits for its previous TMA store to drain (64 KB of staging: one mainloop stage less)
+    static constexpr int STG_BUFS = CG == 2 ? 2 : 1;
+    static constexpr int STAGES = CG == 2 ? 5 : (BN != 256 ? 6 : 4);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two: 256 / 512)
     static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
+    static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_BYTES * STG_BUFS;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -212,6 +215,7 @@ PZ_DEVINL void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0
 }
 PZ_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 PZ_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PZ_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 PZ_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 PZ_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -219,7 +223,12 @@ PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_
                  : "memory");
 }
 
-template <int BN, int CG>
+// EPI: the epilogue flavour is a compile-time parameter -- with run-time flag tests inside the fully unrolled
+// per-element loops the epilogue cost ~11 instructions per output element and, for the short-K SigLIP GEMMs
+// (7 us of MMA per 256 x 256 tile), became the bottleneck (tensor pipe 40-52 % active; profiles/).
+enum { E_PLAIN = 0, E_GELU = 1, E_SILU = 2, E_F32 = 3, E_GEGLU = 4, E_ROPE = 5 };
+
+template <int BN, int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
@@ -353,16 +362,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // full 128-byte lines and out-of-range rows/columns are clipped by the hardware.
         const int q = warp & 3;
         const int half = (warp - EPI_WARP0) >> 2;
-        uint8_t *stg = smem + cfg::STG_OFF + (warp - EPI_WARP0) * STG_BYTES;
+        uint8_t *stg0 = smem + cfg::STG_OFF + (warp - EPI_WARP0) * STG_BYTES * cfg::STG_BUFS;
+        int sbuf = 0;                            // staging buffer of the next store (double-buffered for CTA pairs)
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool geglu = p.flags & LIN_GEGLU;
-        const bool out_f32 = p.flags & LIN_OUT_F32;
+        constexpr bool geglu = EPI == E_GEGLU;
+        constexpr bool out_f32 = EPI == E_F32;
+        constexpr bool rope = EPI == E_ROPE;
         const bool accum = p.flags & LIN_ACCUM;
-        const bool rope = p.flags & LIN_ROPE;
         const int n_out = geglu ? p.N / 2 : p.N;
         const int sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
-        uint8_t *stg_row = stg + lane * 128;
         pdl_wait();                              // C may still be read / written by the previous kernel
         const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
         for (int t = wid; t < num_tiles; t += nworkers) {
@@ -438,17 +447,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             } else {
                 // output columns of this warp inside the tile
-                const int cols_out_tile = geglu ? BN / 2 : BN;
-                const int per_store = out_f32 ? 32 : 64;                 // output columns per 128-byte staging row
+                constexpr int cols_out_tile = geglu ? BN / 2 : BN;
+                constexpr int per_store = out_f32 ? 32 : 64;             // output columns per 128-byte staging row
                 const int my_cols0 = half * (cols_out_tile / 2);
                 for (int oc = 0; oc < cols_out_tile / 2; oc += per_store) {
                     const int col_tile = my_cols0 + oc;                   // first output column (tile-local)
                     const int col_glob = tn * cols_out_tile + col_tile;
                     if (col_glob >= n_out) break;
-                    // make sure the previous TMA store has finished reading the staging buffer
-                    if (lane == 0) bulk_wait_read0();
+                    // make sure the TMA store that last used this staging buffer has finished reading it
+                    if (lane == 0) { if (cfg::STG_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0(); }
                     __syncwarp();
-                    const int n_sub = out_f32 ? 1 : 2;                    // 32-column TMEM chunks per staging row
+                    uint8_t *stg = stg0 + sbuf * STG_BYTES;
+                    uint8_t *stg_row = stg + lane * 128;
+                    constexpr int n_sub = out_f32 ? 1 : 2;                // 32-column TMEM chunks per staging row
                     for (int sb = 0; sb < n_sub; ++sb) {
                         const int ct = col_tile + sb * 32;                // tile-local output column of this chunk
                         uint32_t r[32];
@@ -480,9 +491,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     float x = __uint_as_float(r[i + j]) + b4[j];
-                                    if (p.flags & LIN_GELU) x = out_f32 ? gelu_tanh(x) : gelu_fast(x);
-                                    if (p.flags & LIN_SILU) x = silu(x);
-                                    v[i + j] = x * p.alpha;
+                                    if (EPI == E_GELU) x = gelu_fast(x);
+                                    if (EPI == E_SILU) x = silu(x);
+                                    if (EPI == E_F32) {   // rare combinations stay run-time here
+                                        if (p.flags & LIN_GELU) x = gelu_tanh(x);
+                                        if (p.flags & LIN_SILU) x = silu(x);
+                                    }
+                                    v[i + j] = (EPI == E_F32) ? x * p.alpha : x;
                                 }
                             }
                         }
@@ -507,6 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         else tma_store_2d(&map_c, stg, col_glob, row0);
                         bulk_commit();
                     }
+                    if (cfg::STG_BUFS == 2) sbuf ^= 1;
                 }
             }
             tc_fence_before();
@@ -568,12 +584,12 @@ bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld,
 
 int g_num_sms = 0;
 
-template <int BN, int CG>
-int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
+template <int BN, int CG, int EPI>
+int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
     using cfg = Cfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cfg::SMEM_BYTES) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(max dynamic smem) failed";
             return PZ_ERR_CUDA;
@@ -633,13 +649,35 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
         ++na;
     }
     lc.attrs = attr; lc.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&lc, gemm_tc_kernel<BN, CG>, ma, mw, mc, p);
+    cudaError_t e = cudaLaunchKernelEx(&lc, gemm_tc_kernel<BN, CG, EPI>, ma, mw, mc, p);
     count_launch();
     if (e != cudaSuccess) {
         if (err) *err = cudaGetErrorString(e);
         return PZ_ERR_CUDA;
     }
     return 0;
+}
+
+// pick the epilogue instantiation from the run-time flags (bf16 outputs with an activation and a non-unit
+// alpha do not occur on this path; they take the fp32-capable flavour's run-time tests)
+template <int BN, int CG>
+int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
+    if (extra) {
+        if constexpr (BN == 256) return launch_epi<BN, CG, E_ROPE>(a, st, err, extra);
+        else return PZ_ERR_INVALID;
+    }
+    if (a.flags & LIN_GEGLU) {
+        if constexpr (BN == 256) return launch_epi<BN, CG, E_GEGLU>(a, st, err);
+        else return PZ_ERR_INVALID;
+    }
+    if (a.flags & LIN_OUT_F32) return launch_epi<BN, CG, E_F32>(a, st, err);
+    if (a.alpha == 1.f) {
+        if (a.flags & LIN_GELU) return launch_epi<BN, CG, E_GELU>(a, st, err);
+        if (a.flags & LIN_SILU) return launch_epi<BN, CG, E_SILU>(a, st, err);
+        if (!(a.flags & (LIN_GELU | LIN_SILU))) return launch_epi<BN, CG, E_PLAIN>(a, st, err);
+    }
+    if (err) *err = "tcgen05 gemm: bf16 output with activation and alpha != 1 is not instantiated";
+    return PZ_ERR_INVALID;
 }
 
 // CTA pairs pay off when there are enough 256-row tiles to keep every pair busy
@@ -659,6 +697,7 @@ int gemm_tc_supported(const LinearArgs &a) {
     if (n_out % 8 || a.ldc % 8) return 0;                    // TMA store: 16-byte global strides
     if ((a.flags & LIN_GEGLU) && (a.N % 256)) return 0;      // gate|up blocks of 128 pair up inside one 256-wide tile
     if ((a.flags & LIN_ACCUM) && !(a.flags & LIN_OUT_F32)) return 0;
+    if (!(a.flags & (LIN_OUT_F32 | LIN_GEGLU)) && a.alpha != 1.f) return 0;   // bf16 epilogues are instantiated without alpha
     return 1;
 }
 
