@@ -347,7 +347,8 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
         if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess)
             return fail(h, PZ_ERR_CUDA, "cannot create the side stream");
     }
-    cudaStream_t sp = h->side;
+    static const bool no_side = [] { const char *e = getenv("PZ_NO_SIDE"); return e && e[0] == '1'; }();
+    cudaStream_t sp = no_side ? st : h->side;   // PZ_NO_SIDE=1: both chains on one stream (measurement only)
     size_t ev = 0;
     if (ext_x) copy_f32(ws.x, ext_x, (size_t)B * S_v * H, st);   // JointModel.forward entry: embeddings given
     cudaEvent_t e_fork = sync_event(h, ev++);

@@ -621,8 +621,13 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
     int workers_max = g_num_sms / CG;
     p.ksplit = 1;
     if ((a.flags & LIN_ACCUM) && !(a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU)) && !extra) {
+        // as many K slices as it takes to give every SM (pair) a work item, at least 4 k-blocks each: at M = 276
+        // (bs=1 prefix) the 128 x 128 tiles of down_proj are MMA-rate bound per CTA (256 clk per k-block), so the
+        // K loop must be spread over all SMs, not over a power-of-two subset
         int mn = p.tiles_m * p.tiles_n;
-        while (mn * p.ksplit * 2 <= workers_max && num_kb / (p.ksplit * 2) >= 4) p.ksplit *= 2;
+        int by_sms = workers_max / mn, by_k = num_kb / 4;
+        p.ksplit = by_sms < by_k ? by_sms : by_k;
+        if (p.ksplit < 1) p.ksplit = 1;
     }
     // A bigger than what L2 keeps and only a few N tiles: let the CTAs that run together share the A
     // tile (read from HBM once) instead of the W tile (which then stays L2 resident as a whole)
@@ -707,6 +712,16 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err) {
     bool geglu = a.flags & LIN_GEGLU;
     long tiles256 = (long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
     bool use256 = geglu || (a.N >= 256 && tiles256 >= 120);
+    if (!use256 && a.N >= 256 && a.K >= 8192 && (a.flags & LIN_ACCUM) && !(a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU))) {
+        // split-K capable (fp32 reduce-add), long K and too few tiles: a weight-streaming problem (down_proj at bs=1).  Wider tiles move fewer
+        // activation bytes per weight byte through each SM (the per-SM bytes in flight are the limit), as long as
+        // the K split still yields a work item for (almost) every SM.
+        if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
+        long tiles128 = (long)((a.M + BM - 1) / BM) * ((a.N + 127) / 128);
+        long by_k = ((a.K + BK - 1) / BK) / 4;
+        auto items = [&](long tiles) { long s = g_num_sms / tiles; if (s > by_k) s = by_k; if (s < 1) s = 1; return tiles * s; };
+        use256 = items(tiles256) * 10 >= items(tiles128) * 9;
+    }
     if (use256 && use_pair(a)) return launch<256, 2>(a, st, err);
     return use256 ? launch<256, 1>(a, st, err) : launch<128, 1>(a, st, err);
 }
