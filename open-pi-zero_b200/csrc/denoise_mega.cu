@@ -102,12 +102,17 @@ PZ_DEVINL void ldsm_x4_t(uint32_t (&r)[4], const void *p) {
 PZ_DEVINL float tanh_fast_acc(float y) { float t = __expf(2.f * y); return 1.f - __fdividef(2.f, t + 1.f); }
 
 // ---- grid barrier: monotonic arrive counter, acquire spin, bounded (never hangs the GPU) ----
-PZ_DEVINL void grid_barrier(unsigned int *bar, unsigned int &target) {
+template <typename F>
+PZ_DEVINL void grid_barrier(unsigned int *bar, unsigned int &target, F between) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         __threadfence();
         atomicAdd(bar, 1u);
+    }
+    // work that does not depend on the other CTAs (weight / KV prefetch issue) hides behind the barrier latency
+    between();
+    if (threadIdx.x == 0) {
         unsigned int v;
         long spins = 0;
         do {
@@ -394,6 +399,24 @@ PZ_DEVINL void rope_pair(const MegaParams &p, bf16 *dst_row, const bf16 *src_row
     *reinterpret_cast<uint4 *>(dst_row + 128 + c * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
 }
 
+// cached K / V rows of one (sample, key tile): cp.async into the tile buffers (no dependence on the current step)
+PZ_DEVINL void attention_prefetch_kv(const MegaParams &p, uint8_t *smem, int layer, int b, int tile) {
+    bf16 *sK = reinterpret_cast<bf16 *>(smem + SM_K);
+    bf16 *sV = reinterpret_cast<bf16 *>(smem + SM_V);
+    const bf16 *Kc = p.kcache + (long)layer * p.kv_layer_stride + (long)b * p.kv_batch_stride;
+    const bf16 *Vc = p.vcache + (long)layer * p.kv_layer_stride + (long)b * p.kv_batch_stride;
+    for (int i = threadIdx.x; i < KT * 32; i += NT) {
+        int r = i >> 5, c = i & 31;
+        int j = tile * KT + r;
+        if (j < p.S_c) {
+            cp_async16(sK + r * LDQ + c * 8, Kc + (long)j * 256 + c * 8);
+            cp_async16(sV + r * LDQ + c * 8, Vc + (long)j * 256 + c * 8);
+        }
+    }
+    cp_async_commit();
+}
+
+template <bool KV_PREFETCHED = false>
 PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int b, int tile) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     bf16 *sQ = reinterpret_cast<bf16 *>(smem + SM_Q);
@@ -416,6 +439,7 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
         int j = tile * KT + r;
         bool cached = j < p.S_c;
         bool fresh = !cached && j < n_keys;
+        if (KV_PREFETCHED && cached) continue;   // already in flight (issued before the grid barrier)
         if (!fresh) cp_async16_zfill(sK + r * LDQ + c * 8, cached ? Kc + (long)j * 256 + c * 8 : Kc, cached);
         const bf16 *vsrc = cached ? Vc + (long)j * 256 + c * 8 : (fresh ? qkv_b + (long)(j - p.S_c) * qkvd + qd + 256 + c * 8 : Vc);
         cp_async16_zfill(sV + r * LDQ + c * 8, vsrc, cached || fresh);
@@ -523,7 +547,7 @@ __global__ void __launch_bounds__(NT, 2) decode_attn_kernel(const __grid_constan
     pdl_trigger();
     pdl_wait();
     const int it = blockIdx.x;
-    attention_item(p, smem, layer, it / p.n_splits, it % p.n_splits);
+    attention_item<false>(p, smem, layer, it / p.n_splits, it % p.n_splits);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -549,6 +573,17 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
             trace[idx] = t;
         }
     };
+    // Ring refills are not issued between the items of a phase (their address arithmetic and 8 cp.async per
+    // thread cost ~0.5 us on the critical path each): they are deferred to `flush_refills`, which runs behind the
+    // latency of the next grid barrier.  Every item still gets exactly one commit group, in consumption order.
+    int deferred = 0;
+    auto flush_refills = [&]() {
+        for (; deferred > 0; --deferred) {
+            const int slot = (consumed - deferred) % SLOTS;
+            if (seq_normalize(p, pre)) { prefetch_item(p, smem, slot, pre); ++pre.k; }
+            cp_async_commit();
+        }
+    };
     auto run_phase = [&](int step, int pidx) {
         int type = seq_type(p, pidx), layer = seq_layer(pidx);
         int items = phase_items(p, type);
@@ -569,19 +604,15 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
                 }
                 staged_ks = ks;
             }
-            const bool tr = type == PH_GU && k < 2;
-            if (tr) stamp(step, layer, 11 + k * 4);
-            cp_async_wait<SLOTS - 1>();   // this thread's chunks of the oldest outstanding item have landed
-            if (tr) stamp(step, layer, 12 + k * 4);
+            if (deferred >= SLOTS) flush_refills();   // more items than ring slots in one phase: refill now
+            cp_async_wait<0>();                       // every outstanding item (issued one phase or more ago) has landed
             gemv_item<MT>(p, smem, consumed % SLOTS, type, layer, item, step, consumed & 1);
-            if (tr) stamp(step, layer, 13 + k * 4);
-            // refill the slot just consumed with the next item of the sequence (any later phase / layer / step)
-            if (seq_normalize(p, pre)) { prefetch_item(p, smem, consumed % SLOTS, pre); ++pre.k; }
-            cp_async_commit();
-            if (tr) stamp(step, layer, 14 + k * 4);
             ++consumed;
+            ++deferred;
         }
     };
+    auto nothing = [&]() {};
+    (void)nothing;
 
     const int n_att_items = p.B * p.n_splits;
     for (int step = 0; step < p.n_steps; ++step) {
@@ -602,37 +633,41 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
                 p.e1[i] = __float2bfloat16_rn(v);
             }
         }
-        grid_barrier(p.barrier, target);
+        grid_barrier(p.barrier, target, flush_refills);
         run_phase(step, 0);   // ENC2
-        grid_barrier(p.barrier, target);
+        grid_barrier(p.barrier, target, flush_refills);
         run_phase(step, 1);   // ENC3
-        grid_barrier(p.barrier, target);
+        grid_barrier(p.barrier, target, flush_refills);
         for (int l = 0; l < p.n_layers; ++l) {
             stamp(step, l, 0);
             run_phase(step, 2 + 4 * l);          // QKV
             stamp(step, l, 1);
-            grid_barrier(p.barrier, target);
+            // attention CTAs start fetching their cached K / V tile behind the barrier (the tile buffers alias the
+            // GEMV staging area, which is idle after the barrier's leading __syncthreads)
+            grid_barrier(p.barrier, target, [&]() {
+                flush_refills();
+                if ((int)blockIdx.x < n_att_items) attention_prefetch_kv(p, smem, l, blockIdx.x / p.n_splits, blockIdx.x % p.n_splits);
+            });
             stamp(step, l, 2);
-            for (int it = blockIdx.x; it < n_att_items; it += gridDim.x)
-                attention_item(p, smem, l, it / p.n_splits, it % p.n_splits);
+            if ((int)blockIdx.x < n_att_items) attention_item<true>(p, smem, l, blockIdx.x / p.n_splits, blockIdx.x % p.n_splits);
             stamp(step, l, 3);
-            grid_barrier(p.barrier, target);
+            grid_barrier(p.barrier, target, flush_refills);
             stamp(step, l, 4);
             run_phase(step, 2 + 4 * l + 1);      // O
             stamp(step, l, 5);
-            grid_barrier(p.barrier, target);
+            grid_barrier(p.barrier, target, flush_refills);
             stamp(step, l, 6);
             run_phase(step, 2 + 4 * l + 2);      // GU
             stamp(step, l, 7);
-            grid_barrier(p.barrier, target);
+            grid_barrier(p.barrier, target, flush_refills);
             stamp(step, l, 8);
             run_phase(step, 2 + 4 * l + 3);      // D
             stamp(step, l, 9);
-            grid_barrier(p.barrier, target);
+            grid_barrier(p.barrier, target, flush_refills);
             stamp(step, l, 10);
         }
         run_phase(step, 2 + 4 * p.n_layers);     // DEC (+ Euler; last step also clamps into out)
-        grid_barrier(p.barrier, target);
+        grid_barrier(p.barrier, target, flush_refills);
     }
     cp_async_wait<0>();
 }
@@ -649,6 +684,7 @@ int denoise_mega_supported(const pz_config &c, int B) {
     if (c.act_hidden != KI || c.act_inter % KI || (c.n_heads * 256) % KI) return 0;
     if (c.n_layers > MAX_LAYERS || c.action_dim > 8) return 0;
     if ((c.s_vlm + c.cond_steps + c.horizon + KT - 1) / KT > 8) return 0;
+    if (B * ((c.s_vlm + c.cond_steps + c.horizon + KT - 1) / KT) > 128) return 0;   // one attention item per CTA
     return 1;
 }
 
