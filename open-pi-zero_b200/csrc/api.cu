@@ -482,9 +482,9 @@ static int action_layers(pz_handle *h, Workspace &ws, const int32_t *valid_len, 
         if (n_splits == 0 && fused_rope && decode_attention_supported(c) &&
             a.scratch_bytes >= (size_t)B * ((S_c + Hz + 63) / 64) * nh * Hz * (hd + 2) * sizeof(float)) {
             // one CTA per (sample, key tile), all 8 warps busy, RoPE fused; then the combine kernel
-            int ns = launch_decode_attention(c, w, ws.qkva, ws.kcache, ws.vcache, B, valid_len, ws.att_scratch, l, B, st);
+            int ns = launch_decode_attention(c, w, ws.qkva, ws.kcache, ws.vcache, B, valid_len, ws.att_scratch, l, B,
+                                             ws.atta, (long)Hz * qd, qd, st);
             if (ns < 0) return fail(h, ns, "decode attention launch failed");
-            launch_attn_combine(a, ns, st);
         } else if (n_splits == 0) {
             PZ_TRY(Ops<T>::attention(h, a, st));
         }

@@ -101,6 +101,17 @@ PZ_DEVINL void ldsm_x4_t(uint32_t (&r)[4], const void *p) {
 }
 PZ_DEVINL float tanh_fast_acc(float y) { float t = __expf(2.f * y); return 1.f - __fdividef(2.f, t + 1.f); }
 
+// fine-grained trace (CTA 0, thread 0, one layer of one step): tools/stage_times.py prints it
+__device__ unsigned long long *g_trace_ptr;
+__device__ int g_trace_on;
+PZ_DEVINL void tstamp(int idx) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_trace_on) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_trace_ptr[idx] = t;
+    }
+}
+
 // ---- grid barrier: monotonic arrive counter, acquire spin, bounded (never hangs the GPU) ----
 template <typename F>
 PZ_DEVINL void grid_barrier(unsigned int *bar, unsigned int &target, F between) {
@@ -336,45 +347,43 @@ PZ_DEVINL void stage_copy(const MegaParams &p, uint8_t *smem, const bf16 *src, i
     __syncthreads();
 }
 PZ_DEVINL void stage_combine(const MegaParams &p, uint8_t *smem, int ks) {
-    // softmax-combine of the split-key attention partials for heads [4*ks, 4*ks+4) (k range ks*1024..):
-    // A[m][k] = sum_s w_s o_s[k],  w_s = exp(m_s - max) / sum_s l_s exp(m_s - max).
-    // Every thread fetches the (m_s, l_s) pairs together with its o_s chunks -- one L2 round trip, no
-    // shared-memory exchange -- and recomputes the few weights in registers.
+    // combine of the split-key attention partials for heads [4*ks, 4*ks+4) (k range ks*1024..):
+    // A[m][k] = sum_s o_s[k] / sum_s l_s   (no maxima: see attention_item).  One L2 round trip for the
+    // denominators, one for the bf16 partials.
     bf16 *As = reinterpret_cast<bf16 *>(smem + SM_ASTAGE);
-    const int rows_total = p.nh * p.H, stride = 256 + 2, hpk = KI / 256;
-    const long split_stride = (long)rows_total * stride;
+    float *inv = reinterpret_cast<float *>(smem + SM_CW);   // [m][head 0..3 of this k slice]
+    const int rows_total = p.nh * p.H, hpk = KI / 256;
+    const uint32_t *po = reinterpret_cast<const uint32_t *>(p.partials);
+    const float *pl = p.partials + (long)p.B * p.n_splits * rows_total * 128;
+    if (threadIdx.x < p.M * hpk) {
+        const int m = threadIdx.x / hpk, hh = ks * hpk + threadIdx.x % hpk;
+        const int b = m / p.H, tok = m % p.H;
+        float l = 0.f;
+        for (int sp = 0; sp < p.n_splits; ++sp) l += __ldcg(pl + ((long)b * p.n_splits + sp) * rows_total + hh * p.H + tok);
+        inv[threadIdx.x] = l > 0.f ? 1.f / l : 0.f;
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < p.M * (KI / 8); i += NT) {
         int m = i / (KI / 8), c = i % (KI / 8);
         int hl = (c * 8) / 256, d = (c * 8) % 256, hh = ks * hpk + hl;
         int b = m / p.H, tok = m % p.H;
-        const float *row = p.partials + ((long)b * p.n_splits * rows_total + (hh * p.H + tok)) * stride;
-        float2 v[8][4];
-        float ms[8], ls[8];
+        const uint32_t *row = po + (((long)b * p.n_splits) * rows_total + (hh * p.H + tok)) * 128 + (d >> 1);
+        const long split_stride = (long)rows_total * 128;
+        uint4 v[8];
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp)
+            v[sp] = sp < p.n_splits ? __ldcg(reinterpret_cast<const uint4 *>(row + sp * split_stride)) : make_uint4(0, 0, 0, 0);
+        float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int sp = 0; sp < 8; ++sp) {
-            bool ok = sp < p.n_splits;
-            const float *q = row + sp * split_stride;
-            ms[sp] = ok ? __ldcg(q + 256) : -INFINITY;
-            ls[sp] = ok ? __ldcg(q + 257) : 0.f;
+            uint32_t w[4] = {v[sp].x, v[sp].y, v[sp].z, v[sp].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                v[sp][j] = ok ? __ldcg(reinterpret_cast<const float2 *>(q + d) + j) : make_float2(0.f, 0.f);
+            for (int j = 0; j < 4; ++j) { o8[2 * j] += bf16lo(w[j]); o8[2 * j + 1] += bf16hi(w[j]); }
         }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int sp = 0; sp < 8; ++sp) mx = fmaxf(mx, ms[sp]);
-        float l = 0.f, o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int sp = 0; sp < 8; ++sp) {
-            float wgt = (ms[sp] == -INFINITY) ? 0.f : __expf(ms[sp] - mx);
-            l += ls[sp] * wgt;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { o8[2 * j] += v[sp][j].x * wgt; o8[2 * j + 1] += v[sp][j].y * wgt; }
-        }
-        float inv = l > 0.f ? 1.f / l : 0.f;
+        const float wgt = inv[m * hpk + hl];
         *reinterpret_cast<uint4 *>(As + m * LDA + c * 8) =
-            make_uint4(pack_bf16x2(o8[0] * inv, o8[1] * inv), pack_bf16x2(o8[2] * inv, o8[3] * inv),
-                       pack_bf16x2(o8[4] * inv, o8[5] * inv), pack_bf16x2(o8[6] * inv, o8[7] * inv));
+            make_uint4(pack_bf16x2(o8[0] * wgt, o8[1] * wgt), pack_bf16x2(o8[2] * wgt, o8[3] * wgt),
+                       pack_bf16x2(o8[4] * wgt, o8[5] * wgt), pack_bf16x2(o8[6] * wgt, o8[7] * wgt));
     }
     __syncthreads();
 }
@@ -422,9 +431,8 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
     bf16 *sQ = reinterpret_cast<bf16 *>(smem + SM_Q);
     bf16 *sK = reinterpret_cast<bf16 *>(smem + SM_K);
     bf16 *sV = reinterpret_cast<bf16 *>(smem + SM_V);
-    float(*sS)[KT + 1] = reinterpret_cast<float(*)[KT + 1]>(smem + SM_S);
+    float(*sRS)[QROWS] = reinterpret_cast<float(*)[QROWS]>(smem + SM_S);   // [4 key groups][row] partial row sums
     bf16 *sP = reinterpret_cast<bf16 *>(smem + SM_P);
-    float(*sML)[2] = reinterpret_cast<float(*)[2]>(smem + SM_ML);
     const int qkvd = (p.nh + 2) * 256, qd = p.nh * 256;
     const int rows_total = p.nh * p.H;
     const int vlen = p.valid_len[b];
@@ -466,6 +474,7 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
     }
     cp_async_wait<0>();   // (also drains this thread's ring prefetches; they are far ahead anyway)
     __syncthreads();
+    tstamp(11);
 
     // S = Q K^T : warp -> (16-row tile mt, 16-key group kg)
     {
@@ -480,31 +489,33 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
             mma_bf16(s[1], qa[0], qa[1], qa[2], qa[3], kb[2], kb[3]);
         }
         const float scale = 0.0625f, cap = 50.f;   // 1/sqrt(256); soft-cap (joint_model.py:139,261-268)
+        // The soft-cap bounds every logit to +-50, so exp() cannot overflow and the softmax needs no running
+        // maximum: P = exp(logit) goes straight to shared memory (bf16) with per-row partial sums; the split-key
+        // partials combine as sum(o) / sum(l) without any rescaling.
+        float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < 2; ++nt) {
+            float pe[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int col = kg * 16 + nt * 8 + 2 * t + (e & 1);
-                int row = mt * 16 + g + (e >> 1) * 8;
                 int j = tile * KT + col;
                 bool vis = (j < vlen) || (j >= p.S_v && j < n_keys);
-                float v = tanh_fast_acc(s[nt][e] * scale * (1.f / cap)) * cap;
-                sS[row][col] = vis ? v : -INFINITY;
+                pe[e] = vis ? __expf(tanh_fast_acc(s[nt][e] * scale * (1.f / cap)) * cap) : 0.f;
             }
+            rs0 += pe[0] + pe[1];
+            rs1 += pe[2] + pe[3];
+            const int col = kg * 16 + nt * 8 + 2 * t;
+            *reinterpret_cast<uint32_t *>(sP + (mt * 16 + g) * (KT + 8) + col) = pack_bf16x2(pe[0], pe[1]);
+            *reinterpret_cast<uint32_t *>(sP + (mt * 16 + g + 8) * (KT + 8) + col) = pack_bf16x2(pe[2], pe[3]);
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        if (t == 0) { sRS[kg][mt * 16 + g] = rs0; sRS[kg][mt * 16 + g + 8] = rs1; }
     }
     __syncthreads();
-    // per-row softmax statistics of this tile; P (bf16) for the PV product
-    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
-        float a = sS[r][lane], c = sS[r][lane + 32];
-        float mx = warp_max(fmaxf(a, c));
-        float ms = (mx == -INFINITY) ? 0.f : mx;
-        float pa = __expf(a - ms), pc = __expf(c - ms);
-        float l = warp_sum(pa + pc);
-        sP[r * (KT + 8) + lane] = __float2bfloat16_rn(pa);
-        sP[r * (KT + 8) + lane + 32] = __float2bfloat16_rn(pc);
-        if (lane == 0) { sML[r][0] = mx; sML[r][1] = l; }
-    }
-    __syncthreads();
+    tstamp(12);
+    tstamp(13);
     // O = P V : warp -> (16-row tile mt, 64-wide slice of d)
     {
         const int mt = warp & 1, dq = warp >> 1;
@@ -523,16 +534,17 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
                 mma_bf16(o[2 * dp + 1], pa[0], pa[1], pa[2], pa[3], vb[2], vb[3]);
             }
         }
-        float *base = p.partials + (((long)b * p.n_splits + tile) * rows_total) * (256 + 2);
+        // partial layout: bf16 pairs o[b][split][row][128] (unnormalised), then fp32 l[b][split][row]
+        uint32_t *po = reinterpret_cast<uint32_t *>(p.partials) + (((long)b * p.n_splits + tile) * rows_total) * 128;
+        float *pl = p.partials + (long)p.B * p.n_splits * rows_total * 128 + ((long)b * p.n_splits + tile) * rows_total;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             int row = mt * 16 + g + rr * 8;
             if (row >= rows_total) continue;
-            float *dst = base + (long)row * (256 + 2);
+            uint32_t *dst = po + (long)row * 128;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float2 *>(dst + dq * 64 + i * 8 + 2 * t) = make_float2(o[i][2 * rr], o[i][2 * rr + 1]);
-            if (dq == 0 && t == 0) { dst[256] = sML[row][0]; dst[257] = sML[row][1]; }
+            for (int i = 0; i < 8; ++i) dst[(dq * 64 + i * 8 + 2 * t) >> 1] = pack_bf16x2(o[i][2 * rr], o[i][2 * rr + 1]);
+            if (dq == 0 && t == 0) pl[row] = (sRS[0][row] + sRS[1][row]) + (sRS[2][row] + sRS[3][row]);
         }
     }
     __syncthreads();
@@ -548,6 +560,33 @@ __global__ void __launch_bounds__(NT, 2) decode_attn_kernel(const __grid_constan
     pdl_wait();
     const int it = blockIdx.x;
     attention_item<false>(p, smem, layer, it / p.n_splits, it % p.n_splits);
+}
+
+// combine of the stand-alone decode attention's partials: one warp per (sample, query row) -> bf16 attention output
+__global__ void __launch_bounds__(128) decode_combine_kernel(const __grid_constant__ MegaParams p, bf16 *out, long out_batch_stride,
+                                                             int out_row_stride) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int rows_total = p.nh * p.H;
+    const long wid = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wid >= (long)p.B * rows_total) return;
+    const int b = wid / rows_total, row = wid % rows_total;
+    const uint32_t *po = reinterpret_cast<const uint32_t *>(p.partials) + (((long)b * p.n_splits) * rows_total + row) * 128;
+    const float *pl = p.partials + (long)p.B * p.n_splits * rows_total * 128 + (long)b * p.n_splits * rows_total + row;
+    float l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sp = 0; sp < p.n_splits; ++sp) {
+        l += pl[(long)sp * rows_total];
+        uint4 v = *reinterpret_cast<const uint4 *>(po + (long)sp * rows_total * 128 + lane * 4);   // dims 8*lane .. 8*lane+7
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16lo(w[j]); acc[2 * j + 1] += bf16hi(w[j]); }
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const int h = row / p.H, tok = row % p.H;
+    bf16 *dst = out + b * out_batch_stride + (long)tok * out_row_stride + h * 256 + lane * 8;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                                                 pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -566,8 +605,10 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
     }
     int consumed = 0;
     unsigned long long *trace = reinterpret_cast<unsigned long long *>(p.barrier + 32);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g_trace_ptr = trace; g_trace_on = 0; }
     auto stamp = [&](int step, int l, int idx) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && step == 1 && l == 1) {
+            g_trace_on = (idx < 10);   // sub-phase stamps (slots 11..) only inside the traced layer
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             trace[idx] = t;
@@ -597,7 +638,7 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
                     case PH_ENC2: stage_copy(p, smem, p.e1, p.A, 0); break;
                     case PH_ENC3: stage_copy(p, smem, p.z, p.A, 0); break;
                     case PH_QKV: stage_norm(p, smem, p.layers[layer].norm_in); break;
-                    case PH_O: stage_combine(p, smem, ks); break;
+                    case PH_O: stage_combine(p, smem, ks); tstamp(14); break;
                     case PH_GU: stage_norm(p, smem, p.layers[layer].norm_post); break;
                     case PH_D: stage_copy(p, smem, p.mlp, p.AI, ks * KI); break;
                     default: stage_norm(p, smem, p.final_norm); break;
@@ -690,7 +731,7 @@ int denoise_mega_supported(const pz_config &c, int B) {
 
 int launch_decode_attention(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache,
                             const void *vcache, int batch_total, const int32_t *valid_len, float *partials, int layer,
-                            int B, cudaStream_t st) {
+                            int B, void *out, long out_batch_stride, int out_row_stride, cudaStream_t st) {
     static bool attr_set = false;
     constexpr int smem = SM_ATT_END - SM_U + 256;
     if (!attr_set) {
@@ -708,6 +749,10 @@ int launch_decode_attention(const pz_config &c, const pz_weights &w, const void 
     p.kv_batch_stride = (long)p.S_c * 256; p.kv_layer_stride = (long)batch_total * p.kv_batch_stride;
     p.valid_len = valid_len; p.partials = partials; p.qkv = (bf16 *)const_cast<void *>(qkv);
     launch_k(decode_attn_kernel, dim3(B * p.n_splits), dim3(NT), smem, st, p, layer);
+    // split-key partials -> attention output [B][horizon][n_heads * 256]
+    const long warps = (long)B * p.nh * p.H;
+    launch_k(decode_combine_kernel, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, st, p, (bf16 *)out, out_batch_stride,
+             out_row_stride);
     return p.n_splits;
 }
 

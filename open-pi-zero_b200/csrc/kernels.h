@@ -85,9 +85,10 @@ int launch_denoise_mega2(const pz_config &c, const pz_weights &w, const pz_mix_l
                          int B, cudaStream_t st, const char **err);
 
 // stand-alone decode attention (one CTA per (sample, 64-key tile), RoPE fused, 8 warps): writes split-key
-// partials [B][splits][heads*horizon][258]; returns the number of splits (or < 0 on error)
+// partials (bf16 o [B][splits][heads*horizon][256], then fp32 l) and combines them into `out` [B][horizon][heads*256];
+// returns the number of splits (or < 0 on error)
 int decode_attention_supported(const pz_config &c);
 int launch_decode_attention(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache,
                             const void *vcache, int batch_total, const int32_t *valid_len, float *partials, int layer,
-                            int B, cudaStream_t st);
+                            int B, void *out, long out_batch_stride, int out_row_stride, cudaStream_t st);
 int launch_attn_combine(const AttnArgs &a, int n_splits, cudaStream_t st);

@@ -60,3 +60,6 @@ if raw[0] > 0:
     print("mega trace (us):", " ".join(f"{n}={(raw[i+1]-raw[i])/1e3:.2f}" for i, n in enumerate(names2)), f"layer={(raw[10]-raw[0])/1e3:.2f}")
     print("GU items (us): stage->", f"{(raw[11]-raw[6])/1e3:.2f}", " ".join(
         f"[wait={(raw[12+4*k]-raw[11+4*k])/1e3:.2f} gemv={(raw[13+4*k]-raw[12+4*k])/1e3:.2f} prefetch={(raw[14+4*k]-raw[13+4*k])/1e3:.2f}]" for k in range(2)))
+    if raw[11] > 0:
+        print(f"  attention (us): stage={(raw[11]-raw[2])/1e3:.2f} S={(raw[12]-raw[11])/1e3:.2f} softmax={(raw[13]-raw[12])/1e3:.2f} PV+store={(raw[3]-raw[13])/1e3:.2f};"
+              f"  o_proj: combine-stage={(raw[14]-raw[4])/1e3:.2f} item={(raw[5]-raw[14])/1e3:.2f}")
