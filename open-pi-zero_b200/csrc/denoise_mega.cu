@@ -186,6 +186,11 @@ PZ_DEVINL ItemAddr item_addr(const MegaParams &p, int type, int layer, int item,
         int c = nb * 8 + g;
         r0 = (long)(c / PZ_GU_BLOCK) * (2 * PZ_GU_BLOCK) + (c % PZ_GU_BLOCK);
         r1 = r0 + PZ_GU_BLOCK;
+    } else if (type == PH_QKV) {
+        // item = (head nb / 16, dims d0 = 8 * (nb % 16)): rows d0.. and 128 + d0.. -- the two halves a rotary pair
+        // lives in, so the epilogue rotates q and k (model/utils.py:4-16) and attention stages plain copies
+        r0 = (long)(nb >> 4) * 256 + (nb & 15) * 8 + g;
+        r1 = r0 + 128;
     } else {
         r0 = nb * 16 + g; r1 = r0 + 8;
         if (r0 >= nrows) r0 = nrows - 1;
@@ -255,6 +260,7 @@ PZ_DEVINL void gemv_item(const MegaParams &p, uint8_t *smem, int slot, int type,
         for (int w = 0; w < NW; ++w) {
             v += red[w][r][m];
             if (type == PH_GU) v2 += red[w][r + 8][m];
+            if (type == PH_QKV) v2 += red[w][r ^ 8][m];   // the rotary partner (dim d +- 128)
         }
         switch (type) {
             case PH_ENC2: {   // linear_2 (action half) + per-step time bias, SiLU (vla/modules.py:50-52)
@@ -265,9 +271,15 @@ PZ_DEVINL void gemv_item(const MegaParams &p, uint8_t *smem, int slot, int type,
                 int n = item * 16 + r;
                 p.xa[m * p.A + n] = (v + p.enc_b3[n]) * sqrtf((float)p.A);
             } break;
-            case PH_QKV: {
-                int n = item * 16 + r;
-                p.qkv[m * ((p.nh + 2) * 256) + n] = __float2bfloat16_rn(v);
+            case PH_QKV: {   // q / k rows leave rotated (fp32, table row S_p + token: positions 2.., pizero.py:312-318)
+                const int head = item >> 4, d = (item & 15) * 8 + (r & 7);
+                float o = v;
+                if (head <= p.nh) {
+                    const long ti = (long)(p.S_p + m % p.H) * 128 + d;
+                    const float cs = __ldg(p.rope_cos + ti), sn = __ldg(p.rope_sin + ti);
+                    o = (r < 8) ? v * cs - v2 * sn : v * cs + v2 * sn;
+                }
+                p.qkv[m * ((p.nh + 2) * 256) + head * 256 + (r < 8 ? d : 128 + d)] = __float2bfloat16_rn(o);
             } break;
             case PH_O: case PH_D: {
                 int n = (item & (NB_A - 1)) * 16 + r;
@@ -355,32 +367,32 @@ PZ_DEVINL void stage_combine(const MegaParams &p, uint8_t *smem, int ks) {
     const int rows_total = p.nh * p.H, hpk = KI / 256;
     const uint32_t *po = reinterpret_cast<const uint32_t *>(p.partials);
     const float *pl = p.partials + (long)p.B * p.n_splits * rows_total * 128;
-    if (threadIdx.x < p.M * hpk) {
-        const int m = threadIdx.x / hpk, hh = ks * hpk + threadIdx.x % hpk;
-        const int b = m / p.H, tok = m % p.H;
-        float l = 0.f;
-        for (int sp = 0; sp < p.n_splits; ++sp) l += __ldcg(pl + ((long)b * p.n_splits + sp) * rows_total + hh * p.H + tok);
-        inv[threadIdx.x] = l > 0.f ? 1.f / l : 0.f;
-    }
-    __syncthreads();
+    (void)inv;
     for (int i = threadIdx.x; i < p.M * (KI / 8); i += NT) {
         int m = i / (KI / 8), c = i % (KI / 8);
         int hl = (c * 8) / 256, d = (c * 8) % 256, hh = ks * hpk + hl;
         int b = m / p.H, tok = m % p.H;
         const uint32_t *row = po + (((long)b * p.n_splits) * rows_total + (hh * p.H + tok)) * 128 + (d >> 1);
+        const float *lrow = pl + (long)b * p.n_splits * rows_total + hh * p.H + tok;
         const long split_stride = (long)rows_total * 128;
+        // denominators and partials in the same L2 round trip (every thread sums its row's few l values itself)
         uint4 v[8];
+        float ls[8];
 #pragma unroll
-        for (int sp = 0; sp < 8; ++sp)
-            v[sp] = sp < p.n_splits ? __ldcg(reinterpret_cast<const uint4 *>(row + sp * split_stride)) : make_uint4(0, 0, 0, 0);
-        float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sp = 0; sp < 8; ++sp) {
+            const bool ok = sp < p.n_splits;
+            v[sp] = ok ? __ldcg(reinterpret_cast<const uint4 *>(row + sp * split_stride)) : make_uint4(0, 0, 0, 0);
+            ls[sp] = ok ? __ldcg(lrow + (long)sp * rows_total) : 0.f;
+        }
+        float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, l = 0.f;
 #pragma unroll
         for (int sp = 0; sp < 8; ++sp) {
             uint32_t w[4] = {v[sp].x, v[sp].y, v[sp].z, v[sp].w};
+            l += ls[sp];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { o8[2 * j] += bf16lo(w[j]); o8[2 * j + 1] += bf16hi(w[j]); }
         }
-        const float wgt = inv[m * hpk + hl];
+        const float wgt = l > 0.f ? 1.f / l : 0.f;
         *reinterpret_cast<uint4 *>(As + m * LDA + c * 8) =
             make_uint4(pack_bf16x2(o8[0] * wgt, o8[1] * wgt), pack_bf16x2(o8[2] * wgt, o8[3] * wgt),
                        pack_bf16x2(o8[4] * wgt, o8[5] * wgt), pack_bf16x2(o8[6] * wgt, o8[7] * wgt));
@@ -425,7 +437,7 @@ PZ_DEVINL void attention_prefetch_kv(const MegaParams &p, uint8_t *smem, int lay
     cp_async_commit();
 }
 
-template <bool KV_PREFETCHED = false>
+template <bool KV_PREFETCHED = false, bool ROPED = false>   // ROPED: q / k rows of p.qkv are already rotated
 PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int b, int tile) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     bf16 *sQ = reinterpret_cast<bf16 *>(smem + SM_Q);
@@ -453,25 +465,41 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
         cp_async16_zfill(sV + r * LDQ + c * 8, vsrc, cached || fresh);
     }
     cp_async_commit();
-    // Q (and fresh keys) with RoPE: row i = (head i / H, token i % H), position S_p + token (table row)
+    // Q (and fresh keys): row i = (head i / H, token i % H); RoPE at position S_p + token (table row) unless the
+    // producer already applied it
     for (int i = tid; i < QROWS * 16; i += NT) {
         int r = i >> 4, c = i & 15;
         bf16 *dst = sQ + r * LDQ;
         if (r < rows_total) {
             int h = r / p.H, tok = r % p.H;
-            rope_pair(p, dst, qkv_b + (long)tok * qkvd + h * 256, c, p.S_p + tok);
+            const bf16 *src = qkv_b + (long)tok * qkvd + h * 256;
+            if (ROPED) {   // plain asynchronous copies: everything of this staging is in flight at once
+                cp_async16(dst + c * 8, src + c * 8);
+                cp_async16(dst + 128 + c * 8, src + 128 + c * 8);
+            } else {
+                rope_pair(p, dst, src, c, p.S_p + tok);
+            }
         } else {
             *reinterpret_cast<uint4 *>(dst + c * 8) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4 *>(dst + 128 + c * 8) = make_uint4(0, 0, 0, 0);
         }
     }
-    {   // fresh (action) keys of this step: raw projections, rotated while staged
+    {   // fresh (action) keys of this step
         int first = p.S_c - tile * KT;   // tile-local row of the first fresh key
         for (int i = tid; i < p.H * 16; i += NT) {
             int r = first + (i >> 4), c = i & 15;
-            if (r >= 0 && r < KT) rope_pair(p, sK + r * LDQ, qkv_b + (long)(i >> 4) * qkvd + qd, c, p.S_p + (i >> 4));
+            if (r >= 0 && r < KT) {
+                const bf16 *src = qkv_b + (long)(i >> 4) * qkvd + qd;
+                if (ROPED) {
+                    cp_async16(sK + r * LDQ + c * 8, src + c * 8);
+                    cp_async16(sK + r * LDQ + 128 + c * 8, src + 128 + c * 8);
+                } else {
+                    rope_pair(p, sK + r * LDQ, src, c, p.S_p + (i >> 4));
+                }
+            }
         }
     }
+    cp_async_commit();
     cp_async_wait<0>();   // (also drains this thread's ring prefetches; they are far ahead anyway)
     __syncthreads();
     tstamp(11);
@@ -559,7 +587,7 @@ __global__ void __launch_bounds__(NT, 2) decode_attn_kernel(const __grid_constan
     pdl_trigger();
     pdl_wait();
     const int it = blockIdx.x;
-    attention_item<false>(p, smem, layer, it / p.n_splits, it % p.n_splits);
+    attention_item<false, false>(p, smem, layer, it / p.n_splits, it % p.n_splits);
 }
 
 // combine of the stand-alone decode attention's partials: one warp per (sample, query row) -> bf16 attention output
@@ -690,7 +718,7 @@ __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_consta
                 if ((int)blockIdx.x < n_att_items) attention_prefetch_kv(p, smem, l, blockIdx.x / p.n_splits, blockIdx.x % p.n_splits);
             });
             stamp(step, l, 2);
-            if ((int)blockIdx.x < n_att_items) attention_item<true>(p, smem, l, blockIdx.x / p.n_splits, blockIdx.x % p.n_splits);
+            if ((int)blockIdx.x < n_att_items) attention_item<true, true>(p, smem, l, blockIdx.x / p.n_splits, blockIdx.x % p.n_splits);
             stamp(step, l, 3);
             grid_barrier(p.barrier, target, flush_refills);
             stamp(step, l, 4);
