@@ -223,17 +223,20 @@ class PiZero(nn.Module):
         self.joint_model.mixtures._modules["proprio"] = self.joint_model.mixtures._modules["action"]
         self._tied = True
         self._packed_key = None
+        self.__dict__.pop("_param_list", None)
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         # checkpoints written from a torch.compile'd model carry "_orig_mod." (eval.py:184-188)
         sd = {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
         out = super().load_state_dict(sd, strict=strict, assign=assign)
         self._packed_key = None
+        self.__dict__.pop("_param_list", None)
         return out
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         self._packed_key = None
+        self.__dict__.pop("_param_list", None)
         return out
 
     # ------------------------------------------------------ input preparation
@@ -266,8 +269,19 @@ class PiZero(nn.Module):
 
     # ---------------------------------------------------------------- packing
     def _param_key(self):
-        ps = list(self.parameters())
-        return (ps[0].dtype, ps[0].device, sum(p._version for p in ps), ps[0].data_ptr(), self._tied,
+        """Cheap staleness key of the packed weights, evaluated on every call (it is on the bs=1 latency
+        path: walking all 938 parameters cost ~0.5 ms).  `.to()` / `load_state_dict` / `_apply` drop the cached
+        parameter list, so moves and reloads are always seen; in-place edits are seen through the version
+        counters of a fixed sample of parameters (all of them with PZ_CHECK_INPUTS=1) -- after editing single
+        weights in place call `pack(force=True)`."""
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = list(self.parameters())
+            step = max(1, len(ps) // 16)
+            self.__dict__["_param_list"] = ps
+            self.__dict__["_param_sample"] = ps[::step] + [ps[-1]]
+        sample = ps if os.environ.get("PZ_CHECK_INPUTS") == "1" else self.__dict__["_param_sample"]
+        return (ps[0].dtype, ps[0].device, sum(p._version for p in sample), ps[0].data_ptr(), self._tied,
                 self._flags)
 
     @torch.no_grad()
@@ -448,6 +462,7 @@ class PiZero(nn.Module):
         for mod in self.modules():
             for name in list(mod._parameters):
                 mod._parameters[name] = nn.Parameter(torch.empty(0, device="cpu"), requires_grad=False)
+        self.__dict__.pop("_param_list", None)
         self._packed_key = self._param_key()
 
     def _ensure_workspace(self, batch: int):
