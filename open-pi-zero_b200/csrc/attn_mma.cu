@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int ROWS_PER_CTA = 64, KEY_TILE = 64, NTHREADS = 128;
+constexpr int KEY_TILE = 64;
 
 PZ_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 PZ_DEVINL void cp_async16(void *dst, const void *src, bool valid) {
@@ -56,8 +56,11 @@ enum { CLS_ALL = 0, CLS_VLM = 1, CLS_PROPRIO = 2, CLS_ACTION = 3 };
 
 // PRELOAD: all keys fit in shared memory (SigLIP: 256 keys x head_dim 72) -- K and V are staged once and
 // the tile loop runs without loads or block barriers.
-template <int HD, bool PRELOAD = false>   // true head_dim; HDP = padded to a multiple of 16
-__global__ void __launch_bounds__(NTHREADS, 2) attn_mma_kernel(AttnArgs a, int cls, int mqa, int split) {
+// NW warps x 16 query rows per CTA.  The preload variant takes 16 warps (256 rows) when a (sample, head) has that
+// many rows (SigLIP: 256 patches): K and V are then read once per (sample, head) instead of once per 64 rows.
+template <int HD, bool PRELOAD = false, int NW = 4>   // true head_dim; HDP = padded to a multiple of 16
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) attn_mma_kernel(AttnArgs a, int cls, int mqa, int split) {
+    constexpr int ROWS_PER_CTA = NW * 16, NTHREADS = NW * 32;
     constexpr int HDP = (HD + 15) / 16 * 16;
     constexpr int LDS = HDP + 8;            // +16 B per row: conflict-free ldmatrix
     constexpr int CHUNKS = HD / 8;          // 16-byte chunks of real data per row
@@ -388,6 +391,7 @@ template <int HD>
 int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_only = 0) {
     constexpr int HDP = (HD + 15) / 16 * 16;
     constexpr int LDS = HDP + 8;
+    constexpr int ROWS_PER_CTA = 64, NTHREADS = 128;   // default: 4 warps
     size_t smem = (size_t)(ROWS_PER_CTA + 2 * KEY_TILE) * LDS * sizeof(bf16);
     static bool attr_set = false;
     if (!attr_set) {
@@ -416,6 +420,22 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_on
     dim3 grid((rows_total + ROWS_PER_CTA - 1) / ROWS_PER_CTA, mqa ? 1 : a.n_heads, a.batch);
     if constexpr (HD <= 128) {
         int kv_rows = (a.s_cache + a.n_fresh + KEY_TILE - 1) / KEY_TILE * KEY_TILE;
+        // (only when that still leaves a few CTAs per SM: at bs=1 the 64-row CTAs spread better)
+        if (cls == CLS_ALL && rows_total % 256 == 0 && (long)(rows_total / 256) * (mqa ? 1 : a.n_heads) * a.batch >= 296) {
+            // all rows of a (sample, head) in one 16-warp CTA
+            size_t smem_big = (size_t)(256 + 2 * kv_rows) * LDS * sizeof(bf16);
+            if (smem_big <= 200 * 1024) {
+                static bool attr3 = false;
+                if (!attr3) {
+                    if (cudaFuncSetAttribute(attn_mma_kernel<HD, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+                        return PZ_ERR_CUDA;
+                    attr3 = true;
+                }
+                dim3 grid16(rows_total / 256, mqa ? 1 : a.n_heads, a.batch);
+                launch_k(attn_mma_kernel<HD, true, 16>, dim3(grid16), dim3(512), smem_big, st, a, cls, mqa, 0);
+                return 0;
+            }
+        }
         size_t smem_all = (size_t)(ROWS_PER_CTA + 2 * kv_rows) * LDS * sizeof(bf16);
         if (cls == CLS_ALL && smem_all <= 110 * 1024) {
             static bool attr2 = false;
