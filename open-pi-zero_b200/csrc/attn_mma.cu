@@ -11,6 +11,8 @@
 //
 // CTA = 4 warps x 16 query rows; keys in tiles of 64; cp.async staging, ldmatrix
 // fragments, mma.sync.m16n8k16.  (<1 % of the path's FLOPs: 11.3 of 1268 GFLOP.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -445,6 +447,23 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_on
                 attr2 = true;
             }
             launch_k(attn_mma_kernel<HD, true>, dim3(grid), dim3(NTHREADS), smem_all, st, a, cls, mqa, 0);
+            return 0;
+        }
+    }
+    if constexpr (HD == 256) {
+        // 128 query rows per CTA (K/V tiles read half as often) once the batch fills the machine with such CTAs
+        // (59.4 -> 58.9 ms on the bs=64 prefix pass); PZ_ATTN_NW=4 forces the 64-row CTAs
+        static const int nw = [] { const char *e = getenv("PZ_ATTN_NW"); return e ? atoi(e) : 8; }();
+        if (nw == 8 && rows_total >= 1024 && a.batch >= 16) {
+            size_t smem8 = (size_t)(128 + 2 * KEY_TILE) * LDS * sizeof(bf16);
+            static bool attr8 = false;
+            if (!attr8) {
+                if (cudaFuncSetAttribute(attn_mma_kernel<HD, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8) != cudaSuccess)
+                    return PZ_ERR_CUDA;
+                attr8 = true;
+            }
+            dim3 grid8((rows_total + 127) / 128, mqa ? 1 : a.n_heads, a.batch);
+            launch_k(attn_mma_kernel<HD, false, 8>, dim3(grid8), dim3(256), smem8, st, a, cls, mqa, 0);
             return 0;
         }
     }
