@@ -113,3 +113,22 @@ def test_synthetic_inputs_follow_processor_layout():
     assert vl.min() >= 257 + 4 and vl.max() <= 276 and len(set(vl.tolist())) > 1
     for b in range(8):
         assert (ids[b, int(vl[b]):] == 0).all() and (ids[b, : int(vl[b])] != 0).all()
+
+
+def test_packed_weight_staleness_key_is_cheap_and_sees_moves():
+    """The per-call staleness key (on the bs=1 latency path) samples the version counters of a few parameters;
+    `.to()`, `load_state_dict` and in-place edits of a sampled parameter must all change it."""
+    from open_pi_zero_b200.pizero import PiZero
+    d = SMALL
+    m = PiZero(pz.cfg_from_dims(d), init="empty")
+    k0 = m._param_key()
+    assert m._param_key() == k0 and "_param_list" in m.__dict__
+    m.to(torch.bfloat16)
+    assert "_param_list" not in m.__dict__          # dropped by _apply
+    k1 = m._param_key()
+    assert k1 != k0
+    m.load_state_dict(m.state_dict())
+    assert "_param_list" not in m.__dict__
+    with torch.no_grad():
+        next(iter(m.parameters())).add_(1.0)         # the first parameter is always in the sample
+    assert m._param_key() != k1
