@@ -33,7 +33,9 @@ METRIC = "action chunks/s per box (bridge-shape infer_action, bf16); p50 infer_a
 UNIT = "action_chunks/s"
 PER_GPU_BATCH = int(os.environ.get("PZ_BENCH_BATCH", "64"))
 # DRAM bytes of one VLM gate|up GEMM launch at bs=64 (cta_group::2 kernel), from the committed ncu capture
-GATE_UP_DRAM_BYTES = 2.053190e9 + 571.228416e6
+GATE_UP_DRAM_BYTES = 2.091388e9 + 570.776320e6
+# DRAM bytes of the bs=1 sampler launch (10 Euler steps), same file
+MEGA_BS1_DRAM_BYTES = 6.323853e9 + 4.368128e6
 
 
 def measured_peaks():
@@ -272,7 +274,9 @@ def denoise_bs1_roofline(model, dims, device, peaks):
     bytes_per_launch = n_steps * (629.3e6 + 5.11e6)
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
     return dict(bound="hbm", kernel="denoise_mega_kernel (10 Euler steps, persistent cooperative)", achieved=achieved,
-                peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+                peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=MEGA_BS1_DRAM_BYTES,
+                traffic_source="profiles/r01_ncu_full_final.txt (dram read + write of one launch); algorithmic bytes "
+                               f"{bytes_per_launch / 1e9:.3f} GB",
                 avg_launch_ms=ms, launches_timed=reps, kernels_per_launch=int(n_launch),
                 peak_source=peaks["source"] + ", copy bandwidth")
 
@@ -443,7 +447,7 @@ def main():
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm_tc_kernel<256, cta_group::2> (VLM gate|up + GeGLU)", achieved=achieved,
                     peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
-                    traffic=GATE_UP_DRAM_BYTES, traffic_source="profiles/r01_ncu_full_gemm_tc.txt (ncu --set full, "
+                    traffic=GATE_UP_DRAM_BYTES, traffic_source="profiles/r01_ncu_full_final.txt (ncu --set full, "
                     "dram__bytes_read.sum + dram__bytes_write.sum of one launch); algorithmic bytes 785 MB",
                     avg_launch_ms=avg_ms, launches_timed=gu_n,
                     share_of_step=gu_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps, peak_source=peaks["source"] + ", sustained figure")
