@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 3
+#define PZ_ABI_VERSION 4
 
 typedef enum pz_status {
     PZ_OK = 0,
@@ -105,6 +105,10 @@ typedef struct pz_weights {
     const float *rope_vlm_cos, *rope_vlm_sin;      /* [s_vlm, hd/2] fp32, positions 1..s_vlm */
     const float *rope_act_cos, *rope_act_sin;      /* [cond+horizon, hd/2] fp32, positions 1.. */
     int32_t small_k_pad;                /* padded K of enc_w1 / prop_w (>= action_dim, proprio_dim; mult of 8) */
+    /* ABI 4: the time half of the action encoder for an arbitrary per-sample t (training forward, pz_velocity) */
+    const void  *enc_w2t;               /* action_encoder.linear_2.weight[:, :A] -> [A, A] (time half) */
+    const float *enc_b2;                /* action_encoder.linear_2.bias [A] */
+    const float *time_freq;             /* [A/2] fp32: exp(-i ln(time_max_period) / (A/2 - 1)), vla/modules.py:15-19 */
 } pz_weights;
 
 /* Optional capture taps for per-layer parity tests (all fp32 device buffers,
@@ -196,6 +200,29 @@ int pz_joint_prefix(pz_handle *h, const float *d_x_vlm, const float *d_x_proprio
                     void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 int pz_joint_action(pz_handle *h, const float *d_x_action, const int32_t *d_valid_len, float *d_out_hidden,
                     void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+
+/* One evaluation of the velocity field v(psi, t) over the prefix KV that pz_prefill left in the workspace:
+ * time_embedding (vla/modules.py:9-22) + action_encoder (:25-53) + the action expert's layers + final norm +
+ * action_decoder, i.e. the body of the Euler loop (pizero.py:456-479) for an arbitrary per-sample time.
+ *   d_psi fp32 [B, horizon, action_dim]; d_t fp32 [B]; d_v_out fp32 [B, horizon, action_dim] */
+int pz_velocity(pz_handle *h, const int32_t *d_valid_len, const float *d_psi, const float *d_t, float *d_v_out,
+                void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+
+/* PiZero.forward (pizero.py:607-661): the flow-matching training loss, FORWARD VALUE ONLY (no gradients).
+ * The reference runs one joint pass with all three mixtures active under the full block mask and no cache;
+ * vlm / proprio rows never see action keys (pizero.py:271-310), so that equals the prefix pass followed by one
+ * action pass over the cached prefix: the call runs pz_embed_prefix, pz_prefill, psi_t (pizero.py:597-605),
+ * pz_velocity and the mean-squared error.
+ *   d_actions fp32 [B, horizon, action_dim]  x1, the ground-truth chunk
+ *   d_noise   fp32 [B, horizon, action_dim]  x0 (the reference's torch.randn_like, pizero.py:622)
+ *   d_t       fp32 [B]                       flow-matching time per sample (train.py:239-247 samples it)
+ *   sig_min                                  cfg.flow_sig_min (pizero.py:58, default 0.001)
+ *   d_loss    fp32 [1]                       mean((v_psi - (x1 - (1 - sig_min) x0))^2)
+ *   d_v_psi   fp32 [B, horizon, action_dim]  optional (may be NULL): the predicted velocity */
+int pz_flow_matching_loss(pz_handle *h, const int64_t *d_input_ids, const void *d_pixels,
+                          const int32_t *d_valid_len, const float *d_proprio, const float *d_actions,
+                          const float *d_noise, const float *d_t, float sig_min, float *d_loss, float *d_v_psi,
+                          void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);

@@ -43,7 +43,8 @@ class PzWeights(C.Structure):
                 ("enc_w3", vp), ("enc_b3", vp), ("prop_w", vp), ("prop_b", vp),
                 ("dec_w", vp), ("dec_b", vp),
                 ("rope_vlm_cos", vp), ("rope_vlm_sin", vp), ("rope_act_cos", vp),
-                ("rope_act_sin", vp), ("small_k_pad", C.c_int32)]
+                ("rope_act_sin", vp), ("small_k_pad", C.c_int32),
+                ("enc_w2t", vp), ("enc_b2", vp), ("time_freq", vp)]
 
 
 class PzCapture(C.Structure):
@@ -52,7 +53,7 @@ class PzCapture(C.Structure):
                                   "action_preclip")]
 
 
-PZ_ABI_VERSION = 3
+PZ_ABI_VERSION = 4
 PZ_F32, PZ_BF16 = 0, 1
 PZ_FLAG_SIMPLE_KERNELS = 1
 LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
@@ -60,7 +61,8 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_debug_ll_trace_offset", "pz_infer_action", "pz_embed_prefix",
-           "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
+           "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss",
+           "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
 _lib = None
 
@@ -104,6 +106,8 @@ def load(build_if_needed: bool = True):
     lib.pz_denoise.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PzCapture), vp]
     lib.pz_joint_prefix.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_joint_action.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_velocity.argtypes = [hp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_flow_matching_loss.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_launch_count.argtypes = [hp]
     lib.pz_launch_count.restype = C.c_int64
     lib.pz_timing_begin.argtypes = [hp, C.c_int]

@@ -22,6 +22,8 @@ BRIDGE_DIMS = dict(
     cond_steps=1, horizon_steps=4, action_dim=7, proprio_dim=7,
     # sampler (bridge.yaml:85-86)
     num_inference_steps=10, final_action_clip_value=1.0,
+    # flow matching (pizero.py:58: cfg.get("flow_sig_min", 0.001))
+    flow_sig_min=0.001,
     # joint transformer (bridge.yaml:174-179)
     num_layers=18, num_heads=8, num_kv_heads=1, head_dim=256,
     # mixtures (bridge.yaml:96-126)
@@ -87,6 +89,7 @@ def cfg_from_dims(d: dict) -> AttrDict:
         proprio_dim=d["proprio_dim"], final_action_clip_value=d["final_action_clip_value"],
         action_expert_adaptive_mode=None, time_hidden_size=256,
         time_max_period=d["time_max_period"], num_images=d.get("num_images", 1),
+        flow_sig_min=d.get("flow_sig_min", 0.001),
         mixture=mixture,
         vision=dict(config=dict(hidden_size=d["vit_hidden"], intermediate_size=d["vit_inter"],
                                 num_hidden_layers=d["vit_layers"],
@@ -142,6 +145,7 @@ def dims_from_cfg(cfg) -> dict:
         action_dim=cfg["action_dim"], proprio_dim=cfg["proprio_dim"],
         num_inference_steps=cfg["num_inference_steps"],
         final_action_clip_value=cfg["final_action_clip_value"],
+        flow_sig_min=float(_g(cfg, "flow_sig_min", 0.001)),
         num_layers=joint["num_hidden_layers"], num_heads=joint["num_attention_heads"],
         num_kv_heads=joint["num_key_value_heads"], head_dim=joint["head_dim"],
         vlm_hidden=mixture["vlm"]["hidden_size"], vlm_inter=mixture["vlm"]["intermediate_size"],

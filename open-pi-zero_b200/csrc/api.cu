@@ -565,6 +565,49 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
     return 0;
 }
 
+// ------------------------- one evaluation of the velocity field at a per-sample time -------
+// (the body of the Euler loop, pizero.py:456-479, with time_embedding(t) computed on the device for an
+//  arbitrary t per sample instead of the per-step constants; used by the training forward)
+template <typename T>
+static int run_velocity(pz_handle *h, const int32_t *valid_len, const float *psi, const float *t, float *v_out,
+                        int v_ld, void *wsp, int B, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    if (!w.enc_w2t || !w.enc_b2 || !w.time_freq) return fail(h, PZ_ERR_UNBOUND, "enc_w2t / enc_b2 / time_freq not bound");
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int A = c.act_hidden, Hz = c.horizon, Ma = B * Hz;
+    float *tbias = (float *)ws.mlpa;   // [B, A] fp32; the MLP scratch is idle until the first layer
+    // time_cond = SinusoidalPosEmb(t) (vla/modules.py:9-22); its product with the time half of linear_2 (+ bias)
+    launch_time_embed<T>(t, w.time_freq, (T *)ws.ha, B, A / 2, st);
+    PZ_TRY(Ops<T>::linear(h, lin(ws.ha, A, w.enc_w2t, w.enc_b2, tbias, A, B, A, A, LIN_OUT_F32), st));
+    // action encoder (vla/modules.py:39-53)
+    launch_cast_pad<T>(psi, (T *)ws.a_in, Ma, c.action_dim, w.small_k_pad, st);
+    PZ_TRY(Ops<T>::linear(h, lin(ws.a_in, w.small_k_pad, w.enc_w1, w.enc_b1, ws.e1, A, Ma, A, w.small_k_pad), st));
+    PZ_TRY(Ops<T>::linear(h, lin(ws.e1, A, w.enc_w2a, nullptr, ws.xa, A, Ma, A, A, LIN_OUT_F32), st));
+    launch_rowbias_silu<T>(ws.xa, tbias, (T *)ws.z, Ma, A, Hz, st);
+    PZ_TRY(Ops<T>::linear(h, lin(ws.z, A, w.enc_w3, w.enc_b3, ws.xa, A, Ma, A, A, LIN_OUT_F32, sqrtf((float)A)), st));
+    PZ_TRY(action_layers<T>(h, ws, valid_len, B, nullptr, st));
+    // final norm + decoder (joint_model.py:375-380, pizero.py:479)
+    PZ_TRY(norm_linear<T>(h, ws.xa, w.action_final_norm, ws.ha,
+                          lin(nullptr, A, w.dec_w, w.dec_b, ws.vel, 8, Ma, c.action_dim, A, LIN_OUT_F32), A, st));
+    if (v_out) cudaMemcpy2DAsync(v_out, (size_t)v_ld * 4, ws.vel, 8 * 4, (size_t)c.action_dim * 4, Ma,
+                                 cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+// PiZero.forward (pizero.py:607-661), forward value: psi_t, one velocity evaluation, mean squared error
+template <typename T>
+static int run_flow_loss(pz_handle *h, const int32_t *valid_len, const float *actions, const float *noise,
+                         const float *t, float sig_min, float *loss, float *v_psi, void *wsp, int B, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int Ma = B * c.horizon;
+    launch_psi(noise, actions, t, ws.act, B, c.horizon * c.action_dim, sig_min, st);
+    PZ_TRY(run_velocity<T>(h, valid_len, ws.act, t, nullptr, 0, wsp, B, st));
+    launch_fm_loss(ws.vel, 8, noise, actions, loss, v_psi, Ma, c.action_dim, sig_min, st);
+    return 0;
+}
+
 // ------------------------------------------------------------------- ABI ----
 extern "C" {
 
@@ -743,6 +786,31 @@ int pz_infer_action(pz_handle *h, const int64_t *ids, const void *pixels, const 
     PZ_TRY(pz_prefill(h, valid_len, proprio, ws, ws_bytes, B, cap, stream));
     PZ_TRY(pz_denoise(h, valid_len, noise, out, ws, ws_bytes, B, cap, stream));
     return PZ_OK;
+}
+
+int pz_velocity(pz_handle *h, const int32_t *valid_len, const float *psi, const float *t, float *v_out, void *ws,
+                size_t ws_bytes, int B, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!valid_len || !psi || !t || !v_out) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_velocity<bf16>(h, valid_len, psi, t, v_out, h->cfg.action_dim, ws, B, st)
+                                     : run_velocity<float>(h, valid_len, psi, t, v_out, h->cfg.action_dim, ws, B, st);
+    return finish(h, rc);
+}
+
+int pz_flow_matching_loss(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len,
+                          const float *proprio, const float *actions, const float *noise, const float *t,
+                          float sig_min, float *loss, float *v_psi, void *ws, size_t ws_bytes, int B, void *stream) {
+    if (h) h->lc.n = 0;
+    PZ_TRY(pz_embed_prefix(h, ids, pixels, ws, ws_bytes, B, nullptr, stream));
+    PZ_TRY(pz_prefill(h, valid_len, proprio, ws, ws_bytes, B, nullptr, stream));
+    if (!actions || !noise || !t || !loss) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_flow_loss<bf16>(h, valid_len, actions, noise, t, sig_min, loss, v_psi, ws, B, st)
+                                     : run_flow_loss<float>(h, valid_len, actions, noise, t, sig_min, loss, v_psi, ws, B, st);
+    return finish(h, rc);
 }
 
 int64_t pz_launch_count(const pz_handle *h) { return h ? h->lc.n : 0; }

@@ -333,3 +333,86 @@ __global__ void clamp_copy_kernel(const float *__restrict__ src, float *__restri
 void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStream_t st) {
     launch_k(clamp_copy_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, dst, n, clip);
 }
+
+// ---- flow-matching training forward (pizero.py:597-661): the small pieces around the joint model ----
+// psi_t (pizero.py:597-605): (1 - (1 - sig_min) t_b) x0 + t_b x1
+__global__ void psi_kernel(const float *__restrict__ x0, const float *__restrict__ x1, const float *__restrict__ t,
+                           float *__restrict__ out, long total, int per_sample, float sig_min) {
+    pdl_trigger();
+    pdl_wait();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float tb = t[i / per_sample];
+    out[i] = (1.f - (1.f - sig_min) * tb) * x0[i] + tb * x1[i];
+}
+void launch_psi(const float *x0, const float *x1, const float *t, float *out, long batch, int per_sample, float sig_min,
+                cudaStream_t st) {
+    long total = batch * per_sample;
+    launch_k(psi_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x0, x1, t, out, total, per_sample, sig_min);
+}
+
+// SinusoidalPosEmb (vla/modules.py:9-22): out[b] = cat(sin(t_b f), cos(t_b f)), f_i = exp(-i ln(P) / (half - 1)) (fp32 table)
+template <typename T>
+__global__ void time_embed_kernel(const float *__restrict__ t, const float *__restrict__ freq, T *__restrict__ out, int batch,
+                                  int half) {
+    pdl_trigger();
+    pdl_wait();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * half) return;
+    const int b = i / half, j = i % half;
+    float s, c;
+    sincosf(t[b] * freq[j], &s, &c);
+    out[(long)b * 2 * half + j] = from_f32<T>(s);
+    out[(long)b * 2 * half + half + j] = from_f32<T>(c);
+}
+template <typename T>
+void launch_time_embed(const float *t, const float *freq, T *out, int batch, int half, cudaStream_t st) {
+    launch_k(time_embed_kernel<T>, dim3((unsigned)((batch * half + 255) / 256)), dim3(256), 0, st, t, freq, out, batch, half);
+}
+template void launch_time_embed<float>(const float *, const float *, float *, int, int, cudaStream_t);
+template void launch_time_embed<bf16>(const float *, const float *, bf16 *, int, int, cudaStream_t);
+
+// ActionEncoder.linear_2 + SiLU with a per-sample time half (vla/modules.py:46-52): the concatenated input
+// [time_emb | linear_1(a)] splits the product into a per-sample vector (bias, [batch, cols]) plus the action half (zpre)
+template <typename T>
+__global__ void rowbias_silu_kernel(const float *__restrict__ zpre, const float *__restrict__ bias, T *__restrict__ out,
+                                    long total, int cols, int rows_per_sample) {
+    pdl_trigger();
+    pdl_wait();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long r = i / cols;
+    const int c = i % cols;
+    out[i] = from_f32<T>(silu(zpre[i] + bias[(r / rows_per_sample) * cols + c]));
+}
+template <typename T>
+void launch_rowbias_silu(const float *zpre, const float *bias, T *out, long rows, int cols, int rows_per_sample,
+                         cudaStream_t st) {
+    long total = rows * cols;
+    launch_k(rowbias_silu_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, zpre, bias, out, total, cols,
+             rows_per_sample);
+}
+template void launch_rowbias_silu<float>(const float *, const float *, float *, long, int, int, cudaStream_t);
+template void launch_rowbias_silu<bf16>(const float *, const float *, bf16 *, long, int, int, cudaStream_t);
+
+// flow-matching loss (pizero.py:658-661): mean((v - (x1 - (1 - sig_min) x0))^2); one CTA (the tensor is B*horizon*action_dim)
+__global__ void __launch_bounds__(1024) fm_loss_kernel(const float *__restrict__ vel, int vel_ld, const float *__restrict__ x0,
+                                                       const float *__restrict__ x1, float *__restrict__ loss,
+                                                       float *__restrict__ v_out, long total, int adim, float sig_min) {
+    __shared__ float scratch[32];
+    pdl_trigger();
+    pdl_wait();
+    float acc = 0.f;
+    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+        const float v = vel[(i / adim) * vel_ld + (i % adim)];
+        if (v_out) v_out[i] = v;
+        const float d = v - (x1[i] - (1.f - sig_min) * x0[i]);
+        acc += d * d;
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) *loss = acc / (float)total;
+}
+void launch_fm_loss(const float *vel, int vel_ld, const float *x0, const float *x1, float *loss, float *v_out, long rows,
+                    int adim, float sig_min, cudaStream_t st) {
+    launch_k(fm_loss_kernel, dim3(1), dim3(1024), 0, st, vel, vel_ld, x0, x1, loss, v_out, rows * adim, adim, sig_min);
+}

@@ -37,6 +37,16 @@ void launch_to_f32(const T *src, float *dst, long n, cudaStream_t st);
 void launch_euler(float *action, const float *vel, int vel_ld, float dt, long rows, int adim,
                   float *vel_capture, cudaStream_t st);
 void launch_clamp_copy(const float *src, float *dst, long n, float clip, cudaStream_t st);
+// flow-matching training forward (pizero.py:597-661)
+void launch_psi(const float *x0, const float *x1, const float *t, float *out, long batch, int per_sample, float sig_min,
+                cudaStream_t st);
+template <typename T>
+void launch_time_embed(const float *t, const float *freq, T *out, int batch, int half, cudaStream_t st);
+template <typename T>
+void launch_rowbias_silu(const float *zpre, const float *bias, T *out, long rows, int cols, int rows_per_sample,
+                         cudaStream_t st);
+void launch_fm_loss(const float *vel, int vel_ld, const float *x0, const float *x1, float *loss, float *v_out, long rows,
+                    int adim, float sig_min, cudaStream_t st);
 
 // gemm_tc.cu (tcgen05 + TMA, bf16)
 int gemm_tc_supported(const LinearArgs &a);

@@ -180,6 +180,7 @@ class PiZero(nn.Module):
         self.action_dim = d["action_dim"]
         self.proprio_dim = d["proprio_dim"]
         self.final_action_clip_value = d["final_action_clip_value"]
+        self.flow_sig_min = float(d.get("flow_sig_min", 0.001))   # pizero.py:58
 
         self.joint_model = JointModel(d)
         import weakref
@@ -375,6 +376,8 @@ class PiZero(nn.Module):
         w.enc_b1 = own(f32(sd["action_encoder.linear_1.bias"]))
         w2 = sd["action_encoder.linear_2.weight"]
         w.enc_w2a = own(mat(w2[:, A:]))
+        w.enc_w2t = own(mat(w2[:, :A]))     # time half, for an arbitrary per-sample t (training forward)
+        w.enc_b2 = own(f32(sd["action_encoder.linear_2.bias"]))
         # time conditioning is a per-step constant: t_i accumulates
         # dt in fp32 exactly as pizero.py:460-481 does in an fp32 run; the embedding
         # follows vla/modules.py:15-22.
@@ -382,6 +385,7 @@ class PiZero(nn.Module):
         half = A // 2
         freq = torch.exp(torch.arange(half, device=dev, dtype=torch.float32)
                          * -(math.log(d["time_max_period"]) / (half - 1)))
+        w.time_freq = own(freq.contiguous())
         t = torch.zeros(1, device=dev, dtype=torch.float32)
         tb = []
         for _ in range(n_steps):
@@ -695,9 +699,78 @@ class PiZero(nn.Module):
             raise PzError("pz_timing_end failed")
         return ms.value, n.value
 
-    def forward(self, *args, **kwargs):
-        raise PzError("PiZero.forward (flow-matching training loss, pizero.py:607-661) is outside "
-                      "this library's scope; use infer_action / PiZeroInference")
+    # ------------------------------------------------- flow-matching training forward (value only)
+    def psi_t(self, x: torch.Tensor, x1: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """pizero.py:597-605 (conditional flow); host-side helper, the loss call computes it on the device."""
+        t = t[:, None, None]
+        return (1 - (1 - self.flow_sig_min) * t) * x + t * x1
+
+    @torch.no_grad()
+    def forward(
+        self,
+        input_ids: torch.LongTensor,
+        pixel_values: torch.Tensor,
+        causal_mask: Optional[torch.Tensor] = None,
+        vlm_position_ids: Optional[torch.LongTensor] = None,
+        proprio_position_ids: Optional[torch.LongTensor] = None,
+        action_position_ids: Optional[torch.LongTensor] = None,
+        proprios: Optional[torch.Tensor] = None,
+        actions: Optional[torch.Tensor] = None,
+        t: Optional[torch.Tensor] = None,
+        *,
+        noise: Optional[torch.Tensor] = None,
+        valid_len: Optional[torch.Tensor] = None,
+        return_velocity: bool = False,
+    ):
+        """pizero.py:607-661: the flow-matching loss `mean((v_psi - (x1 - (1 - sig_min) x0))^2)` for a batch,
+        same nine arguments.  FORWARD VALUE ONLY: the result carries no autograd graph (the backward pass of the
+        training step, SURVEY 8f-1, is not built) -- it serves validation / loss monitoring and pins the joint
+        all-mixtures-active pass against the reference.  The reference's single joint pass (no cache, full block
+        mask) is computed as prefix pass + one action pass over the cached prefix, which is the same function
+        because vlm / proprio rows never attend to action keys (pizero.py:271-310).
+        Extras: `noise` (x0; default torch.randn_like(actions) as pizero.py:622), `valid_len` (int32 [B], instead
+        of reading it from row 0 of `causal_mask`), `return_velocity` (also return v_psi [B,H,A])."""
+        if proprios is None or actions is None or t is None:
+            raise TypeError("forward() needs proprios, actions and t")
+        self.pack()
+        lib = _lib.load()
+        dev = self._packed[0][0].device
+        B = input_ids.shape[0]
+        Sv, H, Adim = self.max_image_text_tokens, self.horizon_steps, self.action_dim
+        if input_ids.shape != (B, Sv):
+            raise ValueError(f"input_ids must be [B, {Sv}], got {tuple(input_ids.shape)}")
+        if actions.shape != (B, H, Adim):
+            raise ValueError(f"actions must be [B, {H}, {Adim}], got {tuple(actions.shape)}")
+        if t.shape != (B,):
+            raise ValueError(f"t must be [B], got {tuple(t.shape)}")
+        if proprios.shape != (B, self.num_proprio_tokens, self.proprio_dim):
+            raise ValueError(f"proprios must be [B, {self.num_proprio_tokens}, {self.proprio_dim}]")
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        u8 = pixel_values.dtype == torch.uint8
+        pix = pixel_values.to(device=dev).contiguous() if u8 else pixel_values.to(device=dev, dtype=self._T).contiguous()
+        prop = proprios.to(device=dev, dtype=torch.float32).contiguous()
+        if valid_len is None and causal_mask is not None:
+            valid_len = (causal_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32)
+        vlen = self._valid_len(None, ids, valid_len)
+        x1 = actions.to(device=dev, dtype=torch.float32).contiguous()
+        if noise is None:   # pizero.py:622
+            noise = torch.randn_like(x1)
+        x0 = noise.to(device=dev, dtype=torch.float32).contiguous()
+        tt = t.to(device=dev, dtype=torch.float32).contiguous()
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        vel = torch.empty((B, H, Adim), device=dev, dtype=torch.float32) if return_velocity else None
+        ws, ws_bytes = self._ensure_workspace(B)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.pz_set_pixel_format(self._handle, 1 if u8 else 0)
+        rc = lib.pz_flow_matching_loss(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(), prop.data_ptr(),
+                                       x1.data_ptr(), x0.data_ptr(), tt.data_ptr(), float(self.flow_sig_min),
+                                       loss.data_ptr(), vel.data_ptr() if vel is not None else None, ws, ws_bytes, B,
+                                       stream)
+        if rc != 0:
+            raise PzError(f"pz_flow_matching_loss failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
+        self.last_launch_count = int(lib.pz_launch_count(self._handle))
+        self._inflight = (ids, pix, prop, vlen, x1, x0, tt)
+        return (loss, vel) if return_velocity else loss
 
 
 class PiZeroInference(PiZero):

@@ -325,3 +325,31 @@ def infer_action_naive(sd, dims, input_ids, pixel_values, attention_mask, propri
     if clip is not None:
         action = torch.clamp(action, -clip, clip)
     return action
+
+
+# --------------------------------------------------------------------------
+# flow-matching training forward (value only)
+# --------------------------------------------------------------------------
+@torch.no_grad()
+def flow_matching_loss(sd, dims, input_ids, pixel_values, attention_mask, proprios, actions, t, noise,
+                       capture=None):
+    """pizero.py:597-661 (`psi_t` + `PiZero.forward`): one joint pass with all three
+    mixtures active under the full block mask, no KV cache; returns the scalar loss.
+    `noise` is x0 (the reference draws it with torch.randn_like, pizero.py:622).
+    `capture` (dict) receives psi_t, v_psi and d_psi."""
+    dtype = pixel_values.dtype
+    sig_min = dims.get("flow_sig_min", 0.001)
+    full_mask, _, _, pos = build_masks_and_positions(dims, attention_mask, dtype)
+    x0, x1 = noise.to(dtype), actions.to(dtype)
+    tt = t.to(dtype)[:, None, None]
+    psi = (1 - (1 - sig_min) * tt) * x0 + tt * x1                            # pizero.py:597-605
+    emb = embed_prefix(sd, dims, input_ids, pixel_values)
+    pe = F.linear(proprios, sd["proprio_encoder.weight"], sd["proprio_encoder.bias"])
+    temb = sinusoidal_time_embedding(t.to(dtype), dims["act_hidden"], dims["time_max_period"])
+    ae = action_encoder(sd, psi, temb)
+    h = joint_forward(sd, dims, full_mask, pos, {"vlm": emb, "proprio": pe, "action": ae}, {})["action"]
+    v_psi = F.linear(h, sd["action_decoder.weight"], sd["action_decoder.bias"])
+    d_psi = x1 - (1 - sig_min) * x0                                          # pizero.py:659
+    if capture is not None:
+        capture.update(psi_t=psi.clone(), v_psi=v_psi.clone(), d_psi=d_psi.clone())
+    return torch.mean((v_psi - d_psi) ** 2)
