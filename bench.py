@@ -438,6 +438,31 @@ def main():
         lat = dict(p50_ms=statistics.median(ts), min_ms=min(ts), launches=model.last_launch_count)
     sync_all()
 
+    # ---- extra: forward half of BASELINE configs[4] (flow-matching loss value, per-GPU bs=32; no backward) ----
+    fm = None
+    if rank == 0 and not args.skip_latency:
+        from open_pi_zero_b200.pizero import PiZero as _PiZero
+        Bt = min(32, B)
+        g = torch.Generator().manual_seed(7)
+        acts = (torch.rand((Bt, dims["horizon_steps"], dims["action_dim"]), generator=g) * 2 - 1).to(device)
+        x0 = torch.randn((Bt, dims["horizon_steps"], dims["action_dim"]), generator=g).to(device)
+        tt = torch.rand((Bt,), generator=g).to(device)
+        fm_in = dict(input_ids=dev_in["input_ids"][:Bt], pixel_values=dev_in["pixel_values"][:Bt], proprios=dev_in["proprios"][:Bt],
+                     valid_len=dev_in["valid_len"][:Bt], actions=acts, t=tt, noise=x0)
+        for _ in range(2):
+            loss = _PiZero.forward(model, **fm_in)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            loss = _PiZero.forward(model, **fm_in)
+        b.record()
+        b.synchronize()
+        fm = dict(what="PiZero.forward flow-matching loss, FORWARD ONLY (no backward / optimizer): the forward half of "
+                       "BASELINE configs[4], per-GPU batch 32, eager launches", batch=Bt, ms=a.elapsed_time(b) / 5,
+                  samples_per_s=Bt * 5 / (a.elapsed_time(b) / 1e3), loss=float(loss), launches=model.last_launch_count)
+    sync_all()
+
     # ---- roofline of the dominant kernel (VLM gate|up GEMM, tensor-bound) -----
     Mchunk = min(B, 64) * dims["max_image_text_tokens"]
     flops_per_launch = 2.0 * Mchunk * (2 * dims["vlm_inter"]) * dims["vlm_hidden"]
@@ -479,7 +504,7 @@ def main():
             config=workload_config(world, B),
             clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=launches, latency_bs1=lat, roofline=roof, roofline_denoise_bs1=roof_denoise,
-            cpu_baseline=cpu, reference_gpu_eager=ref_gpu)
+            cpu_baseline=cpu, reference_gpu_eager=ref_gpu, train_forward=fm)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -103,9 +103,10 @@ class JointModel(_Holder):
                 final_layer_post_attn_skip_names=("vlm", "proprio"), kv_caches={},
                 cache_mode="append_non_active", return_caches=False):
         """joint_model.py:328-383 for (a) the prefix pass (vlm + proprio active, caches filled,
-        nothing returned for the skipped mixtures) and (b) the action pass over the cached prefix
-        (`cache_mode="append_non_active"`).  Other combinations (training forward with all three
-        active, "append"/"no_append" text generation) are outside this library's scope.
+        nothing returned for the skipped mixtures), (b) the action pass over the cached prefix
+        (`cache_mode="append_non_active"`) and (c) all three mixtures active with no cache (the training
+        forward, pizero.py:637-652, and infer_action_naive, pizero.py:529-544).  "append" / "no_append"
+        text generation is outside this library's scope.
         Like the reference, `embeds_all[*]` is scaled by sqrt(hidden) IN PLACE (joint_model.py:355)."""
         assert cache_mode in ["no_append", "append", "append_non_active"], f"Invalid cache mode: {cache_mode}"
         owner = self._owner() if self._owner is not None else None
@@ -144,9 +145,26 @@ class JointModel(_Holder):
                 raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
             res = {"action": out.to(embeds_all["action"].dtype)}
             return (res, kv_caches) if return_caches else res
+        if names == ["vlm", "proprio", "action"] and not kv_caches and \
+                tuple(final_layer_post_attn_skip_names) == ("vlm", "proprio"):
+            # the training call pattern (pizero.py:637-652) and infer_action_naive's (pizero.py:529-544): all three
+            # mixtures active under the full block mask, no cache.  vlm / proprio rows never attend to action keys
+            # (pizero.py:271-310), so this is the prefix pass followed by the action pass over the prefix's K/V.
+            xv, xp, xa = f32(embeds_all["vlm"]), f32(embeds_all["proprio"]), f32(embeds_all["action"])
+            rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
+                                     B, stream)
+            if rc != 0:
+                raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+            out = torch.empty_like(xa)
+            rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
+                                     B, stream)
+            if rc != 0:
+                raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+            res = {"action": out.to(embeds_all["action"].dtype)}
+            return (res, kv_caches) if return_caches else res
         raise NotImplementedError(
             f"JointModel.forward with active mixtures {names} / cache_mode {cache_mode!r} is outside the "
-            "infer_action path (training forward and text generation are not built)")
+            "infer_action / training-forward paths (\"append\" / \"no_append\" text generation is not built)")
 
 
 class PiZero(nn.Module):

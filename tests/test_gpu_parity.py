@@ -312,6 +312,15 @@ def test_joint_model_forward_api():
     e = rel_err(got, want)
     print(f"[JointModel.forward] action hidden rel err {e:.3e}")
     assert e < BF16_LAYER_TOL
+    # (c) all three mixtures active, full mask, no cache: the training-forward / infer_action_naive call pattern
+    full_mask, _, _, _ = O.build_masks_and_positions(d, attn, torch.float32)
+    got3 = jm(attention_mask=full_mask.cuda(), position_ids_all={n: p.cuda() for n, p in pos.items()},
+              embeds_all={"vlm": ev.cuda(), "proprio": ep.cuda(), "action": ea.cuda()}, kv_caches={})["action"]
+    want3 = O.joint_forward(sd, d, full_mask, pos, {"vlm": ev.clone(), "proprio": ep.clone(), "action": ea.clone()}, {})["action"]
+    torch.cuda.synchronize()
+    e3 = rel_err(got3, want3)
+    print(f"[JointModel.forward, all active] action hidden rel err {e3:.3e}")
+    assert e3 < BF16_LAYER_TOL
     with pytest.raises(NotImplementedError):
         jm(attention_mask=amask.cuda(), position_ids_all={}, embeds_all={"vlm": ev.cuda(), "action": ea.cuda()})
     with pytest.raises(AssertionError):
@@ -344,7 +353,10 @@ def test_errors_are_python_exceptions():
           proprios=inp["proprios"].cuda())
     with pytest.raises(TypeError):
         m(input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda())
-    with pytest.raises(PzError):
-        m.train_forward = None
-        from open_pi_zero_b200.pizero import PiZero
-        PiZero.forward(m)
+    from open_pi_zero_b200.pizero import PiZero
+    with pytest.raises(TypeError):   # the training forward needs proprios, actions and t (pizero.py:607-618)
+        PiZero.forward(m, input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda())
+    with pytest.raises(ValueError):
+        PiZero.forward(m, input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda(),
+                       proprios=inp["proprios"].cuda(), actions=torch.zeros(2, 1, 1).cuda(), t=torch.zeros(2).cuda())
+    assert PzError is not None
