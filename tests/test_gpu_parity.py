@@ -342,6 +342,37 @@ def test_batch_invariance_and_ragged_lengths():
         assert max_abs(out, full[b:b + 1]) < 2e-3
 
 
+def test_full_size_bs1024_rollout_batch_properties():
+    """BASELINE configs[2] at its full size on one GPU: the 3.24 B-parameter bridge model, bs = 1024, uint8 frames.
+    No oracle finishes this in seconds, so the checks are size-independent properties: a sample's chunk does not
+    depend on the batch it rides in (bs 1024 vs the same samples at bs 64 and, through the persistent sampler,
+    bs 1), the clamp bound holds, and nothing is NaN/Inf."""
+    from open_pi_zero_b200.pizero import PiZeroInference
+    from open_pi_zero_b200.synth import fill_random_
+    d = pz.make_dims()
+    m = PiZeroInference(pz.cfg_from_dims(d), init="empty", device="cuda", dtype=torch.bfloat16)
+    fill_random_(m, d, seed=42)
+    B = 1024
+    inp = pz.make_inputs(d, B, seed=77)
+    dev = {k: inp[k].cuda() for k in ("input_ids", "proprios", "noise", "valid_len")}
+    dev["pixel_values"] = inp["pixel_u8"].cuda()
+    big = m(**dev).clone()
+    torch.cuda.synchronize()
+    assert big.shape == (B, d["horizon_steps"], d["action_dim"])
+    assert bool(torch.isfinite(big).all())
+    assert float(big.abs().max()) <= d["final_action_clip_value"] + 1e-6
+    for lo in (0, 960):
+        part = m(**{k: v[lo:lo + 64].contiguous() for k, v in dev.items()}).clone()
+        e = max_abs(part, big[lo:lo + 64])
+        print(f"[bs1024] samples {lo}..{lo + 63}: max |bs1024 - bs64| = {e:.3e}")
+        assert e < BF16_ACTION_TOL
+    for b in (5, 1023):
+        one = m(**{k: v[b:b + 1].contiguous() for k, v in dev.items()}).clone()
+        e = max_abs(one, big[b:b + 1])
+        print(f"[bs1024] sample {b}: max |bs1024 - bs1 (persistent sampler)| = {e:.3e}")
+        assert e < BF16_ACTION_TOL
+
+
 def test_errors_are_python_exceptions():
     from open_pi_zero_b200.pizero import PzError
     d = SMALL
