@@ -177,6 +177,8 @@ template <> struct Ops<bf16> {
         return 0;
     }
     static int attention(pz_handle *h, const AttnArgs &a, cudaStream_t st) {
+        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_tc_supported(a))
+            return launch_attn_tc(a, st);     // prefix vlm rows: tcgen05
         if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_mma_supported(a))
             return launch_attn_mma(a, st);
         launch_attn_simple<bf16>(a, st);
@@ -885,6 +887,10 @@ int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const
     } else if (impl == 1) {
         if (dtype != PZ_BF16 || !attn_mma_supported(a)) return PZ_ERR_INVALID;
         int rc = launch_attn_mma(a, st);
+        if (rc) return rc;
+    } else if (impl == 3) {
+        if (dtype != PZ_BF16 || !attn_tc_supported(a)) return PZ_ERR_INVALID;
+        int rc = launch_attn_tc(a, st);
         if (rc) return rc;
     } else {
         return PZ_ERR_INVALID;

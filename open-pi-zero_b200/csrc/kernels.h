@@ -66,6 +66,10 @@ int launch_attn_mma(const AttnArgs &a, cudaStream_t st);
 // launches just the partial kernel (no combine); 0 if it does not apply (nothing launched).
 int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st);
 
+// attn_tc.cu (tcgen05 attention for the vlm rows of the prefix pass: bf16, head_dim 256, 8 query heads on one K/V head)
+int attn_tc_supported(const AttnArgs &a);
+int launch_attn_tc(const AttnArgs &a, cudaStream_t st);
+
 // denoise_mega.cu (persistent cooperative sampler for B * horizon <= 16)
 struct MegaBuffers {
     const void *kcache, *vcache;   // [L][batch_total][S_c][256] bf16

@@ -141,7 +141,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])   # 2 = tensor-core kernel with the split-key scratch
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])   # 2 = mma.sync kernel with the split-key scratch, 3 = tcgen05 kernel
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
 def test_attention(impl, case):
     name, B, nh, hd, R, q0, s_cache, s_vlm, n_fresh, kvh, softcap, use_len = case
@@ -159,7 +159,7 @@ def test_attention(impl, case):
     scratch = torch.empty(B * 8 * nh * R * (hd + 2), device="cuda") if impl == 2 else None
     if impl == 2 and R * nh > 64:
         pytest.skip("split-key path is for decode-sized query blocks")
-    rc = lib.pz_op_attention(min(impl, 1), 1, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+    rc = lib.pz_op_attention(3 if impl == 3 else min(impl, 1), 1, q.data_ptr(), k.data_ptr(), v.data_ptr(),
                              k2.data_ptr() if n_fresh else None, v2.data_ptr() if n_fresh else None,
                              vlen.data_ptr() if use_len else None, out.data_ptr(), B, nh, hd, R, q0,
                              s_cache, s_vlm, n_fresh, kvh, scale, softcap,
@@ -174,3 +174,33 @@ def test_attention(impl, case):
     e = rel_err(out.float(), want)
     print(f"attention[{name}] impl={impl}: rel err {e:.3e}")
     assert e < 8e-3
+
+
+@pytest.mark.parametrize("lens", [[16, 100, 128, 129], [256, 257, 272, 276], [1, 15, 17, 144]])
+def test_attention_tcgen05_chunk_boundaries(lens):
+    """tcgen05 prefix attention (attn_tc.cu) at valid lengths around the 16-key MMA granule, the 128-key chunk and the
+    16-token tile boundaries; pad rows must come back as zeros; poisoned (NaN) K/V rows beyond the valid length must not leak."""
+    lib = _lib()
+    B, nh, hd, R, s_cache = len(lens), 8, 256, 276, 277
+    g = torch.Generator(device="cuda").manual_seed(3)
+    bf = torch.bfloat16
+    q = torch.randn(B, R, nh, hd, device="cuda", generator=g).to(bf)
+    k = torch.randn(B, s_cache, 1, hd, device="cuda", generator=g).to(bf)
+    v = torch.randn(B, s_cache, 1, hd, device="cuda", generator=g).to(bf)
+    vlen = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    want = _attn_ref(q, k, v, None, None, vlen, 0, R, hd ** -0.5, 50.0)
+    for b, L in enumerate(lens):          # rows no valid query may read
+        k[b, L:] = float("nan")
+        v[b, L:] = float("nan")
+    out = torch.full((B, R, nh, hd), 7.0, device="cuda", dtype=bf)
+    rc = lib.pz_op_attention(3, 1, q.data_ptr(), k.data_ptr(), v.data_ptr(), None, None, vlen.data_ptr(), out.data_ptr(),
+                             B, nh, hd, R, 0, s_cache, R, 0, 1, hd ** -0.5, 50.0, None, 0,
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
+    e = rel_err(out.float(), want)
+    print(f"attention tcgen05 lens={lens}: rel err {e:.3e}")
+    assert e < 8e-3
+    for b, L in enumerate(lens):
+        assert float(out[b, L:].float().abs().max()) == 0.0 if L < R else True
