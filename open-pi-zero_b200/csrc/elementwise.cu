@@ -88,13 +88,64 @@ void launch_bcast_rows(float *x, const float *table, long rows, int cols, int pe
                                                                       period);
 }
 
-// ---- LayerNorm (siglip.py:211,217,298): one warp per row, fp32 statistics ----
+// ---- norms: one warp per row, the row lives in registers (one HBM read), vectorised stores -------------
+// (rows of up to 32 * 4 * NI floats; NI float4 per lane, all loads issued before the first use)
+template <typename T> PZ_DEVINL void store4(T *o, float a, float b, float c, float d);
+template <> PZ_DEVINL void store4<float>(float *o, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(o) = make_float4(a, b, c, d);
+}
+template <> PZ_DEVINL void store4<bf16>(bf16 *o, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2 *>(o) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+
+// LayerNorm (siglip.py:211,217,298), fp32 statistics, two-pass variance on the register copy
+template <typename T, int NI>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                        const float *__restrict__ b, T *__restrict__ out, long rows,
+                                                        int cols, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * cols);
+    const int n4 = cols >> 2;
+    float4 v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < n4 ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (lane + 32 * i < n4) {
+            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+    const float4 *wr = reinterpret_cast<const float4 *>(w), *br = reinterpret_cast<const float4 *>(b);
+    T *o = out + row * cols;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float4 g = __ldg(wr + c), h = __ldg(br + c);
+            store4<T>(o + 4 * c, (v[i].x - mean) * rstd * g.x + h.x, (v[i].y - mean) * rstd * g.y + h.y,
+                      (v[i].z - mean) * rstd * g.z + h.z, (v[i].w - mean) * rstd * g.w + h.w);
+        }
+    }
+}
+// any width (scalar, three passes): rows wider than 2048 or not a multiple of 4
 template <typename T>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x,
-                                                        const float *__restrict__ w,
-                                                        const float *__restrict__ b,
-                                                        T *__restrict__ out, long rows, int cols,
-                                                        float eps) {
+__global__ void __launch_bounds__(256) layernorm_generic_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                const float *__restrict__ b, T *__restrict__ out,
+                                                                long rows, int cols, float eps) {
     pdl_trigger();
     pdl_wait();
     long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -113,46 +164,75 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 template <typename T>
 void launch_layernorm(const float *x, const float *w, const float *b, T *out, long rows, int cols,
                       float eps, cudaStream_t st) {
-    launch_k(layernorm_kernel<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, w, b, out, rows, cols, eps);
+    const dim3 grid((unsigned)((rows + 7) / 8)), block(256);
+    const int ni = ((cols >> 2) + 31) / 32;
+    if (cols % 4 == 0 && ni <= 4) launch_k(layernorm_kernel<T, 4>, grid, block, 0, st, x, w, b, out, rows, cols, eps);
+    else if (cols % 4 == 0 && ni <= 9) launch_k(layernorm_kernel<T, 9>, grid, block, 0, st, x, w, b, out, rows, cols, eps);
+    else if (cols % 4 == 0 && ni <= 16) launch_k(layernorm_kernel<T, 16>, grid, block, 0, st, x, w, b, out, rows, cols, eps);
+    else launch_k(layernorm_generic_kernel<T>, grid, block, 0, st, x, w, b, out, rows, cols, eps);
 }
 template void launch_layernorm<float>(const float *, const float *, const float *, float *, long,
                                       int, float, cudaStream_t);
 template void launch_layernorm<bf16>(const float *, const float *, const float *, bf16 *, long,
                                      int, float, cudaStream_t);
 
-// ---- Gemma RMSNorm (paligemma/modules.py:13-21): x*rsqrt(mean x^2+eps)*(1+w) --
+// Gemma RMSNorm (paligemma/modules.py:13-21): x * rsqrt(mean x^2 + eps) * (1 + w)
+template <typename T, int NI>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                      T *__restrict__ out, long rows, int cols, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * cols);
+    const int n4 = cols >> 2;
+    float4 v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < n4 ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) s += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    const float r = rsqrtf(warp_sum(s) / cols + eps);
+    const float4 *wr = reinterpret_cast<const float4 *>(w);
+    T *o = out + row * cols;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float4 g = __ldg(wr + c);
+            store4<T>(o + 4 * c, v[i].x * r * (1.f + g.x), v[i].y * r * (1.f + g.y), v[i].z * r * (1.f + g.z),
+                      v[i].w * r * (1.f + g.w));
+        }
+    }
+}
 template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const float *__restrict__ x,
-                                                      const float *__restrict__ w,
-                                                      T *__restrict__ out, long rows, int cols,
-                                                      float eps) {
+__global__ void __launch_bounds__(256) rmsnorm_generic_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                              T *__restrict__ out, long rows, int cols, float eps) {
     pdl_trigger();
     pdl_wait();
     long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float4 *xr = reinterpret_cast<const float4 *>(x + row * cols);
-    int n4 = cols >> 2;
+    const float *xr = x + row * cols;
     float s = 0.f;
-    for (int c = lane; c < n4; c += 32) {
-        float4 v = xr[c];
-        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
+    for (int c = lane; c < cols; c += 32) s += xr[c] * xr[c];
     float r = rsqrtf(warp_sum(s) / cols + eps);
-    const float4 *wr = reinterpret_cast<const float4 *>(w);
     T *o = out + row * cols;
-    for (int c = lane; c < n4; c += 32) {
-        float4 v = xr[c], g = wr[c];
-        o[4 * c + 0] = from_f32<T>(v.x * r * (1.f + g.x));
-        o[4 * c + 1] = from_f32<T>(v.y * r * (1.f + g.y));
-        o[4 * c + 2] = from_f32<T>(v.z * r * (1.f + g.z));
-        o[4 * c + 3] = from_f32<T>(v.w * r * (1.f + g.w));
-    }
+    for (int c = lane; c < cols; c += 32) o[c] = from_f32<T>(xr[c] * r * (1.f + w[c]));
 }
 template <typename T>
 void launch_rmsnorm(const float *x, const float *w, T *out, long rows, int cols, float eps,
                     cudaStream_t st) {
-    launch_k(rmsnorm_kernel<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, w, out, rows, cols, eps);
+    const dim3 grid((unsigned)((rows + 7) / 8)), block(256);
+    const int ni = ((cols >> 2) + 31) / 32;
+    if (cols % 4 == 0 && ni <= 2) launch_k(rmsnorm_kernel<T, 2>, grid, block, 0, st, x, w, out, rows, cols, eps);
+    else if (cols % 4 == 0 && ni <= 8) launch_k(rmsnorm_kernel<T, 8>, grid, block, 0, st, x, w, out, rows, cols, eps);
+    else if (cols % 4 == 0 && ni <= 16) launch_k(rmsnorm_kernel<T, 16>, grid, block, 0, st, x, w, out, rows, cols, eps);
+    else launch_k(rmsnorm_generic_kernel<T>, grid, block, 0, st, x, w, out, rows, cols, eps);
 }
 template void launch_rmsnorm<float>(const float *, const float *, float *, long, int, float,
                                     cudaStream_t);
