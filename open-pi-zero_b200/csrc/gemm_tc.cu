@@ -159,6 +159,8 @@ struct TcParams {
     int tiles_m, tiles_n;
     int ksplit, kb_per_split;           // split-K (fp32 reduce-add outputs only)
     int n_fastest;                      // tile raster: 1 = consecutive CTAs share the A tile (few N tiles, big A)
+    int group_m;                        // M-fastest raster in groups of group_m M tiles (0 = one group): the A rows of a
+                                        // group stay L2 resident while the N tiles sweep past them
     // fused RoPE + Q/K/V split (LIN_ROPE): BN = 256 = head_dim, one N tile per head
     const float *rope_cos, *rope_sin;   // [s_x, 128] fp32
     bf16 *k_out, *v_out;                // cache rows: base + b*kv_batch_stride + s*256
@@ -228,6 +230,20 @@ PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_
 // (7 us of MMA per 256 x 256 tile), became the bottleneck (tensor pipe 40-52 % active; profiles/).
 enum { E_PLAIN = 0, E_GELU = 1, E_SILU = 2, E_F32 = 3, E_GEGLU = 4, E_ROPE = 5 };
 
+// tile raster (the workers that run together take consecutive tile indices)
+PZ_DEVINL void tile_coords(const TcParams &p, int tmn, int &tm, int &tn) {
+    if (p.n_fastest) {
+        tm = tmn / p.tiles_n; tn = tmn % p.tiles_n;
+    } else if (p.group_m > 0) {
+        const int per_group = p.group_m * p.tiles_n;
+        const int g = tmn / per_group, r = tmn - g * per_group;
+        const int gm0 = g * p.group_m, gsz = min(p.group_m, p.tiles_m - gm0);
+        tm = gm0 + r % gsz; tn = r / gsz;
+    } else {
+        tm = tmn % p.tiles_m; tn = tmn / p.tiles_m;
+    }
+}
+
 template <int BN, int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -287,7 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (wid < num_tiles) {
                 int t = wid;
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
-                int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
+                int tm_unused, tn;
+                tile_coords(p, tmn, tm_unused, tn);
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 pre = min(cfg::STAGES, kb1 - kb0);
                 for (int i = 0; i < pre; ++i) {
@@ -304,8 +321,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int t = wid; t < num_tiles; t += nworkers) {
                 int tmn = t % tiles_mn, ks = t / tiles_mn;
                 // raster: m fastest -> concurrent CTAs share the W tile in L2; n fastest -> they share the A tile
-                int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
-                int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
+                int tm, tn;
+                tile_coords(p, tmn, tm, tn);
                 int kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     uint8_t *sa = smem + stage * cfg::STAGE_BYTES;
@@ -376,8 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
         for (int t = wid; t < num_tiles; t += nworkers) {
             int tmn = t % tiles_mn, ksp = t / tiles_mn;
-            int tm = p.n_fastest ? tmn / p.tiles_n : tmn % p.tiles_m;
-            int tn = p.n_fastest ? tmn % p.tiles_n : tmn / p.tiles_m;
+            int tm, tn;
+            tile_coords(p, tmn, tm, tn);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = (tm * CG + crank) * BM + q * 32;       // first row of this warp
@@ -634,6 +651,19 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
     {
         double a_bytes = (double)a.M * a.K * 2, w_bytes = (double)a.N * a.K * 2;
         p.n_fastest = (!extra && a_bytes > 48e6 && w_bytes < 96e6 && p.tiles_n <= 32) ? 1 : 0;
+        // M-fastest raster: A is swept once per N tile.  A bigger than what one L2 partition keeps (~60 MB: measured
+        // 24 % of the gate|up A reads came from DRAM at 72 MB) is cut into groups of <= 24 MB of A rows; W is then read
+        // once per group instead of once
+        static const int group_mb = [] { const char *e = getenv("PZ_GEMM_GROUP_MB"); return e ? atoi(e) : 24; }();
+        p.group_m = 0;
+        if (!p.n_fastest && group_mb > 0 && a_bytes > 40e6 && p.tiles_n > 1) {
+            double tile_bytes = (double)BM * CG * a.K * 2;
+            int g = (int)(group_mb * 1e6 / tile_bytes);
+            if (g < 1) g = 1;
+            int ngroups = (p.tiles_m + g - 1) / g;
+            p.group_m = (p.tiles_m + ngroups - 1) / ngroups;   // equal-sized groups
+            if (p.group_m >= p.tiles_m) p.group_m = 0;
+        }
     }
     p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
