@@ -59,10 +59,11 @@ PZ_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-PZ_DEVINL void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+// `hint`: L2 eviction priority of the lines this load touches (L2_EVICT_*)
+PZ_DEVINL void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 PZ_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -109,10 +110,10 @@ PZ_DEVINL void cluster_sync_all() {
 }
 // both CTAs of the pair load their own tiles; the transaction bytes are credited to the LEADER's
 // barrier (CTA rank bit cleared in the shared::cluster address)
-PZ_DEVINL void tma_load_2d_pair(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+PZ_DEVINL void tma_load_2d_pair(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 PZ_DEVINL void tc_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in BOTH CTAs
@@ -159,6 +160,7 @@ struct TcParams {
     int tiles_m, tiles_n;
     int ksplit, kb_per_split;           // split-K (fp32 reduce-add outputs only)
     int n_fastest;                      // tile raster: 1 = consecutive CTAs share the A tile (few N tiles, big A)
+    uint64_t a_hint, w_hint;            // L2 eviction priority of the A / W tile loads
     int group_m;                        // M-fastest raster in groups of group_m M tiles (0 = one group): the A rows of a
                                         // group stay L2 resident while the N tiles sweep past them
     // fused RoPE + Q/K/V split (LIN_ROPE): BN = 256 = head_dim, one N tile per head
@@ -204,7 +206,8 @@ PZ_DEVINL float gelu_fast(float x) {
 
 // L2 policy for the output stream: the C tile is not re-read by this kernel, so it must not evict
 // the A / W tiles that the other CTAs are still streaming from L2 (evict-first)
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_NORMAL = 0x1000000000000000ull,
+                   L2_EVICT_LAST = 0x14F0000000000000ull;
 PZ_DEVINL void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(L2_EVICT_FIRST)
@@ -310,8 +313,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int i = 0; i < pre; ++i) {
                     uint8_t *sa = smem + i * cfg::STAGE_BYTES;
                     if (crank == 0) mbar_expect_tx(&full_bar[i], cfg::STAGE_BYTES * CG);
-                    if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN + crank * (BN / 2));
-                    else tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN);
+                    if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN + crank * (BN / 2), p.w_hint);
+                    else tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN, p.w_hint);
                 }
             }
             pdl_wait();
@@ -329,11 +332,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (it >= pre) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (crank == 0) mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES * CG);
-                        if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN + crank * (BN / 2));
-                        else tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN);
+                        if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN + crank * (BN / 2), p.w_hint);
+                        else tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN, p.w_hint);
                     }
-                    if (CG == 2) tma_load_2d_pair(&map_a, &full_bar[stage], sa, kb * BK, (tm * CG + crank) * BM);
-                    else tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM);
+                    if (CG == 2) tma_load_2d_pair(&map_a, &full_bar[stage], sa, kb * BK, (tm * CG + crank) * BM, p.a_hint);
+                    else tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM, p.a_hint);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -664,6 +667,13 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
             p.group_m = (p.tiles_m + ngroups - 1) / ngroups;   // equal-sized groups
             if (p.group_m >= p.tiles_m) p.group_m = 0;
         }
+        // L2 eviction priorities (experiment, off unless PZ_GEMM_HINTS=1): keep the operand every concurrently running
+        // worker re-reads, drop the streaming one first.  Measured: no effect on gate|up (610 vs 611 MB of DRAM reads) and
+        // HARMFUL for down_proj (1333 -> 2759 MB: the 8 workers of an M tile no longer find each other's A lines in L2).
+        static const bool hints = [] { const char *e = getenv("PZ_GEMM_HINTS"); return e && e[0] == '1'; }();
+        p.a_hint = p.w_hint = L2_EVICT_NORMAL;
+        if (hints && p.n_fastest && a_bytes > 96e6) { p.a_hint = L2_EVICT_FIRST; p.w_hint = L2_EVICT_LAST; }
+        else if (hints && p.group_m > 0) { p.a_hint = L2_EVICT_LAST; }
     }
     p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
