@@ -33,7 +33,7 @@ METRIC = "action chunks/s per box (bridge-shape infer_action, bf16); p50 infer_a
 UNIT = "action_chunks/s"
 PER_GPU_BATCH = int(os.environ.get("PZ_BENCH_BATCH", "64"))
 # DRAM bytes of one VLM gate|up GEMM launch at bs=64 (cta_group::2 kernel), from the committed ncu capture
-GATE_UP_DRAM_BYTES = 2.091388e9 + 570.776320e6
+GATE_UP_DRAM_BYTES = 609.5e6 + 552.6e6   # dram read + write of one launch (profiles/r01_ncu_gemm_dram_raster.txt)
 # DRAM bytes of the bs=1 sampler launch (10 Euler steps), same file
 MEGA_BS1_DRAM_BYTES = 6.323853e9 + 4.368128e6
 
@@ -472,8 +472,8 @@ def main():
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm_tc_kernel<256, cta_group::2> (VLM gate|up + GeGLU)", achieved=achieved,
                     peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["tflops_sustained"],
-                    traffic=GATE_UP_DRAM_BYTES, traffic_source="profiles/r01_ncu_full_final.txt (ncu --set full, "
-                    "dram__bytes_read.sum + dram__bytes_write.sum of one launch); algorithmic bytes 785 MB",
+                    traffic=GATE_UP_DRAM_BYTES, traffic_source="profiles/r01_ncu_gemm_dram_raster.txt (ncu, "
+                    "dram__bytes_read.sum + dram__bytes_write.sum of one launch, grouped raster; 2.6 GB before it); algorithmic bytes 785 MB",
                     avg_launch_ms=avg_ms, launches_timed=gu_n,
                     share_of_step=gu_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps, peak_source=peaks["source"] + ", sustained figure")
 
