@@ -34,6 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("PZ_NVCC_EXTRA", "").split()   # e.g. -DPZ_MEGA_TRACE for tools/stage_times.py's per-phase stamps
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

@@ -77,6 +77,10 @@ SHAPES = [
     (2304, 4304, 1152, GELU, True, 1.0),
     (2500, 2560, 2048, 0, False, 1.0),               # M tail inside a pair tile (2500 = 9*256 + 196)
     (2049, 1152, 4304, OUT_F32 | ACCUM, True, 1.0),  # second CTA of the last pair almost empty
+    # N = 1152 at M >= 2048 (4.5 pair tiles of 256 columns)
+    (4096, 1152, 1152, OUT_F32 | ACCUM, True, 1.0),  # SigLIP out_proj + residual
+    (2304, 1152, 1152, 0, True, 1.0),
+    (2100, 1152, 640, GELU, True, 1.0),
 ]
 
 

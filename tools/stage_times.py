@@ -1,4 +1,6 @@
-"""Time the three stages of infer_action separately (each captured in its own CUDA graph)."""
+"""Time the three stages of infer_action separately (each captured in its own CUDA graph).
+The per-phase stamps of the persistent sampler need a trace build:
+    PZ_NVCC_EXTRA=-DPZ_MEGA_TRACE python open-pi-zero_b200/build.py --force"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
