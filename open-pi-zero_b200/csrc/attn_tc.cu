@@ -24,8 +24,10 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace {
+using namespace tcptx;
 
 constexpr int HD = 256, TOK = 16, NH = 8, ROWS = TOK * NH, KC = 128;
 constexpr int THREADS = 12 * 32;
@@ -33,85 +35,6 @@ constexpr int SM_WARP0 = 4, SM_THREADS = 256;
 constexpr int BLK = 16384;                       // one [128 rows x 64 elements] swizzled block
 constexpr int OFF_Q = 0, OFF_K = 4 * BLK, OFF_V = 8 * BLK, OFF_P = 12 * BLK, OFF_MISC = 14 * BLK;
 constexpr int SMEM_BYTES = OFF_MISC + 2048 + 1024 /*alignment slack*/;
-
-PZ_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-PZ_DEVINL void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-PZ_DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-PZ_DEVINL void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-PZ_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-PZ_DEVINL void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-PZ_DEVINL void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-PZ_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-PZ_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-PZ_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-PZ_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-PZ_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-PZ_DEVINL void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-PZ_DEVINL void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-PZ_DEVINL void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-PZ_DEVINL void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-PZ_DEVINL void st_shared_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// UMMA shared-memory descriptors (bf16, 128-byte swizzle, descriptor version 1 = Blackwell).
-// K-major operand: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
-PZ_DEVINL uint64_t desc_kmajor(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// MN-major operand (V in its [key][d] layout: d = N is the contiguous dimension): a swizzle atom is 64 N-elements x
-// 8 K-rows; the next 64 N-elements are LBO bytes away (the next [128 keys x 64 d] block), the next 8 K-rows SBO = 1024 B.
-PZ_DEVINL uint64_t desc_mnmajor(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(BLK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// instruction descriptor: D fp32, A / B bf16, M x N; b_mn = 1: B is MN-major
-PZ_DEVINL uint32_t umma_idesc(int M, int N, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct AttnTcParams {
     const int32_t *valid_len;
@@ -207,21 +130,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 mbar_wait(p_full, c & 1);
                 mbar_wait(v_full, c & 1);
                 tc_fence_after();
-                const uint32_t idesc = umma_idesc(ROWS, HD, 1);
+                const uint32_t idesc = umma_idesc_bmn(ROWS, HD);
                 const int ks = nk16(c) >> 4;
                 for (int k = 0; k < ks; ++k)
-                    tc_mma(tmem_o, desc_kmajor(aP + (k >> 2) * BLK + (k & 3) * 32), desc_mnmajor(aV + k * 2048), idesc, (c | k) != 0);
+                    tc_mma(tmem_o, umma_desc_sw128(aP + (k >> 2) * BLK + (k & 3) * 32), umma_desc_sw128_mn(aV + k * 2048, BLK), idesc, (c | k) != 0);
                 tc_commit(pv_done);
             };
             mbar_wait(q_full, 0);
             for (int c = 0; c < NC; ++c) {
                 mbar_wait(k_full, c & 1);
                 tc_fence_after();
-                const uint32_t idesc = umma_idesc(ROWS, nk16(c), 0);
+                const uint32_t idesc = umma_idesc(ROWS, nk16(c));
                 const uint32_t d_s = tmem_base + (c & 1) * KC;
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk)
-                    tc_mma(d_s, desc_kmajor(aQ + (kk >> 2) * BLK + (kk & 3) * 32), desc_kmajor(aK + (kk >> 2) * BLK + (kk & 3) * 32), idesc, kk != 0);
+                    tc_mma(d_s, umma_desc_sw128(aQ + (kk >> 2) * BLK + (kk & 3) * 32), umma_desc_sw128(aK + (kk >> 2) * BLK + (kk & 3) * 32), idesc, kk != 0);
                 tc_commit(&s_full[c & 1]);
                 if (c >= 1) issue_pv(c - 1);
             }
@@ -329,22 +252,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
 // bf16 tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B-swizzled box
 bool make_map3(CUtensorMap *map, const void *base, long d0, long d1, long d2, long stride1, long stride2, int b0, int b1, int b2) {
     EncodeTiledFn enc = get_encode();

@@ -81,6 +81,9 @@ SHAPES = [
     (4096, 1152, 1152, OUT_F32 | ACCUM, True, 1.0),  # SigLIP out_proj + residual
     (2304, 1152, 1152, 0, True, 1.0),
     (2100, 1152, 640, GELU, True, 1.0),
+    # A = 72 MB (> 40 MB): the M-fastest raster walks M in groups of <= 24 MB of A rows (3 groups of 23 pair tiles)
+    (17664, 768, 2048, 0, True, 1.0),
+    (17000, 512, 2048, GEGLU, False, 1.0),           # last group smaller than the others, M tail
 ]
 
 
