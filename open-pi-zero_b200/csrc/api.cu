@@ -179,6 +179,8 @@ template <> struct Ops<bf16> {
     static int attention(pz_handle *h, const AttnArgs &a, cudaStream_t st) {
         if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_tc_supported(a))
             return launch_attn_tc(a, st);     // prefix vlm rows: tcgen05
+        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_tc_vit_supported(a))
+            return launch_attn_tc_vit(a, st); // SigLIP encoder: tcgen05
         if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_mma_supported(a))
             return launch_attn_mma(a, st);
         launch_attn_simple<bf16>(a, st);
@@ -889,8 +891,11 @@ int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const
         int rc = launch_attn_mma(a, st);
         if (rc) return rc;
     } else if (impl == 3) {
-        if (dtype != PZ_BF16 || !attn_tc_supported(a)) return PZ_ERR_INVALID;
-        int rc = launch_attn_tc(a, st);
+        if (dtype != PZ_BF16) return PZ_ERR_INVALID;
+        int rc;
+        if (attn_tc_supported(a)) rc = launch_attn_tc(a, st);
+        else if (attn_tc_vit_supported(a)) rc = launch_attn_tc_vit(a, st);
+        else return PZ_ERR_INVALID;
         if (rc) return rc;
     } else {
         return PZ_ERR_INVALID;

@@ -251,6 +251,194 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
+// =====================================================================================================
+// SigLIP encoder attention (siglip.py:108-166) on tcgen05: 16 heads x head_dim 72, 256 tokens, no mask, no soft-cap.
+// One CTA per (image, head); K and V (256 x 72) are loaded once, the two 128-row query tiles run back to back:
+//   S = Q K^T (128 x 256 x 80: head_dim padded to 80 by the tensor map's out-of-bounds zero fill, five k-steps) into
+//   256 TMEM columns -> 8 softmax warps, exact two-pass softmax (row maximum, then exp and row sum; the scores are
+//   unbounded here, unlike the soft-capped Gemma attention) -> P (128 x 256 bf16, K-major swizzled, 64 KB) ->
+//   O = P V (128 x 80 x 256; V MN-major, N = 80 spans 1.25 swizzle atoms) into 80 more TMEM columns -> O / rowsum ->
+//   TMA store.  Operand blocks keep the 128-byte swizzle: d 64..71 live in a second [rows x 64] block whose d >= 72
+//   columns are zeros.
+constexpr int V_HDP = 80, V_TOK = 256, V_QT = 128;
+constexpr int V_QBLK = V_QT * 128, V_KBLK = V_TOK * 128;                 // bytes of one [rows x 64 d] block
+constexpr int V_OFF_Q = 0, V_OFF_K = 2 * V_QBLK, V_OFF_V = V_OFF_K + 2 * V_KBLK, V_OFF_P = V_OFF_V + 2 * V_KBLK,
+              V_OFF_MISC = V_OFF_P + 4 * BLK;
+constexpr int V_SMEM_BYTES = V_OFF_MISC + 128 + 1024 /*row exchange*/ + 1024 /*alignment slack*/;   // 231 552 <= 232 448
+
+struct AttnVitParams {
+    int n_heads;
+    float scale_log2e;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_tc_vit_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const AttnVitParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sQ = smem + V_OFF_Q, *sK = smem + V_OFF_K, *sV = smem + V_OFF_V, *sP = smem + V_OFF_P;
+    uint64_t *bars = (uint64_t *)(smem + V_OFF_MISC);
+    uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *pv_done = bars + 5;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 8);
+    float *sX = (float *)(smem + V_OFF_MISC + 128);           // [2][128] partial row maxima, then partial row sums
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x / p.n_heads, head = blockIdx.x % p.n_heads;
+    const int row_base = img * V_TOK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1);
+        mbar_init(p_full, SM_THREADS / 32); mbar_init(pv_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + V_TOK;
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            pdl_wait();   // q | k | v come from the preceding projection
+            mbar_expect_tx(k_full, 2 * V_KBLK);
+            for (int kd = 0; kd < 2; ++kd) tma_load_3d(&map_k, k_full, sK + kd * V_KBLK, 64 * kd, head, row_base);
+            mbar_expect_tx(q_full, 2 * V_QBLK);
+            for (int kd = 0; kd < 2; ++kd) tma_load_3d(&map_q, q_full, sQ + kd * V_QBLK, 64 * kd, head, row_base);
+            mbar_expect_tx(v_full, 2 * V_KBLK);
+            for (int kd = 0; kd < 2; ++kd) tma_load_3d(&map_v, v_full, sV + kd * V_KBLK, 64 * kd, head, row_base);
+            mbar_wait(s_full, 0);   // S of the first query tile has consumed the Q buffer
+            mbar_expect_tx(q_full, 2 * V_QBLK);
+            for (int kd = 0; kd < 2; ++kd) tma_load_3d(&map_q, q_full, sQ + kd * V_QBLK, 64 * kd, head, row_base + V_QT);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+            mbar_wait(k_full, 0);
+            for (int qt = 0; qt < 2; ++qt) {
+                mbar_wait(q_full, qt);
+                if (qt > 0) mbar_wait(pv_done, 0);   // (the softmax warps have read S and O of tile 0 by then: see p_full / epilogue order)
+                tc_fence_after();
+                {
+                    const uint32_t idesc = umma_idesc(V_QT, V_TOK);
+#pragma unroll
+                    for (int kk = 0; kk < V_HDP / 16; ++kk)
+                        tc_mma(tmem_base, umma_desc_sw128(aQ + (kk >> 2) * V_QBLK + (kk & 3) * 32),
+                               umma_desc_sw128(aK + (kk >> 2) * V_KBLK + (kk & 3) * 32), idesc, kk != 0);
+                    tc_commit(s_full);
+                }
+                mbar_wait(p_full, qt);
+                if (qt == 0) mbar_wait(v_full, 0);
+                tc_fence_after();
+                {
+                    const uint32_t idesc = umma_idesc_bmn(V_QT, V_HDP);
+                    for (int k = 0; k < V_TOK / 16; ++k)
+                        tc_mma(tmem_o, umma_desc_sw128(aP + (k >> 2) * BLK + (k & 3) * 32), umma_desc_sw128_mn(aV + k * 2048, V_KBLK), idesc, k != 0);
+                    tc_commit(pv_done);
+                }
+            }
+        }
+    } else if (warp >= SM_WARP0) {
+        const int q = warp & 3, half = (warp - SM_WARP0) >> 2;
+        const int row = q * 32 + lane;
+        const int sw = row & 7;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int qt = 0; qt < 2; ++qt) {
+            mbar_wait(s_full, qt);
+            tc_fence_after();
+            // pass 1: row maximum over this warp's 128 key columns
+            float m = -INFINITY;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + lane_addr + half * 128 + cc * 32, v);
+                tc_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+            sX[half * V_QT + row] = m;
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");
+            m = fmaxf(sX[row], sX[V_QT + row]);
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // everybody has read the maxima: sX is reused for the sums
+            // pass 2: P = exp((s - m) * scale), row sum
+            float lsum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + lane_addr + half * 128 + cc * 32, v);
+                tc_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = ex2_approx((__uint_as_float(v[j]) - m) * p.scale_log2e);
+                    const float p1 = ex2_approx((__uint_as_float(v[j + 1]) - m) * p.scale_log2e);
+                    lsum += p0 + p1;
+                    pk[j >> 1] = pack_bf16x2(p0, p1);
+                }
+                // keys half*128 + cc*32 .. +32 -> atom (64 keys) half*2 + cc/2, 16-byte chunks (cc & 1)*4 .. +3
+                uint8_t *prow = sP + (half * 2 + (cc >> 1)) * BLK + row * 128;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    st_shared_v4(prow + ((((cc & 1) * 4 + i) ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
+            sX[half * V_QT + row] = lsum;
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            // ---- epilogue of this query tile
+            mbar_wait(pv_done, qt);
+            tc_fence_after();
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // row sums complete; P consumed -> its buffer is the staging area
+            const float l = sX[row] + sX[V_QT + row];
+            const float inv = 1.f / l;
+            // O columns: half 0 -> d 0..63 (block 0), half 1 -> d 64..79 (block 1; only d < 72 is stored)
+            const int ncc = half == 0 ? 2 : 1;
+            for (int cc = 0; cc < ncc; ++cc) {
+                const int col0 = half * 64 + cc * 32;
+                uint32_t v[32];
+                tc_ld32(tmem_o + lane_addr + col0, v);
+                tc_ld_wait();
+                uint8_t *orow = sP + (col0 >> 6) * V_QBLK + row * 128;
+                const int ch0 = (col0 & 63) >> 3;
+                const int nch = half == 0 ? 4 : 2;                         // 16 valid columns in block 1
+                for (int i = 0; i < nch; ++i) {
+                    uint32_t w0 = pack_bf16x2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+                    uint32_t w1 = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+                    uint32_t w2 = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+                    uint32_t w3 = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+                    st_shared_v4(orow + (((ch0 + i) ^ sw) << 4), w0, w1, w2, w3);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");
+            if (threadIdx.x == SM_WARP0 * 32) {
+                for (int kd = 0; kd < 2; ++kd) tma_store_3d(&map_o, sP + kd * V_QBLK, 64 * kd, head, row_base + qt * V_QT);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");   // staging (= P buffer) free again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 // bf16 tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B-swizzled box
 bool make_map3(CUtensorMap *map, const void *base, long d0, long d1, long d2, long stride1, long stride2, int b0, int b1, int b2) {
@@ -266,6 +454,41 @@ bool make_map3(CUtensorMap *map, const void *base, long d0, long d1, long d2, lo
 }
 
 }  // namespace
+
+int attn_tc_vit_supported(const AttnArgs &a) {
+    static const bool off = [] { const char *e = getenv("PZ_ATTN_TC_VIT"); return e && e[0] == '0'; }();
+    if (off) return 0;
+    if (a.head_dim <= 64 || a.head_dim > V_HDP || a.head_dim % 8 || a.valid_len || a.n_fresh != 0 || a.q_row0 != 0) return 0;
+    if (a.q_rows != V_TOK || a.s_cache != V_TOK || a.softcap != 0.f) return 0;
+    if (a.kv_head_stride != a.head_dim || a.q_head_stride != a.head_dim || a.o_head_stride != a.head_dim) return 0;
+    if (a.kv_row_stride % 8 || a.q_row_stride % 8 || a.o_row_stride % 8) return 0;
+    if (a.q_batch_stride != (long)V_TOK * a.q_row_stride || a.kv_batch_stride != (long)V_TOK * a.kv_row_stride ||
+        a.o_batch_stride != (long)V_TOK * a.o_row_stride) return 0;
+    if (((uintptr_t)a.Q | (uintptr_t)a.K | (uintptr_t)a.V | (uintptr_t)a.O) & 15) return 0;
+    return 1;
+}
+
+int launch_attn_tc_vit(const AttnArgs &a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_tc_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES) != cudaSuccess)
+            return PZ_ERR_CUDA;
+        attr_set = true;
+    }
+    CUtensorMap mq, mk, mv, mo;
+    const long rows = (long)a.batch * V_TOK;
+    // [d (head_dim; the 64-wide boxes at d = 64 are zero-filled beyond it)][head][token row]
+    if (!make_map3(&mq, a.Q, a.head_dim, a.n_heads, rows, a.q_head_stride, a.q_row_stride, 64, 1, V_QT) ||
+        !make_map3(&mo, a.O, a.head_dim, a.n_heads, rows, a.o_head_stride, a.o_row_stride, 64, 1, V_QT) ||
+        !make_map3(&mk, a.K, a.head_dim, a.n_heads, rows, a.kv_head_stride, a.kv_row_stride, 64, 1, V_TOK) ||
+        !make_map3(&mv, a.V, a.head_dim, a.n_heads, rows, a.kv_head_stride, a.kv_row_stride, 64, 1, V_TOK))
+        return PZ_ERR_CUDA;
+    AttnVitParams p;
+    p.n_heads = a.n_heads;
+    p.scale_log2e = a.scale * 1.4426950408889634f;
+    launch_k(attn_tc_vit_kernel, dim3((unsigned)(a.batch * a.n_heads)), dim3(THREADS), (size_t)V_SMEM_BYTES, st, mq, mk, mv, mo, p);
+    return 0;
+}
 
 int attn_tc_supported(const AttnArgs &a) {
     static const bool off = [] { const char *e = getenv("PZ_ATTN_TC"); return e && e[0] == '0'; }();

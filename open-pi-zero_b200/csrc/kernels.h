@@ -69,6 +69,9 @@ int launch_attn_mma_partials(const AttnArgs &a, cudaStream_t st);
 // attn_tc.cu (tcgen05 attention for the vlm rows of the prefix pass: bf16, head_dim 256, 8 query heads on one K/V head)
 int attn_tc_supported(const AttnArgs &a);
 int launch_attn_tc(const AttnArgs &a, cudaStream_t st);
+// SigLIP encoder attention on tcgen05 (256 tokens, head_dim 72, no mask)
+int attn_tc_vit_supported(const AttnArgs &a);
+int launch_attn_tc_vit(const AttnArgs &a, cudaStream_t st);
 
 // denoise_mega.cu (persistent cooperative sampler for B * horizon <= 16)
 struct MegaBuffers {
