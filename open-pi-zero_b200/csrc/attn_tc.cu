@@ -327,7 +327,9 @@ attn_tc_vit_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_wait(k_full, 0);
             for (int qt = 0; qt < 2; ++qt) {
                 mbar_wait(q_full, qt);
-                if (qt > 0) mbar_wait(pv_done, 0);   // (the softmax warps have read S and O of tile 0 by then: see p_full / epilogue order)
+                // tile 1: S may be overwritten as soon as the softmax warps have read tile 0's (p_full(0), waited for below
+                // in the previous iteration); O is overwritten by P V of tile 1, which waits for p_full(1) -- every softmax
+                // warp arrives there only after its epilogue of tile 0 has read O
                 tc_fence_after();
                 {
                     const uint32_t idesc = umma_idesc(V_QT, V_TOK);
