@@ -33,6 +33,7 @@ constexpr int HD = 256, TOK = 16, NH = 8, ROWS = TOK * NH, KC = 128;
 constexpr int THREADS = 12 * 32;
 constexpr int SM_WARP0 = 4, SM_THREADS = 256;
 constexpr int BLK = 16384;                       // one [128 rows x 64 elements] swizzled block
+constexpr int TBLK = 32 * 128;                   // the same for a 32-row box
 constexpr int OFF_Q = 0, OFF_K = 4 * BLK, OFF_V = 8 * BLK, OFF_P = 12 * BLK, OFF_MISC = 14 * BLK;
 constexpr int SMEM_BYTES = OFF_MISC + 2048 + 1024 /*alignment slack*/;
 
@@ -65,7 +66,8 @@ PZ_DEVINL float softcap_tanh(float y) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const AttnTcParams p) {
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+               const __grid_constant__ CUtensorMap map_k32, const __grid_constant__ CUtensorMap map_v32, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sQ = smem + OFF_Q, *sK = smem + OFF_K, *sV = smem + OFF_V, *sP = smem + OFF_P;
@@ -83,12 +85,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int vlen = min(max(p.valid_len[b], 0), p.s_vlm);
     const int NC = t0 < vlen ? (vlen + KC - 1) / KC : 0;   // key chunks; a tile of pad rows only writes zeros
     auto nk16 = [&](int c) { int nk = min(vlen - c * KC, KC); return (nk + 15) & ~15; };
+    // a chunk of <= 32 keys (the last one: 276 = 2 * 128 + 20) is loaded through 32-row boxes: 4 x 4 KB per operand
+    // instead of 4 x 16 KB; its [rows x 64 d] blocks are then TBLK apart
+    auto blk_of = [&](int c) { return nk16(c) <= 32 ? TBLK : BLK; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k32) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v32) : "memory");
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
@@ -115,11 +122,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (int kd = 0; kd < 4; ++kd) tma_load_3d(&map_q, q_full, sQ + kd * BLK, 64 * kd, 0, row0);
             for (int c = 0; c < NC; ++c) {
                 if (c > 0) mbar_wait(&s_full[(c - 1) & 1], ((c - 1) >> 1) & 1);   // S_{c-1} has consumed the K buffer
-                mbar_expect_tx(k_full, 4 * BLK);
-                for (int kd = 0; kd < 4; ++kd) tma_load_3d(&map_k, k_full, sK + kd * BLK, 64 * kd, KC * c, b);
+                const int blk = blk_of(c);
+                const CUtensorMap *mk = blk == BLK ? &map_k : &map_k32, *mv = blk == BLK ? &map_v : &map_v32;
+                mbar_expect_tx(k_full, 4 * blk);
+                for (int kd = 0; kd < 4; ++kd) tma_load_3d(mk, k_full, sK + kd * blk, 64 * kd, KC * c, b);
                 if (c > 0) mbar_wait(pv_done, (c - 1) & 1);                       // P V_{c-1} has consumed the V buffer
-                mbar_expect_tx(v_full, 4 * BLK);
-                for (int kd = 0; kd < 4; ++kd) tma_load_3d(&map_v, v_full, sV + kd * BLK, 64 * kd, KC * c, b);
+                mbar_expect_tx(v_full, 4 * blk);
+                for (int kd = 0; kd < 4; ++kd) tma_load_3d(mv, v_full, sV + kd * blk, 64 * kd, KC * c, b);
             }
         }
     } else if (warp == 1) {
@@ -133,7 +142,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const uint32_t idesc = umma_idesc_bmn(ROWS, HD);
                 const int ks = nk16(c) >> 4;
                 for (int k = 0; k < ks; ++k)
-                    tc_mma(tmem_o, umma_desc_sw128(aP + (k >> 2) * BLK + (k & 3) * 32), umma_desc_sw128_mn(aV + k * 2048, BLK), idesc, (c | k) != 0);
+                    tc_mma(tmem_o, umma_desc_sw128(aP + (k >> 2) * BLK + (k & 3) * 32), umma_desc_sw128_mn(aV + k * 2048, blk_of(c)), idesc, (c | k) != 0);
                 tc_commit(pv_done);
             };
             mbar_wait(q_full, 0);
@@ -142,9 +151,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc(ROWS, nk16(c));
                 const uint32_t d_s = tmem_base + (c & 1) * KC;
+                const int kblk = blk_of(c);
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk)
-                    tc_mma(d_s, umma_desc_sw128(aQ + (kk >> 2) * BLK + (kk & 3) * 32), umma_desc_sw128(aK + (kk >> 2) * BLK + (kk & 3) * 32), idesc, kk != 0);
+                    tc_mma(d_s, umma_desc_sw128(aQ + (kk >> 2) * BLK + (kk & 3) * 32), umma_desc_sw128(aK + (kk >> 2) * kblk + (kk & 3) * 32), idesc, kk != 0);
                 tc_commit(&s_full[c & 1]);
                 if (c >= 1) issue_pv(c - 1);
             }
@@ -193,7 +203,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     mbar_wait(v_full, c & 1);
                     for (int i = lane; i < (n16 - nk) * 32; i += 32) {
                         const int r = nk + (i >> 5), ch = i & 31;   // row, 16-byte chunk across the four d blocks
-                        st_shared_v4(sV + (ch >> 3) * BLK + r * 128 + ((ch & 7) << 4), 0u, 0u, 0u, 0u);
+                        st_shared_v4(sV + (ch >> 3) * blk_of(c) + r * 128 + ((ch & 7) << 4), 0u, 0u, 0u, 0u);
                     }
                 }
             }
@@ -511,12 +521,14 @@ int launch_attn_tc(const AttnArgs &a, cudaStream_t st) {
             return PZ_ERR_CUDA;
         attr_set = true;
     }
-    CUtensorMap mq, mk, mv, mo;
+    CUtensorMap mq, mk, mv, mo, mk32, mv32;
     const long rows = (long)a.batch * a.q_rows;
     if (!make_map3(&mq, a.Q, HD, NH, rows, a.q_head_stride, a.q_row_stride, 64, NH, TOK) ||
         !make_map3(&mo, a.O, HD, NH, rows, a.o_head_stride, a.o_row_stride, 64, NH, TOK) ||
         !make_map3(&mk, a.K, HD, a.s_cache, a.batch, a.kv_row_stride, a.kv_batch_stride, 64, KC, 1) ||
-        !make_map3(&mv, a.V, HD, a.s_cache, a.batch, a.kv_row_stride, a.kv_batch_stride, 64, KC, 1))
+        !make_map3(&mv, a.V, HD, a.s_cache, a.batch, a.kv_row_stride, a.kv_batch_stride, 64, KC, 1) ||
+        !make_map3(&mk32, a.K, HD, a.s_cache, a.batch, a.kv_row_stride, a.kv_batch_stride, 64, 32, 1) ||
+        !make_map3(&mv32, a.V, HD, a.s_cache, a.batch, a.kv_row_stride, a.kv_batch_stride, 64, 32, 1))
         return PZ_ERR_CUDA;
     AttnTcParams p;
     p.valid_len = a.valid_len;
@@ -524,6 +536,6 @@ int launch_attn_tc(const AttnArgs &a, cudaStream_t st) {
     p.tiles_per_sample = (a.s_vlm + TOK - 1) / TOK;
     p.y_scale = a.scale / a.softcap;
     p.cap_log2e = a.softcap * 1.4426950408889634f;
-    launch_k(attn_tc_kernel, dim3((unsigned)(a.batch * p.tiles_per_sample)), dim3(THREADS), (size_t)SMEM_BYTES, st, mq, mk, mv, mo, p);
+    launch_k(attn_tc_kernel, dim3((unsigned)(a.batch * p.tiles_per_sample)), dim3(THREADS), (size_t)SMEM_BYTES, st, mq, mk, mv, mo, mk32, mv32, p);
     return 0;
 }
