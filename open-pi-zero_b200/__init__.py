@@ -9,11 +9,14 @@ from .synth import init_state_dict, make_inputs, state_dict_spec
 
 __all__ = ["BRIDGE_DIMS", "PI0_PAPER_DIMS", "AttrDict", "cfg_from_dims", "dims_from_cfg",
            "make_dims", "init_state_dict", "make_inputs", "state_dict_spec", "PiZero",
-           "PiZeroInference", "JointModel", "KVCache"]
+           "PiZeroInference", "JointModel", "KVCache", "FlowTimeSampler"]
 
 
 def __getattr__(name):   # lazy: importing the package must not need torch.cuda / the .so
     if name in ("PiZero", "PiZeroInference", "JointModel", "KVCache", "PzError"):
         from . import pizero
         return getattr(pizero, name)
+    if name == "FlowTimeSampler":
+        from .flow import FlowTimeSampler
+        return FlowTimeSampler
     raise AttributeError(name)

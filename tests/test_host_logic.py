@@ -132,3 +132,37 @@ def test_packed_weight_staleness_key_is_cheap_and_sees_moves():
     with torch.no_grad():
         next(iter(m.parameters())).add_(1.0)         # the first parameter is always in the sample
     assert m._param_key() != k1
+
+
+def test_flow_time_sampler_matches_reference_formulas():
+    """train.py:217-247: beta sampling t = (1 - sig_min)(1 - Beta(1.5, 1)) and the stratified uniform variant --
+    same torch RNG stream, so the draws are bit-equal to the reference's expressions."""
+    import torch
+    from open_pi_zero_b200.flow import FlowTimeSampler
+    s = FlowTimeSampler.from_cfg(pz.cfg_from_dims(pz.make_dims()))
+    torch.manual_seed(5)
+    t = s.sample_fm_time(4096)
+    torch.manual_seed(5)
+    want = (1 - 0.001) * (1 - torch.distributions.Beta(1.5, 1).sample((4096,)))
+    assert torch.equal(t, want)
+    assert 0.0 <= float(t.min()) and float(t.max()) <= 0.999
+    assert abs(float(t.mean()) - 0.999 * (1 - 1.5 / 2.5)) < 0.02      # E[Beta(a, b)] = a / (a + b)
+    u = FlowTimeSampler("uniform")
+    torch.manual_seed(7)
+    tu = u.sample_fm_time(8)
+    torch.manual_seed(7)
+    wu = (torch.rand(1) + torch.arange(8) / 8) % (1 - 1e-5)
+    assert torch.equal(tu, wu)
+    import pytest
+    with pytest.raises(AssertionError):
+        FlowTimeSampler("gaussian")
+
+
+def test_flow_sig_min_travels_through_the_config():
+    d = pz.make_dims(flow_sig_min=0.01)
+    cfg = pz.cfg_from_dims(d)
+    assert cfg.flow_sig_min == 0.01
+    assert pz.dims_from_cfg(cfg)["flow_sig_min"] == 0.01
+    plain = pz.cfg_from_dims(pz.make_dims())
+    del plain["flow_sig_min"]                      # the reference's yaml does not carry it (pizero.py:58 default)
+    assert pz.dims_from_cfg(plain)["flow_sig_min"] == 0.001
