@@ -63,6 +63,27 @@ def run_reference(dims, sd, inp, actions, noise, t):
     return dict(loss=loss.clone(), v_psi=cap["v_psi"], seconds=dt)
 
 
+def run_reference_grads(dims, sd, inp, actions, noise, t):
+    """d loss / d parameter of the unmodified reference (its own autograd), fp32 CPU; small configs only."""
+    ref_shims.install()
+    model = ref_shims.build_reference_model(dims)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    cm, vpos, ppos, apos = model.build_causal_mask_and_position_ids(inp["attention_mask"], torch.float32)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, **kw: noise.to(kw.get("dtype", x.dtype)).clone()
+    try:
+        loss = model.forward(input_ids=inp["input_ids"], pixel_values=inp["pixel_values"], causal_mask=cm,
+                             vlm_position_ids=vpos, proprio_position_ids=ppos, action_position_ids=apos,
+                             proprios=inp["proprios"], actions=actions, t=t)
+        loss.backward()
+    finally:
+        torch.randn_like = orig
+    return {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+
+
 def main(argv):
     for name in argv or ["tiny", "width2"]:
         case = CASES[name]
@@ -79,6 +100,7 @@ def main(argv):
         if case["store_weights"]:
             fx["state_dict"] = sd
             fx["inputs"] = inp
+            fx["ref"]["grads"] = run_reference_grads(dims, sd, inp, actions, noise, t)   # the training step's backward
         path = os.path.join(ROOT, "tests", "golden", f"fm_{name}.pt")
         torch.save(fx, path)
         print(f"[fm_{name}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB)", flush=True)

@@ -353,3 +353,16 @@ def flow_matching_loss(sd, dims, input_ids, pixel_values, attention_mask, propri
     if capture is not None:
         capture.update(psi_t=psi.clone(), v_psi=v_psi.clone(), d_psi=d_psi.clone())
     return torch.mean((v_psi - d_psi) ** 2)
+
+
+def flow_matching_loss_and_grads(sd, dims, input_ids, pixel_values, attention_mask, proprios, actions, t, noise):
+    """The training step's backward, as autograd of the restatement above (the checker for the backward kernels of
+    SURVEY 8f-1; the reference's own backward is `normalized_loss.backward()`, train.py:355-368).  Returns
+    (loss, {key: d loss / d parameter}); parameters the loss does not depend on (the vlm / proprio post-attention
+    half of the last layer, joint_model.py:297-299; `embed_tokens` rows never looked up) get zeros."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        loss = flow_matching_loss.__wrapped__(leaf, dims, input_ids, pixel_values, attention_mask, proprios, actions, t, noise)
+        loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+    return loss.detach(), grads
