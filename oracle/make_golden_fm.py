@@ -101,6 +101,14 @@ def main(argv):
             fx["state_dict"] = sd
             fx["inputs"] = inp
             fx["ref"]["grads"] = run_reference_grads(dims, sd, inp, actions, noise, t)   # the training step's backward
+        elif name == "width2":
+            # real widths: per-tensor Frobenius norm of the reference's gradient plus the first 4 rows (or elements) of each
+            # tensor -- enough to pin a backward at these shapes without storing 2.6 GB
+            g = run_reference_grads(dims, sd, inp, actions, noise, t)
+            fx["ref"]["grad_norms"] = {k: v.double().norm().float() for k, v in g.items()}
+            fx["ref"]["grad_heads"] = {k: v.reshape(v.shape[0], -1)[:4, :64].clone() if v.dim() > 1 else v[:64].clone()
+                                       for k, v in g.items()}
+            del g
         path = os.path.join(ROOT, "tests", "golden", f"fm_{name}.pt")
         torch.save(fx, path)
         print(f"[fm_{name}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB)", flush=True)
