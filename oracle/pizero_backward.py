@@ -1,15 +1,19 @@
 """TEST INFRASTRUCTURE ONLY -- the backward pass of the flow-matching training step
 (`PiZero.forward` + `loss.backward()`, pizero.py:607-661 / train.py:350-368) written
-out op by op, without autograd, for the part of the model the CUDA backward kernels of
-SURVEY 8f-1 will cover first: the loss, `action_decoder`, the joint mixture-of-
-transformers (all three mixtures active, full block mask, no cache) and
-`action_encoder`.  Everything upstream of the joint model's inputs (SigLIP, projector,
-token embedding, `proprio_encoder`) receives `d loss / d embeds` from here.
+out op by op, without autograd: the statement the CUDA backward kernels of SURVEY 8f-1
+will follow.
+
+  flow_matching_backward       loss, `action_decoder`, the joint mixture-of-transformers
+                               (all three mixtures active, full block mask, no cache),
+                               `action_encoder`; returns d loss / d embeds for the rest
+  flow_matching_backward_full  + `proprio_encoder`, the embedding merge / token embedding,
+                               projector and SigLIP (patch matmul, LayerNorm, attention, MLP)
 
 Each formula is the derivative of the forward statement in `oracle/pizero_oracle.py`
 (which cites the reference lines); `tests/test_flow_matching.py` checks the result
-against autograd of that restatement and against the unmodified reference's own
-`loss.backward()` (tests/golden/fm_tiny.pt).  fp32, CPU, small cases.
+against d loss / d parameter of the unmodified reference's own `loss.backward()`
+(tests/golden/fm_tiny.pt: every tensor; fm_width2.pt: norms and leading rows at the real
+widths).  fp32, CPU, small cases.
 """
 import math
 
@@ -225,3 +229,121 @@ def flow_matching_backward(sd, dims, input_ids, pixel_values, attention_mask, pr
         A = dims["act_hidden"]
         _, grads["action_encoder.linear_1.weight"], grads["action_encoder.linear_1.bias"] = linear_bwd(psi, w1, g_cat[..., A:], bias=True)
     return loss, grads, {"vlm": g_emb["vlm"], "proprio": g_emb["proprio"]}
+
+
+# ---------------------------------------------------------------- upstream of the joint model
+def layer_norm_fwd(x, w, b, eps=1e-6):
+    mu = x.mean(-1, keepdim=True)
+    xc = x - mu
+    rstd = torch.rsqrt(xc.pow(2).mean(-1, keepdim=True) + eps)
+    xh = xc * rstd
+    return xh * w + b, xh, rstd
+
+
+def layer_norm_bwd(xh, rstd, w, gy):
+    """y = xh w + b, xh = (x - mean) rstd: gx = rstd (g - mean g - xh mean(g xh)), g = gy w."""
+    g = gy * w
+    gx = rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    D = xh.shape[-1]
+    return gx, (gy * xh).reshape(-1, D).sum(0), gy.reshape(-1, D).sum(0)
+
+
+def siglip_forward_saved(sd, dims, pixel_values):
+    """`pizero_oracle.siglip_forward` (siglip.py:59-78, 220-238, 298) with the patch convolution as a matrix product over
+    unfolded patches (what the CUDA path does) and everything the backward needs."""
+    p = "vision_tower.vision_model."
+    ps = dims["patch_size"]
+    wconv = sd[p + "embeddings.patch_embedding.weight"]
+    D = wconv.shape[0]
+    patches = F.unfold(pixel_values, kernel_size=ps, stride=ps).transpose(1, 2)           # [B, S, 3*ps*ps], (c, ky, kx) order
+    x = patches @ wconv.reshape(D, -1).t() + sd[p + "embeddings.patch_embedding.bias"]
+    x = x + sd[p + "embeddings.position_embedding.weight"][None]
+    B, S, _ = x.shape
+    nh = dims["vit_heads"]
+    hd = D // nh
+    layers = []
+    for i in range(dims["vit_layers"]):
+        q = p + f"encoder.layers.{i}."
+        sv = dict(x=x)
+        h, sv["xh1"], sv["rstd1"] = layer_norm_fwd(x, sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"])
+        sv["h1"] = h
+        qs, ks, vs = (F.linear(h, sd[q + f"self_attn.{n}_proj.weight"], sd[q + f"self_attn.{n}_proj.bias"])
+                      .view(B, S, nh, hd).transpose(1, 2) for n in "qkv")
+        pr = F.softmax(torch.matmul(qs, ks.transpose(2, 3)) * hd ** -0.5, dim=-1)
+        a = torch.matmul(pr, vs).transpose(1, 2).reshape(B, S, D)
+        sv.update(q=qs, k=ks, v=vs, pr=pr, a=a)
+        x = x + F.linear(a, sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"])
+        sv["x_mid"] = x
+        h, sv["xh2"], sv["rstd2"] = layer_norm_fwd(x, sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"])
+        sv["h2"] = h
+        f1 = F.linear(h, sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"])
+        sv["f1"] = f1
+        sv["act"] = F.gelu(f1, approximate="tanh")
+        x = x + F.linear(sv["act"], sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"])
+        layers.append(sv)
+    y, xh, rstd = layer_norm_fwd(x, sd[p + "post_layernorm.weight"], sd[p + "post_layernorm.bias"])
+    return y, dict(layers=layers, patches=patches, xh=xh, rstd=rstd, B=B, S=S, D=D, nh=nh, hd=hd)
+
+
+def siglip_backward(sd, dims, saved, gy):
+    p = "vision_tower.vision_model."
+    B, S, D, nh, hd = saved["B"], saved["S"], saved["D"], saved["nh"], saved["hd"]
+    grads = {}
+    gx, grads[p + "post_layernorm.weight"], grads[p + "post_layernorm.bias"] = layer_norm_bwd(
+        saved["xh"], saved["rstd"], sd[p + "post_layernorm.weight"], gy)
+    for i in reversed(range(dims["vit_layers"])):
+        q = p + f"encoder.layers.{i}."
+        sv = saved["layers"][i]
+        g_act, grads[q + "mlp.fc2.weight"], grads[q + "mlp.fc2.bias"] = linear_bwd(sv["act"], sd[q + "mlp.fc2.weight"], gx, bias=True)
+        g_h2, grads[q + "mlp.fc1.weight"], grads[q + "mlp.fc1.bias"] = linear_bwd(
+            sv["h2"], sd[q + "mlp.fc1.weight"], g_act * gelu_tanh_grad(sv["f1"]), bias=True)
+        g_mid, grads[q + "layer_norm2.weight"], grads[q + "layer_norm2.bias"] = layer_norm_bwd(
+            sv["xh2"], sv["rstd2"], sd[q + "layer_norm2.weight"], g_h2)
+        gx = gx + g_mid
+        g_a, grads[q + "self_attn.out_proj.weight"], grads[q + "self_attn.out_proj.bias"] = linear_bwd(
+            sv["a"], sd[q + "self_attn.out_proj.weight"], gx, bias=True)
+        g_a = g_a.view(B, S, nh, hd).transpose(1, 2)
+        g_v = torch.matmul(sv["pr"].transpose(2, 3), g_a)
+        g_pr = torch.matmul(g_a, sv["v"].transpose(2, 3))
+        g_s = sv["pr"] * (g_pr - (g_pr * sv["pr"]).sum(-1, keepdim=True)) * hd ** -0.5
+        g_q = torch.matmul(g_s, sv["k"])
+        g_k = torch.matmul(g_s.transpose(2, 3), sv["q"])
+        g_h1 = 0
+        for n, g in (("q", g_q), ("k", g_k), ("v", g_v)):
+            a, grads[q + f"self_attn.{n}_proj.weight"], grads[q + f"self_attn.{n}_proj.bias"] = linear_bwd(
+                sv["h1"], sd[q + f"self_attn.{n}_proj.weight"], g.transpose(1, 2).reshape(B, S, D), bias=True)
+            g_h1 = g_h1 + a
+        g_in, grads[q + "layer_norm1.weight"], grads[q + "layer_norm1.bias"] = layer_norm_bwd(
+            sv["xh1"], sv["rstd1"], sd[q + "layer_norm1.weight"], g_h1)
+        gx = gx + g_in
+    grads[p + "embeddings.position_embedding.weight"] = gx.sum(0)
+    wconv = sd[p + "embeddings.patch_embedding.weight"]
+    _, gw, gb = linear_bwd(saved["patches"], wconv.reshape(D, -1), gx, bias=True)
+    grads[p + "embeddings.patch_embedding.weight"] = gw.view_as(wconv)
+    grads[p + "embeddings.patch_embedding.bias"] = gb
+    return grads
+
+
+def flow_matching_backward_full(sd, dims, input_ids, pixel_values, attention_mask, proprios, actions, t, noise):
+    """`flow_matching_backward` plus everything upstream of the joint model: proprio_encoder, the embedding merge
+    (pizero.py:376-414: text rows <- embed_tokens, image rows <- projector(SigLIP) / sqrt(hidden)), projector, SigLIP.
+    Returns (loss, {parameter key: grad}) for every parameter the loss depends on."""
+    loss, grads, g_emb = flow_matching_backward(sd, dims, input_ids, pixel_values, attention_mask, proprios, actions, t, noise)
+    with torch.no_grad():
+        A, H = dims["act_hidden"], dims["vlm_hidden"]
+        _, grads["proprio_encoder.weight"], grads["proprio_encoder.bias"] = linear_bwd(proprios.float(), sd["proprio_encoder.weight"],
+                                                                                       g_emb["proprio"], bias=True)
+        gv = g_emb["vlm"]                                                 # [B, S_v, H]
+        is_img = input_ids == dims["image_token_index"]
+        is_txt = (~is_img) & (input_ids != dims["pad_token_id"])
+        ge = torch.zeros_like(sd["embed_tokens.weight"])
+        ge.index_add_(0, input_ids[is_txt], gv[is_txt])                   # F.embedding backward (text rows only)
+        grads["embed_tokens.weight"] = ge
+        B = input_ids.shape[0]
+        vit, saved = siglip_forward_saved(sd, dims, pixel_values)
+        n_img_tok = vit.shape[1]
+        g_feat = torch.stack([gv[b][is_img[b]][:n_img_tok] for b in range(B)]) / H ** 0.5
+        g_vit, grads["multi_modal_projector.linear.weight"], grads["multi_modal_projector.linear.bias"] = linear_bwd(
+            vit, sd["multi_modal_projector.linear.weight"], g_feat, bias=True)
+        grads.update(siglip_backward(sd, dims, saved, g_vit))
+    return loss, grads
