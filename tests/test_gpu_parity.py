@@ -87,6 +87,24 @@ def test_small_every_layer_vs_oracle(dtype, layer_tol, act_tol):
     assert m.last_launch_count > 0
 
 
+def test_small_fractal_config_proprio_dim8_vs_oracle():
+    """The reference's second shipped robot config (config/eval/fractal_apple.yaml:49): proprio_dim = 8."""
+    d = pz.make_dims(SMALL, proprio_dim=8)
+    sd = pz.init_state_dict(d, seed=6, randomize_norms=True)
+    inp = pz.make_inputs(d, 3, seed=12)
+    assert inp["proprios"].shape[-1] == 8
+    ocap = {}
+    want = O.infer_action(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                          inp["proprios"], inp["noise"], capture=ocap)
+    m = _model(d, sd, torch.bfloat16)
+    out, cap = _run(m, d, inp)
+    for l, w in enumerate(ocap["prefix_layers"]):
+        if w["proprio"] is not None:
+            assert rel_err(cap["prefix_proprio"][l], w["proprio"]) < BF16_LAYER_TOL
+    assert max_abs(cap["action_preclip"], ocap["action_preclip"]) < BF16_ACTION_TOL
+    assert max_abs(out, want) < BF16_ACTION_TOL
+
+
 def test_small_simple_kernels_match_fast_path(monkeypatch):
     """The tcgen05 / mma / skinny kernels against the plain SIMT kernels, same bf16 inputs."""
     d = SMALL
