@@ -105,6 +105,22 @@ def test_small_fractal_config_proprio_dim8_vs_oracle():
     assert max_abs(out, want) < BF16_ACTION_TOL
 
 
+@pytest.mark.parametrize("batch", [1, 3, 6])   # 1, 3: persistent sampler (MT = 1 / 2); 6: separate kernels
+def test_small_no_clip_five_steps_vs_oracle(batch):
+    """Config knobs off the bridge defaults: `final_action_clip_value: null` (pizero.py:484-489 skipped) and
+    `num_inference_steps: 5` (the per-step time constants and dt follow), through both sampler implementations."""
+    d = pz.make_dims(SMALL, final_action_clip_value=None, num_inference_steps=5)
+    sd = pz.init_state_dict(d, seed=8, randomize_norms=True)
+    inp = pz.make_inputs(d, batch, seed=14)
+    inp["noise"] = inp["noise"] * 2.0          # push some components beyond +-1 so that a wrong clamp would show
+    want = O.infer_action(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                          inp["proprios"], inp["noise"])
+    assert float(want.abs().max()) > 1.0
+    m = _model(d, sd, torch.bfloat16)
+    out, _ = _run(m, d, inp, capture=False)
+    assert max_abs(out, want) < 2 * BF16_ACTION_TOL   # values up to ~4: same relative bar as the clamped case
+
+
 def test_small_simple_kernels_match_fast_path(monkeypatch):
     """The tcgen05 / mma / skinny kernels against the plain SIMT kernels, same bf16 inputs."""
     d = SMALL
