@@ -121,6 +121,25 @@ def test_small_no_clip_five_steps_vs_oracle(batch):
     assert max_abs(out, want) < 2 * BF16_ACTION_TOL   # values up to ~4: same relative bar as the clamped case
 
 
+def test_small_eval_yaml_rope_and_time_periods_vs_oracle():
+    """The released checkpoints' parameter set (config/eval/bridge.yaml:72-73, README.md:151): action / proprio RoPE theta and
+    the time embedding's max period are 10 000 instead of the training yaml's 100."""
+    d = pz.make_dims(SMALL, act_rope_theta=10000.0, time_max_period=10000.0)
+    sd = pz.init_state_dict(d, seed=10, randomize_norms=True)
+    inp = pz.make_inputs(d, 2, seed=16)
+    ocap = {}
+    want = O.infer_action(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                          inp["proprios"], inp["noise"], capture=ocap)
+    m = _model(d, sd, torch.bfloat16)
+    out, cap = _run(m, d, inp)
+    L = d["num_layers"]
+    for i, w in enumerate(ocap["denoise_layers"]):
+        assert rel_err(cap["denoise_action"][i // L, i % L], w["action"]) < BF16_LAYER_TOL
+    assert max_abs(out, want) < BF16_ACTION_TOL
+    fast, _ = _run(m, d, inp, capture=False)      # the persistent sampler reads the same tables
+    assert max_abs(fast, want) < BF16_ACTION_TOL
+
+
 def test_small_simple_kernels_match_fast_path(monkeypatch):
     """The tcgen05 / mma / skinny kernels against the plain SIMT kernels, same bf16 inputs."""
     d = SMALL
