@@ -439,11 +439,11 @@ def main():
     lat = None
     if rank == 0 and not args.skip_latency:
         one = {k: v[:1].contiguous() for k, v in dev_in.items()}
-        for _ in range(10):
+        for _ in range(20):
             model(**one)
         torch.cuda.synchronize()
         ts = []
-        for _ in range(50):
+        for _ in range(200):   # p50 of >= 200 calls after 20 warm-up
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             model(**one)
