@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 4
+#define PZ_ABI_VERSION 5
 
 typedef enum pz_status {
     PZ_OK = 0,
@@ -159,8 +159,26 @@ int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offs
 
 /* Debug: workspace offset of the persistent sampler's barrier / phase-timestamp words. */
 size_t pz_debug_trace_offset(const pz_handle *h, int batch);
-/* Same for the flag-exchange sampler (denoise_mega2.cu): 128 globaltimer words. */
-size_t pz_debug_ll_trace_offset(const pz_handle *h, int batch);
+/* The bs = 1 / 2 Euler sampler (pizero.py:454-489 at batch <= 2) runs as one persistent kernel that streams the
+ * action expert's weights from a per-SM re-packed copy (csrc/denoise_mega3.cu).  The copy depends on the device's SM
+ * count and on the batch (1 or 2), lives in caller-owned device memory and is optional: without it the call uses the
+ * grid-barrier sampler (csrc/denoise_mega.cu).
+ *   pz_sampler_stream_bytes : bytes of the copy for `batch` on the current device (0: configuration not covered)
+ *   pz_sampler_pack         : builds it in `d_stream` (1 KiB aligned) on `stream`; call again after re-binding weights.
+ *                             Synchronises `stream` once (table upload). */
+size_t pz_sampler_stream_bytes(pz_handle *h, int batch);
+/* Which implementation of the Euler loop pz_denoise uses (all give the same result within bf16 rounding):
+ *   AUTO     the stream sampler when packed and the batch is covered, else the grid-barrier kernel (B * horizon <= 16),
+ *            else one kernel per op
+ *   KERNELS  always one kernel per op (the path large batches take)
+ *   BARRIER  csrc/denoise_mega.cu or an error
+ *   STREAM   csrc/denoise_mega3.cu or an error */
+#define PZ_SAMPLER_AUTO 0
+#define PZ_SAMPLER_KERNELS 1
+#define PZ_SAMPLER_BARRIER 2
+#define PZ_SAMPLER_STREAM 3
+int pz_set_sampler(pz_handle *h, int mode);
+int pz_sampler_pack(pz_handle *h, int batch, void *d_stream, size_t bytes, void *stream);
 
 /* PiZero.infer_action (pizero.py:416-490), whole call.
  *   d_input_ids  int64 [B, s_vlm]

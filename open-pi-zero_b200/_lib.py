@@ -53,14 +53,15 @@ class PzCapture(C.Structure):
                                   "action_preclip")]
 
 
-PZ_ABI_VERSION = 4
+PZ_ABI_VERSION = 5
 PZ_F32, PZ_BF16 = 0, 1
 PZ_FLAG_SIMPLE_KERNELS = 1
+PZ_SAMPLER_AUTO, PZ_SAMPLER_KERNELS, PZ_SAMPLER_BARRIER, PZ_SAMPLER_STREAM = 0, 1, 2, 3
 LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
-           "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_debug_ll_trace_offset", "pz_infer_action", "pz_embed_prefix",
+           "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_sampler_stream_bytes", "pz_sampler_pack", "pz_set_sampler", "pz_infer_action", "pz_embed_prefix",
            "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss",
            "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
@@ -95,8 +96,10 @@ def load(build_if_needed: bool = True):
     lib.pz_workspace_bytes.restype = C.c_size_t
     lib.pz_debug_trace_offset.argtypes = [hp, C.c_int]
     lib.pz_debug_trace_offset.restype = C.c_size_t
-    lib.pz_debug_ll_trace_offset.argtypes = [hp, C.c_int]
-    lib.pz_debug_ll_trace_offset.restype = C.c_size_t
+    lib.pz_sampler_stream_bytes.argtypes = [hp, C.c_int]
+    lib.pz_sampler_stream_bytes.restype = C.c_size_t
+    lib.pz_sampler_pack.argtypes = [hp, C.c_int, vp, C.c_size_t, vp]
+    lib.pz_set_sampler.argtypes = [hp, C.c_int]
     lib.pz_kv_layout.argtypes = [hp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                  C.POINTER(C.c_size_t)]
     lib.pz_infer_action.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int,

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpz_b200.so")
 SOURCES = ["api.cu", "simple.cu", "elementwise.cu", "gemm_tc.cu", "skinny.cu", "attn_mma.cu", "attn_tc.cu",
-           "denoise_mega.cu", "denoise_mega2.cu"]
+           "denoise_mega.cu", "denoise_mega3.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared"]
 

@@ -34,6 +34,9 @@ struct pz_handle {
     // fork/join side stream: the proprio token's chain of small kernels runs beside the VLM chain
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> sync_ev;
+    Mega3State mega3[2];                      // packed item streams of the persistent sampler for batch 1 and 2
+    int num_sms = 0;
+    int sampler = PZ_SAMPLER_AUTO;            // pz_set_sampler
     int timing_tag = 0;                       // 0 = off
     std::vector<cudaEvent_t> ev;              // pairs (start, stop)
     size_t ev_used = 0;
@@ -136,7 +139,7 @@ static Workspace carve(const pz_config &c, int B, int chunk, void *base) {
     w.mlpa = b.take<void>(Ma * c.act_inter * es);
     w.vel = b.take<float>(Ma * 8 * 4);
     w.mega_barrier = b.take<unsigned int>(128 * sizeof(unsigned int));
-    w.mega_ll_bytes = denoise_mega2_ll_bytes(c, B < 2 ? B : 2);
+    w.mega_ll_bytes = denoise_mega3_ll_bytes(c, B);   // 0 unless the flag-exchange sampler covers this batch
     w.mega_ll = b.take<void>(w.mega_ll_bytes);
     {   // split-key attention partials (decode): [B][key tiles][heads*rows][hd + 2] fp32
         size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
@@ -514,17 +517,21 @@ static int run_denoise(pz_handle *h, const int32_t *valid_len, const float *nois
     const float dt = (float)(1.0 / c.n_steps);
     copy_f32(ws.act, noise, (size_t)Ma * c.action_dim, st);
     const bool no_taps = !(cap && (cap->denoise_action || cap->velocities || cap->action_preclip));
-    if (std::is_same<T, bf16>::value && no_taps && denoise_mega2_supported(c, B)) {
-        // bs 1-2: barrier-free persistent sampler (denoise_mega2.cu)
-        Mega2Buffers mb;
+    const int smode = h->sampler;
+    if (std::is_same<T, bf16>::value && no_taps && (smode == PZ_SAMPLER_AUTO || smode == PZ_SAMPLER_STREAM) &&
+        denoise_mega3_supported(c, B) && B <= 2 && h->mega3[B - 1].buf) {
+        // bs 1-2: barrier-free persistent sampler over the re-packed weight streams (denoise_mega3.cu)
+        Mega3Buffers mb;
         mb.kcache = ws.kcache; mb.vcache = ws.vcache; mb.batch_total = B; mb.valid_len = valid_len;
         mb.noise = ws.act; mb.out = out; mb.ll = ws.mega_ll; mb.ll_bytes = ws.mega_ll_bytes;
         const char *e = nullptr;
-        int rc = launch_denoise_mega2(c, w, h->action.data(), mb, B, st, &e);
-        if (rc) return fail(h, rc, std::string("denoise_mega2 launch failed: ") + (e ? e : "?"));
+        int rc = launch_denoise_mega3(c, w, h->action.data(), h->mega3[B - 1], mb, B, st, &e);
+        if (rc) return fail(h, rc, std::string("persistent sampler launch failed: ") + (e ? e : "?"));
         return 0;
     }
-    if (std::is_same<T, bf16>::value && denoise_mega_supported(c, B) && no_taps) {
+    if (smode == PZ_SAMPLER_STREAM) return fail(h, PZ_ERR_INVALID, "PZ_SAMPLER_STREAM: not packed (pz_sampler_pack) or batch / configuration not covered");
+    if (std::is_same<T, bf16>::value && denoise_mega_supported(c, B) && no_taps &&
+        (smode == PZ_SAMPLER_AUTO || smode == PZ_SAMPLER_BARRIER)) {
         // small batch: the whole sampler as one persistent cooperative kernel (denoise_mega.cu)
         MegaBuffers mb;
         mb.kcache = ws.kcache; mb.vcache = ws.vcache; mb.batch_total = B; mb.valid_len = valid_len;
@@ -674,6 +681,34 @@ int pz_set_pixel_format(pz_handle *h, int format) {
     return PZ_OK;
 }
 
+static int device_sms(pz_handle *h) {
+    h->num_sms = device_sm_count();
+    return h->num_sms;
+}
+
+int pz_set_sampler(pz_handle *h, int mode) {
+    if (!h) return PZ_ERR_INVALID;
+    if (mode < PZ_SAMPLER_AUTO || mode > PZ_SAMPLER_STREAM) return fail(h, PZ_ERR_INVALID, "unknown sampler mode");
+    h->sampler = mode;
+    return PZ_OK;
+}
+
+size_t pz_sampler_stream_bytes(pz_handle *h, int batch) {
+    if (!h || batch < 1 || batch > 2) return 0;
+    return denoise_mega3_stream_bytes(h->cfg, batch, device_sms(h));
+}
+
+int pz_sampler_pack(pz_handle *h, int batch, void *d_stream, size_t bytes, void *stream) {
+    if (!h) return PZ_ERR_INVALID;
+    if (!h->bound) return fail(h, PZ_ERR_UNBOUND, "pz_bind_weights has not been called");
+    if (batch < 1 || batch > 2 || !d_stream) return fail(h, PZ_ERR_INVALID, "pz_sampler_pack: batch must be 1 or 2");
+    const char *e = nullptr;
+    int rc = denoise_mega3_pack(h->cfg, h->w, h->action.data(), batch, device_sms(h), d_stream, bytes, &h->mega3[batch - 1],
+                                (cudaStream_t)stream, &e);
+    if (rc) return fail(h, rc, e ? e : "pz_sampler_pack failed");
+    return PZ_OK;
+}
+
 size_t pz_workspace_bytes(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     return carve(h->cfg, batch, h->prefix_chunk, nullptr).total;
@@ -683,12 +718,6 @@ size_t pz_debug_trace_offset(const pz_handle *h, int batch) {
     if (!h || batch < 1) return 0;
     Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
     return (size_t)((char *)ws.mega_barrier - (char *)0x1000);
-}
-
-size_t pz_debug_ll_trace_offset(const pz_handle *h, int batch) {
-    if (!h || batch < 1) return 0;
-    Workspace ws = carve(h->cfg, batch, h->prefix_chunk, (void *)0x1000);
-    return (size_t)((char *)ws.mega_ll - (char *)0x1000) + ws.mega_ll_bytes - 32768;
 }
 
 int pz_kv_layout(const pz_handle *h, int batch, size_t *k_offset, size_t *v_offset,

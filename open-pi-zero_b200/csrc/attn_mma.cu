@@ -395,11 +395,10 @@ int launch(const AttnArgs &a, int cls, int mqa, cudaStream_t st, int partials_on
     constexpr int LDS = HDP + 8;
     constexpr int ROWS_PER_CTA = 64, NTHREADS = 128;   // default: 4 warps
     size_t smem = (size_t)(ROWS_PER_CTA + 2 * KEY_TILE) * LDS * sizeof(bf16);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(attn_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return PZ_ERR_CUDA;
-        attr_set = true;
     }
     int rows_total = mqa ? a.n_heads * a.q_rows : a.q_rows;
     if constexpr (HD % 32 == 0) {

@@ -481,11 +481,10 @@ int attn_tc_vit_supported(const AttnArgs &a) {
 }
 
 int launch_attn_tc_vit(const AttnArgs &a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(attn_tc_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES) != cudaSuccess)
             return PZ_ERR_CUDA;
-        attr_set = true;
     }
     CUtensorMap mq, mk, mv, mo;
     const long rows = (long)a.batch * V_TOK;
@@ -515,11 +514,10 @@ int attn_tc_supported(const AttnArgs &a) {
 }
 
 int launch_attn_tc(const AttnArgs &a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
             return PZ_ERR_CUDA;
-        attr_set = true;
     }
     CUtensorMap mq, mk, mv, mo, mk32, mv32;
     const long rows = (long)a.batch * a.q_rows;

@@ -119,6 +119,28 @@ struct AttnArgs {
 PZ_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 PZ_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// host-side, per device: one process may drive several GPUs (the reference's callers do `.to(f"cuda:{gpu_id}")`), so
+// "done once" function attributes and the SM count are keyed by the current device ordinal
+struct PerDeviceOnce {
+    unsigned long long done = 0;
+    bool need() {   // true the first time it is asked on the current device
+        int d = 0;
+        cudaGetDevice(&d);
+        if (d < 0 || d > 63) return true;
+        if ((done >> d) & 1ull) return false;
+        done |= 1ull << d;
+        return true;
+    }
+};
+static inline int device_sm_count() {
+    static int sms[64] = {0};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d > 63) d = 0;
+    if (!sms[d]) cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+    return sms[d];
+}
+
 // host-side: every launch goes through this counter (bench.py: gpu_launches)
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter *g_launch_counter;

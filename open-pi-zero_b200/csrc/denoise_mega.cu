@@ -766,12 +766,11 @@ int denoise_mega_supported(const pz_config &c, int B) {
 int launch_decode_attention(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache,
                             const void *vcache, int batch_total, const int32_t *valid_len, float *partials, int layer,
                             int B, void *out, long out_batch_stride, int out_row_stride, cudaStream_t st) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
     constexpr int smem = SM_ATT_END - SM_U + 256;
-    if (!attr_set) {
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return PZ_ERR_CUDA;
-        attr_set = true;
     }
     MegaParams p;
     memset(&p, 0, sizeof(p));
@@ -797,20 +796,14 @@ int decode_attention_supported(const pz_config &c) {
 
 int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const MegaBuffers &bf,
                         int B, cudaStream_t st, const char **err) {
-    static int num_sms = 0;
-    static bool attr_set = false;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    const int num_sms = device_sm_count();
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(denoise_mega_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess ||
             cudaFuncSetAttribute(denoise_mega_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
             if (err) *err = "denoise_mega: cannot set the shared-memory size";
             return PZ_ERR_CUDA;
         }
-        attr_set = true;
     }
     MegaParams p;
     memset(&p, 0, sizeof(p));

@@ -1,0 +1,1084 @@
+// denoise_mega3.cu -- the Euler sampler (pizero.py:454-489) for B * horizon <= 8 action rows as ONE persistent
+// kernel without grid barriers: the bs = 1 latency path.
+//
+// What the first persistent sampler (denoise_mega.cu) spends its time on is not HBM but five grid-wide phase
+// boundaries per layer (barrier + reductions + restaging, ~3.2 us each, profiles/r01_probe_barrier*.txt) and
+// per-item reductions.  This kernel is organised around what tools/probe_ll.cu measured on B200:
+//   * one thread per CTA feeding an mbarrier ring with contiguous 32 KB cp.async.bulk copies streams at the full HBM
+//     rate (6.7-7.2 TB/s over 148 CTAs; 16 KB copies: 5.1, 8 KB: 2.5) -- so the action-expert weights are re-packed
+//     once (pz_sampler_pack) into one contiguous stream per CTA, in the order that CTA consumes them and in the
+//     register-fragment order of mma.sync (no address arithmetic, no bank conflicts, nothing to transpose);
+//   * exchanging values through 64-bit {payload, sequence} words needs no barrier and no fence, but polling the
+//     whole payload from every CTA saturates L2 (148 x 32 KB per round): gathers re-read only the words that are
+//     still missing.
+// Structure:
+//   * CTAs [0, G): weight streaming.  Per layer five stages, each = gather inputs -> all of the CTA's items of that
+//     stage accumulated in registers by 8 warps that split k -> one cross-warp reduction -> publish:
+//       QKV (16-row rotary-pair blocks, RoPE in the epilogue) | o_proj (8-row blocks, full K) | gate-up (16-row blocks:
+//       8 gate + 8 up rows, GeGLU in the epilogue) | down (8-row blocks, full K = 4096).
+//     Every output element has one producer (no split-K across CTAs, no atomics: results are deterministic).  The
+//     owner of an 8-column block of the residual stream keeps it in fp32 in shared memory for the whole call.
+//   * CTAs [G, G + 16 B): attention, one per (sample, head, half of head_dim).  The layer's cached K (all 256 dims)
+//     and its half of V live in shared memory as 128-byte-swizzled tiles loaded by TMA one layer ahead (the prefix
+//     KV is step-invariant; L2 evict-last), so attention is q arrival -> S^T = K q^T (keys are the MMA M dimension)
+//     -> soft-cap / mask / exp -> O^T = V^T P^T -> publish; no split-key partials, no combine.
+//   * every wait is bounded: a lost CTA raises an error flag and the output becomes NaN instead of hanging the GPU.
+// Numerics are those of denoise_mega.cu: bf16 operands, fp32 accumulation, fp32 residual stream and action state.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int NCW = 8, NCT = NCW * 32, NT3 = NCT;        // 8 warps; one elected thread also feeds the weight ring
+constexpr int SLOT = 32768;                              // ring slot = one weight item
+constexpr int KI = 1024;                                 // act_hidden
+constexpr int MAXQ = 3, MAXO = 2, MAXGU = 5, MAXJ = 5;   // items of one stage per CTA
+constexpr int MAX_LAYERS = 24;
+constexpr int KEYS = 288, KBOX = 144;                    // key rows per attention CTA (two TMA boxes)
+constexpr int KT_BYTES = KEYS * 128;                     // one swizzled tile: KEYS rows x 64 dims
+constexpr int NATT = 16;                                 // attention CTAs per sample: 8 heads x 2 halves of head_dim
+constexpr unsigned long long WAIT_LIMIT_NS = 250ull * 1000 * 1000;   // any single wait: 0.25 s, then the error flag
+
+struct CtaSched {           // what one weight-streaming CTA does in every layer / step (80 bytes)
+    int n_qkv, qkv_blk[MAXQ];      // 16-row rotary-pair blocks of the fused q|k|v projection
+    int n_o, o_blk[MAXO];          // 8-column blocks of the residual stream this CTA owns (o_proj, down, linear_3 rows)
+    int n_gu, gu_tile[MAXGU];      // 8-column tiles of the MLP intermediate (8 gate + 8 up rows)
+    int e2_blk;                    // 16-row block of action_encoder.linear_2, or -1
+    int is_dec;                    // runs the final norm + action_decoder + Euler update
+    int slots_per_step;
+    int pad;
+    long long stream_off;          // byte offset of this CTA's item stream
+};
+static_assert(sizeof(CtaSched) == 80, "CtaSched layout");
+
+enum SlotKind { SK_QKV = 0, SK_GU, SK_O, SK_D, SK_E2, SK_E3, SK_DEC };
+struct SlotDesc { int kind, layer, blk, aux; };
+
+struct Mega3Params {
+    int B, H, M, nh, S_v, S_p, S_c, n_layers, n_steps, action_dim, skp, AI;
+    int G, NA;
+    float dt, clip;
+    const float *norm_in[MAX_LAYERS], *norm_post[MAX_LAYERS];
+    const float *final_norm;
+    const bf16 *enc_w1;
+    const float *enc_b1, *enc_time_bias, *enc_b3, *dec_b;
+    const float *rope_cos, *rope_sin;
+    const int32_t *valid_len;
+    const float *noise;
+    float *out;
+    const uint8_t *stream;
+    const CtaSched *sched;
+    int batch_total;
+    // exchange buffers: 64-bit words {payload, sequence number}, zeroed before every launch
+    unsigned long long *ll_act;       // [M][8]       fp32
+    unsigned long long *ll_z;         // [M][A/2]     bf16x2
+    unsigned long long *ll_x[2];      // [M][A]       fp32: residual stream entering layer l (buffer l & 1)
+    unsigned long long *ll_x1[2];     // [M][A]       fp32: residual stream after o_proj
+    unsigned long long *ll_qkv[2];    // [M][1280]    bf16x2, q and k rotated
+    unsigned long long *ll_att[2];    // [M][1024]    bf16x2 attention output
+    unsigned long long *ll_mlp[2];    // [M][AI/2]    bf16x2 GeGLU output
+    unsigned int *err;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers ----
+PZ_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PZ_DEVINL void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+PZ_DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PZ_DEVINL void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+PZ_DEVINL bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+PZ_DEVINL bool err_set(const Mega3Params &p) { return *reinterpret_cast<volatile unsigned int *>(p.err) != 0; }
+PZ_DEVINL void raise_err(const Mega3Params &p, unsigned int kind) { atomicCAS(p.err, 0u, 0x80000000u | (kind << 16) | blockIdx.x); }
+PZ_DEVINL unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded (a bug or a lost CTA must never hang the device): after WAIT_LIMIT_NS, or as soon as somebody else has raised
+// the error flag, give up
+PZ_DEVINL void mbar_wait(const Mega3Params &p, uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 0x3F) == 0) {
+            if (err_set(p)) return;
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > WAIT_LIMIT_NS) { raise_err(p, 1); return; }
+        }
+    }
+}
+PZ_DEVINL void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+PZ_DEVINL void tma_load_3d_hint(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+PZ_DEVINL uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+PZ_DEVINL uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+PZ_DEVINL void bar_compute() { __syncthreads(); }
+PZ_DEVINL void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+PZ_DEVINL void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+PZ_DEVINL float gelu_fast(float x) {   // hardware tanh: rel. error 2^-11, below the bf16 rounding of the output
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(k0 * (x + k1 * x * x * x)));
+    return 0.5f * x * (1.0f + y);
+}
+PZ_DEVINL float tanh_fast_acc(float y) { float t = __expf(2.f * y); return 1.f - __fdividef(2.f, t + 1.f); }
+
+// ---- exchange words ------------------------------------------------------------------------------------
+PZ_DEVINL void ll_store(unsigned long long *dst, uint32_t payload, uint32_t seq) {
+    unsigned long long v = ((unsigned long long)seq << 32) | payload;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+}
+PZ_DEVINL void ll_load2(const unsigned long long *src, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+}
+// N double-words (two exchange words each) per thread, all in flight; only the ones whose sequence numbers are not
+// there yet are read again (polling whole payloads from every CTA saturates L2: tools/probe_ll.cu)
+template <int N, typename AddrFn>
+PZ_DEVINL void ll_gather(const Mega3Params &p, uint32_t seq, uint32_t pend, AddrFn addr, unsigned long long (&v)[2 * N]) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (pend) {
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            if ((pend >> u) & 1u) ll_load2(addr(u), v[2 * u], v[2 * u + 1]);
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            if (((pend >> u) & 1u) && (uint32_t)(v[2 * u] >> 32) == seq && (uint32_t)(v[2 * u + 1] >> 32) == seq) pend &= ~(1u << u);
+        if (pend) {
+            if (++spins > 16) __nanosleep(32);
+            if ((spins & 0xFF) == 0) {
+                if (err_set(p)) return;
+                const unsigned long long now = gtime_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WAIT_LIMIT_NS) { raise_err(p, 2); return; }
+            }
+        }
+    }
+}
+
+// sequence numbers: one per exchange and step
+PZ_DEVINL uint32_t seq_of(const Mega3Params &p, int step, int idx) { return 1u + (uint32_t)(step * (3 + 5 * p.n_layers) + idx); }
+constexpr int IDX_ACT = 0, IDX_Z = 1, IDX_X0 = 2;
+PZ_DEVINL int IDX_QKV(int l) { return 3 + 5 * l; }
+PZ_DEVINL int IDX_ATT(int l) { return 4 + 5 * l; }
+PZ_DEVINL int IDX_X1(int l) { return 5 + 5 * l; }
+PZ_DEVINL int IDX_MLP(int l) { return 6 + 5 * l; }
+PZ_DEVINL int IDX_X2(int l) { return 7 + 5 * l; }
+
+// ======================================== weight-streaming role =========================================
+template <int MAXM> struct GemvSmem {
+    static constexpr int SLOTS = MAXM <= 4 ? 5 : 4;
+    static constexpr int LDA_MAX = 4096 + 32;
+    static constexpr int RING = 0;
+    static constexpr int AST = RING + SLOTS * SLOT;                        // bf16 [MAXM][K + 32]
+    static constexpr int RED = AST + MAXM * LDA_MAX * 2;                   // float [NCW][MAXJ][16][9]
+    static constexpr int MISC = RED + NCW * MAXJ * 16 * 9 * 4;             // floats: part[16], xpriv[MAXO][8][8], acts[64]
+    static constexpr int BARS = MISC + (16 + MAXO * 64 + 64) * 4;          // full[SLOTS]
+    static constexpr int SCHED = BARS + SLOTS * 8;
+    static constexpr int END = SCHED + (int)sizeof(CtaSched);
+};
+
+struct GemvCtx {
+    uint8_t *smem;
+    uint64_t *full;
+    uint32_t cnt;        // ring items consumed so far
+    uint32_t issued;     // ring items requested so far (refill thread only)
+    uint32_t total;      // items of the whole call
+    int in_step;         // position of the next request inside the step's stream
+    const uint8_t *base;
+    int slots_per_step;
+    uint64_t pol;
+};
+constexpr int REFILL_TID = 7 * 32;   // the elected thread (a warp with little epilogue work)
+// Request the items that fit into the ring slots the CTA has finished reading.  Call after a block barrier that
+// follows the reads (all warps are past their last use of the consumed slots), from every thread.
+template <typename SM>
+PZ_DEVINL void ring_refill(GemvCtx &cx) {
+    if (threadIdx.x != REFILL_TID) return;
+    while (cx.issued < cx.cnt + SM::SLOTS && cx.issued < cx.total) {
+        const int slot = cx.issued % SM::SLOTS;
+        mbar_expect_tx(&cx.full[slot], SLOT);
+        bulk_g2s(cx.smem + SM::RING + slot * SLOT, cx.base + (long)cx.in_step * SLOT, SLOT, &cx.full[slot], cx.pol);
+        if (++cx.in_step == cx.slots_per_step) cx.in_step = 0;
+        ++cx.issued;
+    }
+}
+
+PZ_DEVINL float *red_ptr(uint8_t *red, int w, int j, int r) { return reinterpret_cast<float *>(red) + ((w * MAXJ + j) * 16 + r) * 9; }
+
+// acc[j] = (16-row item j of this stage) . A^T over this warp's 128-wide k slice; K = 1024
+template <typename SM, int NJ>
+PZ_DEVINL void gemv16(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[NJ][4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bf16 *As = reinterpret_cast<const bf16 *>(cx.smem + SM::AST);
+    constexpr int lda = KI + 32;
+    uint4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        x[u] = g < p.M ? *reinterpret_cast<const uint4 *>(As + g * lda + warp * 128 + u * 32 + 8 * t) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        if (j < n) {
+            const int slot = cx.cnt % SM::SLOTS;
+            mbar_wait(p, &cx.full[slot], (cx.cnt / SM::SLOTS) & 1);
+            const uint8_t *w = cx.smem + SM::RING + slot * SLOT + warp * 4096 + lane * 16;
+            float a2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(w + u * 1024);
+                const uint4 hi = *reinterpret_cast<const uint4 *>(w + u * 1024 + 512);
+                mma_bf16(acc[j], lo.x, hi.x, lo.y, hi.y, x[u].x, x[u].y);
+                mma_bf16(a2, lo.z, hi.z, lo.w, hi.w, x[u].z, x[u].w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] += a2[e];
+            cx.cnt += 1;
+            if (NJ > SM::SLOTS && j + 1 == SM::SLOTS && n > SM::SLOTS) {   // more items than ring slots (CTA-uniform)
+                __syncthreads();
+                    ring_refill<SM>(cx);
+            }
+        }
+    }
+}
+// 8-row items with the full K (K = 256 * KU: 1024 / 2048 / 4096; 4096 spans two ring slots)
+template <typename SM, int KU>
+PZ_DEVINL void gemv8(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[MAXO][4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bf16 *As = reinterpret_cast<const bf16 *>(cx.smem + SM::AST);
+    constexpr int K = 256 * KU, lda = K + 32;
+    constexpr int NS = KU == 16 ? 2 : 1;
+#pragma unroll
+    for (int j = 0; j < MAXO; ++j) {
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        if (j < n) {
+            const int mine = NS == 2 ? (warp >> 2) : 0;
+            const uint32_t c = cx.cnt + mine;
+            const int slot = c % SM::SLOTS;
+            mbar_wait(p, &cx.full[slot], (c / SM::SLOTS) & 1);
+            const int unit0 = warp * KU - mine * 64;   // first unit of this warp inside its slot
+            const uint8_t *w = cx.smem + SM::RING + slot * SLOT + unit0 * 512 + lane * 16;
+            const bf16 *xa = As + g * lda + warp * (KU * 32) + 8 * t;
+            float a2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int u = 0; u < KU; ++u) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(w + u * 512);
+                const uint4 x = g < p.M ? *reinterpret_cast<const uint4 *>(xa + u * 32) : make_uint4(0, 0, 0, 0);
+                mma_bf16(acc[j], a.x, 0u, a.y, 0u, x.x, x.y);
+                mma_bf16(a2, a.z, 0u, a.w, 0u, x.z, x.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] += a2[e];
+            cx.cnt += NS;
+        }
+    }
+}
+template <int NJ>
+PZ_DEVINL void red_write(uint8_t *red, int n, const float (&acc)[NJ][4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (j < n) {
+            float *r0 = red_ptr(red, warp, j, g), *r1 = red_ptr(red, warp, j, g + 8);
+            r0[2 * t] = acc[j][0]; r0[2 * t + 1] = acc[j][1];
+            r1[2 * t] = acc[j][2]; r1[2 * t + 1] = acc[j][3];
+        }
+    }
+}
+PZ_DEVINL float red_sum(uint8_t *red, int j, int r, int m) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) v += red_ptr(red, w, j, r)[m];
+    return v;
+}
+
+// ---- activation staging ------------------------------------------------------------------------------
+// fp32 words [M][1024] -> Gemma RMSNorm (paligemma/modules.py:13-21) -> As[m][k] (bf16, row stride K + 32: conflict-free fragment loads)
+template <typename SM>
+PZ_DEVINL void stage_norm(const Mega3Params &p, uint8_t *smem, const unsigned long long *buf, const float *norm_w, uint32_t seq) {
+    bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
+    float *part = reinterpret_cast<float *>(smem + SM::MISC);
+    constexpr int lda = KI + 32;
+    const int tid = threadIdx.x, lane = tid & 31, c = tid & 63, rsub = tid >> 6;
+    float4 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const float4 *>(norm_w) + c + 64 * j);
+    for (int m0 = 0; m0 < p.M; m0 += 4) {
+        const int m = m0 + rsub;
+        const bool ok = m < p.M;
+        unsigned long long v[16];
+        // columns (c + 64 j) * 4 .. + 3: two double-words per j
+        ll_gather<8>(p, seq, ok ? 0xFFu : 0u, [&](int u) { return buf + (long)m * KI + (c + 64 * (u >> 1)) * 4 + (u & 1) * 2; }, v);
+        float x[16];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { x[i] = ok ? __uint_as_float((uint32_t)v[i]) : 0.f; ss += x[i] * x[i]; }
+        ss = warp_sum(ss);
+        if (lane == 0) part[rsub * 2 + ((tid >> 5) & 1)] = ss;
+        bar_compute();
+        const float r = rsqrtf((part[rsub * 2] + part[rsub * 2 + 1]) / KI + 1e-6f);
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 o;
+                o.x = pack_bf16x2(x[4 * j] * r * (1.f + w[j].x), x[4 * j + 1] * r * (1.f + w[j].y));
+                o.y = pack_bf16x2(x[4 * j + 2] * r * (1.f + w[j].z), x[4 * j + 3] * r * (1.f + w[j].w));
+                *reinterpret_cast<uint2 *>(As + m * lda + (c + 64 * j) * 4) = o;
+            }
+        }
+        bar_compute();
+    }
+}
+// bf16x2 words [M][K/2] -> As[m][k] (row stride K + 32)
+template <typename SM, int K>
+PZ_DEVINL void stage_pairs(const Mega3Params &p, uint8_t *smem, const unsigned long long *buf, uint32_t seq) {
+    bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
+    constexpr int lda = K + 32, DPR = K / 4;     // double-words (4 bf16) per row
+    const int total = p.M * DPR;
+    for (int i0 = 0; i0 < total; i0 += NCT * 8) {
+        unsigned long long v[16];
+        uint32_t pend = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (i0 + u * NCT + (int)threadIdx.x < total) pend |= 1u << u;
+        ll_gather<8>(p, seq, pend, [&](int u) { return buf + 2 * (long)(i0 + u * NCT + threadIdx.x); }, v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * NCT + threadIdx.x;
+            if (i < total) {
+                const int m = i / DPR, dw = i % DPR;
+                *reinterpret_cast<uint2 *>(As + m * lda + dw * 4) = make_uint2((uint32_t)v[2 * u], (uint32_t)v[2 * u + 1]);
+            }
+        }
+    }
+    bar_compute();
+}
+// action words [M][8] -> linear_1 (vla/modules.py:39-41) -> As[m][0..1024)
+template <typename SM>
+PZ_DEVINL void stage_enc1(const Mega3Params &p, uint8_t *smem, uint32_t seq) {
+    bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
+    float *sact = reinterpret_cast<float *>(smem + SM::MISC) + 16 + MAXO * 64;   // [M][8], bf16-rounded like a GEMM input
+    constexpr int lda = KI + 32;
+    {
+        unsigned long long v[2];
+        const bool ok = (int)threadIdx.x < p.M * 4;
+        ll_gather<1>(p, seq, ok ? 1u : 0u, [&](int) { return p.ll_act + 2 * threadIdx.x; }, v);
+        if (ok) {
+            sact[2 * threadIdx.x] = __bfloat162float(__float2bfloat16_rn(__uint_as_float((uint32_t)v[0])));
+            sact[2 * threadIdx.x + 1] = __bfloat162float(__float2bfloat16_rn(__uint_as_float((uint32_t)v[1])));
+        }
+    }
+    bar_compute();
+    for (int n = threadIdx.x; n < KI; n += NCT) {
+        const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(p.enc_w1 + (long)n * p.skp));   // skp >= 8
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        const float b1 = p.enc_b1[n];
+        for (int m = 0; m < p.M; ++m) {
+            float v = b1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < p.action_dim) v += ((k & 1) ? bf16hi(ww[k >> 1]) : bf16lo(ww[k >> 1])) * sact[m * 8 + k];
+            As[m * lda + n] = __float2bfloat16_rn(v);
+        }
+    }
+    bar_compute();
+}
+
+template <int MAXM>
+PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc) {
+    using SM = GemvSmem<MAXM>;
+    GemvCtx cx;
+    cx.smem = smem; cx.full = reinterpret_cast<uint64_t *>(smem + SM::BARS);
+    cx.cnt = 0; cx.issued = 0; cx.in_step = 0;
+    cx.total = (uint32_t)(p.n_steps * sc.slots_per_step);
+    cx.base = p.stream + sc.stream_off; cx.slots_per_step = sc.slots_per_step;
+    cx.pol = policy_evict_first();
+    ring_refill<SM>(cx);   // start streaming
+    uint8_t *red = smem + SM::RED;
+    float *xpriv = reinterpret_cast<float *>(smem + SM::MISC) + 16;   // [MAXO][8 rows m][8 cols]
+    const int tid = threadIdx.x;
+    const int qkvw = (p.nh + 2) * 128;
+    // the fp32 action state lives in registers of the decoder CTA: thread i < M*8 owns element (i / 8, i % 8);
+    // it starts as the caller's noise (pizero.py:454-458)
+    float my_act = 0.f;
+    if (sc.is_dec && tid < p.M * 8) {
+        const int m = tid >> 3, a = tid & 7;
+        my_act = a < p.action_dim ? p.noise[m * p.action_dim + a] : 0.f;
+        ll_store(p.ll_act + tid, __float_as_uint(my_act), seq_of(p, 0, IDX_ACT));
+    }
+    for (int step = 0; step < p.n_steps; ++step) {
+        // ---- action encoder (vla/modules.py:39-53): linear_1 on the fly, linear_2 (action half) + per-step time
+        //      bias + SiLU, linear_3 + sqrt(hidden) embed scale (joint_model.py:348-355)
+        if (sc.e2_blk >= 0) {
+            stage_enc1<SM>(p, smem, seq_of(p, step, IDX_ACT));
+            float acc[1][4];
+            gemv16<SM, 1>(p, cx, 1, acc);
+            red_write<1>(red, 1, acc);
+            bar_compute();
+                ring_refill<SM>(cx);
+            for (int i = tid; i < 8 * p.M; i += NCT) {   // (row pair, m)
+                const int rp = i & 7, m = i >> 3, n = sc.e2_blk * 16 + 2 * rp;
+                const float v0 = red_sum(red, 0, 2 * rp, m) + p.enc_time_bias[step * KI + n];
+                const float v1 = red_sum(red, 0, 2 * rp + 1, m) + p.enc_time_bias[step * KI + n + 1];
+                ll_store(p.ll_z + (long)m * (KI / 2) + (n >> 1), pack_bf16x2(silu(v0), silu(v1)), seq_of(p, step, IDX_Z));
+            }
+            bar_compute();
+        }
+        if (sc.n_o > 0) {
+            stage_pairs<SM, KI>(p, smem, p.ll_z, seq_of(p, step, IDX_Z));
+            float acc[MAXO][4];
+            gemv8<SM, 4>(p, cx, sc.n_o, acc);
+            red_write<MAXO>(red, sc.n_o, acc);
+            bar_compute();
+                ring_refill<SM>(cx);
+            if (tid < sc.n_o * 8 * p.M) {
+                const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
+                const int n = sc.o_blk[j] * 8 + r;
+                const float v = (red_sum(red, j, r, m) + p.enc_b3[n]) * sqrtf((float)KI);
+                xpriv[(j * 8 + m) * 8 + r] = v;
+                ll_store(p.ll_x[0] + (long)m * KI + n, __float_as_uint(v), seq_of(p, step, IDX_X0));
+            }
+            bar_compute();
+        }
+        for (int l = 0; l < p.n_layers; ++l) {
+            const int pb = l & 1;
+            // ---- QKV: x -> RMSNorm -> fused q|k|v projection (mixture.py:187-215), RoPE on q and k
+            if (sc.n_qkv > 0) {
+                stage_norm<SM>(p, smem, p.ll_x[pb], p.norm_in[l], seq_of(p, step, l == 0 ? IDX_X0 : IDX_X2(l - 1)));
+                float acc[MAXQ][4];
+                gemv16<SM, MAXQ>(p, cx, sc.n_qkv, acc);
+                red_write<MAXQ>(red, sc.n_qkv, acc);
+                bar_compute();
+                ring_refill<SM>(cx);
+                const uint32_t fo = seq_of(p, step, IDX_QKV(l));
+                // one (item, m, row) sum per thread.  Rows 0-7 / 8-15 of an item are the dims d / d + 128 of one head:
+                // rotate q and k here (fp32, table row S_p + token: positions 2.., pizero.py:312-318), then
+                // neighbouring dims pair up through a shuffle
+                for (int i0 = 0; i0 < sc.n_qkv * 16 * p.M; i0 += NCT) {
+                    const int i = i0 + tid;
+                    const bool ok = i < sc.n_qkv * 16 * p.M;
+                    const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
+                    float v0 = ok ? red_sum(red, j, r, m) : 0.f;
+                    const float other = __shfl_xor_sync(0xffffffffu, v0, 8);
+                    const int blk = sc.qkv_blk[j], hh = blk >> 4, d = (blk & 15) * 8 + (r & 7);
+                    if (hh <= p.nh) {
+                        const long ti = (long)(p.S_p + (m % p.H)) * 128 + d;
+                        const float cs = __ldg(p.rope_cos + ti), sn = __ldg(p.rope_sin + ti);
+                        v0 = (r < 8) ? v0 * cs - other * sn : v0 * cs + other * sn;
+                    }
+                    const float v1 = __shfl_down_sync(0xffffffffu, v0, 1);
+                    const int n = hh * 256 + (r < 8 ? d : 128 + d);
+                    if (ok && !(r & 1)) ll_store(p.ll_qkv[pb] + (long)m * qkvw + (n >> 1), pack_bf16x2(v0, v1), fo);
+                }
+                bar_compute();
+            }
+            // ---- o_proj + residual (mixture.py:217-218, joint_model.py:65-75)
+            if (sc.n_o > 0) {
+                stage_pairs<SM, 2048>(p, smem, p.ll_att[pb], seq_of(p, step, IDX_ATT(l)));
+                float acc[MAXO][4];
+                gemv8<SM, 8>(p, cx, sc.n_o, acc);
+                red_write<MAXO>(red, sc.n_o, acc);
+                bar_compute();
+                ring_refill<SM>(cx);
+                if (tid < sc.n_o * 8 * p.M) {
+                    const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
+                    const float v = xpriv[(j * 8 + m) * 8 + r] + red_sum(red, j, r, m);
+                    xpriv[(j * 8 + m) * 8 + r] = v;
+                    ll_store(p.ll_x1[pb] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X1(l)));
+                }
+                bar_compute();
+            }
+            // ---- gate|up + GeGLU (paligemma/modules.py:86-95)
+            if (sc.n_gu > 0) {
+                stage_norm<SM>(p, smem, p.ll_x1[pb], p.norm_post[l], seq_of(p, step, IDX_X1(l)));
+                float acc[MAXGU][4];
+                gemv16<SM, MAXGU>(p, cx, sc.n_gu, acc);
+                red_write<MAXGU>(red, sc.n_gu, acc);
+                bar_compute();
+                ring_refill<SM>(cx);
+                const uint32_t fo = seq_of(p, step, IDX_MLP(l));
+                for (int i0 = 0; i0 < sc.n_gu * 16 * p.M; i0 += NCT) {
+                    const int i = i0 + tid;
+                    const bool ok = i < sc.n_gu * 16 * p.M;
+                    const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
+                    const float v = ok ? red_sum(red, j, r, m) : 0.f;      // rows 0-7: gate, rows 8-15: the matching up rows
+                    const float u = __shfl_down_sync(0xffffffffu, v, 8);
+                    const float h0 = gelu_fast(v) * u;
+                    const float h1 = __shfl_down_sync(0xffffffffu, h0, 1);
+                    if (ok && r < 8 && !(r & 1))
+                        ll_store(p.ll_mlp[pb] + (long)m * (p.AI / 2) + sc.gu_tile[j] * 4 + (r >> 1), pack_bf16x2(h0, h1), fo);
+                }
+                bar_compute();
+            }
+            // ---- down + residual
+            if (sc.n_o > 0) {
+                stage_pairs<SM, 4096>(p, smem, p.ll_mlp[pb], seq_of(p, step, IDX_MLP(l)));
+                float acc[MAXO][4];
+                gemv8<SM, 16>(p, cx, sc.n_o, acc);
+                red_write<MAXO>(red, sc.n_o, acc);
+                bar_compute();
+                ring_refill<SM>(cx);
+                if (tid < sc.n_o * 8 * p.M) {
+                    const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
+                    const float v = xpriv[(j * 8 + m) * 8 + r] + red_sum(red, j, r, m);
+                    xpriv[(j * 8 + m) * 8 + r] = v;
+                    ll_store(p.ll_x[(l + 1) & 1] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X2(l)));
+                }
+                bar_compute();
+            }
+        }
+        // ---- final norm + decoder + Euler update (joint_model.py:375-380, pizero.py:479-481)
+        if (sc.is_dec) {
+            stage_norm<SM>(p, smem, p.ll_x[p.n_layers & 1], p.final_norm, seq_of(p, step, IDX_X2(p.n_layers - 1)));
+            float acc[MAXO][4];
+            gemv8<SM, 4>(p, cx, 1, acc);
+            red_write<MAXO>(red, 1, acc);
+            bar_compute();
+                ring_refill<SM>(cx);
+            if (tid < 8 * p.M) {
+                const int a = tid & 7, m = tid >> 3;
+                if (a < p.action_dim) my_act += p.dt * (red_sum(red, 0, a, m) + p.dec_b[a]);
+                if (step + 1 < p.n_steps) {
+                    ll_store(p.ll_act + tid, __float_as_uint(my_act), seq_of(p, step + 1, IDX_ACT));
+                } else if (a < p.action_dim) {
+                    float v = my_act;
+                    if (p.clip >= 0.f) v = fminf(fmaxf(v, -p.clip), p.clip);
+                    if (err_set(p)) v = __int_as_float(0x7fc00000);   // a wait ran into its bound: fail loudly
+                    p.out[m * p.action_dim + a] = v;
+                }
+            }
+            bar_compute();
+        }
+    }
+}
+
+// ============================================ attention role ============================================
+// shared memory: K tiles [4 dim-quarters][KEYS rows][64 dims] and V tiles [2][KEYS][64], 128-byte swizzled (TMA),
+// q rows, P, row-sum partials
+struct AttSmem {
+    static constexpr int K = 0;
+    static constexpr int V = K + 4 * KT_BYTES;
+    static constexpr int Q = V + 2 * KT_BYTES;             // bf16 [8][264]
+    static constexpr int P = Q + 8 * 264 * 2;              // bf16 [8][KEYS + 8]
+    static constexpr int LS = P + 8 * (KEYS + 8) * 2;      // float [NCW][8]
+    static constexpr int BARS = LS + NCW * 8 * 4;          // kv_full
+    static constexpr int END = BARS + 16;
+};
+PZ_DEVINL uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// one thread: request the cached K (all 256 dims) and this CTA's half of V of (layer, sample b): 12 boxes of 144 keys x 64 dims
+PZ_DEVINL void att_request_kv(const Mega3Params &p, uint8_t *smem, const CUtensorMap *kmap, const CUtensorMap *vmap, int l, int b,
+                              int dh, uint64_t pol) {
+    uint64_t *kv_full = reinterpret_cast<uint64_t *>(smem + AttSmem::BARS);
+    mbar_expect_tx(kv_full, 6u * KT_BYTES);
+    const int slab = l * p.batch_total + b;
+#pragma unroll
+    for (int dq = 0; dq < 4; ++dq)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)
+            tma_load_3d_hint(kmap, kv_full, smem + AttSmem::K + dq * KT_BYTES + hb * KBOX * 128, dq * 64, hb * KBOX, slab, pol);
+#pragma unroll
+    for (int dq = 0; dq < 2; ++dq)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)
+            tma_load_3d_hint(vmap, kv_full, smem + AttSmem::V + dq * KT_BYTES + hb * KBOX * 128, (dh * 2 + dq) * 64, hb * KBOX, slab, pol);
+}
+
+PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *kmap, const CUtensorMap *vmap, int b, int head, int dh) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    bf16 *sQ = reinterpret_cast<bf16 *>(smem + AttSmem::Q);
+    bf16 *sP = reinterpret_cast<bf16 *>(smem + AttSmem::P);
+    float *sLS = reinterpret_cast<float *>(smem + AttSmem::LS);
+    uint64_t *kv_full = reinterpret_cast<uint64_t *>(smem + AttSmem::BARS);
+    constexpr int LDQ = 264, LDP = KEYS + 8;
+    const uint64_t pol = policy_evict_last();
+    if (tid == 0) att_request_kv(p, smem, kmap, vmap, 0, b, dh, pol);   // layer 0 of step 0
+    const int H = p.H, S_c = p.S_c, n_keys = S_c + H;
+    const int vlen = p.valid_len[b];
+    const int n_mt = (n_keys + 15) >> 4;               // 16-key tiles
+    const int qkvw = (p.nh + 2) * 128;
+    const uint32_t sK = smem_u32(smem + AttSmem::K), sV = smem_u32(smem + AttSmem::V);
+    // rows no exchange ever writes must be zero: P x (anything finite) stays 0, q pad rows contribute nothing
+    for (int i = tid; i < 8 * LDQ / 2; i += NCT) reinterpret_cast<uint32_t *>(sQ)[i] = 0u;
+    for (int i = tid; i < 8 * LDP / 2; i += NCT) reinterpret_cast<uint32_t *>(sP)[i] = 0u;
+    bar_compute();
+
+    uint32_t it = 0;
+    for (int step = 0; step < p.n_steps; ++step) {
+        for (int l = 0; l < p.n_layers; ++l, ++it) {
+            const int pb = l & 1;
+            const uint32_t fin = seq_of(p, step, IDX_QKV(l));
+            // ---- this step's rotated q rows of (sample b, head), the fresh k rows and this CTA's half of the fresh
+            //      v rows: per token 64 + 64 + 32 double-words
+            unsigned long long v[6];
+            const int per_tok = 160, total = H * per_tok;
+            uint32_t pend = 0;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (tid + u * NCT < total) pend |= 1u << u;
+            ll_gather<3>(p, fin, pend, [&](int u) {
+                const int i = tid + u * NCT, tok = i / per_tok, e = i % per_tok;
+                const unsigned long long *row = p.ll_qkv[pb] + (long)(b * H + tok) * qkvw;
+                if (e < 64) return row + head * 128 + 2 * e;                       // q: dims 4e .. 4e+3
+                if (e < 128) return row + p.nh * 128 + 2 * (e - 64);               // k
+                return row + (p.nh + 1) * 128 + dh * 64 + 2 * (e - 128);           // v, dims dh*128 + 4(e-128) ..
+            }, v);
+            mbar_wait(p, kv_full, it & 1);   // the cached rows of this layer (loaded one layer ahead); also orders the
+                                             // fresh rows below after the TMA zero fill of rows >= S_c
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = tid + u * NCT;
+                if (i < total) {
+                    const int tok = i / per_tok, e = i % per_tok;
+                    const uint2 val = make_uint2((uint32_t)v[2 * u], (uint32_t)v[2 * u + 1]);
+                    if (e < 64) {
+                        *reinterpret_cast<uint2 *>(sQ + tok * LDQ + 4 * e) = val;
+                    } else if (e < 128) {
+                        const int d = 4 * (e - 64), row = S_c + tok;
+                        *reinterpret_cast<uint2 *>(smem + AttSmem::K + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2) = val;
+                    } else {
+                        const int d = 4 * (e - 128), row = S_c + tok;
+                        *reinterpret_cast<uint2 *>(smem + AttSmem::V + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2) = val;
+                    }
+                }
+            }
+            bar_compute();
+            // ---- S^T = K q^T: keys are the MMA M dimension (16-key tiles over the warps), the query rows the 8-wide N;
+            //      k index permuted so that every thread feeds two MMAs from one 16-byte load (as the GEMV items)
+            {
+                uint4 qf[8];
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc)
+                    qf[kc] = g < H ? *reinterpret_cast<const uint4 *>(sQ + g * LDQ + kc * 32 + 8 * t) : make_uint4(0, 0, 0, 0);
+                float ls0 = 0.f, ls1 = 0.f;   // partial row sums of query rows 2t, 2t+1
+                for (int mt = warp; mt < n_mt; mt += NCW) {
+                    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+                    for (int kc = 0; kc < 8; ++kc) {
+                        const uint8_t *tile = smem + AttSmem::K + (kc >> 1) * KT_BYTES;
+                        const int ch = (kc & 1) * 4 + t;
+                        const uint4 lo = *reinterpret_cast<const uint4 *>(tile + swz(r0, ch));
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(tile + swz(r1, ch));
+                        mma_bf16(s0, lo.x, hi.x, lo.y, hi.y, qf[kc].x, qf[kc].y);
+                        mma_bf16(s1, lo.z, hi.z, lo.w, hi.w, qf[kc].z, qf[kc].w);
+                    }
+                    const float scale = 0.0625f, cap = 50.f;   // 1/sqrt(256); soft-cap (joint_model.py:139,261-268)
+                    // |logit| <= 50 after the soft-cap: exp() needs no running maximum
+                    float pe[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = (e < 2) ? r0 : r1;
+                        const bool vis = (j < vlen) || (j >= p.S_v && j < n_keys);
+                        pe[e] = vis ? __expf(tanh_fast_acc((s0[e] + s1[e]) * scale * (1.f / cap)) * cap) : 0.f;
+                    }
+                    ls0 += pe[0] + pe[2];
+                    ls1 += pe[1] + pe[3];
+                    if (2 * t < H) {
+                        sP[(2 * t) * LDP + r0] = __float2bfloat16_rn(pe[0]);
+                        sP[(2 * t) * LDP + r1] = __float2bfloat16_rn(pe[2]);
+                    }
+                    if (2 * t + 1 < H) {
+                        sP[(2 * t + 1) * LDP + r0] = __float2bfloat16_rn(pe[1]);
+                        sP[(2 * t + 1) * LDP + r1] = __float2bfloat16_rn(pe[3]);
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { ls0 += __shfl_xor_sync(0xffffffffu, ls0, o); ls1 += __shfl_xor_sync(0xffffffffu, ls1, o); }
+                if (g == 0) { sLS[warp * 8 + 2 * t] = ls0; sLS[warp * 8 + 2 * t + 1] = ls1; }
+            }
+            bar_compute();
+            // ---- O^T = V^T P^T: warp -> 16 dims of this CTA's 128; V^T fragments by transposing ldmatrix
+            {
+                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t tile = sV + (warp >> 2) * KT_BYTES;
+                const int c0 = (warp & 3) * 2;
+                const int mi = lane >> 3, rr = lane & 7;
+                for (int kk = 0; kk < n_mt; ++kk) {
+                    uint32_t a[4];
+                    const int key = kk * 16 + (mi >> 1) * 8 + rr;
+                    ldsm_x4_t(a, tile + swz(key, c0 + (mi & 1)));
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(sP + g * LDP + kk * 16 + 2 * t);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(sP + g * LDP + kk * 16 + 8 + 2 * t);
+                    if (kk & 1) mma_bf16(o1, a[0], a[1], a[2], a[3], b0, b1);
+                    else mma_bf16(o0, a[0], a[1], a[2], a[3], b0, b1);
+                }
+                float inv0, inv1;   // 1 / row sum of query rows 2t, 2t+1
+                {
+                    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NCW; ++w) { l0 += sLS[w * 8 + 2 * t]; l1 += sLS[w * 8 + 2 * t + 1]; }
+                    inv0 = l0 > 0.f ? 1.f / l0 : 0.f;
+                    inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+                }
+                // c0, c1: O^T[d = warp*16 + g][m = 2t, 2t+1]; c2, c3: d + 8.  Pair neighbouring dims (lane + 4) into bf16x2
+                const uint32_t fo = seq_of(p, step, IDX_ATT(l));
+                const float e[4] = {(o0[0] + o1[0]) * inv0, (o0[1] + o1[1]) * inv1, (o0[2] + o1[2]) * inv0, (o0[3] + o1[3]) * inv1};
+                float nb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nb[i] = __shfl_down_sync(0xffffffffu, e[i], 4);
+                if (!(g & 1)) {
+                    const int n0 = head * 256 + dh * 128 + warp * 16 + g;
+#pragma unroll
+                    for (int mm = 0; mm < 2; ++mm) {
+                        const int tok = 2 * t + mm;
+                        if (tok < H) {
+                            unsigned long long *row = p.ll_att[pb] + (long)(b * H + tok) * 1024;
+                            ll_store(row + (n0 >> 1), pack_bf16x2(e[mm], nb[mm]), fo);
+                            ll_store(row + ((n0 + 8) >> 1), pack_bf16x2(e[2 + mm], nb[2 + mm]), fo);
+                        }
+                    }
+                }
+            }
+            bar_compute();   // every warp is done with the layer's K / V; q / P / row sums are rewritten by the next layer
+            if (tid == 0 && !(step == p.n_steps - 1 && l == p.n_layers - 1)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the fresh rows were ordinary stores
+                att_request_kv(p, smem, kmap, vmap, l + 1 == p.n_layers ? 0 : l + 1, b, dh, pol);   // one layer ahead
+            }
+        }
+    }
+}
+
+template <int MAXM>
+__global__ void __launch_bounds__(NT3, 1) denoise_mega3_kernel(const __grid_constant__ Mega3Params p,
+                                                              const __grid_constant__ CUtensorMap kmap,
+                                                              const __grid_constant__ CUtensorMap vmap) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    using SM = GemvSmem<MAXM>;
+    const bool is_att = (int)blockIdx.x >= p.G;
+    if (threadIdx.x == 0) {
+        if (is_att) {
+            mbar_init(reinterpret_cast<uint64_t *>(smem + AttSmem::BARS), 1);
+        } else {
+            uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::BARS);
+            for (int i = 0; i < SM::SLOTS; ++i) mbar_init(&full[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (!is_att) {
+        // this CTA's schedule entry -> shared memory
+        const int *src = reinterpret_cast<const int *>(p.sched + blockIdx.x);
+        int *dst = reinterpret_cast<int *>(smem + SM::SCHED);
+        if (threadIdx.x < sizeof(CtaSched) / 4) dst[threadIdx.x] = src[threadIdx.x];
+    }
+    __syncthreads();
+    if (is_att) {
+        const int a = blockIdx.x - p.G, b = a / NATT, head = (a % NATT) >> 1, dh = a & 1;
+        att_role(p, smem, &kmap, &vmap, b, head, dh);
+    } else {
+        gemv_role<MAXM>(p, smem, *reinterpret_cast<const CtaSched *>(smem + SM::SCHED));
+    }
+}
+
+// ------------------------------------------------------------------------------------- re-packing ----
+// One block per stream slot: 2048 16-byte chunks in the register-fragment order of mma.sync.m16n8k16 with the weights
+// as the A operand and the k index permuted so that one 16-byte load feeds two MMAs (skinny.cu):
+//   16-row items (unit = 32 k, 1 KB): chunk [unit][half][lane] = W[row(half, lane / 4)][32 unit + 8 (lane % 4) .. + 8]
+//   8-row items  (unit = 32 k, 512 B): chunk [unit][lane]       = W[8 blk + lane / 4][32 unit + 8 (lane % 4) .. + 8]
+struct RepackParams {
+    pz_mix_layer layers[MAX_LAYERS];
+    const bf16 *enc_w2a, *enc_w3, *dec_w;
+    const SlotDesc *descs;
+    uint8_t *slots;
+    int nh, AI;
+};
+__global__ void __launch_bounds__(256) mega3_repack_kernel(const __grid_constant__ RepackParams p) {
+    const SlotDesc d = p.descs[blockIdx.x];
+    uint4 *dst = reinterpret_cast<uint4 *>(p.slots + (size_t)blockIdx.x * SLOT);
+    const int qd = p.nh * 256;
+    for (int ci = threadIdx.x; ci < SLOT / 16; ci += 256) {
+        uint4 val = make_uint4(0, 0, 0, 0);
+        const bf16 *src = nullptr;
+        if (d.kind == SK_QKV || d.kind == SK_GU || d.kind == SK_E2) {
+            const int unit = ci >> 6, half = (ci >> 5) & 1, lane = ci & 31, g = lane >> 2, t = lane & 3;
+            const int k = unit * 32 + 8 * t;
+            long row;
+            const bf16 *W;
+            if (d.kind == SK_QKV) {          // rows d0.. and 128 + d0.. of one head: a rotary pair lives in one item
+                W = (const bf16 *)p.layers[d.layer].w_qkv;
+                row = (long)(d.blk >> 4) * 256 + (d.blk & 15) * 8 + g + half * 128;
+            } else if (d.kind == SK_GU) {    // 8 gate rows + the 8 matching up rows of the packed [128 gate | 128 up] layout
+                W = (const bf16 *)p.layers[d.layer].w_gate_up;
+                const int n = d.blk * 8 + g;
+                row = (long)(n / PZ_GU_BLOCK) * (2 * PZ_GU_BLOCK) + (n % PZ_GU_BLOCK) + half * PZ_GU_BLOCK;
+            } else {
+                W = p.enc_w2a;
+                row = (long)d.blk * 16 + g + half * 8;
+            }
+            src = W + row * KI + k;
+        } else {
+            const int unit = ci >> 5, lane = ci & 31, g = lane >> 2, t = lane & 3;
+            if (d.kind == SK_O) {
+                src = (const bf16 *)p.layers[d.layer].w_o + (long)(d.blk * 8 + g) * qd + unit * 32 + 8 * t;
+            } else if (d.kind == SK_D) {     // aux = which half of K = AI
+                src = (const bf16 *)p.layers[d.layer].w_down + (long)(d.blk * 8 + g) * p.AI + (d.aux * 64 + unit) * 32 + 8 * t;
+            } else if (unit < 32) {          // K = 1024: half a slot
+                const bf16 *W = d.kind == SK_E3 ? p.enc_w3 : p.dec_w;
+                src = W + (long)(d.blk * 8 + g) * KI + unit * 32 + 8 * t;
+            }
+        }
+        if (src) val = *reinterpret_cast<const uint4 *>(src);
+        dst[ci] = val;
+    }
+}
+
+// host: who does what.  Balances the bytes per CTA and layer (16 KB granules: QKV / gate-up item 2, o_proj block 2,
+// down block 4) with a greedy least-loaded assignment.
+struct Mega3Plan {
+    int G = 0, NA = 0;
+    std::vector<CtaSched> sched;
+    std::vector<SlotDesc> descs;
+};
+static bool build_plan(const pz_config &c, int B, int num_sms, Mega3Plan &pl) {
+    pl.NA = NATT * B;
+    pl.G = num_sms - pl.NA;
+    const int G = pl.G;
+    const int n_own = c.act_hidden / 8, n_qkv = (c.n_heads + 2) * 16, n_gu = c.act_inter / 8, n_e2 = c.act_hidden / 16;
+    if (G < 1 || n_own > MAXO * G || n_e2 > G) return false;
+    pl.sched.assign(G, CtaSched{});
+    std::vector<int> load(G, 0);
+    for (auto &s : pl.sched) s.e2_blk = -1;
+    for (int j = 0; j < n_own; ++j) {
+        CtaSched &s = pl.sched[j % G];
+        s.o_blk[s.n_o++] = j;
+        load[j % G] += 6;
+    }
+    auto least = [&](auto ok) {
+        int best = -1;
+        for (int i = 0; i < G; ++i)
+            if (ok(pl.sched[i]) && (best < 0 || load[i] < load[best])) best = i;
+        return best;
+    };
+    for (int tl = 0; tl < n_gu; ++tl) {
+        int i = least([](const CtaSched &s) { return s.n_gu < MAXGU; });
+        if (i < 0) return false;
+        pl.sched[i].gu_tile[pl.sched[i].n_gu++] = tl;
+        load[i] += 2;
+    }
+    for (int q = 0; q < n_qkv; ++q) {
+        int i = least([](const CtaSched &s) { return s.n_qkv < MAXQ; });
+        if (i < 0) return false;
+        pl.sched[i].qkv_blk[pl.sched[i].n_qkv++] = q;
+        load[i] += 2;
+    }
+    for (int e = 0; e < n_e2; ++e) pl.sched[e].e2_blk = e;
+    pl.sched[G - 1].is_dec = 1;
+    // slot order = consumption order (gemv_role)
+    pl.descs.clear();
+    for (int i = 0; i < G; ++i) {
+        CtaSched &s = pl.sched[i];
+        s.stream_off = (long long)pl.descs.size() * SLOT;
+        const size_t first = pl.descs.size();
+        if (s.e2_blk >= 0) pl.descs.push_back({SK_E2, 0, s.e2_blk, 0});
+        for (int j = 0; j < s.n_o; ++j) pl.descs.push_back({SK_E3, 0, s.o_blk[j], 0});
+        for (int l = 0; l < c.n_layers; ++l) {
+            for (int j = 0; j < s.n_qkv; ++j) pl.descs.push_back({SK_QKV, l, s.qkv_blk[j], 0});
+            for (int j = 0; j < s.n_o; ++j) pl.descs.push_back({SK_O, l, s.o_blk[j], 0});
+            for (int j = 0; j < s.n_gu; ++j) pl.descs.push_back({SK_GU, l, s.gu_tile[j], 0});
+            for (int j = 0; j < s.n_o; ++j) { pl.descs.push_back({SK_D, l, s.o_blk[j], 0}); pl.descs.push_back({SK_D, l, s.o_blk[j], 1}); }
+        }
+        if (s.is_dec) pl.descs.push_back({SK_DEC, 0, 0, 0});
+        s.slots_per_step = (int)(pl.descs.size() - first);
+    }
+    return true;
+}
+
+constexpr size_t HDR_BYTES = 65536;   // schedule table + slot descriptors' home at the head of the stream buffer
+
+bool make_kv_map(CUtensorMap *map, const void *base, int S_c, long slabs) {
+    tcptx::EncodeTiledFn enc = tcptx::get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {256, (cuuint64_t)S_c, (cuuint64_t)slabs};
+    cuuint64_t strides[2] = {512, (cuuint64_t)S_c * 512};
+    cuuint32_t box[3] = {64, KBOX, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t ll_words(const pz_config &c, int B) {
+    const size_t M = (size_t)B * c.horizon, A = c.act_hidden, qkvw = (size_t)(c.n_heads + 2) * 128;
+    // act, z, 2 x, 2 x1, 2 qkv, 2 att, 2 mlp (each rounded up to 16 words)
+    auto r = [](size_t w) { return (w + 15) & ~(size_t)15; };
+    return r(M * 8) + r(M * A / 2) + 2 * r(M * A) + 2 * r(M * A) + 2 * r(M * qkvw) + 2 * r(M * (size_t)c.n_heads * 128) + 2 * r(M * c.act_inter / 2);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------- host side ----
+int denoise_mega3_supported(const pz_config &c, int B) {
+    static const bool off = [] { const char *e = getenv("PZ_MEGA3"); return e && e[0] == '0'; }();
+    if (off) return 0;
+    if (c.dtype != PZ_BF16 || (c.flags & PZ_FLAG_SIMPLE_KERNELS)) return 0;
+    if (B < 1 || B * c.horizon > 8) return 0;
+    if (c.head_dim != 256 || c.n_kv_heads != 1 || c.n_heads != 8) return 0;
+    if (c.act_hidden != KI || c.act_inter != 4096) return 0;
+    if (c.n_layers > MAX_LAYERS || c.action_dim > 8) return 0;
+    if (c.s_vlm + c.cond_steps + c.horizon > KEYS) return 0;
+    return 1;
+}
+
+size_t denoise_mega3_ll_bytes(const pz_config &c, int B) {
+    if (!denoise_mega3_supported(c, B)) return 0;
+    return ll_words(c, B) * 8 + 256;
+}
+
+size_t denoise_mega3_stream_bytes(const pz_config &c, int B, int num_sms) {
+    if (!denoise_mega3_supported(c, B)) return 0;
+    Mega3Plan pl;
+    if (!build_plan(c, B, num_sms, pl)) return 0;
+    return HDR_BYTES + pl.descs.size() * sizeof(SlotDesc) + 1024 + pl.descs.size() * (size_t)SLOT;
+}
+
+// Builds the schedule for `num_sms` CTAs and re-packs the action expert's weights into the per-CTA item streams.
+// Synchronous with respect to the host for the (small) table upload; the re-pack kernel runs on `st`.
+int denoise_mega3_pack(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, int B, int num_sms, void *buf,
+                       size_t bytes, Mega3State *state, cudaStream_t st, const char **err) {
+    Mega3Plan pl;
+    if (!denoise_mega3_supported(c, B) || !build_plan(c, B, num_sms, pl)) {
+        if (err) *err = "persistent sampler: configuration / SM count not supported";
+        return PZ_ERR_INVALID;
+    }
+    const size_t desc_bytes = pl.descs.size() * sizeof(SlotDesc);
+    const size_t slots_off = (HDR_BYTES + desc_bytes + 1023) & ~(size_t)1023;
+    if (bytes < slots_off + pl.descs.size() * (size_t)SLOT || pl.sched.size() * sizeof(CtaSched) > HDR_BYTES) {
+        if (err) *err = "persistent sampler: stream buffer too small";
+        return PZ_ERR_WORKSPACE;
+    }
+    if (((uintptr_t)buf) & 1023) {
+        if (err) *err = "persistent sampler: stream buffer must be 1 KiB aligned";
+        return PZ_ERR_INVALID;
+    }
+    uint8_t *base = (uint8_t *)buf;
+    if (cudaMemcpyAsync(base, pl.sched.data(), pl.sched.size() * sizeof(CtaSched), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(base + HDR_BYTES, pl.descs.data(), desc_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {   // the host vectors go out of scope
+        if (err) *err = "persistent sampler: table upload failed";
+        return PZ_ERR_CUDA;
+    }
+    RepackParams rp;
+    memset(&rp, 0, sizeof(rp));
+    for (int l = 0; l < c.n_layers; ++l) rp.layers[l] = layers[l];
+    rp.enc_w2a = (const bf16 *)w.enc_w2a; rp.enc_w3 = (const bf16 *)w.enc_w3; rp.dec_w = (const bf16 *)w.dec_w;
+    rp.descs = (const SlotDesc *)(base + HDR_BYTES);
+    rp.slots = base + slots_off;
+    rp.nh = c.n_heads; rp.AI = c.act_inter;
+    mega3_repack_kernel<<<(unsigned)pl.descs.size(), 256, 0, st>>>(rp);
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        if (err) *err = "persistent sampler: re-pack launch failed";
+        return PZ_ERR_CUDA;
+    }
+    state->buf = buf; state->bytes = bytes; state->B = B; state->G = pl.G; state->NA = pl.NA; state->num_sms = num_sms;
+    state->slots_off = slots_off;
+    return 0;
+}
+
+int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const Mega3State &state,
+                         const Mega3Buffers &bf, int B, cudaStream_t st, const char **err) {
+    constexpr int SMEM4 = (GemvSmem<4>::END > AttSmem::END ? GemvSmem<4>::END : AttSmem::END) + 1024;
+    constexpr int SMEM8 = (GemvSmem<8>::END > AttSmem::END ? GemvSmem<8>::END : AttSmem::END) + 1024;
+    static_assert(SMEM4 <= 227 * 1024 && SMEM8 <= 227 * 1024, "shared memory budget");
+    const int M = B * c.horizon;
+    const void *fn = M <= 4 ? (const void *)denoise_mega3_kernel<4> : (const void *)denoise_mega3_kernel<8>;
+    const int smem = M <= 4 ? SMEM4 : SMEM8;
+    static PerDeviceOnce attr_once[2];
+    if (attr_once[M <= 4 ? 0 : 1].need() &&
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        if (err) *err = "persistent sampler: cannot set the shared-memory size";
+        return PZ_ERR_CUDA;
+    }
+    if (state.B != B || !state.buf) {
+        if (err) *err = "persistent sampler: weights not packed for this batch";
+        return PZ_ERR_UNBOUND;
+    }
+    Mega3Params p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = c.horizon; p.M = M; p.nh = c.n_heads; p.AI = c.act_inter;
+    p.S_v = c.s_vlm; p.S_p = c.cond_steps; p.S_c = c.s_vlm + c.cond_steps; p.n_layers = c.n_layers; p.n_steps = c.n_steps;
+    p.action_dim = c.action_dim; p.skp = w.small_k_pad;
+    p.G = state.G; p.NA = state.NA;
+    p.dt = (float)(1.0 / c.n_steps); p.clip = c.clip;
+    for (int l = 0; l < c.n_layers; ++l) { p.norm_in[l] = layers[l].norm_in; p.norm_post[l] = layers[l].norm_post; }
+    p.final_norm = w.action_final_norm;
+    p.enc_w1 = (const bf16 *)w.enc_w1;
+    p.enc_b1 = w.enc_b1; p.enc_time_bias = w.enc_time_bias; p.enc_b3 = w.enc_b3; p.dec_b = w.dec_b;
+    p.rope_cos = w.rope_act_cos; p.rope_sin = w.rope_act_sin;
+    p.valid_len = bf.valid_len; p.noise = bf.noise; p.out = bf.out;
+    p.stream = (const uint8_t *)state.buf + state.slots_off;
+    p.sched = (const CtaSched *)state.buf;
+    p.batch_total = bf.batch_total;
+    {   // carve the exchange buffers
+        unsigned long long *q = (unsigned long long *)bf.ll;
+        auto take = [&](size_t words) { unsigned long long *r = q; q += (words + 15) & ~(size_t)15; return r; };
+        const size_t Mz = M, A = c.act_hidden, qkvw = (size_t)(c.n_heads + 2) * 128;
+        p.ll_act = take(Mz * 8); p.ll_z = take(Mz * A / 2);
+        for (int i = 0; i < 2; ++i) p.ll_x[i] = take(Mz * A);
+        for (int i = 0; i < 2; ++i) p.ll_x1[i] = take(Mz * A);
+        for (int i = 0; i < 2; ++i) p.ll_qkv[i] = take(Mz * qkvw);
+        for (int i = 0; i < 2; ++i) p.ll_att[i] = take(Mz * (size_t)c.n_heads * 128);
+        for (int i = 0; i < 2; ++i) p.ll_mlp[i] = take(Mz * c.act_inter / 2);
+        p.err = (unsigned int *)q;
+        if ((size_t)((char *)q - (char *)bf.ll) + 256 > bf.ll_bytes) {
+            if (err) *err = "persistent sampler: exchange workspace too small";
+            return PZ_ERR_WORKSPACE;
+        }
+        if (cudaMemsetAsync(bf.ll, 0, bf.ll_bytes, st) != cudaSuccess) {
+            if (err) *err = "persistent sampler: memset failed";
+            return PZ_ERR_CUDA;
+        }
+    }
+    CUtensorMap kmap, vmap;
+    const long slabs = (long)c.n_layers * bf.batch_total;
+    if (!make_kv_map(&kmap, bf.kcache, p.S_c, slabs) || !make_kv_map(&vmap, bf.vcache, p.S_c, slabs)) {
+        if (err) *err = "persistent sampler: cuTensorMapEncodeTiled failed";
+        return PZ_ERR_CUDA;
+    }
+    void *args[] = {&p, &kmap, &vmap};
+    // cooperative launch: all CTAs are guaranteed co-resident (the polled exchanges rely on it)
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(state.num_sms), dim3(NT3), args, (size_t)smem, st);
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return PZ_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}

@@ -442,25 +442,19 @@ bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld,
     return r == CUDA_SUCCESS;
 }
 
-int g_num_sms = 0;
 
 template <int BN, int CG, int EPI>
 int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
     using cfg = Cfg<BN, CG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cfg::SMEM_BYTES) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(max dynamic smem) failed";
             return PZ_ERR_CUDA;
         }
-        attr_set = true;
     }
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int g_num_sms = device_sm_count();
     CUtensorMap ma, mw, mc;
     const bool f32out = a.flags & LIN_OUT_F32;
     const int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
@@ -596,7 +590,7 @@ int launch_linear_tc(const LinearArgs &a, cudaStream_t st, const char **err) {
         // split-K capable (fp32 reduce-add), long K and too few tiles: a weight-streaming problem (down_proj at bs=1).  Wider tiles move fewer
         // activation bytes per weight byte through each SM (the per-SM bytes in flight are the limit), as long as
         // the K split still yields a work item for (almost) every SM.
-        if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int g_num_sms = device_sm_count();
         long tiles128 = (long)((a.M + BM - 1) / BM) * ((a.N + 127) / 128);
         long by_k = ((a.K + BK - 1) / BK) / 4;
         auto items = [&](long tiles) { long s = g_num_sms / tiles; if (s > by_k) s = by_k; if (s < 1) s = 1; return tiles * s; };

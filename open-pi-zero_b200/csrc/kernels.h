@@ -86,20 +86,29 @@ int denoise_mega_supported(const pz_config &c, int B);
 int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const MegaBuffers &bf,
                         int B, cudaStream_t st, const char **err);
 
-// denoise_mega2.cu (barrier-free persistent sampler for B * horizon <= 8: flagged 64-bit exchanges,
-// attention CTAs with shared-memory-resident KV, TMA bulk weight ring)
-struct Mega2Buffers {
+// denoise_mega3.cu (barrier-free persistent sampler for B * horizon <= 8: exchanges through {payload, sequence}
+// words, per-CTA weight streams re-packed in MMA fragment order and fed by 32 KB bulk copies, attention CTAs with
+// the layer's K / V resident in shared memory)
+struct Mega3State {      // filled by denoise_mega3_pack
+    void *buf = nullptr;
+    size_t bytes = 0, slots_off = 0;
+    int B = 0, G = 0, NA = 0, num_sms = 0;
+};
+struct Mega3Buffers {
     const void *kcache, *vcache;   // [L][batch_total][S_c][256] bf16
     int batch_total;
     const int32_t *valid_len;
     const float *noise;            // [B*horizon][action_dim] initial action
     float *out;
-    void *ll; size_t ll_bytes;     // exchange buffers, >= denoise_mega2_ll_bytes()
+    void *ll; size_t ll_bytes;     // exchange buffers, >= denoise_mega3_ll_bytes()
 };
-size_t denoise_mega2_ll_bytes(const pz_config &c, int B);
-int denoise_mega2_supported(const pz_config &c, int B);
-int launch_denoise_mega2(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const Mega2Buffers &bf,
-                         int B, cudaStream_t st, const char **err);
+int denoise_mega3_supported(const pz_config &c, int B);
+size_t denoise_mega3_ll_bytes(const pz_config &c, int B);
+size_t denoise_mega3_stream_bytes(const pz_config &c, int B, int num_sms);
+int denoise_mega3_pack(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, int B, int num_sms, void *buf,
+                       size_t bytes, Mega3State *state, cudaStream_t st, const char **err);
+int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const Mega3State &state,
+                         const Mega3Buffers &bf, int B, cudaStream_t st, const char **err);
 
 // stand-alone decode attention (one CTA per (sample, 64-key tile), RoPE fused, 8 warps): writes split-key
 // partials (bf16 o [B][splits][heads*horizon][256], then fp32 l) and combines them into `out` [B][horizon][heads*256];

@@ -223,6 +223,11 @@ class PiZero(nn.Module):
         self._ws_batch = 0
         self._flags = _lib.PZ_FLAG_SIMPLE_KERNELS if os.environ.get("PZ_SIMPLE_KERNELS") == "1" else 0
         self.use_cuda_graph = os.environ.get("PZ_CUDA_GRAPH", "1") != "0"
+        # which Euler-loop implementation (include/pz_b200.h PZ_SAMPLER_*): 0 auto, 1 kernels, 2 barrier, 3 stream
+        self._sampler_mode = int(os.environ.get("PZ_SAMPLER", "0"))
+        self._sampler_pack_batches = tuple(int(b) for b in os.environ.get("PZ_SAMPLER_BATCHES", "1,2").split(",") if b)
+        self._sampler_batches = []
+        self.max_graphs = int(os.environ.get("PZ_MAX_GRAPHS", "8"))
         self._graphs = {}
         self._timing_armed = False
         self.last_launch_count = 0
@@ -288,20 +293,20 @@ class PiZero(nn.Module):
 
     # ---------------------------------------------------------------- packing
     def _param_key(self):
-        """Cheap staleness key of the packed weights, evaluated on every call (it is on the bs=1 latency
-        path: walking all 938 parameters cost ~0.5 ms).  `.to()` / `load_state_dict` / `_apply` drop the cached
-        parameter list, so moves and reloads are always seen; in-place edits are seen through the version
-        counters of a fixed sample of parameters (all of them with PZ_CHECK_INPUTS=1) -- after editing single
-        weights in place call `pack(force=True)`."""
+        """Staleness key of the packed weights, evaluated on every call: dtype, device, storage address and the SUM OF
+        ALL parameters' version counters (any in-place edit of any tensor -- optimizer step, EMA update as in the
+        reference's train.py:419,433, manual surgery -- bumps one of them).  Walking a cached list of the 938
+        parameters costs ~80 us of host time; `.to()` / `load_state_dict` / `_apply` drop the cached list."""
         ps = self.__dict__.get("_param_list")
         if ps is None:
             ps = list(self.parameters())
-            step = max(1, len(ps) // 16)
             self.__dict__["_param_list"] = ps
-            self.__dict__["_param_sample"] = ps[::step] + [ps[-1]]
-        sample = ps if os.environ.get("PZ_CHECK_INPUTS") == "1" else self.__dict__["_param_sample"]
-        return (ps[0].dtype, ps[0].device, sum(p._version for p in sample), ps[0].data_ptr(), self._tied,
-                self._flags)
+        if not ps or ps[0].numel() == 0:
+            if self._handle is None:
+                raise PzError("the parameters were released (release_unpacked_parameters) and the packed weights are "
+                              "gone: reload the state dict before calling again")
+            return self._packed_key
+        return (ps[0].dtype, ps[0].device, sum(p._version for p in ps), ps[0].data_ptr(), self._tied, self._flags)
 
     @torch.no_grad()
     def pack(self, force: bool = False):
@@ -460,6 +465,25 @@ class PiZero(nn.Module):
             msg = lib.pz_last_error(hnd).decode()
             lib.pz_destroy(hnd)
             raise PzError(f"pz_bind_weights failed ({rc}): {msg}")
+        # bs 1 / 2: per-SM re-packed copy of the action expert for the stream sampler (csrc/denoise_mega3.cu)
+        self._sampler_batches = []
+        if T == torch.bfloat16 and not self._flags:
+            with torch.cuda.device(dev):
+                st = torch.cuda.current_stream(dev).cuda_stream
+                for b in self._sampler_pack_batches:
+                    nbytes = lib.pz_sampler_stream_bytes(hnd, b)
+                    if nbytes == 0:
+                        continue
+                    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                    base = (buf.data_ptr() + 1023) // 1024 * 1024
+                    rc = lib.pz_sampler_pack(hnd, b, base, nbytes, st)
+                    if rc != 0:
+                        msg = lib.pz_last_error(hnd).decode()
+                        lib.pz_destroy(hnd)
+                        raise PzError(f"pz_sampler_pack failed ({rc}): {msg}")
+                    keep.append(buf)
+                    self._sampler_batches.append(b)
+        lib.pz_set_sampler(hnd, self._sampler_mode)
         self._handle, self._packed, self._packed_key = hnd, (keep, w), key
         self._T = T
         self._workspace, self._ws_batch = None, 0
@@ -508,7 +532,7 @@ class PiZero(nn.Module):
             # row 0 is an image token: its visible columns are exactly the valid image/text
             # positions (pizero.py:296-300)
             Sv = self.max_image_text_tokens
-            return (image_text_proprio_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).contiguous()
+            return (image_text_proprio_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).to(input_ids.device).contiguous()
         return (input_ids != self.pad_token_id).sum(-1, dtype=torch.int32).contiguous()
 
     @torch.no_grad()
@@ -611,11 +635,18 @@ class PiZero(nn.Module):
 
     def _launch(self, ids, pix, vlen, prop, nz, out, ws, ws_bytes, B, cap_struct=None):
         lib = _lib.load()
-        stream = torch.cuda.current_stream(out.device).cuda_stream
-        lib.pz_set_pixel_format(self._handle, 1 if pix.dtype == torch.uint8 else 0)
-        rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
-                                 prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
-                                 C.byref(cap_struct) if cap_struct is not None else None, stream)
+        dev = out.device
+        for t in (ids, pix, vlen, prop, nz):
+            if t.device != dev:
+                raise PzError(f"internal: input on {t.device}, model on {dev}")
+        # kernels are launched into a stream of `dev`: it must be the current device (the reference's callers do
+        # `.to(f"cuda:{gpu_id}")` without set_device, eval.py / try_checkpoint_in_simpler.py)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            lib.pz_set_pixel_format(self._handle, 1 if pix.dtype == torch.uint8 else 0)
+            rc = lib.pz_infer_action(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(),
+                                     prop.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, ws_bytes, B,
+                                     C.byref(cap_struct) if cap_struct is not None else None, stream)
         if rc != 0:
             raise PzError(f"pz_infer_action failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
         self.last_launch_count = int(lib.pz_launch_count(self._handle))

@@ -1,19 +1,32 @@
-"""Compare / time the persistent samplers: PZ_MEGA=1 (grid-barrier kernel) vs PZ_MEGA=2 (flag-exchange kernel)."""
-import sys, os
+"""Compare / time the three implementations of the Euler loop at small batch: one kernel per op (PZ_SAMPLER_KERNELS),
+the grid-barrier persistent kernel (denoise_mega.cu) and the stream sampler (denoise_mega3.cu).
+  python tools/mega_check.py [B ...] [--layers N]"""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 import open_pi_zero_b200 as pz
 from open_pi_zero_b200 import _lib
 from open_pi_zero_b200.pizero import PiZeroInference
 from open_pi_zero_b200.synth import fill_random_
 
-dims = pz.make_dims()
+args = sys.argv[1:]
+kw = {}
+if "--layers" in args:
+    i = args.index("--layers")
+    kw = dict(num_layers=int(args[i + 1]), vit_layers=2)
+    del args[i:i + 2]
+dims = pz.make_dims(**kw)
 dev = torch.device("cuda")
 m = PiZeroInference(pz.cfg_from_dims(dims), init="empty", device=dev, dtype=torch.bfloat16)
 fill_random_(m, dims)
 m.pack()
+print("stream sampler packed for batches", m._sampler_batches)
 lib = _lib.load()
-for B in [int(a) for a in sys.argv[1:]] or [1, 2]:
+NAMES = {1: "kernels", 2: "barrier", 3: "stream"}
+for B in [int(a) for a in args] or [1, 2]:
     inp = pz.make_inputs(dims, B, seed=0)
     ids = inp["input_ids"].to(dev); pix = inp["pixel_values"].to(dev, torch.bfloat16)
     prop = inp["proprios"].to(dev); nz = inp["noise"].to(dev); vlen = inp["valid_len"].to(dev)
@@ -25,41 +38,29 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 2]:
     assert lib.pz_prefill(m._handle, vlen.data_ptr(), prop.data_ptr(), ws, nbytes, B, None, st) == 0
     torch.cuda.synchronize()
     outs = {}
-    for ver in ("0", "1", "2"):
-        os.environ["PZ_MEGA"] = ver
-        out = torch.zeros(B, 4, 7, device=dev)
+    for mode in (1, 2, 3):
+        if mode == 3 and B not in m._sampler_batches:
+            continue
+        assert lib.pz_set_sampler(m._handle, mode) == 0
+        out = torch.zeros(B, dims["horizon_steps"], dims["action_dim"], device=dev)
+
         def run():
             rc = lib.pz_denoise(m._handle, vlen.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, nbytes, B, None,
                                 torch.cuda.current_stream().cuda_stream)
             assert rc == 0, lib.pz_last_error(m._handle)
         run(); torch.cuda.synchronize()
-        outs[ver] = out.clone()
-        if ver == "0":
-            continue
-        for _ in range(3): run()
+        outs[mode] = out.clone()
+        for _ in range(3):
+            run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20): run()
+        for _ in range(20):
+            run()
         e1.record(); torch.cuda.synchronize()
-        print(f"B={B} PZ_MEGA={ver}: {e0.elapsed_time(e1) / 20:.3f} ms per 10-step denoise; "
-              f"max|out - separate kernels| = {float((out - outs['0']).abs().max()):.3e}; finite={bool(torch.isfinite(out).all())}")
-    off = lib.pz_debug_ll_trace_offset(m._handle, B) + (ws - ws_t.data_ptr())
-    raw = ws_t[off: off + 148 * 16 * 8].view(torch.int64).cpu().view(148, 16)
-    G = 148 - 2 * B
-    for errw in [int(x) & 0xFFFFFFFF for x in ws_t[off - 256: off - 256 + 20].view(torch.int32).cpu()]:
-      if errw:
-        print(f"ERR word {errw:#x}: kind={(errw >> 24) & 0x7f} cta={(errw >> 12) & 0xfff} site={errw & 0xf} layer={(errw >> 4) & 0x1f} step&3={(errw >> 9) & 3}")
-    if int(raw[0, 0]) > 0:
-        t0 = int(raw[:G, 0].min())
-        g = (raw[:G].double() - t0) / 1e3
-        n = ["start", "QKV.stage", "QKV.acc", "QKV.st", "O.stage", "O.acc", "O.st", "GU.stage", "GU.acc", "GU.st", "D.stage", "D.acc", "D.st", "GU.acc.enter", "GU.acc.firstfull", "GU.acc.mmadone"]
-        print("event: min / median / max over streaming CTAs (us since first CTA entered the layer)")
-        for i, name in enumerate(n):
-            col = g[:, i][raw[:G, i] > 0]
-            if len(col): print(f"  {name:10s} {col.min():7.2f} {col.median():7.2f} {col.max():7.2f}  (n={len(col)})")
-        a = (raw[G:G + 2 * B].double() - t0) / 1e3
-        an = ["start", "stage", "kv", "S+P", "PV+st"]
-        for r in range(2 * B):
-            print(f"  ATT cta {r}: " + " ".join(f"{an[i]}={a[r, i]:.2f}" for i in range(5)))
-    print(f"B={B} max|v2 - v1| = {float((outs['2'] - outs['1']).abs().max()):.3e}")
+        ms = e0.elapsed_time(e1) / 20
+        gb = dims["num_inference_steps"] * (629.3e6 * dims["num_layers"] / 18 + 5.11e6 * B * dims["num_layers"] / 18)
+        print(f"B={B} {NAMES[mode]:8s}: {ms:.3f} ms per {dims['num_inference_steps']}-step denoise "
+              f"({gb / ms / 1e6:.0f} GB/s algorithmic); max|out - kernels| = {float((out - outs[1]).abs().max()):.3e}; "
+              f"finite={bool(torch.isfinite(out).all())}", flush=True)
+    lib.pz_set_sampler(m._handle, 0)
