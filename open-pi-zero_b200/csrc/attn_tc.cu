@@ -69,7 +69,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                const __grid_constant__ CUtensorMap map_k32, const __grid_constant__ CUtensorMap map_v32, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = align_smem(smem_raw, 1024);
     uint8_t *sQ = smem + OFF_Q, *sK = smem + OFF_K, *sV = smem + OFF_V, *sP = smem + OFF_P;
     uint64_t *bars = (uint64_t *)(smem + OFF_MISC);
     uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3 /* [2] */, *p_full = bars + 5,
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_vit_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const AttnVitParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = align_smem(smem_raw, 1024);
     uint8_t *sQ = smem + V_OFF_Q, *sK = smem + V_OFF_K, *sV = smem + V_OFF_V, *sP = smem + V_OFF_P;
     uint64_t *bars = (uint64_t *)(smem + V_OFF_MISC);
     uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *pv_done = bars + 5;

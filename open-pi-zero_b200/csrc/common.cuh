@@ -18,6 +18,13 @@ template <typename T> PZ_DEVINL T from_f32(float v);
 template <> PZ_DEVINL float from_f32<float>(float v) { return v; }
 template <> PZ_DEVINL bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// Round the dynamic shared-memory base up to `align` bytes without a round trip through an integer: a pointer rebuilt
+// from uintptr_t loses its address space, and every access through it compiles to a generic LD.E / ST.E (long-scoreboard,
+// slower) instead of LDS / STS.
+PZ_DEVINL uint8_t *align_smem(uint8_t *raw, uint32_t align) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
+    return raw + ((align - (a & (align - 1))) & (align - 1));
+}
 PZ_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);

@@ -589,7 +589,7 @@ PZ_DEVINL void attention_item(const MegaParams &p, uint8_t *smem, int layer, int
 __global__ void __launch_bounds__(NT, 2) decode_attn_kernel(const __grid_constant__ MegaParams p, int layer) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // attention_item addresses shared memory at SM_U + ...; rebase so that the union region starts at 0
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127) - SM_U;
+    uint8_t *smem = align_smem(smem_raw, 128) - SM_U;
     pdl_trigger();
     pdl_wait();
     const int it = blockIdx.x;
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const __grid_consta
 template <int MT>
 __global__ void __launch_bounds__(NT, 1) denoise_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *smem = align_smem(smem_raw, 128);
     unsigned int target = 0;
 
     // start streaming: the first SLOTS items of this CTA's sequence

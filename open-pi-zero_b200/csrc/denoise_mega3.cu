@@ -65,6 +65,7 @@ struct SlotDesc { int kind, layer, blk, aux; };
 struct Mega3Params {
     int B, H, M, nh, S_v, S_p, S_c, n_layers, n_steps, action_dim, skp, AI;
     int G, NA;
+    int pf_dist;                      // ring items ahead of the copy that are prefetched into L2 (0: none)
     float dt, clip;
     const float *norm_in[MAX_LAYERS], *norm_post[MAX_LAYERS];
     const float *final_norm;
@@ -112,6 +113,13 @@ PZ_DEVINL unsigned long long gtime_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// per-CTA stage stamps of (step 1, layer 1), compiled in only with -DPZ_MEGA_TRACE (tools/mega3_trace.py)
+#ifdef PZ_MEGA_TRACE
+__device__ unsigned long long g3_trace[160 * 32];
+#define T3(idx) do { if (threadIdx.x == 0 && step == 1 && l == 1) g3_trace[blockIdx.x * 32 + (idx)] = gtime_ns(); } while (0)
+#else
+#define T3(idx) do { } while (0)
+#endif
 // bounded (a bug or a lost CTA must never hang the device): after WAIT_LIMIT_NS, or as soon as somebody else has raised
 // the error flag, give up
 PZ_DEVINL void mbar_wait(const Mega3Params &p, uint64_t *bar, uint32_t parity) {
@@ -129,6 +137,9 @@ PZ_DEVINL void mbar_wait(const Mega3Params &p, uint64_t *bar, uint32_t parity) {
 PZ_DEVINL void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+PZ_DEVINL void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 PZ_DEVINL void tma_load_3d_hint(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
@@ -227,6 +238,9 @@ struct GemvCtx {
     const uint8_t *base;
     int slots_per_step;
     uint64_t pol;
+    int pf_dist;         // L2 prefetch distance in items
+    int pf_step;         // position of the next prefetch inside the step's stream
+    uint32_t pf_issued;
 };
 constexpr int REFILL_TID = 7 * 32;   // the elected thread (a warp with little epilogue work)
 // Request the items that fit into the ring slots the CTA has finished reading.  Call after a block barrier that
@@ -234,6 +248,14 @@ constexpr int REFILL_TID = 7 * 32;   // the elected thread (a warp with little e
 template <typename SM>
 PZ_DEVINL void ring_refill(GemvCtx &cx) {
     if (threadIdx.x != REFILL_TID) return;
+    if (cx.pf_dist > 0) {   // HBM -> L2 runs pf_dist items ahead of the copies, which then hit L2
+        const uint32_t want = cx.cnt + SM::SLOTS + (uint32_t)cx.pf_dist;
+        while (cx.pf_issued < want && cx.pf_issued < cx.total) {
+            bulk_prefetch_l2(cx.base + (long)cx.pf_step * SLOT, SLOT);
+            if (++cx.pf_step == cx.slots_per_step) cx.pf_step = 0;
+            ++cx.pf_issued;
+        }
+    }
     while (cx.issued < cx.cnt + SM::SLOTS && cx.issued < cx.total) {
         const int slot = cx.issued % SM::SLOTS;
         mbar_expect_tx(&cx.full[slot], SLOT);
@@ -431,6 +453,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
     cx.total = (uint32_t)(p.n_steps * sc.slots_per_step);
     cx.base = p.stream + sc.stream_off; cx.slots_per_step = sc.slots_per_step;
     cx.pol = policy_evict_first();
+    cx.pf_dist = p.pf_dist; cx.pf_step = 0; cx.pf_issued = 0;
     ring_refill<SM>(cx);   // start streaming
     uint8_t *red = smem + SM::RED;
     float *xpriv = reinterpret_cast<float *>(smem + SM::MISC) + 16;   // [MAXO][8 rows m][8 cols]
@@ -480,13 +503,16 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
         }
         for (int l = 0; l < p.n_layers; ++l) {
             const int pb = l & 1;
+            T3(0);
             // ---- QKV: x -> RMSNorm -> fused q|k|v projection (mixture.py:187-215), RoPE on q and k
             if (sc.n_qkv > 0) {
                 stage_norm<SM>(p, smem, p.ll_x[pb], p.norm_in[l], seq_of(p, step, l == 0 ? IDX_X0 : IDX_X2(l - 1)));
+                T3(1);
                 float acc[MAXQ][4];
                 gemv16<SM, MAXQ>(p, cx, sc.n_qkv, acc);
                 red_write<MAXQ>(red, sc.n_qkv, acc);
                 bar_compute();
+                T3(2);
                 ring_refill<SM>(cx);
                 const uint32_t fo = seq_of(p, step, IDX_QKV(l));
                 // one (item, m, row) sum per thread.  Rows 0-7 / 8-15 of an item are the dims d / d + 128 of one head:
@@ -509,14 +535,17 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                     if (ok && !(r & 1)) ll_store(p.ll_qkv[pb] + (long)m * qkvw + (n >> 1), pack_bf16x2(v0, v1), fo);
                 }
                 bar_compute();
+                T3(3);
             }
             // ---- o_proj + residual (mixture.py:217-218, joint_model.py:65-75)
             if (sc.n_o > 0) {
                 stage_pairs<SM, 2048>(p, smem, p.ll_att[pb], seq_of(p, step, IDX_ATT(l)));
+                T3(4);
                 float acc[MAXO][4];
                 gemv8<SM, 8>(p, cx, sc.n_o, acc);
                 red_write<MAXO>(red, sc.n_o, acc);
                 bar_compute();
+                T3(5);
                 ring_refill<SM>(cx);
                 if (tid < sc.n_o * 8 * p.M) {
                     const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
@@ -525,14 +554,17 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                     ll_store(p.ll_x1[pb] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X1(l)));
                 }
                 bar_compute();
+                T3(6);
             }
             // ---- gate|up + GeGLU (paligemma/modules.py:86-95)
             if (sc.n_gu > 0) {
                 stage_norm<SM>(p, smem, p.ll_x1[pb], p.norm_post[l], seq_of(p, step, IDX_X1(l)));
+                T3(7);
                 float acc[MAXGU][4];
                 gemv16<SM, MAXGU>(p, cx, sc.n_gu, acc);
                 red_write<MAXGU>(red, sc.n_gu, acc);
                 bar_compute();
+                T3(8);
                 ring_refill<SM>(cx);
                 const uint32_t fo = seq_of(p, step, IDX_MLP(l));
                 for (int i0 = 0; i0 < sc.n_gu * 16 * p.M; i0 += NCT) {
@@ -547,14 +579,17 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                         ll_store(p.ll_mlp[pb] + (long)m * (p.AI / 2) + sc.gu_tile[j] * 4 + (r >> 1), pack_bf16x2(h0, h1), fo);
                 }
                 bar_compute();
+                T3(9);
             }
             // ---- down + residual
             if (sc.n_o > 0) {
                 stage_pairs<SM, 4096>(p, smem, p.ll_mlp[pb], seq_of(p, step, IDX_MLP(l)));
+                T3(10);
                 float acc[MAXO][4];
                 gemv8<SM, 16>(p, cx, sc.n_o, acc);
                 red_write<MAXO>(red, sc.n_o, acc);
                 bar_compute();
+                T3(11);
                 ring_refill<SM>(cx);
                 if (tid < sc.n_o * 8 * p.M) {
                     const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
@@ -563,6 +598,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                     ll_store(p.ll_x[(l + 1) & 1] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X2(l)));
                 }
                 bar_compute();
+                T3(12);
             }
         }
         // ---- final norm + decoder + Euler update (joint_model.py:375-380, pizero.py:479-481)
@@ -646,6 +682,7 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
         for (int l = 0; l < p.n_layers; ++l, ++it) {
             const int pb = l & 1;
             const uint32_t fin = seq_of(p, step, IDX_QKV(l));
+            T3(20);
             // ---- this step's rotated q rows of (sample b, head), the fresh k rows and this CTA's half of the fresh
             //      v rows: per token 64 + 64 + 32 double-words
             unsigned long long v[6];
@@ -660,6 +697,7 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                 if (e < 128) return row + p.nh * 128 + 2 * (e - 64);               // k
                 return row + (p.nh + 1) * 128 + dh * 64 + 2 * (e - 128);           // v, dims dh*128 + 4(e-128) ..
             }, v);
+            T3(21);
             mbar_wait(p, kv_full, it & 1);   // the cached rows of this layer (loaded one layer ahead); also orders the
                                              // fresh rows below after the TMA zero fill of rows >= S_c
 #pragma unroll
@@ -680,6 +718,7 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                 }
             }
             bar_compute();
+            T3(22);
             // ---- S^T = K q^T: keys are the MMA M dimension (16-key tiles over the warps), the query rows the 8-wide N;
             //      k index permuted so that every thread feeds two MMAs from one 16-byte load (as the GEMV items)
             {
@@ -690,7 +729,9 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                 float ls0 = 0.f, ls1 = 0.f;   // partial row sums of query rows 2t, 2t+1
                 for (int mt = warp; mt < n_mt; mt += NCW) {
                     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-                    const int r0 = mt * 16 + g, r1 = r0 + 8;
+                    // key rows of the tile are visited in the order rho(g) = 0 4 1 5 2 6 3 7: with the 128-byte swizzle
+                    // (chunk ^ row & 7) the eight lanes of a quarter-warp then hit eight different 16-byte bank groups
+                    const int r0 = mt * 16 + (((g & 1) << 2) | (g >> 1)), r1 = r0 + 8;
 #pragma unroll
                     for (int kc = 0; kc < 8; ++kc) {
                         const uint8_t *tile = smem + AttSmem::K + (kc >> 1) * KT_BYTES;
@@ -720,11 +761,13 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                         sP[(2 * t + 1) * LDP + r1] = __float2bfloat16_rn(pe[3]);
                     }
                 }
+                T3(25);
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) { ls0 += __shfl_xor_sync(0xffffffffu, ls0, o); ls1 += __shfl_xor_sync(0xffffffffu, ls1, o); }
                 if (g == 0) { sLS[warp * 8 + 2 * t] = ls0; sLS[warp * 8 + 2 * t + 1] = ls1; }
             }
             bar_compute();
+            T3(23);
             // ---- O^T = V^T P^T: warp -> 16 dims of this CTA's 128; V^T fragments by transposing ldmatrix
             {
                 float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -767,6 +810,7 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                     }
                 }
             }
+            T3(24);
             bar_compute();   // every warp is done with the layer's K / V; q / P / row sums are rewritten by the next layer
             if (tid == 0 && !(step == p.n_steps - 1 && l == p.n_layers - 1)) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the fresh rows were ordinary stores
@@ -781,7 +825,7 @@ __global__ void __launch_bounds__(NT3, 1) denoise_mega3_kernel(const __grid_cons
                                                               const __grid_constant__ CUtensorMap kmap,
                                                               const __grid_constant__ CUtensorMap vmap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = align_smem(smem_raw, 1024);
     using SM = GemvSmem<MAXM>;
     const bool is_att = (int)blockIdx.x >= p.G;
     if (threadIdx.x == 0) {
@@ -945,6 +989,11 @@ size_t ll_words(const pz_config &c, int B) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------- host side ----
+#ifdef PZ_MEGA_TRACE
+extern "C" int pz_debug_mega3_trace(unsigned long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g3_trace, (size_t)n * 8);
+}
+#endif
 int denoise_mega3_supported(const pz_config &c, int B) {
     static const bool off = [] { const char *e = getenv("PZ_MEGA3"); return e && e[0] == '0'; }();
     if (off) return 0;
@@ -1036,6 +1085,10 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
     p.S_v = c.s_vlm; p.S_p = c.cond_steps; p.S_c = c.s_vlm + c.cond_steps; p.n_layers = c.n_layers; p.n_steps = c.n_steps;
     p.action_dim = c.action_dim; p.skp = w.small_k_pad;
     p.G = state.G; p.NA = state.NA;
+    {
+        static const int pf = [] { const char *e = getenv("PZ_M3_PF"); return e ? atoi(e) : 0; }();
+        p.pf_dist = pf;
+    }
     p.dt = (float)(1.0 / c.n_steps); p.clip = c.clip;
     for (int l = 0; l < c.n_layers; ++l) { p.norm_in[l] = layers[l].norm_in; p.norm_post[l] = layers[l].norm_post; }
     p.final_norm = w.action_final_norm;

@@ -116,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
     const int wid = blockIdx.x / CG, nworkers = gridDim.x / CG;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = align_smem(smem_raw, 1024);
     uint64_t *full_bar = (uint64_t *)(smem + cfg::BAR_OFF);
     uint64_t *empty_bar = full_bar + cfg::STAGES;
     uint64_t *tfull_bar = empty_bar + cfg::STAGES;

@@ -51,9 +51,38 @@ def test_sampler_implementations_agree_with_oracle(batch):
         assert torch.isfinite(outs[name]).all()
         assert e < BF16_ACTION_TOL
     assert max_abs(outs["stream"], outs["kernels"]) < 5e-3
-    # every output element of the stream sampler has one producer and a fixed summation order: bit-reproducible
-    again = _call(m, inp, _lib.PZ_SAMPLER_STREAM)
-    assert torch.equal(again, outs["stream"])
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_stream_sampler_is_bit_reproducible_on_one_prefix(batch):
+    """Every output element of the stream sampler has one producer and a fixed summation order: two runs over the SAME
+    cached prefix (the prefill's split-K reductions are not ordered, so the prefix is filled once) give identical bits."""
+    from open_pi_zero_b200 import _lib
+    d = pz.make_dims(vocab_size=1024, image_token_index=1000, num_layers=3, vit_layers=2)
+    sd = pz.init_state_dict(d, seed=45, randomize_norms=True)
+    inp = pz.make_inputs(d, batch, seed=9, min_text=0)
+    m = _model(d, sd)
+    m.pack()
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    ids = inp["input_ids"].to(dev); pix = inp["pixel_values"].to(dev, torch.bfloat16)
+    prop = inp["proprios"].to(dev); nz = inp["noise"].to(dev); vlen = inp["valid_len"].to(dev)
+    nbytes = lib.pz_workspace_bytes(m._handle, batch)
+    ws_t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    ws = (ws_t.data_ptr() + 1023) // 1024 * 1024
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.pz_embed_prefix(m._handle, ids.data_ptr(), pix.data_ptr(), ws, nbytes, batch, None, st) == 0
+    assert lib.pz_prefill(m._handle, vlen.data_ptr(), prop.data_ptr(), ws, nbytes, batch, None, st) == 0
+    assert lib.pz_set_sampler(m._handle, _lib.PZ_SAMPLER_STREAM) == 0
+    outs = []
+    for _ in range(3):
+        out = torch.zeros(batch, d["horizon_steps"], d["action_dim"], device=dev)
+        assert lib.pz_denoise(m._handle, vlen.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, nbytes, batch, None, st) == 0
+        torch.cuda.synchronize()
+        outs.append(out)
+    lib.pz_set_sampler(m._handle, _lib.PZ_SAMPLER_AUTO)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 def test_stream_sampler_ragged_valid_lengths_and_padding_content():
