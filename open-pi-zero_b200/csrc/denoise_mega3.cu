@@ -66,6 +66,7 @@ struct Mega3Params {
     int B, H, M, nh, S_v, S_p, S_c, n_layers, n_steps, action_dim, skp, AI;
     int G, NA;
     int pf_dist;                      // ring items ahead of the copy that are prefetched into L2 (0: none)
+    int sentinel;                     // 1: one thread polls one word of an exchange before the CTA gathers all of it
     float dt, clip;
     const float *norm_in[MAX_LAYERS], *norm_post[MAX_LAYERS];
     const float *final_norm;
@@ -81,8 +82,10 @@ struct Mega3Params {
     // exchange buffers: 64-bit words {payload, sequence number}, zeroed before every launch
     unsigned long long *ll_act;       // [M][8]       fp32
     unsigned long long *ll_z;         // [M][A/2]     bf16x2
-    unsigned long long *ll_x[2];      // [M][A]       fp32: residual stream entering layer l (buffer l & 1)
-    unsigned long long *ll_x1[2];     // [M][A]       fp32: residual stream after o_proj
+    unsigned long long *ll_x[2];      // [M][A/2]     bf16x2: x (1 + w) for the norm that reads it; residual stream entering layer l
+    unsigned long long *ll_x1[2];     // [M][A/2]     bf16x2: the same after o_proj
+    unsigned long long *ll_sx[2];     // [A/8][MAXM]  fp32: sum of squares of x over one 8-column block (exact fp32 x)
+    unsigned long long *ll_sx1[2];
     unsigned long long *ll_qkv[2];    // [M][1280]    bf16x2, q and k rotated
     unsigned long long *ll_att[2];    // [M][1024]    bf16x2 attention output
     unsigned long long *ll_mlp[2];    // [M][AI/2]    bf16x2 GeGLU output
@@ -113,12 +116,27 @@ PZ_DEVINL unsigned long long gtime_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// per-CTA stage stamps of (step 1, layer 1), compiled in only with -DPZ_MEGA_TRACE (tools/mega3_trace.py)
+// per-CTA time accounting over the whole call (thread 0, SM cycles), compiled in only with -DPZ_MEGA_TRACE
+// (tools/mega3_trace.py): T3(i) charges the time since the previous stamp to bucket i; waits for the weight ring inside
+// a GEMV are charged to bucket (current stage + 12)
 #ifdef PZ_MEGA_TRACE
 __device__ unsigned long long g3_trace[160 * 32];
-#define T3(idx) do { if (threadIdx.x == 0 && step == 1 && l == 1) g3_trace[blockIdx.x * 32 + (idx)] = gtime_ns(); } while (0)
+__shared__ unsigned long long t3_acc[32];
+__shared__ unsigned long long t3_last;
+__shared__ int t3_cur;
+#define T3(idx) do { if (threadIdx.x == 0) { const unsigned long long now_ = clock64(); t3_acc[(idx)] += now_ - t3_last; t3_last = now_; } } while (0)
+#define T3CUR(idx) do { if (threadIdx.x == 0) t3_cur = (idx); } while (0)
+#define T3WAIT_BEGIN() T3(t3_cur)
+#define T3WAIT_END() T3(t3_cur + 12)
+#define T3INIT() do { if (threadIdx.x == 0) { for (int i_ = 0; i_ < 32; ++i_) t3_acc[i_] = 0; t3_last = clock64(); t3_cur = 31; } } while (0)
+#define T3FLUSH() do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 32; ++i_) g3_trace[blockIdx.x * 32 + i_] = t3_acc[i_]; } while (0)
 #else
 #define T3(idx) do { } while (0)
+#define T3CUR(idx) do { } while (0)
+#define T3WAIT_BEGIN() do { } while (0)
+#define T3WAIT_END() do { } while (0)
+#define T3INIT() do { } while (0)
+#define T3FLUSH() do { } while (0)
 #endif
 // bounded (a bug or a lost CTA must never hang the device): after WAIT_LIMIT_NS, or as soon as somebody else has raised
 // the error flag, give up
@@ -171,6 +189,12 @@ PZ_DEVINL float gelu_fast(float x) {   // hardware tanh: rel. error 2^-11, below
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(k0 * (x + k1 * x * x * x)));
     return 0.5f * x * (1.0f + y);
 }
+// c ? a : 0 as a select: the caller's `a` is always evaluated (straight-line code for the scheduler to interleave)
+PZ_DEVINL float sel_or_zero(bool c, float a) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tselp.f32 %0, %1, 0f00000000, p;\n\t}" : "=f"(r) : "f"(a), "r"((uint32_t)c));
+    return r;
+}
 PZ_DEVINL float tanh_fast_acc(float y) { float t = __expf(2.f * y); return 1.f - __fdividef(2.f, t + 1.f); }
 
 // ---- exchange words ------------------------------------------------------------------------------------
@@ -206,6 +230,28 @@ PZ_DEVINL void ll_gather(const Mega3Params &p, uint32_t seq, uint32_t pend, Addr
     }
 }
 
+// Optional first phase of a big gather: one thread waits for one word (a different one in every CTA), so that the
+// other 255 threads do not hammer the lines the producers are still writing (tools/probe_ll.cu: 3.2 -> 2.8 us per stage)
+PZ_DEVINL void ll_sentinel(const Mega3Params &p, const unsigned long long *buf, int nwords, uint32_t seq) {
+    if (!p.sentinel) return;
+    if (threadIdx.x == 0) {
+        const unsigned long long *w = buf + (int)((blockIdx.x * 37u) % (unsigned)nwords);
+        uint32_t spins = 0;
+        unsigned long long t0 = 0, v;
+        for (;;) {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if ((uint32_t)(v >> 32) == seq) break;
+            if ((++spins & 0xFF) == 0) {
+                if (err_set(p)) break;
+                const unsigned long long now = gtime_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WAIT_LIMIT_NS) { raise_err(p, 3); break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // sequence numbers: one per exchange and step
 PZ_DEVINL uint32_t seq_of(const Mega3Params &p, int step, int idx) { return 1u + (uint32_t)(step * (3 + 5 * p.n_layers) + idx); }
 constexpr int IDX_ACT = 0, IDX_Z = 1, IDX_X0 = 2;
@@ -222,8 +268,9 @@ template <int MAXM> struct GemvSmem {
     static constexpr int RING = 0;
     static constexpr int AST = RING + SLOTS * SLOT;                        // bf16 [MAXM][K + 32]
     static constexpr int RED = AST + MAXM * LDA_MAX * 2;                   // float [NCW][MAXJ][16][9]
-    static constexpr int MISC = RED + NCW * MAXJ * 16 * 9 * 4;             // floats: part[16], xpriv[MAXO][8][8], acts[64]
-    static constexpr int BARS = MISC + (16 + MAXO * 64 + 64) * 4;          // full[SLOTS]
+    static constexpr int MISC = RED + NCW * MAXJ * 16 * 9 * 4;             // floats: part[NCW][8], xpriv[MAXO][8][8], acts[64]
+    static constexpr int XPRIV = 64, SACT = 64 + MAXO * 64;                // float offsets inside MISC
+    static constexpr int BARS = MISC + (64 + MAXO * 64 + 64) * 4;          // full[SLOTS]
     static constexpr int SCHED = BARS + SLOTS * 8;
     static constexpr int END = SCHED + (int)sizeof(CtaSched);
 };
@@ -282,7 +329,9 @@ PZ_DEVINL void gemv16(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[NJ]
         acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
         if (j < n) {
             const int slot = cx.cnt % SM::SLOTS;
+            T3WAIT_BEGIN();
             mbar_wait(p, &cx.full[slot], (cx.cnt / SM::SLOTS) & 1);
+            T3WAIT_END();
             const uint8_t *w = cx.smem + SM::RING + slot * SLOT + warp * 4096 + lane * 16;
             float a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -316,7 +365,9 @@ PZ_DEVINL void gemv8(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[MAXO
             const int mine = NS == 2 ? (warp >> 2) : 0;
             const uint32_t c = cx.cnt + mine;
             const int slot = c % SM::SLOTS;
+            T3WAIT_BEGIN();
             mbar_wait(p, &cx.full[slot], (c / SM::SLOTS) & 1);
+            T3WAIT_END();
             const int unit0 = warp * KU - mine * 64;   // first unit of this warp inside its slot
             const uint8_t *w = cx.smem + SM::RING + slot * SLOT + unit0 * 512 + lane * 16;
             const bf16 *xa = As + g * lda + warp * (KU * 32) + 8 * t;
@@ -354,41 +405,59 @@ PZ_DEVINL float red_sum(uint8_t *red, int j, int r, int m) {
 }
 
 // ---- activation staging ------------------------------------------------------------------------------
-// fp32 words [M][1024] -> Gemma RMSNorm (paligemma/modules.py:13-21) -> As[m][k] (bf16, row stride K + 32: conflict-free fragment loads)
-template <typename SM>
-PZ_DEVINL void stage_norm(const Mega3Params &p, uint8_t *smem, const unsigned long long *buf, const float *norm_w, uint32_t seq) {
+// Residual stream -> As.  The block owners publish bf16 x (1 + w) (w = the weight of the RMSNorm that reads it,
+// paligemma/modules.py:13-21) and the fp32 sum of squares of their 8 columns; the per-row factor rsqrt(mean x^2 + eps)
+// commutes with the projection, so it is applied to the fp32 accumulators in the epilogue (row_rnorm) and nothing but
+// the copy sits between the exchange and the MMAs.  part[warp][m] <- this warp's share of sum x^2.
+template <typename SM, int MAXM>
+PZ_DEVINL void stage_x(const Mega3Params &p, uint8_t *smem, const unsigned long long *pairs, const unsigned long long *ss, uint32_t seq) {
     bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
     float *part = reinterpret_cast<float *>(smem + SM::MISC);
     constexpr int lda = KI + 32;
-    const int tid = threadIdx.x, lane = tid & 31, c = tid & 63, rsub = tid >> 6;
-    float4 w[4];
+    constexpr int NP = MAXM, NS = MAXM / 4;   // double-words per thread: one per row of x; [A/8][MAXM] sums of squares
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long v[2 * (NP + NS)];
+    uint32_t pend = ((1u << NS) - 1u) << NP;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const float4 *>(norm_w) + c + 64 * j);
-    for (int m0 = 0; m0 < p.M; m0 += 4) {
-        const int m = m0 + rsub;
-        const bool ok = m < p.M;
-        unsigned long long v[16];
-        // columns (c + 64 j) * 4 .. + 3: two double-words per j
-        ll_gather<8>(p, seq, ok ? 0xFFu : 0u, [&](int u) { return buf + (long)m * KI + (c + 64 * (u >> 1)) * 4 + (u & 1) * 2; }, v);
-        float x[16];
-        float ss = 0.f;
+    for (int u = 0; u < NP; ++u) if (u < p.M) pend |= 1u << u;
+    ll_sentinel(p, pairs, p.M * (KI / 2), seq);
+    ll_gather<NP + NS>(p, seq, pend, [&](int u) {
+        return u < NP ? pairs + (long)u * (KI / 2) + 2 * tid : ss + 2 * ((u - NP) * NCT + tid);
+    }, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { x[i] = ok ? __uint_as_float((uint32_t)v[i]) : 0.f; ss += x[i] * x[i]; }
-        ss = warp_sum(ss);
-        if (lane == 0) part[rsub * 2 + ((tid >> 5) & 1)] = ss;
-        bar_compute();
-        const float r = rsqrtf((part[rsub * 2] + part[rsub * 2 + 1]) / KI + 1e-6f);
-        if (ok) {
+    for (int u = 0; u < NP; ++u)
+        if (u < p.M) *reinterpret_cast<uint2 *>(As + u * lda + 4 * tid) = make_uint2((uint32_t)v[2 * u], (uint32_t)v[2 * u + 1]);
+    // words 2 d, 2 d + 1 of [block][MAXM] with d = s * 256 + tid: rows m0, m0 + 1 with m0 = 2 (tid % (MAXM / 2))
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint2 o;
-                o.x = pack_bf16x2(x[4 * j] * r * (1.f + w[j].x), x[4 * j + 1] * r * (1.f + w[j].y));
-                o.y = pack_bf16x2(x[4 * j + 2] * r * (1.f + w[j].z), x[4 * j + 3] * r * (1.f + w[j].w));
-                *reinterpret_cast<uint2 *>(As + m * lda + (c + 64 * j) * 4) = o;
-            }
-        }
-        bar_compute();
-    }
+    for (int u = 0; u < NS; ++u) { s0 += __uint_as_float((uint32_t)v[2 * (NP + u)]); s1 += __uint_as_float((uint32_t)v[2 * (NP + u) + 1]); }
+#pragma unroll
+    for (int o = MAXM / 2; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (lane < MAXM / 2) { part[warp * 8 + 2 * lane] = s0; part[warp * 8 + 2 * lane + 1] = s1; }
+    bar_compute();
+}
+// rsqrt(mean x^2 + eps) of row m of what stage_x staged last
+template <typename SM>
+PZ_DEVINL float row_rnorm(uint8_t *smem, int m) {
+    const float *part = reinterpret_cast<const float *>(smem + SM::MISC);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) t += part[w * 8 + m];
+    return rsqrtf(t * (1.f / KI) + 1e-6f);
+}
+// An owner's epilogue: one (block j, row m, column r) per thread, 8 consecutive lanes = one (j, m).  Publishes bf16 pairs of
+// v (1 + wn) and the block's sum of squares of row m (zeros for the pad rows m >= M: the readers wait for whole double-words).
+template <int MAXM>
+PZ_DEVINL void publish_x(const Mega3Params &p, bool active, bool valid, float v, float wn, int n, int blk, int m,
+                         unsigned long long *pairs, unsigned long long *ss, uint32_t seq) {
+    const float y = v * (1.f + wn);
+    const float y1 = __shfl_down_sync(0xffffffffu, y, 1);
+    float q = v * v;
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    if (valid && !(n & 1)) ll_store(pairs + (long)m * (KI / 2) + (n >> 1), pack_bf16x2(y, y1), seq);
+    if (active && !(n & 7)) ll_store(ss + blk * MAXM + m, __float_as_uint(q), seq);
 }
 // bf16x2 words [M][K/2] -> As[m][k] (row stride K + 32)
 template <typename SM, int K>
@@ -396,6 +465,7 @@ PZ_DEVINL void stage_pairs(const Mega3Params &p, uint8_t *smem, const unsigned l
     bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
     constexpr int lda = K + 32, DPR = K / 4;     // double-words (4 bf16) per row
     const int total = p.M * DPR;
+    ll_sentinel(p, buf, 2 * total, seq);
     for (int i0 = 0; i0 < total; i0 += NCT * 8) {
         unsigned long long v[16];
         uint32_t pend = 0;
@@ -417,7 +487,7 @@ PZ_DEVINL void stage_pairs(const Mega3Params &p, uint8_t *smem, const unsigned l
 template <typename SM>
 PZ_DEVINL void stage_enc1(const Mega3Params &p, uint8_t *smem, uint32_t seq) {
     bf16 *As = reinterpret_cast<bf16 *>(smem + SM::AST);
-    float *sact = reinterpret_cast<float *>(smem + SM::MISC) + 16 + MAXO * 64;   // [M][8], bf16-rounded like a GEMM input
+    float *sact = reinterpret_cast<float *>(smem + SM::MISC) + SM::SACT;   // [M][8], bf16-rounded like a GEMM input
     constexpr int lda = KI + 32;
     {
         unsigned long long v[2];
@@ -456,9 +526,30 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
     cx.pf_dist = p.pf_dist; cx.pf_step = 0; cx.pf_issued = 0;
     ring_refill<SM>(cx);   // start streaming
     uint8_t *red = smem + SM::RED;
-    float *xpriv = reinterpret_cast<float *>(smem + SM::MISC) + 16;   // [MAXO][8 rows m][8 cols]
+    float *xpriv = reinterpret_cast<float *>(smem + SM::MISC) + SM::XPRIV;   // [MAXO][8 rows m][8 cols]
     const int tid = threadIdx.x;
     const int qkvw = (p.nh + 2) * 128;
+    // owner epilogues: thread -> (block j, row m, column r); 8 consecutive lanes share (j, m)
+    const int ow_r = tid & 7, ow_m = (tid >> 3) % MAXM, ow_j = tid / (8 * MAXM);
+    const bool ow_active = ow_j < sc.n_o, ow_valid = ow_active && ow_m < p.M;
+    const int ow_blk = ow_active ? sc.o_blk[ow_j] : 0, ow_n = ow_blk * 8 + ow_r;
+    const bool ow_warp = (tid & ~31) < sc.n_o * 8 * MAXM;   // warp-uniform: this warp holds owner threads
+    // QKV epilogue: (item, m, row) of pass i0 = tid, tid + 256: the rotary factors of q and k never change
+    // (table row S_p + token: positions 2.., pizero.py:312-318)
+    float rope_c[2] = {1.f, 1.f}, rope_s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = u * NCT + tid;
+        if (i < sc.n_qkv * 16 * p.M) {
+            const int r = i & 15, jm = i >> 4, j = jm / p.M, m = jm % p.M;
+            const int blk = sc.qkv_blk[j], hh = blk >> 4, d = (blk & 15) * 8 + (r & 7);
+            if (hh <= p.nh) {
+                const long ti = (long)(p.S_p + (m % p.H)) * 128 + d;
+                rope_c[u] = __ldg(p.rope_cos + ti);
+                rope_s[u] = __ldg(p.rope_sin + ti);
+            }
+        }
+    }
     // the fp32 action state lives in registers of the decoder CTA: thread i < M*8 owns element (i / 8, i % 8);
     // it starts as the caller's noise (pizero.py:454-458)
     float my_act = 0.f;
@@ -476,7 +567,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             gemv16<SM, 1>(p, cx, 1, acc);
             red_write<1>(red, 1, acc);
             bar_compute();
-                ring_refill<SM>(cx);
+            ring_refill<SM>(cx);
             for (int i = tid; i < 8 * p.M; i += NCT) {   // (row pair, m)
                 const int rp = i & 7, m = i >> 3, n = sc.e2_blk * 16 + 2 * rp;
                 const float v0 = red_sum(red, 0, 2 * rp, m) + p.enc_time_bias[step * KI + n];
@@ -486,18 +577,18 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             bar_compute();
         }
         if (sc.n_o > 0) {
+            const float wn = ow_active ? __ldg(p.norm_in[0] + ow_n) : 0.f;
+            const float b3 = ow_active ? __ldg(p.enc_b3 + ow_n) : 0.f;
             stage_pairs<SM, KI>(p, smem, p.ll_z, seq_of(p, step, IDX_Z));
             float acc[MAXO][4];
             gemv8<SM, 4>(p, cx, sc.n_o, acc);
             red_write<MAXO>(red, sc.n_o, acc);
             bar_compute();
-                ring_refill<SM>(cx);
-            if (tid < sc.n_o * 8 * p.M) {
-                const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
-                const int n = sc.o_blk[j] * 8 + r;
-                const float v = (red_sum(red, j, r, m) + p.enc_b3[n]) * sqrtf((float)KI);
-                xpriv[(j * 8 + m) * 8 + r] = v;
-                ll_store(p.ll_x[0] + (long)m * KI + n, __float_as_uint(v), seq_of(p, step, IDX_X0));
+            ring_refill<SM>(cx);
+            if (ow_warp) {
+                const float v = ow_valid ? (red_sum(red, ow_j, ow_r, ow_m) + b3) * sqrtf((float)KI) : 0.f;
+                if (ow_active) xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
+                publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x[0], p.ll_sx[0], seq_of(p, step, IDX_X0));
             }
             bar_compute();
         }
@@ -506,8 +597,9 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             T3(0);
             // ---- QKV: x -> RMSNorm -> fused q|k|v projection (mixture.py:187-215), RoPE on q and k
             if (sc.n_qkv > 0) {
-                stage_norm<SM>(p, smem, p.ll_x[pb], p.norm_in[l], seq_of(p, step, l == 0 ? IDX_X0 : IDX_X2(l - 1)));
+                stage_x<SM, MAXM>(p, smem, p.ll_x[pb], p.ll_sx[pb], seq_of(p, step, l == 0 ? IDX_X0 : IDX_X2(l - 1)));
                 T3(1);
+                T3CUR(2);
                 float acc[MAXQ][4];
                 gemv16<SM, MAXQ>(p, cx, sc.n_qkv, acc);
                 red_write<MAXQ>(red, sc.n_qkv, acc);
@@ -516,20 +608,17 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                 ring_refill<SM>(cx);
                 const uint32_t fo = seq_of(p, step, IDX_QKV(l));
                 // one (item, m, row) sum per thread.  Rows 0-7 / 8-15 of an item are the dims d / d + 128 of one head:
-                // rotate q and k here (fp32, table row S_p + token: positions 2.., pizero.py:312-318), then
-                // neighbouring dims pair up through a shuffle
-                for (int i0 = 0; i0 < sc.n_qkv * 16 * p.M; i0 += NCT) {
-                    const int i = i0 + tid;
+                // rotate q and k here (fp32), then neighbouring dims pair up through a shuffle
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = u * NCT + tid;
+                    if (u * NCT >= sc.n_qkv * 16 * p.M) break;   // CTA-uniform
                     const bool ok = i < sc.n_qkv * 16 * p.M;
                     const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
-                    float v0 = ok ? red_sum(red, j, r, m) : 0.f;
+                    float v0 = ok ? red_sum(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;
                     const float other = __shfl_xor_sync(0xffffffffu, v0, 8);
                     const int blk = sc.qkv_blk[j], hh = blk >> 4, d = (blk & 15) * 8 + (r & 7);
-                    if (hh <= p.nh) {
-                        const long ti = (long)(p.S_p + (m % p.H)) * 128 + d;
-                        const float cs = __ldg(p.rope_cos + ti), sn = __ldg(p.rope_sin + ti);
-                        v0 = (r < 8) ? v0 * cs - other * sn : v0 * cs + other * sn;
-                    }
+                    v0 = (r < 8) ? v0 * rope_c[u] - other * rope_s[u] : v0 * rope_c[u] + other * rope_s[u];
                     const float v1 = __shfl_down_sync(0xffffffffu, v0, 1);
                     const int n = hh * 256 + (r < 8 ? d : 128 + d);
                     if (ok && !(r & 1)) ll_store(p.ll_qkv[pb] + (long)m * qkvw + (n >> 1), pack_bf16x2(v0, v1), fo);
@@ -539,27 +628,32 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             }
             // ---- o_proj + residual (mixture.py:217-218, joint_model.py:65-75)
             if (sc.n_o > 0) {
+                const float wn = ow_active ? __ldg(p.norm_post[l] + ow_n) : 0.f;
                 stage_pairs<SM, 2048>(p, smem, p.ll_att[pb], seq_of(p, step, IDX_ATT(l)));
                 T3(4);
+                T3CUR(5);
                 float acc[MAXO][4];
                 gemv8<SM, 8>(p, cx, sc.n_o, acc);
                 red_write<MAXO>(red, sc.n_o, acc);
                 bar_compute();
                 T3(5);
                 ring_refill<SM>(cx);
-                if (tid < sc.n_o * 8 * p.M) {
-                    const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
-                    const float v = xpriv[(j * 8 + m) * 8 + r] + red_sum(red, j, r, m);
-                    xpriv[(j * 8 + m) * 8 + r] = v;
-                    ll_store(p.ll_x1[pb] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X1(l)));
+                if (ow_warp) {
+                    float v = 0.f;
+                    if (ow_valid) {
+                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] + red_sum(red, ow_j, ow_r, ow_m);
+                        xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
+                    }
+                    publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x1[pb], p.ll_sx1[pb], seq_of(p, step, IDX_X1(l)));
                 }
                 bar_compute();
                 T3(6);
             }
             // ---- gate|up + GeGLU (paligemma/modules.py:86-95)
             if (sc.n_gu > 0) {
-                stage_norm<SM>(p, smem, p.ll_x1[pb], p.norm_post[l], seq_of(p, step, IDX_X1(l)));
+                stage_x<SM, MAXM>(p, smem, p.ll_x1[pb], p.ll_sx1[pb], seq_of(p, step, IDX_X1(l)));
                 T3(7);
+                T3CUR(8);
                 float acc[MAXGU][4];
                 gemv16<SM, MAXGU>(p, cx, sc.n_gu, acc);
                 red_write<MAXGU>(red, sc.n_gu, acc);
@@ -571,7 +665,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                     const int i = i0 + tid;
                     const bool ok = i < sc.n_gu * 16 * p.M;
                     const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
-                    const float v = ok ? red_sum(red, j, r, m) : 0.f;      // rows 0-7: gate, rows 8-15: the matching up rows
+                    const float v = ok ? red_sum(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;   // rows 0-7: gate, 8-15: the matching up rows
                     const float u = __shfl_down_sync(0xffffffffu, v, 8);
                     const float h0 = gelu_fast(v) * u;
                     const float h1 = __shfl_down_sync(0xffffffffu, h0, 1);
@@ -583,19 +677,24 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             }
             // ---- down + residual
             if (sc.n_o > 0) {
+                const float wn = ow_active ? __ldg((l + 1 < p.n_layers ? p.norm_in[l + 1] : p.final_norm) + ow_n) : 0.f;
                 stage_pairs<SM, 4096>(p, smem, p.ll_mlp[pb], seq_of(p, step, IDX_MLP(l)));
                 T3(10);
+                T3CUR(11);
                 float acc[MAXO][4];
                 gemv8<SM, 16>(p, cx, sc.n_o, acc);
                 red_write<MAXO>(red, sc.n_o, acc);
                 bar_compute();
                 T3(11);
                 ring_refill<SM>(cx);
-                if (tid < sc.n_o * 8 * p.M) {
-                    const int r = tid & 7, m = (tid >> 3) % p.M, j = tid / (8 * p.M);
-                    const float v = xpriv[(j * 8 + m) * 8 + r] + red_sum(red, j, r, m);
-                    xpriv[(j * 8 + m) * 8 + r] = v;
-                    ll_store(p.ll_x[(l + 1) & 1] + (long)m * KI + sc.o_blk[j] * 8 + r, __float_as_uint(v), seq_of(p, step, IDX_X2(l)));
+                if (ow_warp) {
+                    float v = 0.f;
+                    if (ow_valid) {
+                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] + red_sum(red, ow_j, ow_r, ow_m);
+                        xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
+                    }
+                    publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x[(l + 1) & 1], p.ll_sx[(l + 1) & 1],
+                                    seq_of(p, step, IDX_X2(l)));
                 }
                 bar_compute();
                 T3(12);
@@ -603,15 +702,15 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
         }
         // ---- final norm + decoder + Euler update (joint_model.py:375-380, pizero.py:479-481)
         if (sc.is_dec) {
-            stage_norm<SM>(p, smem, p.ll_x[p.n_layers & 1], p.final_norm, seq_of(p, step, IDX_X2(p.n_layers - 1)));
+            stage_x<SM, MAXM>(p, smem, p.ll_x[p.n_layers & 1], p.ll_sx[p.n_layers & 1], seq_of(p, step, IDX_X2(p.n_layers - 1)));
             float acc[MAXO][4];
             gemv8<SM, 4>(p, cx, 1, acc);
             red_write<MAXO>(red, 1, acc);
             bar_compute();
-                ring_refill<SM>(cx);
+            ring_refill<SM>(cx);
             if (tid < 8 * p.M) {
                 const int a = tid & 7, m = tid >> 3;
-                if (a < p.action_dim) my_act += p.dt * (red_sum(red, 0, a, m) + p.dec_b[a]);
+                if (a < p.action_dim) my_act += p.dt * (red_sum(red, 0, a, m) * row_rnorm<SM>(smem, m) + p.dec_b[a]);
                 if (step + 1 < p.n_steps) {
                     ll_store(p.ll_act + tid, __float_as_uint(my_act), seq_of(p, step + 1, IDX_ACT));
                 } else if (a < p.action_dim) {
@@ -698,7 +797,8 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
                 return row + (p.nh + 1) * 128 + dh * 64 + 2 * (e - 128);           // v, dims dh*128 + 4(e-128) ..
             }, v);
             T3(21);
-            mbar_wait(p, kv_full, it & 1);   // the cached rows of this layer (loaded one layer ahead); also orders the
+            mbar_wait(p, kv_full, it & 1);
+            T3(26);   // the cached rows of this layer (loaded one layer ahead); also orders the
                                              // fresh rows below after the TMA zero fill of rows >= S_c
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
@@ -720,35 +820,53 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
             bar_compute();
             T3(22);
             // ---- S^T = K q^T: keys are the MMA M dimension (16-key tiles over the warps), the query rows the 8-wide N;
-            //      k index permuted so that every thread feeds two MMAs from one 16-byte load (as the GEMV items)
+            //      k index permuted so that every thread feeds two MMAs from one 16-byte load (as the GEMV items).  The code
+            //      runs at two warps per scheduler, i.e. at the latency of its dependency chains: the warp's (up to) three
+            //      tiles advance together (six independent accumulators) and the soft-cap / exp of all twelve scores is
+            //      straight-line code with selects instead of branches.
             {
+                constexpr int MAXT = (KEYS / 16 + NCW - 1) / NCW;   // 3
                 uint4 qf[8];
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc)
                     qf[kc] = g < H ? *reinterpret_cast<const uint4 *>(sQ + g * LDQ + kc * 32 + 8 * t) : make_uint4(0, 0, 0, 0);
-                float ls0 = 0.f, ls1 = 0.f;   // partial row sums of query rows 2t, 2t+1
-                for (int mt = warp; mt < n_mt; mt += NCW) {
-                    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-                    // key rows of the tile are visited in the order rho(g) = 0 4 1 5 2 6 3 7: with the 128-byte swizzle
-                    // (chunk ^ row & 7) the eight lanes of a quarter-warp then hit eight different 16-byte bank groups
-                    const int r0 = mt * 16 + (((g & 1) << 2) | (g >> 1)), r1 = r0 + 8;
+                // key rows of a tile are visited in the order rho(g) = 0 4 1 5 2 6 3 7: with the 128-byte swizzle
+                // (chunk ^ row & 7) the eight lanes of a quarter-warp then hit eight different 16-byte bank groups
+                const int rho = ((g & 1) << 2) | (g >> 1);
+                float sa[MAXT][4], sb[MAXT][4];
 #pragma unroll
-                    for (int kc = 0; kc < 8; ++kc) {
-                        const uint8_t *tile = smem + AttSmem::K + (kc >> 1) * KT_BYTES;
-                        const int ch = (kc & 1) * 4 + t;
+                for (int i = 0; i < MAXT; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sa[i][e] = sb[i][e] = 0.f;
+                const bool third = warp + 2 * NCW < n_mt;   // warp-uniform: rows >= n_keys are zero-filled, tiles >= n_mt skipped
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    const uint8_t *tile = smem + AttSmem::K + (kc >> 1) * KT_BYTES;
+                    const int ch = (kc & 1) * 4 + t;
+#pragma unroll
+                    for (int i = 0; i < MAXT; ++i) {
+                        if (i == MAXT - 1 && !third) continue;
+                        const int r0 = (warp + i * NCW) * 16 + rho;
                         const uint4 lo = *reinterpret_cast<const uint4 *>(tile + swz(r0, ch));
-                        const uint4 hi = *reinterpret_cast<const uint4 *>(tile + swz(r1, ch));
-                        mma_bf16(s0, lo.x, hi.x, lo.y, hi.y, qf[kc].x, qf[kc].y);
-                        mma_bf16(s1, lo.z, hi.z, lo.w, hi.w, qf[kc].z, qf[kc].w);
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(tile + swz(r0 + 8, ch));
+                        mma_bf16(sa[i], lo.x, hi.x, lo.y, hi.y, qf[kc].x, qf[kc].y);
+                        mma_bf16(sb[i], lo.z, hi.z, lo.w, hi.w, qf[kc].z, qf[kc].w);
                     }
-                    const float scale = 0.0625f, cap = 50.f;   // 1/sqrt(256); soft-cap (joint_model.py:139,261-268)
-                    // |logit| <= 50 after the soft-cap: exp() needs no running maximum
+                }
+                const float scale = 0.0625f, cap = 50.f;   // 1/sqrt(256); soft-cap (joint_model.py:139,261-268)
+                // |logit| <= 50 after the soft-cap: exp() needs no running maximum
+                float ls0 = 0.f, ls1 = 0.f;   // partial row sums of query rows 2t, 2t+1
+#pragma unroll
+                for (int i = 0; i < MAXT; ++i) {
+                    if (i == MAXT - 1 && !third) continue;
+                    const int r0 = (warp + i * NCW) * 16 + rho, r1 = r0 + 8;
+                    const bool vis0 = (r0 < vlen) || (r0 >= p.S_v && r0 < n_keys);
+                    const bool vis1 = (r1 < vlen) || (r1 >= p.S_v && r1 < n_keys);
                     float pe[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int j = (e < 2) ? r0 : r1;
-                        const bool vis = (j < vlen) || (j >= p.S_v && j < n_keys);
-                        pe[e] = vis ? __expf(tanh_fast_acc((s0[e] + s1[e]) * scale * (1.f / cap)) * cap) : 0.f;
+                        const float val = __expf(tanh_fast_acc((sa[i][e] + sb[i][e]) * (scale / cap)) * cap);
+                        pe[e] = sel_or_zero(e < 2 ? vis0 : vis1, val);
                     }
                     ls0 += pe[0] + pe[2];
                     ls1 += pe[1] + pe[3];
@@ -770,19 +888,25 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
             T3(23);
             // ---- O^T = V^T P^T: warp -> 16 dims of this CTA's 128; V^T fragments by transposing ldmatrix
             {
-                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, o2[4] = {0.f, 0.f, 0.f, 0.f}, o3[4] = {0.f, 0.f, 0.f, 0.f};
                 const uint32_t tile = sV + (warp >> 2) * KT_BYTES;
                 const int c0 = (warp & 3) * 2;
                 const int mi = lane >> 3, rr = lane & 7;
-                for (int kk = 0; kk < n_mt; ++kk) {
+#pragma unroll
+                for (int kk = 0; kk < KEYS / 16; ++kk) {   // tiles >= n_mt: P is zero there, V rows are zero-filled
+                    if (kk >= n_mt) break;
                     uint32_t a[4];
                     const int key = kk * 16 + (mi >> 1) * 8 + rr;
                     ldsm_x4_t(a, tile + swz(key, c0 + (mi & 1)));
                     const uint32_t b0 = *reinterpret_cast<const uint32_t *>(sP + g * LDP + kk * 16 + 2 * t);
                     const uint32_t b1 = *reinterpret_cast<const uint32_t *>(sP + g * LDP + kk * 16 + 8 + 2 * t);
-                    if (kk & 1) mma_bf16(o1, a[0], a[1], a[2], a[3], b0, b1);
-                    else mma_bf16(o0, a[0], a[1], a[2], a[3], b0, b1);
+                    if ((kk & 3) == 0) mma_bf16(o0, a[0], a[1], a[2], a[3], b0, b1);
+                    else if ((kk & 3) == 1) mma_bf16(o1, a[0], a[1], a[2], a[3], b0, b1);
+                    else if ((kk & 3) == 2) mma_bf16(o2, a[0], a[1], a[2], a[3], b0, b1);
+                    else mma_bf16(o3, a[0], a[1], a[2], a[3], b0, b1);
                 }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { o0[e] += o2[e]; o1[e] += o3[e]; }
                 float inv0, inv1;   // 1 / row sum of query rows 2t, 2t+1
                 {
                     float l0 = 0.f, l1 = 0.f;
@@ -843,6 +967,7 @@ __global__ void __launch_bounds__(NT3, 1) denoise_mega3_kernel(const __grid_cons
         int *dst = reinterpret_cast<int *>(smem + SM::SCHED);
         if (threadIdx.x < sizeof(CtaSched) / 4) dst[threadIdx.x] = src[threadIdx.x];
     }
+    T3INIT();
     __syncthreads();
     if (is_att) {
         const int a = blockIdx.x - p.G, b = a / NATT, head = (a % NATT) >> 1, dh = a & 1;
@@ -850,6 +975,7 @@ __global__ void __launch_bounds__(NT3, 1) denoise_mega3_kernel(const __grid_cons
     } else {
         gemv_role<MAXM>(p, smem, *reinterpret_cast<const CtaSched *>(smem + SM::SCHED));
     }
+    T3FLUSH();
 }
 
 // ------------------------------------------------------------------------------------- re-packing ----
@@ -981,9 +1107,11 @@ bool make_kv_map(CUtensorMap *map, const void *base, int S_c, long slabs) {
 
 size_t ll_words(const pz_config &c, int B) {
     const size_t M = (size_t)B * c.horizon, A = c.act_hidden, qkvw = (size_t)(c.n_heads + 2) * 128;
-    // act, z, 2 x, 2 x1, 2 qkv, 2 att, 2 mlp (each rounded up to 16 words)
+    // act, z, 2 x, 2 x1, 2 + 2 sums of squares, 2 qkv, 2 att, 2 mlp (each rounded up to 16 words)
     auto r = [](size_t w) { return (w + 15) & ~(size_t)15; };
-    return r(M * 8) + r(M * A / 2) + 2 * r(M * A) + 2 * r(M * A) + 2 * r(M * qkvw) + 2 * r(M * (size_t)c.n_heads * 128) + 2 * r(M * c.act_inter / 2);
+    const size_t MAXM = M <= 4 ? 4 : 8;
+    return r(M * 8) + r(M * A / 2) + 4 * r(M * A / 2) + 4 * r(A / 8 * MAXM) + 2 * r(M * qkvw) + 2 * r(M * (size_t)c.n_heads * 128) +
+           2 * r(M * c.act_inter / 2);
 }
 
 }  // namespace
@@ -1063,8 +1191,13 @@ int denoise_mega3_pack(const pz_config &c, const pz_weights &w, const pz_mix_lay
 
 int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_layer *layers, const Mega3State &state,
                          const Mega3Buffers &bf, int B, cudaStream_t st, const char **err) {
-    constexpr int SMEM4 = (GemvSmem<4>::END > AttSmem::END ? GemvSmem<4>::END : AttSmem::END) + 1024;
-    constexpr int SMEM8 = (GemvSmem<8>::END > AttSmem::END ? GemvSmem<8>::END : AttSmem::END) + 1024;
+#ifdef PZ_MEGA_TRACE   // the trace counters are static shared memory: the dynamic part then starts 1 KiB-aligned, no slack needed
+    constexpr int SLACK = 0;
+#else
+    constexpr int SLACK = 1024;
+#endif
+    constexpr int SMEM4 = (GemvSmem<4>::END > AttSmem::END ? GemvSmem<4>::END : AttSmem::END) + SLACK;
+    constexpr int SMEM8 = (GemvSmem<8>::END > AttSmem::END ? GemvSmem<8>::END : AttSmem::END) + SLACK;
     static_assert(SMEM4 <= 227 * 1024 && SMEM8 <= 227 * 1024, "shared memory budget");
     const int M = B * c.horizon;
     const void *fn = M <= 4 ? (const void *)denoise_mega3_kernel<4> : (const void *)denoise_mega3_kernel<8>;
@@ -1088,6 +1221,8 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
     {
         static const int pf = [] { const char *e = getenv("PZ_M3_PF"); return e ? atoi(e) : 0; }();
         p.pf_dist = pf;
+        static const int sen = [] { const char *e = getenv("PZ_M3_SENTINEL"); return e ? atoi(e) : 1; }();
+        p.sentinel = sen;
     }
     p.dt = (float)(1.0 / c.n_steps); p.clip = c.clip;
     for (int l = 0; l < c.n_layers; ++l) { p.norm_in[l] = layers[l].norm_in; p.norm_post[l] = layers[l].norm_post; }
@@ -1104,8 +1239,11 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
         auto take = [&](size_t words) { unsigned long long *r = q; q += (words + 15) & ~(size_t)15; return r; };
         const size_t Mz = M, A = c.act_hidden, qkvw = (size_t)(c.n_heads + 2) * 128;
         p.ll_act = take(Mz * 8); p.ll_z = take(Mz * A / 2);
-        for (int i = 0; i < 2; ++i) p.ll_x[i] = take(Mz * A);
-        for (int i = 0; i < 2; ++i) p.ll_x1[i] = take(Mz * A);
+        const size_t maxm = M <= 4 ? 4 : 8;
+        for (int i = 0; i < 2; ++i) p.ll_x[i] = take(Mz * A / 2);
+        for (int i = 0; i < 2; ++i) p.ll_x1[i] = take(Mz * A / 2);
+        for (int i = 0; i < 2; ++i) p.ll_sx[i] = take(A / 8 * maxm);
+        for (int i = 0; i < 2; ++i) p.ll_sx1[i] = take(A / 8 * maxm);
         for (int i = 0; i < 2; ++i) p.ll_qkv[i] = take(Mz * qkvw);
         for (int i = 0; i < 2; ++i) p.ll_att[i] = take(Mz * (size_t)c.n_heads * 128);
         for (int i = 0; i < 2; ++i) p.ll_mlp[i] = take(Mz * c.act_inter / 2);

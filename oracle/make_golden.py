@@ -16,6 +16,8 @@ Cases
           states / KV from the reference.
   bridge  the full bridge config (27 SigLIP + 18 joint layers, vocab 257216,
           3.24 B parameters), same storage policy as width2.
+  bridge64  the same model at batch 64 (the batch bench.py times): the actions of
+          every sample; hidden-state / KV rows of the samples listed in `samples`.
 
 How outputs are captured without touching the reference:
 `torch.randn` is patched for the duration of the call to return the shared
@@ -58,6 +60,9 @@ CASES = {
     "tiny": dict(dims=TINY, batch=3, seed=7, store_weights=True, randomize_norms=True),
     "width2": dict(dims=WIDTH2, batch=2, seed=11, store_weights=False, randomize_norms=True),
     "bridge": dict(dims=BRIDGE, batch=2, seed=42, store_weights=False, randomize_norms=False),
+    # the batch the bench times (BASELINE configs[1]): actions of all 64 samples, sampled rows of four of them
+    "bridge64": dict(dims=BRIDGE, batch=64, seed=44, store_weights=False, randomize_norms=True,
+                     samples=[0, 21, 42, 63]),
 }
 
 
@@ -160,26 +165,30 @@ def main(argv):
             fx["ref"] = ref
         else:
             Sv = dims["max_image_text_tokens"]
-            rows = sample_rows(inp["valid_len"], Sv)
+            samples = case.get("samples") or list(range(case["batch"]))
+            all_rows = sample_rows(inp["valid_len"], Sv)
+            rows = [all_rows[b] for b in samples]
             L, T = dims["num_layers"], dims["num_inference_steps"]
-            sub = lambda t: [t[b, rows[b]].clone() for b in range(case["batch"])]  # noqa: E731
+            sub = lambda t: [t[b, all_rows[b]].clone() for b in samples]  # noqa: E731
+            H = dims["horizon_steps"]
             fx["inputs_seed"] = case["seed"] + 100
             fx["rows"] = rows
+            fx["samples"] = samples
             fx["ref"] = dict(
                 action=ref["action"], action_preclip=ref["action_preclip"],
                 naive_preclip=ref["naive_preclip"],
                 vit_rows=[0, 1, 100, 255],
-                vit_out_rows=ref["vit_out"][:, [0, 1, 100, 255]].clone(),
-                image_features_rows=ref["image_features"][:, [0, 1, 100, 255]].clone(),
+                vit_out_rows=ref["vit_out"][samples][:, [0, 1, 100, 255]].clone(),
+                image_features_rows=ref["image_features"][samples][:, [0, 1, 100, 255]].clone(),
                 prefix_embeds_rows=sub(ref["prefix_embeds"]),
                 prefix_layers_rows=[
                     dict(vlm=None if l["vlm"] is None else sub(l["vlm"]),
-                         proprio=None if l["proprio"] is None else l["proprio"].clone())
+                         proprio=None if l["proprio"] is None else l["proprio"][samples].clone())
                     for l in ref["prefix_layers"]],
                 kv_rows=dict(
                     vlm=[(sub(k[:, 0]), sub(v[:, 0])) for k, v in ref["kv"]["vlm"]],
-                    proprio=[(k.clone(), v.clone()) for k, v in ref["kv"]["proprio"]]),
-                denoise_layers={s: [ref["denoise_layers"][s * L + l]["action"].clone()
+                    proprio=[(k[samples].clone(), v[samples].clone()) for k, v in ref["kv"]["proprio"]]),
+                denoise_layers={s: [ref["denoise_layers"][s * L + l]["action"][samples].clone()
                                     for l in range(L)] for s in (0, T - 1)},
                 # norms of every prefix layer's valid rows, for a cheap whole-tensor check
                 prefix_layer_norms=[

@@ -45,25 +45,28 @@ assert fn(buf, N) == 0
 t = np.array(buf, dtype=np.int64).reshape(160, 32)
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 G = sms - 16 * B
-g = t[:G]
-a = t[G:sms]
-t0 = g[:, 0][g[:, 0] > 0].min()
-names = {1: "x gathered+normed", 2: "qkv gemv", 3: "qkv published", 4: "att gathered", 5: "o gemv", 6: "x1 published",
-         7: "x1 gathered+normed", 8: "gu gemv", 9: "mlp published", 10: "mlp gathered", 11: "down gemv", 12: "x published"}
-print(f"B={B}: {G} streaming CTAs, {sms - G} attention CTAs; times in us relative to the earliest layer start")
-print(f"{'event':24s} {'min':>8s} {'mean':>8s} {'max':>8s}   (n CTAs)")
-for e in range(0, 13):
+khz = torch.cuda.get_device_properties(0).clock_rate   # kHz (max SM clock; the kernel runs at it: no power cap at bs 1)
+n_it = dims["num_layers"] * dims["num_inference_steps"]
+g = t[:G].astype(np.float64) / khz * 1e3 / n_it          # us per (layer, step)
+a = t[G:sms].astype(np.float64) / khz * 1e3 / n_it
+names = {0: "(between layers)", 1: "x gather", 2: "qkv gemv", 14: "qkv ring wait", 3: "qkv epilogue+publish",
+         4: "att gather", 5: "o gemv", 17: "o ring wait", 6: "o epilogue+publish",
+         7: "x1 gather", 8: "gu gemv", 20: "gu ring wait", 9: "gu epilogue+publish",
+         10: "mlp gather", 11: "down gemv", 23: "down ring wait", 12: "down epilogue+publish", 31: "encoder/decoder/other"}
+print(f"B={B}: {G} streaming CTAs, {sms - G} attention CTAs; us per (layer, step), thread 0 of each CTA")
+print(f"{'bucket':26s} {'min':>7s} {'mean':>7s} {'max':>7s}")
+tot = 0.0
+for e in (0, 1, 2, 14, 3, 4, 5, 17, 6, 7, 8, 20, 9, 10, 11, 23, 12, 31, 24 + 12):
     col = g[:, e]
-    ok = col > 0
-    if not ok.any():
+    if col.max() == 0:
         continue
-    r = (col[ok] - t0) / 1e3
-    print(f"{e:2d} {names.get(e, 'layer start'):21s} {r.min():8.2f} {r.mean():8.2f} {r.max():8.2f}   ({ok.sum()})")
-an = {20: "loop top", 21: "qkv gathered", 22: "kv ready + staged", 25: "S tiles (thread 0)", 23: "S + softmax", 24: "PV + published"}
-for e in (20, 21, 22, 25, 23, 24):
+    print(f"{e:2d} {names.get(e, '?'):23s} {col.min():7.2f} {col.mean():7.2f} {col.max():7.2f}")
+    tot += col.mean()
+print(f"   sum of means {tot:.2f} us")
+an = {20: "(loop top)", 21: "qkv gather", 26: "kv tiles wait", 22: "stage q/k/v", 25: "S tiles", 23: "S tail + barrier", 24: "PV + publish"}
+tot = 0.0
+for e in (20, 21, 26, 22, 25, 23, 24):
     col = a[:, e]
-    ok = col > 0
-    if not ok.any():
-        continue
-    r = (col[ok] - t0) / 1e3
-    print(f"{e:2d} {an[e]:21s} {r.min():8.2f} {r.mean():8.2f} {r.max():8.2f}   ({ok.sum()})")
+    print(f"{e:2d} {an[e]:23s} {col.min():7.2f} {col.mean():7.2f} {col.max():7.2f}")
+    tot += col.mean()
+print(f"   sum of means {tot:.2f} us")

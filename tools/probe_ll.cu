@@ -55,7 +55,11 @@ struct Params {
     unsigned long long *rs[2];                   // reduce-scatter buffers [reducer][producer][wpr]
     int n_stages, ipc_num, ipc_den, mode;        // items per stage = ipc_num / ipc_den (fractional: accumulated)
     int sentinel;                                // 1: one thread polls a sentinel word before the gather
+    int backoff_ns;                              // sleep between polling rounds
+    int max_inflight;                            // stream: bulk copies in flight per CTA (0: as many as there are free slots)
+    int replicas;                                // all-gather: every producer writes R copies, consumer c reads copy c % R
     unsigned int *err; float *sink;
+    unsigned int *counter; float *cdata[2];      // mode 4 / 5: arrival counter + compact fp32 payload (double buffered)
 };
 
 extern __shared__ __align__(1024) uint8_t smem[];
@@ -80,6 +84,10 @@ __global__ void __launch_bounds__(NT, 1) probe_kernel(const __grid_constant__ Pa
             for (long i = 0; i < total_items; ++i) {
                 const int slot = (int)(i % p.slots);
                 if (i >= p.slots && !mbar_wait(&empty[slot], (uint32_t)((i / p.slots) - 1) & 1)) { atomicExch(p.err, 2u); break; }
+                if (p.max_inflight > 0 && i >= p.max_inflight) {   // copy i - max_inflight must have landed
+                    const long k = i - p.max_inflight;
+                    if (!mbar_wait(&full[k % p.slots], (uint32_t)(k / p.slots) & 1)) { atomicExch(p.err, 8u); break; }
+                }
                 mbar_expect_tx(&full[slot], p.chunk);
                 bulk_g2s(smem + (size_t)slot * p.chunk, base + (i % p.items_per_pass) * (long)p.chunk, p.chunk, &full[slot], pol);
             }
@@ -146,13 +154,69 @@ __global__ void __launch_bounds__(NT, 1) probe_kernel(const __grid_constant__ Pa
             acc += red[0] + red[1] + red[2] + red[3] + red[4] + red[5] + red[6] + red[7];
             bar_compute();
         }
+        if (p.mode == 4 || p.mode == 5) {
+            // counter exchange: compact payload with plain stores, one release-increment per CTA; one thread polls the
+            // counter, then everybody reads the payload once (mode 5: one cp.async.bulk into shared memory instead)
+            float *cd = p.cdata[st & 1];
+            for (int j = tid; j < wpc; j += NCT) { int w = c * wpc + j; if (w < p.words) cd[w] = acc + j; }
+            bar_compute();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(p.counter, 1u);
+                const unsigned int target = (unsigned int)G * seq;
+                long spins = 0;
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.counter) : "memory");
+                    if (++spins > SPIN_LIMIT) { atomicExch(p.err, 6u); break; }
+                } while (v < target);
+            }
+            bar_compute();
+            float part = 0.f;
+            if (p.mode == 4) {
+                const float4 *src = reinterpret_cast<const float4 *>(cd);
+                for (int i = tid; i < p.words / 4; i += NCT) {
+                    float4 v;
+                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));
+                    part += v.x * 1e-9f;
+                }
+            } else {
+                // one thread: bulk copy of the payload into the ring's first bytes beyond the slots (reuse the staging area)
+                float *dst = reinterpret_cast<float *>(smem + (size_t)p.slots * p.chunk + 4096);
+                uint64_t *xbar = full + 2 * p.slots;
+                if (tid == 0) {
+                    if (st == 0) { mbar_init(xbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    mbar_expect_tx(xbar, (uint32_t)p.words * 4);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(dst)), "l"(cd), "r"((uint32_t)p.words * 4), "r"(smem_u32(xbar)) : "memory");
+                    if (!mbar_wait(xbar, (uint32_t)st & 1)) atomicExch(p.err, 7u);
+                }
+                bar_compute();
+                for (int i = tid; i < p.words; i += NCT) part += dst[i] * 1e-9f;
+            }
+            float *stage = reinterpret_cast<float *>(smem + (size_t)p.slots * p.chunk + 512);
+            stage[tid] = part;
+            bar_compute();
+            acc = acc * 0.5f + stage[(tid + 1) % NCT];
+            bar_compute();
+            if (*reinterpret_cast<volatile unsigned int *>(p.err)) break;
+            continue;
+        }
         // all-gather: publish my words, then collect everybody's
-        for (int j = tid; j < wpc; j += NCT) { int w = c * wpc + j; if (w < p.words) ll_store(buf + w, __float_as_uint(acc + j), seq); }
+        const int R = p.replicas > 0 ? p.replicas : 1;
+        for (int j = tid; j < wpc * R; j += NCT) { int w = c * wpc + j % wpc; if (w < p.words) ll_store(buf + (long)(j / wpc) * p.words + w, __float_as_uint(acc + j % wpc), seq); }
+        buf += (long)(c % R) * p.words;
         if (p.sentinel) {
             if (tid == 0) {
-                const unsigned long long *s = buf + ((c + G / 2) % G) * wpc;
+                int sw = ((c + G / 2) % G) * wpc;
+                if (sw >= p.words) sw = p.words - 1;
+                const unsigned long long *s = buf + sw;
                 long spins = 0;
-                while ((uint32_t)(ll_load1(s) >> 32) != seq) if (++spins > SPIN_LIMIT) { atomicExch(p.err, 3u); break; }
+                while ((uint32_t)(ll_load1(s) >> 32) != seq) {
+                    if (++spins > SPIN_LIMIT) { atomicExch(p.err, 3u); break; }
+                    if (p.backoff_ns) __nanosleep(p.backoff_ns);
+                }
             }
             bar_compute();
         }
@@ -170,6 +234,7 @@ __global__ void __launch_bounds__(NT, 1) probe_kernel(const __grid_constant__ Pa
                 }
                 if (!diff) break;
                 if (++spins > SPIN_LIMIT) { atomicExch(p.err, 5u); break; }
+                if (p.backoff_ns) __nanosleep(p.backoff_ns);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) { int i = i0 + u * NCT + tid; if (i < n2) part += __uint_as_float((uint32_t)v[2 * u]) * 1e-9f; }
@@ -191,8 +256,9 @@ static float run(Params p, int grid, size_t smem_bytes, const char *label, doubl
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         CK(cudaMemset(p.err, 0, 4));
+        if (p.counter) CK(cudaMemset(p.counter, 0, 4));
         for (int b = 0; b < 2; ++b) {
-            if (p.ll[b]) CK(cudaMemset(p.ll[b], 0, (size_t)p.words * 8 + 64));
+            if (p.ll[b]) CK(cudaMemset(p.ll[b], 0, (size_t)p.words * 8 * (p.replicas > 0 ? p.replicas : 1) + 64));
             if (p.rs[b]) CK(cudaMemset(p.rs[b], 0, (size_t)grid * grid * ((p.words + grid - 1) / grid) * 8 + 64));
         }
         void *args[] = {&p};
@@ -229,15 +295,17 @@ int main() {
     CK(cudaMalloc(&p.err, 64));
     CK(cudaMalloc(&p.sink, 64));
     const int maxwords = 16384;
+    CK(cudaMalloc(&p.counter, 64));
+    for (int b = 0; b < 2; ++b) CK(cudaMalloc(&p.cdata[b], (size_t)maxwords * 4 + 64));
     for (int b = 0; b < 2; ++b) {
-        CK(cudaMalloc(&p.ll[b], (size_t)maxwords * 8 + 64));
+        CK(cudaMalloc(&p.ll[b], (size_t)maxwords * 8 * 8 + 64));
         CK(cudaMalloc(&p.rs[b], (size_t)grid * grid * ((maxwords + grid - 1) / grid) * 8 + 64));
     }
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     char label[256];
 
     // ---- stream only: chunk size x ring depth
-    const int cfgs[][2] = {{32768, 5}, {32768, 6}, {32768, 4}, {16384, 10}, {16384, 12}, {65536, 3}, {8192, 20}};
+    const int cfgs[][2] = {{32768, 5}, {32768, 4}};
     for (auto &cf : cfgs) {
         p.mode = 0; p.chunk = cf[0]; p.slots = cf[1];
         p.cta_stride = (long)(stream_bytes / grid) & ~(long)1023;
@@ -247,24 +315,46 @@ int main() {
         snprintf(label, sizeof(label), "stream chunk %d ring %d", p.chunk, p.slots);
         run(p, grid, sm, label, (double)p.n_stages * p.chunk);
     }
-    // ---- gather only (no weight traffic): words x sentinel
+    // ---- stream alone and stage = stream + all-gather (93 stages per step, 629 MB per step => 148 CTAs x 1.43 items of
+    //      32 KB per stage) against the number of bulk copies in flight per CTA
     p.chunk = 32768; p.slots = 5;
     size_t sm = (size_t)p.chunk * p.slots + 4096;
-    for (int words : {1024, 4096, 8192}) {
-        for (int sen = 0; sen < 2; ++sen) {
-            p.mode = 1; p.words = words; p.sentinel = sen; p.n_stages = 2000;
-            snprintf(label, sizeof(label), "all-gather %d words (%d KB) sentinel %d", words, words * 8 / 1024, sen);
-            run(p, grid, sm, label, 0);
+    for (int chunk : {32768, 16384}) {
+        for (int mi : {0, 1, 2, 3}) {
+            p.chunk = chunk; p.slots = 5 * 32768 / chunk; p.max_inflight = mi;
+            p.mode = 0; p.cta_stride = (long)(stream_bytes / grid) & ~(long)1023; p.items_per_pass = (int)(p.cta_stride / p.chunk);
+            p.n_stages = (int)(((size_t)3200 << 20) / grid / p.chunk);
+            snprintf(label, sizeof(label), "stream chunk %d ring %d in flight <= %d", p.chunk, p.slots, mi);
+            run(p, grid, sm, label, (double)p.n_stages * p.chunk);
+            for (int words : {1024, 4096}) {
+                p.mode = 2; p.words = words; p.sentinel = 1; p.backoff_ns = 0; p.replicas = 1; p.n_stages = 930;
+                p.ipc_num = 143 * (32768 / chunk); p.ipc_den = 100;
+                snprintf(label, sizeof(label), "  + all-gather %d words (46 KB/stage), in flight <= %d", words, mi);
+                run(p, grid, sm, label, (double)((long)p.n_stages * p.ipc_num / p.ipc_den) * p.chunk);
+            }
         }
     }
-    // ---- stage = stream + all-gather: 93 stages per step, 629 MB per step => 148 CTAs x 1.43 items of 32 KB per stage
-    for (int words : {4096}) {
-        for (int sen = 0; sen < 2; ++sen) {
-            p.mode = 2; p.words = words; p.sentinel = sen; p.n_stages = 930;
-            p.ipc_num = 143; p.ipc_den = 100;
-            snprintf(label, sizeof(label), "stage: 1.43 items + all-gather %d words sentinel %d", words, sen);
-            run(p, grid, sm, label, (double)((long)p.n_stages * p.ipc_num / p.ipc_den) * p.chunk);
+    p.chunk = 32768; p.slots = 5; p.max_inflight = 0;
+    p.sentinel = 0; p.backoff_ns = 0; p.replicas = 1;
+    return 0;
+    // ---- counter exchange (compact payload): without and with the weight stream
+    p.slots = 4;
+    const size_t smx = (size_t)p.chunk * p.slots + 4096 + 36864;
+    for (int mode : {4, 5}) {
+        for (int words : {2048, 4096, 8192}) {
+            p.mode = mode; p.words = words; p.sentinel = 0; p.n_stages = 2000; p.ipc_num = 0; p.ipc_den = 1;
+            snprintf(label, sizeof(label), "counter exchange mode %d, %d fp32 (%d KB)", mode, words, words * 4 / 1024);
+            run(p, grid, smx, label, 0);
         }
+        p.words = 4096; p.n_stages = 930; p.ipc_num = 143; p.ipc_den = 100;
+        snprintf(label, sizeof(label), "stage: 1.43 items + counter exchange mode %d 4096 fp32", mode);
+        run(p, grid, smx, label, (double)((long)p.n_stages * p.ipc_num / p.ipc_den) * p.chunk);
+    }
+    p.slots = 5;
+    for (int words : {2048, 4096}) {   // the LL all-gather with the stream, for comparison at equal payload
+        p.mode = 2; p.words = words; p.sentinel = 0; p.n_stages = 930; p.ipc_num = 143; p.ipc_den = 100;
+        snprintf(label, sizeof(label), "stage: 1.43 items + LL all-gather %d words", words);
+        run(p, grid, sm, label, (double)((long)p.n_stages * p.ipc_num / p.ipc_den) * p.chunk);
     }
     // ---- reduce-scatter + all-gather per stage, without and with the weight stream
     p.sentinel = 0; p.words = 4096; p.n_stages = 930;
