@@ -41,6 +41,9 @@ constexpr int NCW = 8, NCT = NCW * 32, NT3 = NCT;        // 8 warps; one elected
 constexpr int SLOT = 32768;                              // ring slot = one weight item
 constexpr int KI = 1024;                                 // act_hidden
 constexpr int MAXQ = 3, MAXO = 2, MAXGU = 5, MAXJ = 5;   // items of one stage per CTA
+constexpr int MAXKS = (MAXGU + 1) / 2;                   // 16-wide k steps of a CTA's down-projection partial
+constexpr int HS_LD = 16 * MAXKS + 8;                    // row stride of the CTA's GeGLU outputs (bf16)
+constexpr int MAXP = 160;                                // bound on NP for sizing the exchange workspace
 constexpr int MAX_LAYERS = 24;
 constexpr int KEYS = 288, KBOX = 144;                    // key rows per attention CTA (two TMA boxes)
 constexpr int KT_BYTES = KEYS * 128;                     // one swizzled tile: KEYS rows x 64 dims
@@ -54,17 +57,18 @@ struct CtaSched {           // what one weight-streaming CTA does in every layer
     int e2_blk;                    // 16-row block of action_encoder.linear_2, or -1
     int is_dec;                    // runs the final norm + action_decoder + Euler update
     int slots_per_step;
-    int pad;
+    int pid;                       // index among the CTAs that hold gate|up tiles (producers of down partials), or -1
     long long stream_off;          // byte offset of this CTA's item stream
 };
 static_assert(sizeof(CtaSched) == 80, "CtaSched layout");
 
-enum SlotKind { SK_QKV = 0, SK_GU, SK_O, SK_D, SK_E2, SK_E3, SK_DEC };
+enum SlotKind { SK_QKV = 0, SK_GU, SK_O, SK_DP, SK_E2, SK_E3, SK_DEC };
 struct SlotDesc { int kind, layer, blk, aux; };
 
 struct Mega3Params {
     int B, H, M, nh, S_v, S_p, S_c, n_layers, n_steps, action_dim, skp, AI;
     int G, NA;
+    int NP;                           // CTAs that produce down-projection partials
     int pf_dist;                      // ring items ahead of the copy that are prefetched into L2 (0: none)
     int sentinel;                     // 1: one thread polls one word of an exchange before the CTA gathers all of it
     float dt, clip;
@@ -88,7 +92,7 @@ struct Mega3Params {
     unsigned long long *ll_sx1[2];
     unsigned long long *ll_qkv[2];    // [M][1280]    bf16x2, q and k rotated
     unsigned long long *ll_att[2];    // [M][1024]    bf16x2 attention output
-    unsigned long long *ll_mlp[2];    // [M][AI/2]    bf16x2 GeGLU output
+    unsigned long long *ll_rs[2];     // [A/8][NP][8][MAXM] fp32: down-projection partials of one producer for one 8-column block
     unsigned int *err;
 };
 
@@ -202,6 +206,10 @@ PZ_DEVINL void ll_store(unsigned long long *dst, uint32_t payload, uint32_t seq)
     unsigned long long v = ((unsigned long long)seq << 32) | payload;
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
 }
+PZ_DEVINL void ll_store2(unsigned long long *dst, uint32_t pay0, uint32_t pay1, uint32_t seq) {   // 16-byte aligned pair
+    const unsigned long long a = ((unsigned long long)seq << 32) | pay0, b = ((unsigned long long)seq << 32) | pay1;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(a), "l"(b) : "memory");
+}
 PZ_DEVINL void ll_load2(const unsigned long long *src, unsigned long long &a, unsigned long long &b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
 }
@@ -263,14 +271,16 @@ PZ_DEVINL int IDX_X2(int l) { return 7 + 5 * l; }
 
 // ======================================== weight-streaming role =========================================
 template <int MAXM> struct GemvSmem {
-    static constexpr int SLOTS = MAXM <= 4 ? 5 : 4;
-    static constexpr int LDA_MAX = 4096 + 32;
+    static constexpr int SLOTS = MAXM <= 4 ? 6 : 5;
+    static constexpr int RSTRIDE = MAXM + 1;                               // floats per row of the cross-warp reduction buffer
+    static constexpr int LDA_MAX = 2048 + 32;
     static constexpr int RING = 0;
     static constexpr int AST = RING + SLOTS * SLOT;                        // bf16 [MAXM][K + 32]
-    static constexpr int RED = AST + MAXM * LDA_MAX * 2;                   // float [NCW][MAXJ][16][9]
-    static constexpr int MISC = RED + NCW * MAXJ * 16 * 9 * 4;             // floats: part[NCW][8], xpriv[MAXO][8][8], acts[64]
+    static constexpr int RED = AST + MAXM * LDA_MAX * 2;                   // float [NCW][MAXJ][16][RSTRIDE]
+    static constexpr int MISC = RED + NCW * MAXJ * 16 * RSTRIDE * 4;             // floats: part[NCW][8], xpriv[MAXO][8][8], acts[64]
     static constexpr int XPRIV = 64, SACT = 64 + MAXO * 64;                // float offsets inside MISC
-    static constexpr int BARS = MISC + (64 + MAXO * 64 + 64) * 4;          // full[SLOTS]
+    static constexpr int HS = MISC + (64 + MAXO * 64 + 64) * 4;            // bf16 [8][HS_LD]: this CTA's GeGLU outputs
+    static constexpr int BARS = HS + 8 * HS_LD * 2;                        // full[SLOTS]
     static constexpr int SCHED = BARS + SLOTS * 8;
     static constexpr int END = SCHED + (int)sizeof(CtaSched);
 };
@@ -312,10 +322,12 @@ PZ_DEVINL void ring_refill(GemvCtx &cx) {
     }
 }
 
-PZ_DEVINL float *red_ptr(uint8_t *red, int w, int j, int r) { return reinterpret_cast<float *>(red) + ((w * MAXJ + j) * 16 + r) * 9; }
+template <typename SM>
+PZ_DEVINL float *red_ptr(uint8_t *red, int w, int j, int r) { return reinterpret_cast<float *>(red) + ((w * MAXJ + j) * 16 + r) * SM::RSTRIDE; }
 
 // acc[j] = (16-row item j of this stage) . A^T over this warp's 128-wide k slice; K = 1024
-template <typename SM, int NJ>
+// MID > 0: the slots of the first MID items are handed back (and re-requested) as soon as they are consumed, not after the stage
+template <typename SM, int NJ, int MID = 0>
 PZ_DEVINL void gemv16(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[NJ][4]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const bf16 *As = reinterpret_cast<const bf16 *>(cx.smem + SM::AST);
@@ -344,7 +356,8 @@ PZ_DEVINL void gemv16(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[NJ]
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[j][e] += a2[e];
             cx.cnt += 1;
-            if (NJ > SM::SLOTS && j + 1 == SM::SLOTS && n > SM::SLOTS) {   // more items than ring slots (CTA-uniform)
+            if ((NJ > SM::SLOTS && j + 1 == SM::SLOTS && n > SM::SLOTS) ||   // more items than ring slots (CTA-uniform)
+                (MID > 0 && j + 1 == MID && n > MID)) {
                 __syncthreads();
                     ring_refill<SM>(cx);
             }
@@ -385,23 +398,55 @@ PZ_DEVINL void gemv8(const Mega3Params &p, GemvCtx &cx, int n, float (&acc)[MAXO
         }
     }
 }
-template <int NJ>
+template <typename SM, int NJ>
 PZ_DEVINL void red_write(uint8_t *red, int n, const float (&acc)[NJ][4]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    if (2 * t >= SM::RSTRIDE - 1) return;   // token columns beyond the kernel's row count are padding
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         if (j < n) {
-            float *r0 = red_ptr(red, warp, j, g), *r1 = red_ptr(red, warp, j, g + 8);
+            float *r0 = red_ptr<SM>(red, warp, j, g), *r1 = red_ptr<SM>(red, warp, j, g + 8);
             r0[2 * t] = acc[j][0]; r0[2 * t + 1] = acc[j][1];
             r1[2 * t] = acc[j][2]; r1[2 * t + 1] = acc[j][3];
         }
     }
 }
+template <typename SM>
 PZ_DEVINL float red_sum(uint8_t *red, int j, int r, int m) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) v += red_ptr(red, w, j, r)[m];
+    for (int w = 0; w < NCW; ++w) v += red_ptr<SM>(red, w, j, r)[m];
     return v;
+}
+
+// This CTA's share of the down projection (paligemma/modules.py:95): out[1024][m] += W_down[:, my columns] h[my columns][m],
+// K = this CTA's (up to) 8 MAXGU GeGLU outputs, zero-padded to 16-wide steps.  Ring slot ks = k step ks in fragment order
+// [m tile 0..63][lane][a0 a1 a2 a3] (mega3_repack_kernel); warp w owns rows 128 w .. 128 w + 127, so nothing is reduced
+// across warps: acc[i] = rows 128 w + 16 i + {g, g + 8}, tokens 2t, 2t + 1.
+template <typename SM>
+PZ_DEVINL void down_partial(const Mega3Params &p, GemvCtx &cx, int n_ks, float (&acc)[8][4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const bf16 *hs = reinterpret_cast<const bf16 *>(cx.smem + SM::HS);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < MAXKS; ++ks) {
+        if (ks < n_ks) {
+            const int slot = cx.cnt % SM::SLOTS;
+            T3WAIT_BEGIN();
+            mbar_wait(p, &cx.full[slot], (cx.cnt / SM::SLOTS) & 1);
+            T3WAIT_END();
+            const uint32_t b0 = g < p.M ? *reinterpret_cast<const uint32_t *>(hs + g * HS_LD + ks * 16 + 2 * t) : 0u;
+            const uint32_t b1 = g < p.M ? *reinterpret_cast<const uint32_t *>(hs + g * HS_LD + ks * 16 + 8 + 2 * t) : 0u;
+            const uint8_t *w = cx.smem + SM::RING + slot * SLOT + warp * 4096 + lane * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(w + i * 512);
+                mma_bf16(acc[i], a.x, a.y, a.z, a.w, b0, b1);
+            }
+            cx.cnt += 1;
+        }
+    }
 }
 
 // ---- activation staging ------------------------------------------------------------------------------
@@ -528,6 +573,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
     uint8_t *red = smem + SM::RED;
     float *xpriv = reinterpret_cast<float *>(smem + SM::MISC) + SM::XPRIV;   // [MAXO][8 rows m][8 cols]
     const int tid = threadIdx.x;
+    for (int i = tid; i < 8 * HS_LD / 2; i += NCT) reinterpret_cast<uint32_t *>(smem + SM::HS)[i] = 0u;   // k padding stays zero
     const int qkvw = (p.nh + 2) * 128;
     // owner epilogues: thread -> (block j, row m, column r); 8 consecutive lanes share (j, m)
     const int ow_r = tid & 7, ow_m = (tid >> 3) % MAXM, ow_j = tid / (8 * MAXM);
@@ -565,13 +611,13 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             stage_enc1<SM>(p, smem, seq_of(p, step, IDX_ACT));
             float acc[1][4];
             gemv16<SM, 1>(p, cx, 1, acc);
-            red_write<1>(red, 1, acc);
+            red_write<SM, 1>(red, 1, acc);
             bar_compute();
             ring_refill<SM>(cx);
             for (int i = tid; i < 8 * p.M; i += NCT) {   // (row pair, m)
                 const int rp = i & 7, m = i >> 3, n = sc.e2_blk * 16 + 2 * rp;
-                const float v0 = red_sum(red, 0, 2 * rp, m) + p.enc_time_bias[step * KI + n];
-                const float v1 = red_sum(red, 0, 2 * rp + 1, m) + p.enc_time_bias[step * KI + n + 1];
+                const float v0 = red_sum<SM>(red, 0, 2 * rp, m) + p.enc_time_bias[step * KI + n];
+                const float v1 = red_sum<SM>(red, 0, 2 * rp + 1, m) + p.enc_time_bias[step * KI + n + 1];
                 ll_store(p.ll_z + (long)m * (KI / 2) + (n >> 1), pack_bf16x2(silu(v0), silu(v1)), seq_of(p, step, IDX_Z));
             }
             bar_compute();
@@ -582,11 +628,11 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             stage_pairs<SM, KI>(p, smem, p.ll_z, seq_of(p, step, IDX_Z));
             float acc[MAXO][4];
             gemv8<SM, 4>(p, cx, sc.n_o, acc);
-            red_write<MAXO>(red, sc.n_o, acc);
+            red_write<SM, MAXO>(red, sc.n_o, acc);
             bar_compute();
             ring_refill<SM>(cx);
             if (ow_warp) {
-                const float v = ow_valid ? (red_sum(red, ow_j, ow_r, ow_m) + b3) * sqrtf((float)KI) : 0.f;
+                const float v = ow_valid ? (red_sum<SM>(red, ow_j, ow_r, ow_m) + b3) * sqrtf((float)KI) : 0.f;
                 if (ow_active) xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
                 publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x[0], p.ll_sx[0], seq_of(p, step, IDX_X0));
             }
@@ -602,7 +648,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                 T3CUR(2);
                 float acc[MAXQ][4];
                 gemv16<SM, MAXQ>(p, cx, sc.n_qkv, acc);
-                red_write<MAXQ>(red, sc.n_qkv, acc);
+                red_write<SM, MAXQ>(red, sc.n_qkv, acc);
                 bar_compute();
                 T3(2);
                 ring_refill<SM>(cx);
@@ -615,7 +661,7 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                     if (u * NCT >= sc.n_qkv * 16 * p.M) break;   // CTA-uniform
                     const bool ok = i < sc.n_qkv * 16 * p.M;
                     const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
-                    float v0 = ok ? red_sum(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;
+                    float v0 = ok ? red_sum<SM>(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;
                     const float other = __shfl_xor_sync(0xffffffffu, v0, 8);
                     const int blk = sc.qkv_blk[j], hh = blk >> 4, d = (blk & 15) * 8 + (r & 7);
                     v0 = (r < 8) ? v0 * rope_c[u] - other * rope_s[u] : v0 * rope_c[u] + other * rope_s[u];
@@ -634,14 +680,14 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                 T3CUR(5);
                 float acc[MAXO][4];
                 gemv8<SM, 8>(p, cx, sc.n_o, acc);
-                red_write<MAXO>(red, sc.n_o, acc);
+                red_write<SM, MAXO>(red, sc.n_o, acc);
                 bar_compute();
                 T3(5);
                 ring_refill<SM>(cx);
                 if (ow_warp) {
                     float v = 0.f;
                     if (ow_valid) {
-                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] + red_sum(red, ow_j, ow_r, ow_m);
+                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] + red_sum<SM>(red, ow_j, ow_r, ow_m);
                         xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
                     }
                     publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x1[pb], p.ll_sx1[pb], seq_of(p, step, IDX_X1(l)));
@@ -655,42 +701,75 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
                 T3(7);
                 T3CUR(8);
                 float acc[MAXGU][4];
-                gemv16<SM, MAXGU>(p, cx, sc.n_gu, acc);
-                red_write<MAXGU>(red, sc.n_gu, acc);
+                gemv16<SM, MAXGU, 2>(p, cx, sc.n_gu, acc);
+                red_write<SM, MAXGU>(red, sc.n_gu, acc);
                 bar_compute();
                 T3(8);
                 ring_refill<SM>(cx);
-                const uint32_t fo = seq_of(p, step, IDX_MLP(l));
+                bf16 *hs = reinterpret_cast<bf16 *>(smem + SM::HS);
                 for (int i0 = 0; i0 < sc.n_gu * 16 * p.M; i0 += NCT) {
                     const int i = i0 + tid;
                     const bool ok = i < sc.n_gu * 16 * p.M;
                     const int r = i & 15, jm = ok ? (i >> 4) : 0, j = jm / p.M, m = jm % p.M;
-                    const float v = ok ? red_sum(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;   // rows 0-7: gate, 8-15: the matching up rows
+                    const float v = ok ? red_sum<SM>(red, j, r, m) * row_rnorm<SM>(smem, m) : 0.f;   // rows 0-7: gate, 8-15: the matching up rows
                     const float u = __shfl_down_sync(0xffffffffu, v, 8);
-                    const float h0 = gelu_fast(v) * u;
-                    const float h1 = __shfl_down_sync(0xffffffffu, h0, 1);
-                    if (ok && r < 8 && !(r & 1))
-                        ll_store(p.ll_mlp[pb] + (long)m * (p.AI / 2) + sc.gu_tile[j] * 4 + (r >> 1), pack_bf16x2(h0, h1), fo);
+                    if (ok && r < 8) hs[m * HS_LD + j * 8 + r] = __float2bfloat16_rn(gelu_fast(v) * u);
                 }
                 bar_compute();
                 T3(9);
+                T3CUR(16);
+                // ---- down projection of this CTA's columns; the fp32 partials go to the owners of the residual blocks
+                float dacc[8][4];
+                down_partial<SM>(p, cx, (sc.n_gu + 1) >> 1, dacc);
+                T3(16);
+                if (2 * (tid & 3) < MAXM) {
+                    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+                    const uint32_t fo = seq_of(p, step, IDX_MLP(l));
+                    unsigned long long *dst = p.ll_rs[pb] + ((long)(warp * 16) * p.NP + sc.pid) * (8 * MAXM) + g * MAXM + 2 * t;
+                    const long bstride = (long)p.NP * (8 * MAXM);   // one residual block further
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        ll_store2(dst + (2 * i) * bstride, __float_as_uint(dacc[i][0]), __float_as_uint(dacc[i][1]), fo);
+                        ll_store2(dst + (2 * i + 1) * bstride, __float_as_uint(dacc[i][2]), __float_as_uint(dacc[i][3]), fo);
+                    }
+                }
+                bar_compute();
+                ring_refill<SM>(cx);
+                T3(18);
             }
-            // ---- down + residual
+            // ---- owners: sum the partials of their blocks in producer order (deterministic) + residual
             if (sc.n_o > 0) {
                 const float wn = ow_active ? __ldg((l + 1 < p.n_layers ? p.norm_in[l + 1] : p.final_norm) + ow_n) : 0.f;
-                stage_pairs<SM, 4096>(p, smem, p.ll_mlp[pb], seq_of(p, step, IDX_MLP(l)));
-                T3(10);
-                T3CUR(11);
-                float acc[MAXO][4];
-                gemv8<SM, 16>(p, cx, sc.n_o, acc);
-                red_write<MAXO>(red, sc.n_o, acc);
+                constexpr int E = 8 * MAXM, E2 = E / 2, PPU = NCT / E2;   // words / double-words per producer; producers per round
+                float *rsum = reinterpret_cast<float *>(red);             // [NCW][MAXO][E]
+                const uint32_t fin = seq_of(p, step, IDX_MLP(l));
+                const int rounds = (p.NP + PPU - 1) / PPU;
+                for (int j = 0; j < sc.n_o; ++j) {
+                    const unsigned long long *base = p.ll_rs[pb] + (long)sc.o_blk[j] * p.NP * E;
+                    ll_sentinel(p, base, p.NP * E, fin);
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int u0 = 0; u0 < rounds; u0 += 8) {
+                        unsigned long long v[16];
+                        uint32_t pend = 0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if ((u0 + u) * PPU + tid / E2 < p.NP) pend |= 1u << u;
+                        ll_gather<8>(p, fin, pend, [&](int u) { return base + 2 * ((long)(u0 + u) * NCT + tid); }, v);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if ((pend >> u) & 1u) { s0 += __uint_as_float((uint32_t)v[2 * u]); s1 += __uint_as_float((uint32_t)v[2 * u + 1]); }
+                    }
+                    if (E2 < 32) { s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16); }
+                    const int lane = tid & 31, warp = tid >> 5;
+                    if (lane < E2) { rsum[(warp * MAXO + j) * E + 2 * lane] = s0; rsum[(warp * MAXO + j) * E + 2 * lane + 1] = s1; }
+                }
                 bar_compute();
-                T3(11);
-                ring_refill<SM>(cx);
+                T3(10);
                 if (ow_warp) {
                     float v = 0.f;
                     if (ow_valid) {
-                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] + red_sum(red, ow_j, ow_r, ow_m);
+                        v = xpriv[(ow_j * 8 + ow_m) * 8 + ow_r];
+#pragma unroll
+                        for (int w = 0; w < NCW; ++w) v += rsum[(w * MAXO + ow_j) * E + ow_r * MAXM + ow_m];
                         xpriv[(ow_j * 8 + ow_m) * 8 + ow_r] = v;
                     }
                     publish_x<MAXM>(p, ow_active, ow_valid, v, wn, ow_n, ow_blk, ow_m, p.ll_x[(l + 1) & 1], p.ll_sx[(l + 1) & 1],
@@ -705,12 +784,12 @@ PZ_DEVINL void gemv_role(const Mega3Params &p, uint8_t *smem, const CtaSched &sc
             stage_x<SM, MAXM>(p, smem, p.ll_x[p.n_layers & 1], p.ll_sx[p.n_layers & 1], seq_of(p, step, IDX_X2(p.n_layers - 1)));
             float acc[MAXO][4];
             gemv8<SM, 4>(p, cx, 1, acc);
-            red_write<MAXO>(red, 1, acc);
+            red_write<SM, MAXO>(red, 1, acc);
             bar_compute();
             ring_refill<SM>(cx);
             if (tid < 8 * p.M) {
                 const int a = tid & 7, m = tid >> 3;
-                if (a < p.action_dim) my_act += p.dt * (red_sum(red, 0, a, m) * row_rnorm<SM>(smem, m) + p.dec_b[a]);
+                if (a < p.action_dim) my_act += p.dt * (red_sum<SM>(red, 0, a, m) * row_rnorm<SM>(smem, m) + p.dec_b[a]);
                 if (step + 1 < p.n_steps) {
                     ll_store(p.ll_act + tid, __float_as_uint(my_act), seq_of(p, step + 1, IDX_ACT));
                 } else if (a < p.action_dim) {
@@ -776,6 +855,31 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
     for (int i = tid; i < 8 * LDP / 2; i += NCT) reinterpret_cast<uint32_t *>(sP)[i] = 0u;
     bar_compute();
 
+    // what this thread fetches from the q|k|v exchange in every layer and where it goes (layer-invariant)
+    uint32_t att_pend = 0, src_off[3] = {0, 0, 0}, dst_off[3] = {0, 0, 0};
+    {
+        const int per_tok = 160, total = H * per_tok;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int i = tid + u * NCT;
+            if (i >= total) continue;
+            att_pend |= 1u << u;
+            const int tok = i / per_tok, e = i % per_tok, row = S_c + tok;
+            const uint32_t rbase = (uint32_t)((b * H + tok) * qkvw);
+            if (e < 64) {                      // q: dims 4e .. 4e+3
+                src_off[u] = rbase + head * 128 + 2 * e;
+                dst_off[u] = AttSmem::Q + (tok * LDQ + 4 * e) * 2;
+            } else if (e < 128) {              // k
+                const int d = 4 * (e - 64);
+                src_off[u] = rbase + p.nh * 128 + 2 * (e - 64);
+                dst_off[u] = AttSmem::K + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2;
+            } else {                           // v, dims dh*128 + 4(e-128) ..
+                const int d = 4 * (e - 128);
+                src_off[u] = rbase + (p.nh + 1) * 128 + dh * 64 + 2 * (e - 128);
+                dst_off[u] = AttSmem::V + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2;
+            }
+        }
+    }
     uint32_t it = 0;
     for (int step = 0; step < p.n_steps; ++step) {
         for (int l = 0; l < p.n_layers; ++l, ++it) {
@@ -783,40 +887,17 @@ PZ_DEVINL void att_role(const Mega3Params &p, uint8_t *smem, const CUtensorMap *
             const uint32_t fin = seq_of(p, step, IDX_QKV(l));
             T3(20);
             // ---- this step's rotated q rows of (sample b, head), the fresh k rows and this CTA's half of the fresh
-            //      v rows: per token 64 + 64 + 32 double-words
+            //      v rows: per token 64 + 64 + 32 double-words (source offsets / destinations: src_off, dst_off above)
             unsigned long long v[6];
-            const int per_tok = 160, total = H * per_tok;
-            uint32_t pend = 0;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) if (tid + u * NCT < total) pend |= 1u << u;
-            ll_gather<3>(p, fin, pend, [&](int u) {
-                const int i = tid + u * NCT, tok = i / per_tok, e = i % per_tok;
-                const unsigned long long *row = p.ll_qkv[pb] + (long)(b * H + tok) * qkvw;
-                if (e < 64) return row + head * 128 + 2 * e;                       // q: dims 4e .. 4e+3
-                if (e < 128) return row + p.nh * 128 + 2 * (e - 64);               // k
-                return row + (p.nh + 1) * 128 + dh * 64 + 2 * (e - 128);           // v, dims dh*128 + 4(e-128) ..
-            }, v);
+            ll_gather<3>(p, fin, att_pend, [&](int u) { return p.ll_qkv[pb] + src_off[u]; }, v);
             T3(21);
             mbar_wait(p, kv_full, it & 1);
             T3(26);   // the cached rows of this layer (loaded one layer ahead); also orders the
                                              // fresh rows below after the TMA zero fill of rows >= S_c
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int i = tid + u * NCT;
-                if (i < total) {
-                    const int tok = i / per_tok, e = i % per_tok;
-                    const uint2 val = make_uint2((uint32_t)v[2 * u], (uint32_t)v[2 * u + 1]);
-                    if (e < 64) {
-                        *reinterpret_cast<uint2 *>(sQ + tok * LDQ + 4 * e) = val;
-                    } else if (e < 128) {
-                        const int d = 4 * (e - 64), row = S_c + tok;
-                        *reinterpret_cast<uint2 *>(smem + AttSmem::K + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2) = val;
-                    } else {
-                        const int d = 4 * (e - 128), row = S_c + tok;
-                        *reinterpret_cast<uint2 *>(smem + AttSmem::V + (d >> 6) * KT_BYTES + swz(row, (d & 63) >> 3) + (d & 7) * 2) = val;
-                    }
-                }
-            }
+            for (int u = 0; u < 3; ++u)
+                if ((att_pend >> u) & 1u)
+                    *reinterpret_cast<uint2 *>(smem + dst_off[u]) = make_uint2((uint32_t)v[2 * u], (uint32_t)v[2 * u + 1]);
             bar_compute();
             T3(22);
             // ---- S^T = K q^T: keys are the MMA M dimension (16-key tiles over the warps), the query rows the 8-wide N;
@@ -987,6 +1068,7 @@ struct RepackParams {
     pz_mix_layer layers[MAX_LAYERS];
     const bf16 *enc_w2a, *enc_w3, *dec_w;
     const SlotDesc *descs;
+    const CtaSched *sched;
     uint8_t *slots;
     int nh, AI;
 };
@@ -1018,8 +1100,19 @@ __global__ void __launch_bounds__(256) mega3_repack_kernel(const __grid_constant
             const int unit = ci >> 5, lane = ci & 31, g = lane >> 2, t = lane & 3;
             if (d.kind == SK_O) {
                 src = (const bf16 *)p.layers[d.layer].w_o + (long)(d.blk * 8 + g) * qd + unit * 32 + 8 * t;
-            } else if (d.kind == SK_D) {     // aux = which half of K = AI
-                src = (const bf16 *)p.layers[d.layer].w_down + (long)(d.blk * 8 + g) * p.AI + (d.aux * 64 + unit) * 32 + 8 * t;
+            } else if (d.kind == SK_DP) {    // blk = CTA, aux = k step: [m tile][lane][a0 a1 a2 a3] of W_down[:, the CTA's columns]
+                const CtaSched &sc = p.sched[d.blk];
+                const int mt = ci >> 5;
+                const bf16 *W = (const bf16 *)p.layers[d.layer].w_down;
+                uint32_t a[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = mt * 16 + g + (q & 1) * 8, k = d.aux * 16 + 2 * t + (q >> 1) * 8;   // local column k, k + 1
+                    a[q] = 0u;
+                    if ((k >> 3) < sc.n_gu)
+                        a[q] = *reinterpret_cast<const uint32_t *>(W + (long)row * p.AI + sc.gu_tile[k >> 3] * 8 + (k & 7));
+                }
+                val = make_uint4(a[0], a[1], a[2], a[3]);
             } else if (unit < 32) {          // K = 1024: half a slot
                 const bf16 *W = d.kind == SK_E3 ? p.enc_w3 : p.dec_w;
                 src = W + (long)(d.blk * 8 + g) * KI + unit * 32 + 8 * t;
@@ -1030,10 +1123,10 @@ __global__ void __launch_bounds__(256) mega3_repack_kernel(const __grid_constant
     }
 }
 
-// host: who does what.  Balances the bytes per CTA and layer (16 KB granules: QKV / gate-up item 2, o_proj block 2,
-// down block 4) with a greedy least-loaded assignment.
+// host: who does what.  Balances the bytes per CTA and layer (16 KB granules: QKV item 2, o_proj block 2, gate-up tile 2 + its
+// 8 columns of the down projection 1) with a greedy least-loaded assignment.
 struct Mega3Plan {
-    int G = 0, NA = 0;
+    int G = 0, NA = 0, NP = 0;
     std::vector<CtaSched> sched;
     std::vector<SlotDesc> descs;
 };
@@ -1049,7 +1142,7 @@ static bool build_plan(const pz_config &c, int B, int num_sms, Mega3Plan &pl) {
     for (int j = 0; j < n_own; ++j) {
         CtaSched &s = pl.sched[j % G];
         s.o_blk[s.n_o++] = j;
-        load[j % G] += 6;
+        load[j % G] += 2;
     }
     auto least = [&](auto ok) {
         int best = -1;
@@ -1061,7 +1154,7 @@ static bool build_plan(const pz_config &c, int B, int num_sms, Mega3Plan &pl) {
         int i = least([](const CtaSched &s) { return s.n_gu < MAXGU; });
         if (i < 0) return false;
         pl.sched[i].gu_tile[pl.sched[i].n_gu++] = tl;
-        load[i] += 2;
+        load[i] += 3;
     }
     for (int q = 0; q < n_qkv; ++q) {
         int i = least([](const CtaSched &s) { return s.n_qkv < MAXQ; });
@@ -1069,6 +1162,9 @@ static bool build_plan(const pz_config &c, int B, int num_sms, Mega3Plan &pl) {
         pl.sched[i].qkv_blk[pl.sched[i].n_qkv++] = q;
         load[i] += 2;
     }
+    pl.NP = 0;
+    for (auto &s : pl.sched) s.pid = s.n_gu > 0 ? pl.NP++ : -1;
+    if (pl.NP > MAXP) return false;
     for (int e = 0; e < n_e2; ++e) pl.sched[e].e2_blk = e;
     pl.sched[G - 1].is_dec = 1;
     // slot order = consumption order (gemv_role)
@@ -1083,7 +1179,7 @@ static bool build_plan(const pz_config &c, int B, int num_sms, Mega3Plan &pl) {
             for (int j = 0; j < s.n_qkv; ++j) pl.descs.push_back({SK_QKV, l, s.qkv_blk[j], 0});
             for (int j = 0; j < s.n_o; ++j) pl.descs.push_back({SK_O, l, s.o_blk[j], 0});
             for (int j = 0; j < s.n_gu; ++j) pl.descs.push_back({SK_GU, l, s.gu_tile[j], 0});
-            for (int j = 0; j < s.n_o; ++j) { pl.descs.push_back({SK_D, l, s.o_blk[j], 0}); pl.descs.push_back({SK_D, l, s.o_blk[j], 1}); }
+            for (int ks = 0; ks < (s.n_gu + 1) / 2; ++ks) pl.descs.push_back({SK_DP, l, i, ks});
         }
         if (s.is_dec) pl.descs.push_back({SK_DEC, 0, 0, 0});
         s.slots_per_step = (int)(pl.descs.size() - first);
@@ -1107,11 +1203,11 @@ bool make_kv_map(CUtensorMap *map, const void *base, int S_c, long slabs) {
 
 size_t ll_words(const pz_config &c, int B) {
     const size_t M = (size_t)B * c.horizon, A = c.act_hidden, qkvw = (size_t)(c.n_heads + 2) * 128;
-    // act, z, 2 x, 2 x1, 2 + 2 sums of squares, 2 qkv, 2 att, 2 mlp (each rounded up to 16 words)
+    // act, z, 2 x, 2 x1, 2 + 2 sums of squares, 2 qkv, 2 att, 2 down partials (each rounded up to 16 words)
     auto r = [](size_t w) { return (w + 15) & ~(size_t)15; };
     const size_t MAXM = M <= 4 ? 4 : 8;
     return r(M * 8) + r(M * A / 2) + 4 * r(M * A / 2) + 4 * r(A / 8 * MAXM) + 2 * r(M * qkvw) + 2 * r(M * (size_t)c.n_heads * 128) +
-           2 * r(M * c.act_inter / 2);
+           2 * r(A / 8 * (size_t)MAXP * 8 * MAXM);
 }
 
 }  // namespace
@@ -1177,6 +1273,7 @@ int denoise_mega3_pack(const pz_config &c, const pz_weights &w, const pz_mix_lay
     for (int l = 0; l < c.n_layers; ++l) rp.layers[l] = layers[l];
     rp.enc_w2a = (const bf16 *)w.enc_w2a; rp.enc_w3 = (const bf16 *)w.enc_w3; rp.dec_w = (const bf16 *)w.dec_w;
     rp.descs = (const SlotDesc *)(base + HDR_BYTES);
+    rp.sched = (const CtaSched *)base;
     rp.slots = base + slots_off;
     rp.nh = c.n_heads; rp.AI = c.act_inter;
     mega3_repack_kernel<<<(unsigned)pl.descs.size(), 256, 0, st>>>(rp);
@@ -1184,7 +1281,7 @@ int denoise_mega3_pack(const pz_config &c, const pz_weights &w, const pz_mix_lay
         if (err) *err = "persistent sampler: re-pack launch failed";
         return PZ_ERR_CUDA;
     }
-    state->buf = buf; state->bytes = bytes; state->B = B; state->G = pl.G; state->NA = pl.NA; state->num_sms = num_sms;
+    state->buf = buf; state->bytes = bytes; state->B = B; state->G = pl.G; state->NA = pl.NA; state->NP = pl.NP; state->num_sms = num_sms;
     state->slots_off = slots_off;
     return 0;
 }
@@ -1217,7 +1314,7 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
     p.B = B; p.H = c.horizon; p.M = M; p.nh = c.n_heads; p.AI = c.act_inter;
     p.S_v = c.s_vlm; p.S_p = c.cond_steps; p.S_c = c.s_vlm + c.cond_steps; p.n_layers = c.n_layers; p.n_steps = c.n_steps;
     p.action_dim = c.action_dim; p.skp = w.small_k_pad;
-    p.G = state.G; p.NA = state.NA;
+    p.G = state.G; p.NA = state.NA; p.NP = state.NP;
     {
         static const int pf = [] { const char *e = getenv("PZ_M3_PF"); return e ? atoi(e) : 0; }();
         p.pf_dist = pf;
@@ -1246,13 +1343,13 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
         for (int i = 0; i < 2; ++i) p.ll_sx1[i] = take(A / 8 * maxm);
         for (int i = 0; i < 2; ++i) p.ll_qkv[i] = take(Mz * qkvw);
         for (int i = 0; i < 2; ++i) p.ll_att[i] = take(Mz * (size_t)c.n_heads * 128);
-        for (int i = 0; i < 2; ++i) p.ll_mlp[i] = take(Mz * c.act_inter / 2);
+        for (int i = 0; i < 2; ++i) p.ll_rs[i] = take(A / 8 * (size_t)state.NP * 8 * maxm);
         p.err = (unsigned int *)q;
         if ((size_t)((char *)q - (char *)bf.ll) + 256 > bf.ll_bytes) {
             if (err) *err = "persistent sampler: exchange workspace too small";
             return PZ_ERR_WORKSPACE;
         }
-        if (cudaMemsetAsync(bf.ll, 0, bf.ll_bytes, st) != cudaSuccess) {
+        if (cudaMemsetAsync(bf.ll, 0, (size_t)((char *)q - (char *)bf.ll) + 256, st) != cudaSuccess) {   // the part in use
             if (err) *err = "persistent sampler: memset failed";
             return PZ_ERR_CUDA;
         }

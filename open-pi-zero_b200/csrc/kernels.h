@@ -92,7 +92,7 @@ int launch_denoise_mega(const pz_config &c, const pz_weights &w, const pz_mix_la
 struct Mega3State {      // filled by denoise_mega3_pack
     void *buf = nullptr;
     size_t bytes = 0, slots_off = 0;
-    int B = 0, G = 0, NA = 0, num_sms = 0;
+    int B = 0, G = 0, NA = 0, NP = 0, num_sms = 0;
 };
 struct Mega3Buffers {
     const void *kcache, *vcache;   // [L][batch_total][S_c][256] bf16

@@ -51,12 +51,13 @@ g = t[:G].astype(np.float64) / khz * 1e3 / n_it          # us per (layer, step)
 a = t[G:sms].astype(np.float64) / khz * 1e3 / n_it
 names = {0: "(between layers)", 1: "x gather", 2: "qkv gemv", 14: "qkv ring wait", 3: "qkv epilogue+publish",
          4: "att gather", 5: "o gemv", 17: "o ring wait", 6: "o epilogue+publish",
-         7: "x1 gather", 8: "gu gemv", 20: "gu ring wait", 9: "gu epilogue+publish",
-         10: "mlp gather", 11: "down gemv", 23: "down ring wait", 12: "down epilogue+publish", 31: "encoder/decoder/other"}
+         7: "x1 gather", 8: "gu gemv", 20: "gu ring wait", 9: "GeGLU epilogue",
+         16: "down partial mma", 28: "down ring wait", 18: "publish partials",
+         10: "partials gather+sum", 12: "residual + publish x", 31: "encoder/decoder/other"}
 print(f"B={B}: {G} streaming CTAs, {sms - G} attention CTAs; us per (layer, step), thread 0 of each CTA")
 print(f"{'bucket':26s} {'min':>7s} {'mean':>7s} {'max':>7s}")
 tot = 0.0
-for e in (0, 1, 2, 14, 3, 4, 5, 17, 6, 7, 8, 20, 9, 10, 11, 23, 12, 31, 24 + 12):
+for e in (0, 1, 2, 14, 3, 4, 5, 17, 6, 7, 8, 20, 9, 16, 28, 18, 10, 12, 31):
     col = g[:, e]
     if col.max() == 0:
         continue
