@@ -9,6 +9,12 @@ one batch of synthetic observations of the bridge shape (BASELINE.json
 configs[1]): 224 px image, 276 image+text tokens, 1 proprio token, chunk 4.
 Per-GPU batch 64, one full replica per GPU, batch-sharded, no collective
 (weak scaling).  Prints ONE JSON line on rank 0.
+
+    --config bridge64     (default, the driver's line) BASELINE configs[1]
+    --config rollout1024  BASELINE configs[2]: bs = 1024 in total, 1024 / N per GPU (strong scaling)
+    --config pi0paper     BASELINE configs[3]: 3 images, 48 text tokens, chunk 50, bs = 256 in total, 256 / N per GPU
+    --ref-compiled        also time the unmodified reference under torch.compile(mode="default") on this GPU
+                          (eval.py:38-40; the first compiled call takes minutes)
 """
 from __future__ import annotations
 
@@ -281,10 +287,114 @@ def denoise_bs1_roofline(model, dims, device, peaks):
                 peak_source=peaks["source"] + ", copy bandwidth")
 
 
-def workload_config(world, B):
-    return dict(workload=f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
-                         "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
-                         "3.24B-parameter model", global_batch=world * B, per_gpu_batch=B,
+def stage_split_bs1(model, dims, device):
+    """bs=1 latency by stage: SigLIP + embedding merge | Gemma prefix (fills the KV cache) | 10 Euler steps, each captured
+    in its own CUDA graph and replayed 20 times between CUDA events."""
+    from open_pi_zero_b200 import _lib
+    lib = _lib.load()
+    inp = pz.make_inputs(dims, 1, seed=7)
+    ids = inp["input_ids"].to(device); pix = inp["pixel_values"].to(device, torch.bfloat16)
+    prop = inp["proprios"].to(device); nz = inp["noise"].to(device); vlen = inp["valid_len"].to(device)
+    out = torch.empty(1, dims["horizon_steps"], dims["action_dim"], device=device)
+    nbytes = lib.pz_workspace_bytes(model._handle, 1)
+    ws_t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    ws = (ws_t.data_ptr() + 1023) // 1024 * 1024
+
+    def stage(i):
+        st = torch.cuda.current_stream().cuda_stream
+        if i == 0:
+            rc = lib.pz_embed_prefix(model._handle, ids.data_ptr(), pix.data_ptr(), ws, nbytes, 1, None, st)
+        elif i == 1:
+            rc = lib.pz_prefill(model._handle, vlen.data_ptr(), prop.data_ptr(), ws, nbytes, 1, None, st)
+        else:
+            rc = lib.pz_denoise(model._handle, vlen.data_ptr(), nz.data_ptr(), out.data_ptr(), ws, nbytes, 1, None, st)
+        assert rc == 0, lib.pz_last_error(model._handle)
+
+    lib.pz_set_pixel_format(model._handle, 0)
+    for i in range(3):
+        stage(i)
+    torch.cuda.synchronize()
+    res = {}
+    for i, name in enumerate(("siglip_embed", "prefix", "denoise_x10")):
+        n0 = lib.pz_launch_count(model._handle)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            stage(i)
+        n1 = lib.pz_launch_count(model._handle)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            g.replay()
+        b.record()
+        b.synchronize()
+        res[name] = dict(ms=a.elapsed_time(b) / 20, launches=int(n1 - n0))
+    return res
+
+
+def reference_compiled(live):
+    """The bar the reference deploys (eval.py:38-40): its model under torch.compile(mode="default").  The first compiled
+    call takes minutes, so the default run quotes the committed measurement of tools/ref_compiled.py; --ref-compiled
+    measures it live."""
+    if live:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_compiled.py"), "--batches", "1"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            return dict(json.loads(r.stdout.strip().splitlines()[-1]), source="measured in this run")
+        except Exception:
+            return dict(error=(r.stderr or r.stdout)[-300:])
+    path = os.path.join(ROOT, "profiles", "r02_ref_compiled.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return dict(json.load(f), source="profiles/r02_ref_compiled.json (tools/ref_compiled.py, separate run on a B200 of this pool)")
+    return None
+
+
+CONFIGS = {
+    # name: (BASELINE.json configs index, total batch or None = PER_GPU_BATCH per GPU, scaling)
+    "bridge64": (1, None, "weak"),
+    "rollout1024": (2, 1024, "strong"),
+    "pi0paper": (3, 256, "strong"),
+}
+
+
+def config_dims(name):
+    return pz.make_dims(pz.PI0_PAPER_DIMS) if name == "pi0paper" else pz.make_dims()
+
+
+def per_gpu_batch(name, world):
+    total = CONFIGS[name][1]
+    if total is None:
+        return PER_GPU_BATCH
+    if total % world:
+        raise SystemExit(f"--config {name}: total batch {total} does not divide over {world} GPUs")
+    return total // world
+
+
+def active_switches(model=None):
+    """Every PZ_* environment switch that is set (12 of them change kernel selection at run time) + the sampler mode."""
+    sw = {k: v for k, v in sorted(os.environ.items()) if k.startswith("PZ_")}
+    if model is not None:
+        sw["sampler_mode"] = {0: "auto", 1: "kernels", 2: "barrier", 3: "stream"}.get(getattr(model, "_sampler_mode", 0), "?")
+        sw["stream_sampler_batches"] = list(getattr(model, "_sampler_batches", []))
+        sw["cuda_graph"] = bool(model.use_cuda_graph)
+    return sw
+
+
+def workload_config(world, B, name="bridge64"):
+    if name == "pi0paper":
+        what = (f"Pi0-paper shape infer_action (BASELINE configs[3]): bs={B} per GPU ({world * B} in total), 3 x 224px images "
+                "(768 image tokens) + 48 text tokens, 1 proprio, chunk 50, 10 Euler steps, random-init 3.24B-parameter model")
+    elif name == "rollout1024":
+        what = (f"batched rollout infer_action (BASELINE configs[2]): bs={world * B} in total, {B} per GPU, 224px image, "
+                "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init 3.24B-parameter model")
+    else:
+        what = (f"bridge infer_action (BASELINE configs[1]): bs={B} per GPU, 224px image, "
+                "276 image+text tokens, 1 proprio, chunk 4, 10 Euler steps, random-init "
+                "3.24B-parameter model")
+    return dict(workload=what, name=name, global_batch=world * B, per_gpu_batch=B,
                 parallelism=f"replica x{world}, batch-sharded, no collective",
                 l2="working set per step (6.5 GB bf16 weights + activations) >> 126 MB L2; no flush")
 
@@ -292,16 +402,20 @@ def workload_config(world, B):
 def reference_arm(args, rank):
     if rank != 0:
         return
-    dims = pz.make_dims()
+    dims = config_dims(args.config)
     torch.set_num_threads(os.cpu_count() or 1)
     sd = pz.init_state_dict(dims, seed=42)
-    times, _, _, kind = cpu_arm(dims, sd, args.steps, max(args.warmup, 1))
+    if args.config == "pi0paper":   # the reference has no multi-image path: its algorithm through the oracle port
+        times, _, _ = run_cpu_oracle(dims, sd, args.steps, max(args.warmup, 1))
+        kind = "port"
+    else:
+        times, _, _, kind = cpu_arm(dims, sd, args.steps, max(args.warmup, 1))
     total = sum(times)
     value = len(times) / total
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload_config(args.gpus, PER_GPU_BATCH),
+                scaling=CONFIGS[args.config][2], vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload_config(args.gpus, per_gpu_batch(args.config, args.gpus), args.config),
                             reference_sample="each step = one infer_action at bs=1 of the same workload, fp32, "
                                              + ("the unmodified reference (baseline/_ref) " if kind == "reference"
                                                 else "reference algorithm (oracle port) ") + "on the host cores"),
@@ -322,6 +436,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-latency", action="store_true", help="profiling runs only")
+    ap.add_argument("--config", default="bridge64", choices=sorted(CONFIGS))
+    ap.add_argument("--ref-compiled", action="store_true",
+                    help="also time the unmodified reference under torch.compile(mode='default') (minutes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -353,11 +470,12 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     warmup = max(args.warmup, 3)
-    dims = pz.make_dims()
-    B = PER_GPU_BATCH
+    dims = config_dims(args.config)
+    B = per_gpu_batch(args.config, world)
+    extras = args.config == "bridge64"          # latency / roofline / CPU legs belong to the headline configuration
     peaks = measured_peaks()
 
-    do_cpu = (world == 1 and not args.no_cpu_baseline)
+    do_cpu = (world == 1 and not args.no_cpu_baseline and extras)
     sd = pz.init_state_dict(dims, seed=42) if do_cpu else None
     model = build_model(dims, device, sd)
     inp = pz.make_inputs(dims, B, seed=1000 + rank)
@@ -435,9 +553,43 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
 
+    # ---- the same, through the reference's stock 8-keyword signature: the two dense block masks and the three position-id
+    #      tensors travel from pinned host memory every step, as a drop-in caller (eval.py) ships them
+    e2e_stock = None
+    if extras and not args.skip_e2e:
+        cm, vpos, ppos, apos = model.build_causal_mask_and_position_ids(inp["attention_mask"], torch.bfloat16)
+        pmask, amask = model.split_full_mask_into_submasks(cm)
+        host2 = {k: v.contiguous().pin_memory() for k, v in dict(
+            input_ids=inp["input_ids"], pixel_values=inp["pixel_values"].to(torch.bfloat16),
+            image_text_proprio_mask=pmask, action_mask=amask, vlm_position_ids=vpos, proprio_position_ids=ppos,
+            action_position_ids=apos, proprios=inp["proprios"].to(torch.bfloat16)).items()}
+        h2d2 = sum(v.numel() * v.element_size() for v in host2.values())
+        out_host2 = torch.empty((B, dims["horizon_steps"], dims["action_dim"]), dtype=torch.bfloat16).pin_memory()
+
+        def stock_step():
+            dv = {k: v.to(device, non_blocking=True) for k, v in host2.items()}
+            out = model(**dv)                         # noise drawn inside, like the reference (pizero.py:454)
+            out_host2.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            stock_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            stock_step()
+        s2 = time.perf_counter() - t0
+        t = torch.tensor([s2], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_stock = dict(value=world * B * args.steps / float(t.item()), unit=UNIT, h2d_bytes_per_step=h2d2,
+                         d2h_bytes_per_step=out_host2.numel() * out_host2.element_size(),
+                         what="model(input_ids, pixel_values, image_text_proprio_mask, action_mask, vlm/proprio/action "
+                              "position ids, proprios) with host tensors: masks + position ids copied and checked every step")
+
     # ---- bs=1 latency (p50) --------------------------------------------------
     lat = None
-    if rank == 0 and not args.skip_latency:
+    if rank == 0 and not args.skip_latency and extras:
         one = {k: v[:1].contiguous() for k, v in dev_in.items()}
         for _ in range(20):
             model(**one)
@@ -450,12 +602,13 @@ def main():
             b.record()
             b.synchronize()
             ts.append(a.elapsed_time(b))
-        lat = dict(p50_ms=statistics.median(ts), min_ms=min(ts), launches=model.last_launch_count)
+        lat = dict(p50_ms=statistics.median(ts), min_ms=min(ts), launches=model.last_launch_count,
+                   stages_ms=stage_split_bs1(model, dims, device))
     sync_all()
 
     # ---- extra: forward half of BASELINE configs[4] (flow-matching loss value, per-GPU bs=32; no backward) ----
     fm = None
-    if rank == 0 and not args.skip_latency:
+    if rank == 0 and not args.skip_latency and extras:
         from open_pi_zero_b200.pizero import PiZero as _PiZero
         Bt = min(32, B)
         g = torch.Generator().manual_seed(7)
@@ -493,12 +646,13 @@ def main():
                     share_of_step=gu_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps, peak_source=peaks["source"] + ", sustained figure")
 
     roof_denoise = None
-    if rank == 0 and not args.skip_latency:
+    if rank == 0 and not args.skip_latency and extras:
         roof_denoise = denoise_bs1_roofline(model, dims, device, peaks)
     sync_all()
 
     cpu = None
     ref_gpu = None
+    ref_compiled = None
     if do_cpu and rank == 0:
         torch.set_num_threads(os.cpu_count() or 1)
         times, want, cinp, kind = cpu_arm(dims, sd, steps=3, warmup=1)
@@ -506,6 +660,7 @@ def main():
                     proprios=cinp["proprios"].to(device), noise=cinp["noise"].to(device),
                     valid_len=cinp["valid_len"].to(device)).cpu()
         ref_gpu = reference_on_gpu(dims, sd, device, B)
+        ref_compiled = reference_compiled(args.ref_compiled)
         cpu = dict(value=len(times) / sum(times), unit=UNIT, cores=torch.get_num_threads(), kind=kind,
                    sample="3 infer_action calls at bs=1 (fp32, " + ("the unmodified reference from baseline/_ref"
                           if kind == "reference" else "oracle port of the reference") + ", all host threads) after 1 warm-up",
@@ -514,12 +669,14 @@ def main():
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup,
-            ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=CONFIGS[args.config][2], vs_baseline=None,
             dtype="bf16", data="synthetic",
-            config=workload_config(world, B),
+            config=workload_config(world, B, args.config),
             clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+            e2e_stock_signature=e2e_stock,
             gpu_launches=launches, latency_bs1=lat, roofline=roof, roofline_denoise_bs1=roof_denoise,
-            cpu_baseline=cpu, reference_gpu_eager=ref_gpu, train_forward=fm)
+            cpu_baseline=cpu, reference_gpu_eager=ref_gpu, reference_gpu_compiled=ref_compiled, train_forward=fm,
+            switches=active_switches(model))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -61,6 +61,7 @@ typedef struct pz_config {
 } pz_config;
 
 #define PZ_FLAG_SIMPLE_KERNELS 1   /* debug: run every op through the plain SIMT kernels */
+#define PZ_FLAG_ALLOW_FALLBACK 2   /* bf16: a shape without a tensor-core kernel runs on the SIMT kernel instead of failing */
 
 /* One SigLIP encoder layer (src/model/paligemma/siglip.py:197-238).  Matrices
  * are `[out,in]` row-major in the handle dtype; vectors are fp32. */
@@ -244,6 +245,10 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *d_input_ids, const void *
 
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);
+
+/* Ops that ran on the plain SIMT kernels because no tensor-core kernel covers their shape, since pz_create.  Always 0
+ * unless PZ_FLAG_ALLOW_FALLBACK is set (without it such a shape fails the call with PZ_ERR_INVALID). */
+int64_t pz_fallback_count(const pz_handle *h);
 
 /* CUDA-event timing of one kernel family inside real calls (bench.py's roofline
  * object).  tag: 1 = VLM gate|up GEMM, 2 = VLM down GEMM, 3 = action gate|up.

@@ -56,6 +56,7 @@ class PzCapture(C.Structure):
 PZ_ABI_VERSION = 5
 PZ_F32, PZ_BF16 = 0, 1
 PZ_FLAG_SIMPLE_KERNELS = 1
+PZ_FLAG_ALLOW_FALLBACK = 2
 PZ_SAMPLER_AUTO, PZ_SAMPLER_KERNELS, PZ_SAMPLER_BARRIER, PZ_SAMPLER_STREAM = 0, 1, 2, 3
 LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 
@@ -63,7 +64,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_sampler_stream_bytes", "pz_sampler_pack", "pz_set_sampler", "pz_infer_action", "pz_embed_prefix",
            "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss",
-           "pz_launch_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
+           "pz_launch_count", "pz_fallback_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
 _lib = None
 
@@ -113,6 +114,8 @@ def load(build_if_needed: bool = True):
     lib.pz_flow_matching_loss.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_launch_count.argtypes = [hp]
     lib.pz_launch_count.restype = C.c_int64
+    lib.pz_fallback_count.argtypes = [hp]
+    lib.pz_fallback_count.restype = C.c_int64
     lib.pz_timing_begin.argtypes = [hp, C.c_int]
     lib.pz_timing_end.argtypes = [hp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.pz_op_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,

@@ -37,6 +37,7 @@ struct pz_handle {
     Mega3State mega3[2];                      // packed item streams of the persistent sampler for batch 1 and 2
     int num_sms = 0;
     int sampler = PZ_SAMPLER_AUTO;            // pz_set_sampler
+    long long fallbacks = 0;                  // ops that ran on the SIMT kernels under PZ_FLAG_ALLOW_FALLBACK
     int timing_tag = 0;                       // 0 = off
     std::vector<cudaEvent_t> ev;              // pairs (start, stop)
     size_t ev_used = 0;
@@ -165,6 +166,9 @@ template <> struct Ops<float> {
     }
 };
 
+// bf16: every shape of the shipped configurations has a tensor-core / skinny kernel.  A shape none of them covers is an
+// ERROR (a silent drop to the SIMT kernels costs ~50x), unless the caller asked for the SIMT kernels
+// (PZ_FLAG_SIMPLE_KERNELS) or explicitly allowed the fallback (PZ_FLAG_ALLOW_FALLBACK; counted, pz_fallback_count).
 template <> struct Ops<bf16> {
     static int linear(pz_handle *h, const LinearArgs &a, cudaStream_t st) {
         if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS)) {
@@ -175,17 +179,28 @@ template <> struct Ops<bf16> {
                 if (rc) return fail(h, rc, e ? e : "tcgen05 gemm launch failed");
                 return 0;
             }
+            if (!(h->cfg.flags & PZ_FLAG_ALLOW_FALLBACK)) {
+                char msg[256];
+                snprintf(msg, sizeof(msg), "no tensor-core kernel for linear M=%d N=%d K=%d lda=%d ldc=%d flags=0x%x "
+                         "(set PZ_FLAG_ALLOW_FALLBACK / PZ_ALLOW_FALLBACK=1 to run it on the SIMT kernel)",
+                         a.M, a.N, a.K, a.lda, a.ldc, a.flags);
+                return fail(h, PZ_ERR_INVALID, msg);
+            }
+            ++h->fallbacks;
         }
         launch_linear_simple<bf16>(a, st);
         return 0;
     }
     static int attention(pz_handle *h, const AttnArgs &a, cudaStream_t st) {
-        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_tc_supported(a))
-            return launch_attn_tc(a, st);     // prefix vlm rows: tcgen05
-        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_tc_vit_supported(a))
-            return launch_attn_tc_vit(a, st); // SigLIP encoder: tcgen05
-        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS) && attn_mma_supported(a))
-            return launch_attn_mma(a, st);
+        if (!(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS)) {
+            if (attn_tc_supported(a)) return launch_attn_tc(a, st);          // prefix vlm rows: tcgen05
+            if (attn_tc_vit_supported(a)) return launch_attn_tc_vit(a, st);  // SigLIP encoder: tcgen05
+            if (attn_mma_supported(a)) return launch_attn_mma(a, st);
+            if (!(h->cfg.flags & PZ_FLAG_ALLOW_FALLBACK))
+                return fail(h, PZ_ERR_INVALID, "no tensor-core kernel for this attention shape (set PZ_FLAG_ALLOW_FALLBACK / "
+                                               "PZ_ALLOW_FALLBACK=1 to run it on the SIMT kernel)");
+            ++h->fallbacks;
+        }
         launch_attn_simple<bf16>(a, st);
         return 0;
     }
@@ -847,6 +862,7 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *ids, const void *pixels, 
 }
 
 int64_t pz_launch_count(const pz_handle *h) { return h ? h->lc.n : 0; }
+int64_t pz_fallback_count(const pz_handle *h) { return h ? h->fallbacks : 0; }
 
 int pz_timing_begin(pz_handle *h, int tag) {
     if (!h) return PZ_ERR_INVALID;

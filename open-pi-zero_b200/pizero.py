@@ -113,6 +113,25 @@ class JointModel(_Holder):
         if owner is None:
             raise PzError("JointModel.forward needs the owning PiZero (construct it through PiZero)")
         names = list(embeds_all.keys())
+        skip = tuple(final_layer_post_attn_skip_names)
+        # decide BEFORE touching the caller's tensors whether this call pattern is one of the three the kernels cover
+        pattern = None
+        if names == ["vlm", "proprio"] and skip == ("vlm", "proprio"):
+            pattern = "prefix"
+        elif names == ["action"] and cache_mode == "append_non_active":
+            pattern = "action"
+        elif names == ["vlm", "proprio", "action"] and not kv_caches and skip == ("vlm", "proprio"):
+            pattern = "joint"
+        if pattern is None:
+            raise NotImplementedError(
+                f"JointModel.forward with active mixtures {names} / cache_mode {cache_mode!r} / skip {skip} is outside the "
+                "infer_action / training-forward paths (\"append\" / \"no_append\" text generation is not built)")
+        if time_cond is not None:
+            raise NotImplementedError("adaLN time conditioning (time_cond) is not built: action_expert_adaptive_mode must be None")
+        if owner.check_inputs not in ("0", "off") and position_ids_all is not None:
+            B_ = embeds_all[names[0]].shape[0]
+            owner._check_position_ids(B_, position_ids_all.get("vlm"), position_ids_all.get("proprio"),
+                                      position_ids_all.get("action"))
         for n in names:
             e = embeds_all[n]
             e *= torch.tensor(e.shape[-1] ** 0.5, dtype=e.dtype, device=e.device)
@@ -121,50 +140,50 @@ class JointModel(_Holder):
         d = owner.dims
         B = embeds_all[names[0]].shape[0]
         Sv = d["max_image_text_tokens"]
-        vlen = (attention_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).contiguous()
+        dev = owner._packed[0][0].device
+        vlen = (attention_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).to(dev).contiguous()
         ws, ws_bytes = owner._ensure_workspace(B)
-        stream = torch.cuda.current_stream(vlen.device).cuda_stream
+        stream = torch.cuda.current_stream(dev).cuda_stream
         f32 = lambda t: t.to(torch.float32).contiguous()   # noqa: E731
-        if names == ["vlm", "proprio"] and tuple(final_layer_post_attn_skip_names) == ("vlm", "proprio"):
-            xv, xp = f32(embeds_all["vlm"]), f32(embeds_all["proprio"])
-            rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
-                                     B, stream)
-            if rc != 0:
-                raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
-            kv_caches.update(owner.kv_caches(B))
-            out = {}
-            return (out, kv_caches) if return_caches else out
-        if names == ["action"] and cache_mode == "append_non_active":
-            if not all(isinstance(kv_caches.get(n), KVCache) and kv_caches[n].has_item(0) for n in self.cache_names):
-                raise PzError("the action pass needs the caches a prefix JointModel.forward(return_caches=True) filled")
-            xa = f32(embeds_all["action"])
-            out = torch.empty_like(xa)
-            rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
-                                     B, stream)
-            if rc != 0:
-                raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
-            res = {"action": out.to(embeds_all["action"].dtype)}
-            return (res, kv_caches) if return_caches else res
-        if names == ["vlm", "proprio", "action"] and not kv_caches and \
-                tuple(final_layer_post_attn_skip_names) == ("vlm", "proprio"):
-            # the training call pattern (pizero.py:637-652) and infer_action_naive's (pizero.py:529-544): all three
-            # mixtures active under the full block mask, no cache.  vlm / proprio rows never attend to action keys
-            # (pizero.py:271-310), so this is the prefix pass followed by the action pass over the prefix's K/V.
-            xv, xp, xa = f32(embeds_all["vlm"]), f32(embeds_all["proprio"]), f32(embeds_all["action"])
-            rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
-                                     B, stream)
-            if rc != 0:
-                raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
-            out = torch.empty_like(xa)
-            rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
-                                     B, stream)
-            if rc != 0:
-                raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
-            res = {"action": out.to(embeds_all["action"].dtype)}
-            return (res, kv_caches) if return_caches else res
-        raise NotImplementedError(
-            f"JointModel.forward with active mixtures {names} / cache_mode {cache_mode!r} is outside the "
-            "infer_action / training-forward paths (\"append\" / \"no_append\" text generation is not built)")
+        # launches go into a stream of `dev`: it must be the current device
+        with torch.cuda.device(dev):
+            if pattern == "prefix":
+                xv, xp = f32(embeds_all["vlm"]), f32(embeds_all["proprio"])
+                rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
+                                         B, stream)
+                if rc != 0:
+                    raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                kv_caches.update(owner.kv_caches(B))
+                out = {}
+                return (out, kv_caches) if return_caches else out
+            if pattern == "action":
+                if not all(isinstance(kv_caches.get(n), KVCache) and kv_caches[n].has_item(0) for n in self.cache_names):
+                    raise PzError("the action pass needs the caches a prefix JointModel.forward(return_caches=True) filled")
+                xa = f32(embeds_all["action"])
+                out = torch.empty_like(xa)
+                rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
+                                         B, stream)
+                if rc != 0:
+                    raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                res = {"action": out.to(embeds_all["action"].dtype)}
+                return (res, kv_caches) if return_caches else res
+            if pattern == "joint":
+                # the training call pattern (pizero.py:637-652) and infer_action_naive's (pizero.py:529-544): all three
+                # mixtures active under the full block mask, no cache.  vlm / proprio rows never attend to action keys
+                # (pizero.py:271-310), so this is the prefix pass followed by the action pass over the prefix's K/V.
+                xv, xp, xa = f32(embeds_all["vlm"]), f32(embeds_all["proprio"]), f32(embeds_all["action"])
+                rc = lib.pz_joint_prefix(owner._handle, xv.data_ptr(), xp.data_ptr(), vlen.data_ptr(), ws, ws_bytes,
+                                         B, stream)
+                if rc != 0:
+                    raise PzError(f"pz_joint_prefix failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                out = torch.empty_like(xa)
+                rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes,
+                                         B, stream)
+                if rc != 0:
+                    raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                res = {"action": out.to(embeds_all["action"].dtype)}
+                return (res, kv_caches) if return_caches else res
+        raise AssertionError("unreachable")
 
 
 class PiZero(nn.Module):
@@ -221,13 +240,22 @@ class PiZero(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._ws_batch = 0
-        self._flags = _lib.PZ_FLAG_SIMPLE_KERNELS if os.environ.get("PZ_SIMPLE_KERNELS") == "1" else 0
+        # kernel-selection flags (include/pz_b200.h): SIMT kernels for every op (debug), or SIMT only for shapes no tensor-core
+        # kernel covers (otherwise such a shape is an error, never a silent 50x slow-down)
+        self._flags = (_lib.PZ_FLAG_SIMPLE_KERNELS if os.environ.get("PZ_SIMPLE_KERNELS") == "1" else 0) | \
+                      (_lib.PZ_FLAG_ALLOW_FALLBACK if os.environ.get("PZ_ALLOW_FALLBACK") == "1" else 0)
         self.use_cuda_graph = os.environ.get("PZ_CUDA_GRAPH", "1") != "0"
         # which Euler-loop implementation (include/pz_b200.h PZ_SAMPLER_*): 0 auto, 1 kernels, 2 barrier, 3 stream
         self._sampler_mode = int(os.environ.get("PZ_SAMPLER", "0"))
         self._sampler_pack_batches = tuple(int(b) for b in os.environ.get("PZ_SAMPLER_BATCHES", "1,2").split(",") if b)
         self._sampler_batches = []
         self.max_graphs = int(os.environ.get("PZ_MAX_GRAPHS", "8"))
+        # dtype of the action chunk infer_action returns: None = the reference's (the dtype of the pixel values, i.e. the
+        # model dtype, pizero.py:454-456,484-490); torch.float32 = the sampler's own fp32 state, unrounded
+        self.action_dtype = None
+        # position ids are compared with the canonical ones on every call (three tiny device comparisons); the dense masks'
+        # block structure only with PZ_CHECK_INPUTS=1 (the kernels apply the canonical block mask)
+        self.check_inputs = os.environ.get("PZ_CHECK_INPUTS", "pos")
         self._graphs = {}
         self._timing_armed = False
         self.last_launch_count = 0
@@ -467,7 +495,7 @@ class PiZero(nn.Module):
             raise PzError(f"pz_bind_weights failed ({rc}): {msg}")
         # bs 1 / 2: per-SM re-packed copy of the action expert for the stream sampler (csrc/denoise_mega3.cu)
         self._sampler_batches = []
-        if T == torch.bfloat16 and not self._flags:
+        if T == torch.bfloat16 and not (self._flags & _lib.PZ_FLAG_SIMPLE_KERNELS):
             with torch.cuda.device(dev):
                 st = torch.cuda.current_stream(dev).cuda_stream
                 for b in self._sampler_pack_batches:
@@ -525,6 +553,35 @@ class PiZero(nn.Module):
         return base, lib.pz_workspace_bytes(self._handle, batch)
 
     # -------------------------------------------------------------- inference
+    def _check_position_ids(self, B, vlm_pos, proprio_pos, action_pos):
+        """The kernels rotate with the canonical positions (1.., pizero.py:312-318); anything else must not silently give
+        the canonical result.  One device comparison per tensor, one host read for all of them."""
+        Sv, Sp, H = self.max_image_text_tokens, self.num_proprio_tokens, self.num_action_tokens
+        ok = None
+        for got, lo, n, nm in ((vlm_pos, 1, Sv, "vlm"), (proprio_pos, 1, Sp, "proprio"), (action_pos, Sp + 1, H, "action")):
+            if got is None:
+                continue
+            if tuple(got.shape) != (B, n):
+                raise ValueError(f"{nm}_position_ids must be [{B}, {n}], got {tuple(got.shape)}")
+            good = (got == torch.arange(lo, lo + n, device=got.device, dtype=got.dtype)).all()
+            ok = good if ok is None else (ok & good.to(ok.device))
+        if ok is not None and not bool(ok):
+            raise ValueError("position ids differ from build_causal_mask_and_position_ids (vlm 1.., proprio 1.., action "
+                             "after the proprio positions): non-canonical position ids are not supported")
+
+    def _check_masks(self, B, image_text_proprio_mask, action_mask):
+        """PZ_CHECK_INPUTS=1: the dense masks must be the block masks of build_causal_mask_and_position_ids for some
+        per-sample valid length (the kernels only take the valid length from them)."""
+        Sv = self.max_image_text_tokens
+        cnt = (image_text_proprio_mask[:, 0, 0, :Sv] == 0).sum(-1)
+        am = (torch.arange(Sv, device=cnt.device)[None, :] < cnt[:, None]).to(torch.int64)
+        full, _, _, _ = self.build_causal_mask_and_position_ids(am, torch.float32)
+        pm, acm = self.split_full_mask_into_submasks(full)
+        if not torch.equal(image_text_proprio_mask == 0, pm.to(image_text_proprio_mask.device) == 0):
+            raise ValueError("image_text_proprio_mask is not a block mask of build_causal_mask_and_position_ids")
+        if action_mask is not None and not torch.equal(action_mask == 0, acm.to(action_mask.device) == 0):
+            raise ValueError("action_mask is not a block mask of build_causal_mask_and_position_ids")
+
     def _valid_len(self, image_text_proprio_mask, input_ids, valid_len):
         if valid_len is not None:
             return valid_len.to(device=input_ids.device, dtype=torch.int32).contiguous()
@@ -558,8 +615,12 @@ class PiZero(nn.Module):
         `build_causal_mask_and_position_ids` returns (checked when
         PZ_CHECK_INPUTS=1).  Extras: `noise` ([B,H,A]; default: torch.randn as
         the reference), `valid_len` (int32 [B], skips the masks entirely),
-        `capture` (dict filled with per-layer tensors for parity tests).
-        Returns fp32 `[B, horizon, action_dim]`."""
+        `capture` (dict filled with per-layer tensors for parity tests; `capture["action"]` is always the fp32 state).
+        Returns `[B, horizon, action_dim]` in the dtype of `pixel_values` like the reference (pizero.py:454-456), or in
+        `self.action_dtype` when that is set (torch.float32: the sampler's fp32 state, unrounded).
+        Run-to-run: the prefill's split-K reductions are fp32 atomics / TMA reduce-adds, so two calls on the same inputs
+        may differ in the last bits of the cache (<= ~2e-3 in the action); the bs <= 2 stream sampler itself is
+        bit-reproducible (tests/test_gpu_sampler.py)."""
         if proprios is None:
             raise TypeError("infer_action() missing required argument: 'proprios'")
         self.pack()
@@ -577,13 +638,10 @@ class PiZero(nn.Module):
                              f"{d['image_size']}, {d['image_size']}], got {tuple(pixel_values.shape)}")
         if proprios.shape != (B, self.num_proprio_tokens, self.proprio_dim):
             raise ValueError(f"proprios must be [B, {self.num_proprio_tokens}, {self.proprio_dim}]")
-        if os.environ.get("PZ_CHECK_INPUTS") == "1":
-            _, vp_, pp_, ap_ = self.build_causal_mask_and_position_ids(
-                torch.ones((B, Sv), dtype=torch.int64, device=dev), torch.float32)
-            for got, want, nm in ((vlm_position_ids, vp_, "vlm"), (proprio_position_ids, pp_, "proprio"),
-                                  (action_position_ids, ap_, "action")):
-                if got is not None and not torch.equal(got.to(dev), want):
-                    raise ValueError(f"{nm}_position_ids differ from build_causal_mask_and_position_ids")
+        if self.check_inputs not in ("0", "off"):
+            self._check_position_ids(B, vlm_position_ids, proprio_position_ids, action_position_ids)
+            if self.check_inputs == "1" and image_text_proprio_mask is not None:
+                self._check_masks(B, image_text_proprio_mask, action_mask)
         ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
         # uint8 camera frames are normalised on the device while the patches are gathered
         # (processing.py:27-58,108-113 fused into the im2col kernel); floats are the reference's argument
@@ -594,8 +652,11 @@ class PiZero(nn.Module):
         if noise is None:   # pizero.py:454-456
             noise = torch.randn((B, H, Adim), device=dev, dtype=self._T if u8 else pixel_values.dtype)
         nz = noise.to(device=dev, dtype=torch.float32).contiguous()
+        out_dtype = self.action_dtype
+        if out_dtype is None:   # pizero.py:454-456: the action chunk has the dtype of the pixel values
+            out_dtype = pixel_values.dtype if pixel_values.is_floating_point() else self._T
         if capture is None and self.use_cuda_graph and not self._timing_armed:
-            return self._replay_graph(B, ids, pix, vlen, prop, nz)
+            return self._replay_graph(B, ids, pix, vlen, prop, nz).to(out_dtype)
         out = torch.empty((B, H, Adim), device=dev, dtype=torch.float32)
         ws, ws_bytes = self._ensure_workspace(B)
         cap_struct, cap_bufs = None, None
@@ -608,7 +669,7 @@ class PiZero(nn.Module):
             capture["kv"] = self.kv_caches(B)
         # keep the inputs alive until the stream has consumed them
         self._inflight = (ids, pix, prop, vlen, nz)
-        return out
+        return out.to(out_dtype)
 
     @torch.no_grad()
     def infer_action_naive(
@@ -657,15 +718,23 @@ class PiZero(nn.Module):
         size into a CUDA graph over static buffers and replayed: launch overhead
         leaves the critical path (eager dispatch is launch-bound)."""
         key = (B, pix.dtype)
-        g = self._graphs.get(key)
+        g = self._graphs.pop(key, None)
+        if g is not None:
+            self._graphs[key] = g          # most recently used last
         if g is None:
+            while len(self._graphs) >= max(self.max_graphs, 1):   # least recently used first (dicts keep insertion order)
+                old = self._graphs.pop(next(iter(self._graphs)))
+                old.clear()
             lib = _lib.load()
             dev = ids.device
-            st = dict(ids=torch.empty_like(ids), pix=torch.empty_like(pix), vlen=torch.empty_like(vlen),
-                      prop=torch.empty_like(prop), nz=torch.empty_like(nz),
-                      out=torch.empty((B, self.horizon_steps, self.action_dim), device=dev, dtype=torch.float32))
-            nbytes = lib.pz_workspace_bytes(self._handle, B)
-            st["ws_t"] = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            # static buffers must be ordinary tensors even if the first call runs under torch.inference_mode(): a later
+            # call under plain no_grad copies into them in place
+            with torch.inference_mode(False):
+                st = dict(ids=torch.empty_like(ids), pix=torch.empty_like(pix), vlen=torch.empty_like(vlen),
+                          prop=torch.empty_like(prop), nz=torch.empty_like(nz),
+                          out=torch.empty((B, self.horizon_steps, self.action_dim), device=dev, dtype=torch.float32))
+                nbytes = lib.pz_workspace_bytes(self._handle, B)
+                st["ws_t"] = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             st["ws"] = (st["ws_t"].data_ptr() + 1023) // 1024 * 1024
             st["ws_bytes"] = nbytes
             for k, v in (("ids", ids), ("pix", pix), ("vlen", vlen), ("prop", prop), ("nz", nz)):
@@ -809,12 +878,13 @@ class PiZero(nn.Module):
         loss = torch.empty((), device=dev, dtype=torch.float32)
         vel = torch.empty((B, H, Adim), device=dev, dtype=torch.float32) if return_velocity else None
         ws, ws_bytes = self._ensure_workspace(B)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        lib.pz_set_pixel_format(self._handle, 1 if u8 else 0)
-        rc = lib.pz_flow_matching_loss(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(), prop.data_ptr(),
-                                       x1.data_ptr(), x0.data_ptr(), tt.data_ptr(), float(self.flow_sig_min),
-                                       loss.data_ptr(), vel.data_ptr() if vel is not None else None, ws, ws_bytes, B,
-                                       stream)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            lib.pz_set_pixel_format(self._handle, 1 if u8 else 0)
+            rc = lib.pz_flow_matching_loss(self._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(), prop.data_ptr(),
+                                           x1.data_ptr(), x0.data_ptr(), tt.data_ptr(), float(self.flow_sig_min),
+                                           loss.data_ptr(), vel.data_ptr() if vel is not None else None, ws, ws_bytes, B,
+                                           stream)
         if rc != 0:
             raise PzError(f"pz_flow_matching_loss failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
         self.last_launch_count = int(lib.pz_launch_count(self._handle))

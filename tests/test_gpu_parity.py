@@ -22,7 +22,9 @@ def _model(d, sd, dtype):
     from open_pi_zero_b200.pizero import PiZeroInference
     m = PiZeroInference(pz.cfg_from_dims(d), init="empty")
     m.load_state_dict(sd, strict=True)
-    return m.to(dtype).to("cuda")
+    m = m.to(dtype).to("cuda")
+    m.action_dtype = torch.float32      # compare the sampler's fp32 state (the default is the reference's: pixel dtype)
+    return m
 
 
 def _run(m, d, inp, capture=True):
@@ -206,6 +208,46 @@ def test_width2_vs_reference_golden(golden_dir, dtype, layer_tol, act_tol):
 def test_bridge_full_size_bf16_vs_reference_golden(golden_dir):
     """Full bridge config (3.24 B parameters, 27 + 18 layers) in bf16."""
     _check_golden(_golden(golden_dir, "bridge"), torch.bfloat16, BF16_LAYER_TOL, BF16_ACTION_TOL, "bridge")
+
+
+def test_bridge64_production_path_vs_reference_golden(golden_dir):
+    """The batch and the path bench.py times (BASELINE configs[1]: bs = 64, CTA-pair tcgen05 GEMMs with the grouped raster,
+    64-sample prefix chunk, one kernel per op in the sampler, CUDA-graph replay, all 27 + 18 layers) against actions the
+    UNMODIFIED reference produced for the same 64 observations (oracle/make_golden.py bridge64), plus sampled hidden-state
+    and K/V rows of four of the samples through the eager path."""
+    fx = _golden(golden_dir, "bridge64")
+    d, B = fx["dims"], fx["batch"]
+    sd = pz.init_state_dict(d, seed=fx["seed"], randomize_norms=fx["randomize_norms"])
+    inp = pz.make_inputs(d, B, seed=fx["inputs_seed"])
+    m = _model(d, sd, torch.bfloat16)
+    del sd
+    ref = fx["ref"]
+    # production path first: graph capture on the first call, replay on the second
+    for _ in range(2):
+        prod, _ = _run(m, d, inp, capture=False)
+    assert any(k[0] == B for k in m._graphs)
+    e_prod = max_abs(prod, ref["action"])
+    # eager path with capture taps
+    out, cap = _run(m, d, inp)
+    worst = 0.0
+    for i, b in enumerate(fx["samples"]):
+        rows = fx["rows"][i]
+        worst = max(worst, rel_err(cap["vit_out"].view(B, -1, d["vit_hidden"])[b, ref["vit_rows"]], ref["vit_out_rows"][i]))
+        for l, want in enumerate(ref["prefix_layers_rows"]):
+            if want["vlm"] is not None:
+                worst = max(worst, rel_err(cap["prefix_vlm"][l, b, rows], want["vlm"][i]))
+        for l, (k2, v2) in enumerate(ref["kv_rows"]["vlm"]):
+            k, v = cap["kv"]["vlm"].get(l)
+            worst = max(worst, rel_err(k[b, 0, rows].float(), k2[i]), rel_err(v[b, 0, rows].float(), v2[i]))
+    for s_, layers in ref["denoise_layers"].items():
+        for l, want in enumerate(layers):
+            worst = max(worst, rel_err(cap["denoise_action"][s_, l][fx["samples"]], want))
+    pre = max_abs(cap["action_preclip"], ref["action_preclip"])
+    print(f"[bridge64 bf16] graph-replay clamped max-abs vs reference {e_prod:.3e}; eager preclip {pre:.3e}; "
+          f"worst sampled-layer rel {worst:.3e}")
+    assert e_prod < BF16_ACTION_TOL
+    assert pre < BF16_ACTION_TOL and max_abs(out, ref["action"]) < BF16_ACTION_TOL
+    assert worst < BF16_LAYER_TOL
 
 
 def test_pi0_paper_shape_multi_image_chunk50():
@@ -405,6 +447,7 @@ def test_full_size_bs1024_rollout_batch_properties():
     d = pz.make_dims()
     m = PiZeroInference(pz.cfg_from_dims(d), init="empty", device="cuda", dtype=torch.bfloat16)
     fill_random_(m, d, seed=42)
+    m.action_dtype = torch.float32
     B = 1024
     inp = pz.make_inputs(d, B, seed=77)
     dev = {k: inp[k].cuda() for k in ("input_ids", "proprios", "noise", "valid_len")}
@@ -424,6 +467,75 @@ def test_full_size_bs1024_rollout_batch_properties():
         e = max_abs(one, big[b:b + 1])
         print(f"[bs1024] sample {b}: max |bs1024 - bs1 (persistent sampler)| = {e:.3e}")
         assert e < BF16_ACTION_TOL
+
+
+def test_drop_in_defaults_dtype_position_ids_and_inference_mode():
+    """What a stock caller of the reference sees: the action chunk comes back in the dtype of the pixel values
+    (pizero.py:454-456,484-490); position ids other than the canonical ones raise instead of silently giving the
+    canonical result; a first call under torch.inference_mode() followed by one under no_grad works (static graph
+    buffers are ordinary tensors); the graph cache is bounded."""
+    from open_pi_zero_b200.pizero import PiZeroInference
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=12, randomize_norms=True)
+    m = PiZeroInference(pz.cfg_from_dims(d), init="empty")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(torch.bfloat16).to("cuda")
+    inp = pz.make_inputs(d, 2, seed=3)
+    mask, vp, pp, ap = m.build_causal_mask_and_position_ids(inp["attention_mask"], torch.bfloat16)   # CPU masks, as the processor builds them
+    pm, am = m.split_full_mask_into_submasks(mask)
+    kw = dict(input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda().bfloat16(),
+              image_text_proprio_mask=pm, action_mask=am, vlm_position_ids=vp.cuda(), proprio_position_ids=pp.cuda(),
+              action_position_ids=ap.cuda(), proprios=inp["proprios"].cuda().bfloat16())
+    with torch.inference_mode():
+        a = m(**kw, noise=inp["noise"].cuda())
+    assert a.dtype == torch.bfloat16 and a.shape == (2, d["horizon_steps"], d["action_dim"])
+    with torch.no_grad():
+        b = m(**kw, noise=inp["noise"].cuda())
+    assert max_abs(a.float(), b.float()) < 1e-2
+    m.action_dtype = torch.float32
+    c = m(**kw, noise=inp["noise"].cuda())
+    assert c.dtype == torch.float32 and max_abs(c, a.float()) < 1e-2
+    bad = dict(kw, action_position_ids=ap.cuda() + 1)
+    with pytest.raises(ValueError, match="position ids"):
+        m(**bad)
+    m.max_graphs = 2
+    for bsz in (1, 2, 3, 4):
+        i2 = pz.make_inputs(d, bsz, seed=bsz)
+        m(input_ids=i2["input_ids"].cuda(), pixel_values=i2["pixel_values"].cuda().bfloat16(), proprios=i2["proprios"].cuda(),
+          valid_len=i2["valid_len"].cuda())
+    assert len(m._graphs) <= 2 and any(k[0] == 4 for k in m._graphs)
+
+
+def test_unsupported_bf16_shape_is_an_error_not_a_silent_simt_fallback(monkeypatch):
+    """A bf16 configuration whose GEMM / attention shapes no tensor-core kernel covers (every dimension shrunk) fails
+    loudly; with PZ_ALLOW_FALLBACK=1 it runs on the SIMT kernels, is counted, and matches the oracle."""
+    from open_pi_zero_b200 import _lib
+    from open_pi_zero_b200.pizero import PiZeroInference, PzError
+    d = pz.make_dims(vocab_size=320, image_token_index=300, max_image_text_tokens=10, num_image_tokens=4,
+                     num_layers=2, num_heads=4, num_kv_heads=1, head_dim=16, vlm_hidden=64, vlm_inter=128,
+                     act_hidden=32, act_inter=64, vit_hidden=32, vit_inter=64, vit_layers=2, vit_heads=2,
+                     image_size=28, patch_size=14)
+    sd = pz.init_state_dict(d, seed=2, randomize_norms=True)
+    inp = pz.make_inputs(d, 2, seed=1)
+    kw = dict(input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda().bfloat16(),
+              proprios=inp["proprios"].cuda(), noise=inp["noise"].cuda(), valid_len=inp["valid_len"].cuda())
+
+    def build():
+        m = PiZeroInference(pz.cfg_from_dims(d), init="empty")
+        m.load_state_dict(sd, strict=True)
+        m = m.to(torch.bfloat16).to("cuda")
+        m.use_cuda_graph = False
+        m.action_dtype = torch.float32
+        return m
+
+    with pytest.raises(PzError, match="no tensor-core kernel"):
+        build()(**kw)
+    monkeypatch.setenv("PZ_ALLOW_FALLBACK", "1")
+    m = build()
+    out = m(**kw)
+    assert _lib.load().pz_fallback_count(m._handle) > 0
+    want = O.infer_action(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], inp["proprios"], inp["noise"])
+    assert max_abs(out, want) < 2e-2
 
 
 def test_errors_are_python_exceptions():

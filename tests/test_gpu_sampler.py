@@ -18,6 +18,7 @@ def _model(d, sd):
     m.load_state_dict(sd, strict=True)
     m = m.to(torch.bfloat16).to("cuda")
     m.use_cuda_graph = False
+    m.action_dtype = torch.float32
     return m
 
 

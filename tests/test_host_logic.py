@@ -166,3 +166,25 @@ def test_flow_sig_min_travels_through_the_config():
     plain = pz.cfg_from_dims(pz.make_dims())
     del plain["flow_sig_min"]                      # the reference's yaml does not carry it (pizero.py:58 default)
     assert pz.dims_from_cfg(plain)["flow_sig_min"] == 0.001
+
+
+def test_joint_model_forward_rejects_unsupported_patterns_before_touching_inputs():
+    """JointModel.forward scales `embeds_all` in place like the reference (joint_model.py:355) -- but only once it knows
+    the call pattern is one the kernels cover; an unsupported one leaves the caller's tensors alone."""
+    from open_pi_zero_b200.pizero import PiZero
+    d = pz.make_dims(vocab_size=320, image_token_index=300, max_image_text_tokens=10, num_image_tokens=4,
+                     num_layers=2, num_heads=4, num_kv_heads=1, head_dim=16, vlm_hidden=64, vlm_inter=128,
+                     act_hidden=32, act_inter=64, vit_hidden=32, vit_inter=64, vit_layers=2, vit_heads=2,
+                     image_size=28, patch_size=14)
+    m = PiZero(pz.cfg_from_dims(d), init="empty")
+    x = torch.ones(2, 10, 64)
+    keep = x.clone()
+    mask = torch.zeros(2, 1, 10, 10)
+    with pytest.raises(NotImplementedError):
+        m.joint_model.forward(mask, {"vlm": None}, {"vlm": x}, cache_mode="append")
+    assert torch.equal(x, keep)
+    a = torch.ones(2, 4, 32)
+    with pytest.raises(NotImplementedError, match="adaLN"):
+        m.joint_model.forward(mask, {"action": None}, {"action": a}, time_cond=torch.zeros(2, 32),
+                              cache_mode="append_non_active")
+    assert torch.equal(a, torch.ones(2, 4, 32))
