@@ -40,8 +40,9 @@ UNIT = "action_chunks/s"
 PER_GPU_BATCH = int(os.environ.get("PZ_BENCH_BATCH", "64"))
 # DRAM bytes of one VLM gate|up GEMM launch at bs=64 (cta_group::2 kernel), from the committed ncu capture
 GATE_UP_DRAM_BYTES = 609.5e6 + 552.6e6   # dram read + write of one launch (profiles/r01_ncu_gemm_dram_raster.txt)
-# DRAM bytes of the bs=1 sampler launch (10 Euler steps), same file
-MEGA_BS1_DRAM_BYTES = 6.323853e9 + 4.368128e6
+# DRAM bytes of the bs=1 sampler launch (10 Euler steps): profiles/r02_ncu_mega3_stream.txt (read + write; the writes are the
+# exchange buffers and their memset)
+MEGA_BS1_DRAM_BYTES = 6.343199e9 + 99.813632e6
 
 
 def measured_peaks():
@@ -279,9 +280,9 @@ def denoise_bs1_roofline(model, dims, device, peaks):
     n_steps = dims["num_inference_steps"]
     bytes_per_launch = n_steps * (629.3e6 + 5.11e6)
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
-    return dict(bound="hbm", kernel="denoise_mega_kernel (10 Euler steps, persistent cooperative)", achieved=achieved,
+    return dict(bound="hbm", kernel="denoise_mega3_kernel (10 Euler steps, persistent stream sampler: bulk-copy weight ring, flag exchanges)", achieved=achieved,
                 peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=MEGA_BS1_DRAM_BYTES,
-                traffic_source="profiles/r01_ncu_full_final.txt (dram read + write of one launch); algorithmic bytes "
+                traffic_source="profiles/r02_ncu_mega3_stream.txt (dram read + write of one launch); algorithmic bytes "
                                f"{bytes_per_launch / 1e9:.3f} GB",
                 avg_launch_ms=ms, launches_timed=reps, kernels_per_launch=int(n_launch),
                 peak_source=peaks["source"] + ", copy bandwidth")

@@ -507,14 +507,10 @@ def test_drop_in_defaults_dtype_position_ids_and_inference_mode():
 
 
 def test_unsupported_bf16_shape_is_an_error_not_a_silent_simt_fallback(monkeypatch):
-    """A bf16 configuration whose GEMM / attention shapes no tensor-core kernel covers (every dimension shrunk) fails
-    loudly; with PZ_ALLOW_FALLBACK=1 it runs on the SIMT kernels, is counted, and matches the oracle."""
+    """A bf16 configuration with a shape no tensor-core kernel covers (head_dim 128) fails loudly; with PZ_ALLOW_FALLBACK=1 it runs on the SIMT kernels, is counted, and matches the oracle."""
     from open_pi_zero_b200 import _lib
     from open_pi_zero_b200.pizero import PiZeroInference, PzError
-    d = pz.make_dims(vocab_size=320, image_token_index=300, max_image_text_tokens=10, num_image_tokens=4,
-                     num_layers=2, num_heads=4, num_kv_heads=1, head_dim=16, vlm_hidden=64, vlm_inter=128,
-                     act_hidden=32, act_inter=64, vit_hidden=32, vit_inter=64, vit_layers=2, vit_heads=2,
-                     image_size=28, patch_size=14)
+    d = pz.make_dims(SMALL, head_dim=128)    # real widths, but the attention kernels are built for head_dim 256
     sd = pz.init_state_dict(d, seed=2, randomize_norms=True)
     inp = pz.make_inputs(d, 2, seed=1)
     kw = dict(input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda().bfloat16(),
