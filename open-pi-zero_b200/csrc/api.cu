@@ -501,7 +501,15 @@ static int action_layers(pz_handle *h, Workspace &ws, const int32_t *valid_len, 
             probe.cmb_splits = (S_c + Hz + 63) / 64; probe.cmb_q_rows = Hz; probe.cmb_heads = nh; probe.cmb_hd = hd;
             if (skinny_supported(probe)) n_splits = launch_attn_mma_partials(a, st);
         }
-        if (n_splits == 0 && fused_rope && decode_attention_supported(c) &&
+        bool done_attn = false;
+        if (n_splits == 0 && fused_rope && decode_attention2_supported(c)) {
+            // one CTA per sample: K and V read once for all heads, RoPE fused, no partials, no combine kernel
+            int rc = launch_decode_attention2(c, w, ws.qkva, ws.kcache, ws.vcache, B, valid_len, l, B, ws.atta, (long)Hz * qd, qd, st);
+            if (rc) return fail(h, rc, "decode attention launch failed");
+            done_attn = true;
+        }
+        if (done_attn) {
+        } else if (n_splits == 0 && fused_rope && decode_attention_supported(c) &&
             a.scratch_bytes >= (size_t)B * ((S_c + Hz + 63) / 64) * nh * Hz * (hd + 2) * sizeof(float)) {
             // one CTA per (sample, key tile), all 8 warps busy, RoPE fused; then the combine kernel
             int ns = launch_decode_attention(c, w, ws.qkva, ws.kcache, ws.vcache, B, valid_len, ws.att_scratch, l, B,

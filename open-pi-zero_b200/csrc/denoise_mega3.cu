@@ -156,6 +156,11 @@ PZ_DEVINL void mbar_wait(const Mega3Params &p, uint64_t *bar, uint32_t parity) {
         }
     }
 }
+// wait without the error-flag plumbing of the persistent kernel (bounded: a lost TMA must not hang the device)
+PZ_DEVINL void mbar_wait_plain(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) if (++spins > (1u << 26)) break;
+}
 PZ_DEVINL void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
@@ -1210,6 +1215,248 @@ size_t ll_words(const pz_config &c, int B) {
            2 * r(A / 8 * (size_t)MAXP * 8 * MAXM);
 }
 
+
+// ============================ stand-alone decode attention (one CTA per sample) ==========================
+// The action rows of the separate-kernel sampler (bs > 2) and of the training forward: joint_model.py:243-282 for the
+// `horizon` query tokens of ALL heads of one sample over the sample's cached prefix K/V + the fresh action rows.
+// MQA shares K/V between the heads, so one CTA serves the whole sample and reads its K and V exactly once: K (all
+// 256 dims, 144 KB, 128-byte swizzled TMA tiles) -> S^T = K q^T for the n_heads x horizon (<= 32) query rows ->
+// soft-cap / mask / exp (no running maximum: |logit| <= 50) -> P in shared memory; then V is loaded over K's tiles and
+// O^T = V^T P^T.  RoPE of q and of the fresh k rows happens while they are staged (fp32).  No split-key partials, no combine
+// kernel (the round-1 pair decode_attn_kernel + decode_combine_kernel: 22 us per layer at bs=64).
+struct DA2Params {
+    int B, H, nh, S_v, S_p, S_c, layer, batch_total, qkvw;
+    const bf16 *qkv;                  // [B * H][qkvw]: q (nh x 256) | k | v, not rotated
+    const float *rope_cos, *rope_sin; // [pos][128]
+    const int32_t *valid_len;
+    bf16 *out;                        // [b][tok][nh x 256]
+    long out_batch_stride;
+    int out_row_stride;
+};
+struct DA2Smem {
+    static constexpr int LDQ = 264, LDP = KEYS + 8;
+    static constexpr int KV = 0;                               // 4 tiles [KEYS][64 dims]: K, later V
+    static constexpr int Q = KV + 4 * KT_BYTES;                // bf16 [32][LDQ]
+    static constexpr int P = Q + 32 * LDQ * 2;                 // bf16 [32][LDP]
+    static constexpr int VF = P + 32 * LDP * 2;                // bf16 [8][256]: the fresh v rows until V's tiles are there
+    static constexpr int LS = VF + 8 * 256 * 2;                // float [NCW][32]
+    static constexpr int BARS = LS + NCW * 32 * 4;             // k_full, v_full
+    static constexpr int END = BARS + 16;
+};
+PZ_DEVINL void da2_request(const DA2Params &p, uint8_t *smem, const CUtensorMap *map, uint64_t *bar, int b, uint64_t pol) {
+    mbar_expect_tx(bar, 4u * KT_BYTES);
+    const int slab = p.layer * p.batch_total + b;
+#pragma unroll
+    for (int dq = 0; dq < 4; ++dq)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)
+            tma_load_3d_hint(map, bar, smem + DA2Smem::KV + dq * KT_BYTES + hb * KBOX * 128, dq * 64, hb * KBOX, slab, pol);
+}
+// rotate dims (8c .. 8c+7, 128 + 8c ..) of one row (model/utils.py:4-16), fp32 math on the bf16 projections
+PZ_DEVINL void da2_rope(const DA2Params &p, const bf16 *src, int c, int pos, uint4 &lo, uint4 &hi) {
+    const uint4 r1 = *reinterpret_cast<const uint4 *>(src + c * 8), r2 = *reinterpret_cast<const uint4 *>(src + 128 + c * 8);
+    const float4 *cs = reinterpret_cast<const float4 *>(p.rope_cos + (long)pos * 128 + c * 8);
+    const float4 *sn = reinterpret_cast<const float4 *>(p.rope_sin + (long)pos * 128 + c * 8);
+    const float4 c0 = __ldg(cs), c1 = __ldg(cs + 1), s0 = __ldg(sn), s1 = __ldg(sn + 1);
+    const float cf[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sf[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const uint32_t w1[4] = {r1.x, r1.y, r1.z, r1.w}, w2[4] = {r2.x, r2.y, r2.z, r2.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float x1a = bf16lo(w1[j]), x1b = bf16hi(w1[j]), x2a = bf16lo(w2[j]), x2b = bf16hi(w2[j]);
+        o1[j] = pack_bf16x2(x1a * cf[2 * j] - x2a * sf[2 * j], x1b * cf[2 * j + 1] - x2b * sf[2 * j + 1]);
+        o2[j] = pack_bf16x2(x2a * cf[2 * j] + x1a * sf[2 * j], x2b * cf[2 * j + 1] + x1b * sf[2 * j + 1]);
+    }
+    lo = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    hi = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+}
+PZ_DEVINL uint32_t da2_tile_off(int row, int d) {   // byte offset of dims d .. d+7 (d % 8 == 0) of a K / V row inside the 4 tiles
+    return (uint32_t)((d >> 6) * KT_BYTES) + swz(row, (d & 63) >> 3);
+}
+
+// NN: 8-row N tiles of query rows per CTA; 32 / (8 NN) CTAs share a sample (each loads K and V: the extra reads are L2 hits)
+template <int NN>
+__global__ void __launch_bounds__(NCT, 1) decode_attn2_kernel(const __grid_constant__ DA2Params p,
+                                                              const __grid_constant__ CUtensorMap kmap,
+                                                              const __grid_constant__ CUtensorMap vmap) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = align_smem(smem_raw, 1024);
+    using S = DA2Smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    constexpr int GROUPS = 4 / NN;
+    const int b = blockIdx.x / GROUPS, row_base = (blockIdx.x % GROUPS) * (8 * NN);   // first query row of this CTA
+    bf16 *sQ = reinterpret_cast<bf16 *>(smem + S::Q);
+    bf16 *sP = reinterpret_cast<bf16 *>(smem + S::P);
+    bf16 *sVF = reinterpret_cast<bf16 *>(smem + S::VF);
+    float *sLS = reinterpret_cast<float *>(smem + S::LS);
+    uint64_t *k_full = reinterpret_cast<uint64_t *>(smem + S::BARS), *v_full = k_full + 1;
+    const int H = p.H, S_c = p.S_c, n_keys = S_c + H, n_mt = (n_keys + 15) >> 4, rows = p.nh * H;
+    const uint64_t pol = policy_evict_first();
+    if (tid == 0) {
+        mbar_init(k_full, 1); mbar_init(v_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        da2_request(p, smem, &kmap, k_full, b, pol);   // the cached K does not depend on the previous kernel
+    }
+    // rows nobody writes must be zero (pad query rows, P beyond the key count)
+    for (int i = tid; i < 32 * S::LDQ / 2; i += NCT) reinterpret_cast<uint32_t *>(sQ)[i] = 0u;
+    for (int i = tid; i < 32 * S::LDP / 2; i += NCT) reinterpret_cast<uint32_t *>(sP)[i] = 0u;
+    pdl_trigger();
+    pdl_wait();                                        // q | k | v of this layer come from the QKV projection before us
+    __syncthreads();
+    const int vlen = p.valid_len[b];
+    // ---- stage q (all heads, rotated), keep the fresh k rows (rotated) in registers until K's tiles have landed
+    for (int i = tid; i < 8 * NN * 16; i += NCT) {
+        const int rl = i >> 4, r = row_base + rl, c = i & 15, head = r / H, tok = r % H;
+        if (r >= rows) continue;
+        uint4 lo, hi;
+        da2_rope(p, p.qkv + (long)(b * H + tok) * p.qkvw + head * 256, c, p.S_p + tok, lo, hi);
+        *reinterpret_cast<uint4 *>(sQ + rl * S::LDQ + c * 8) = lo;
+        *reinterpret_cast<uint4 *>(sQ + rl * S::LDQ + 128 + c * 8) = hi;
+    }
+    uint4 klo = make_uint4(0, 0, 0, 0), khi = klo;
+    const bool has_k = tid < H * 16;                   // (tok, chunk)
+    if (has_k) da2_rope(p, p.qkv + (long)(b * H + (tid >> 4)) * p.qkvw + p.nh * 256, tid & 15, p.S_p + (tid >> 4), klo, khi);
+    for (int i = tid; i < H * 32; i += NCT) {          // fresh v rows, plain copy
+        const int tok = i >> 5, c = i & 31;
+        *reinterpret_cast<uint4 *>(sVF + tok * 256 + c * 8) =
+            *reinterpret_cast<const uint4 *>(p.qkv + (long)(b * H + tok) * p.qkvw + (p.nh + 1) * 256 + c * 8);
+    }
+    mbar_wait_plain(k_full, 0);
+    if (has_k) {
+        const int row = S_c + (tid >> 4), c = tid & 15;
+        *reinterpret_cast<uint4 *>(smem + S::KV + da2_tile_off(row, c * 8)) = klo;
+        *reinterpret_cast<uint4 *>(smem + S::KV + da2_tile_off(row, 128 + c * 8)) = khi;
+    }
+    __syncthreads();
+    // ---- S^T = K q^T: 16-key tiles over the warps (M), the 32 query rows as four 8-wide N tiles
+    {
+        constexpr int MAXT = (KEYS / 16 + NCW - 1) / NCW;   // 3
+        const int rho = ((g & 1) << 2) | (g >> 1);          // conflict-free row order under the 128-byte swizzle
+        float ls[NN][2];
+#pragma unroll
+        for (int n = 0; n < NN; ++n) ls[n][0] = ls[n][1] = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < MAXT; ++i) {
+            const int mt = warp + i * NCW;
+            if (mt >= n_mt) break;
+            const int r0 = mt * 16 + rho, r1 = r0 + 8;
+            float sa[NN][4], sb[NN][4];
+#pragma unroll
+            for (int n = 0; n < NN; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sa[n][e] = sb[n][e] = 0.f;
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                const uint8_t *tile = smem + S::KV + (kc >> 1) * KT_BYTES;
+                const int ch = (kc & 1) * 4 + t;
+                const uint4 lo = *reinterpret_cast<const uint4 *>(tile + swz(r0, ch));
+                const uint4 hi = *reinterpret_cast<const uint4 *>(tile + swz(r1, ch));
+#pragma unroll
+                for (int n = 0; n < NN; ++n) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sQ + (n * 8 + g) * S::LDQ + kc * 32 + 8 * t);
+                    mma_bf16(sa[n], lo.x, hi.x, lo.y, hi.y, q.x, q.y);
+                    mma_bf16(sb[n], lo.z, hi.z, lo.w, hi.w, q.z, q.w);
+                }
+            }
+            const float scale = 0.0625f, cap = 50.f;   // 1/sqrt(256); soft-cap (joint_model.py:139,261-268)
+            const bool vis0 = (r0 < vlen) || (r0 >= p.S_v && r0 < n_keys);
+            const bool vis1 = (r1 < vlen) || (r1 >= p.S_v && r1 < n_keys);
+#pragma unroll
+            for (int n = 0; n < NN; ++n) {
+                float pe[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    pe[e] = sel_or_zero(e < 2 ? vis0 : vis1, __expf(tanh_fast_acc((sa[n][e] + sb[n][e]) * (scale / cap)) * cap));
+                ls[n][0] += pe[0] + pe[2];
+                ls[n][1] += pe[1] + pe[3];
+                const int q0 = n * 8 + 2 * t;
+                sP[q0 * S::LDP + r0] = __float2bfloat16_rn(pe[0]);
+                sP[q0 * S::LDP + r1] = __float2bfloat16_rn(pe[2]);
+                sP[(q0 + 1) * S::LDP + r0] = __float2bfloat16_rn(pe[1]);
+                sP[(q0 + 1) * S::LDP + r1] = __float2bfloat16_rn(pe[3]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                ls[n][0] += __shfl_xor_sync(0xffffffffu, ls[n][0], o);
+                ls[n][1] += __shfl_xor_sync(0xffffffffu, ls[n][1], o);
+            }
+            if (g == 0) { sLS[warp * 32 + n * 8 + 2 * t] = ls[n][0]; sLS[warp * 32 + n * 8 + 2 * t + 1] = ls[n][1]; }
+        }
+    }
+    __syncthreads();   // every warp is done with K
+    // ---- V over K's tiles
+    if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        da2_request(p, smem, &vmap, v_full, b, pol);
+    }
+    mbar_wait_plain(v_full, 0);
+    for (int i = tid; i < H * 32; i += NCT) {
+        const int tok = i >> 5, c = i & 31;
+        *reinterpret_cast<uint4 *>(smem + S::KV + da2_tile_off(S_c + tok, c * 8)) = *reinterpret_cast<const uint4 *>(sVF + tok * 256 + c * 8);
+    }
+    __syncthreads();
+    // ---- O^T = V^T P^T: warp -> 32 dims (two 16-dim M tiles), the 32 query rows as four N tiles, keys = K dimension
+    {
+        float o[2][NN][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NN; ++n) o[m][n][0] = o[m][n][1] = o[m][n][2] = o[m][n][3] = 0.f;
+        const uint32_t tile = smem_u32(smem + S::KV) + (warp >> 1) * KT_BYTES;
+        const int c00 = (warp & 1) * 4;
+        const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll 2
+        for (int kk = 0; kk < n_mt; ++kk) {
+            const int key = kk * 16 + (mi >> 1) * 8 + rr;
+            uint32_t a0[4], a1[4];
+            ldsm_x4_t(a0, tile + swz(key, c00 + (mi & 1)));
+            ldsm_x4_t(a1, tile + swz(key, c00 + 2 + (mi & 1)));
+#pragma unroll
+            for (int n = 0; n < NN; ++n) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(sP + (n * 8 + g) * S::LDP + kk * 16 + 2 * t);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(sP + (n * 8 + g) * S::LDP + kk * 16 + 8 + 2 * t);
+                mma_bf16(o[0][n], a0[0], a0[1], a0[2], a0[3], b0, b1);
+                mma_bf16(o[1][n], a1[0], a1[1], a1[2], a1[3], b0, b1);
+            }
+        }
+        // c0, c1: O^T[d = 32 warp + 16 m + g][query row 8 n + 2t, + 1]; c2, c3: d + 8.  Neighbouring dims (lane + 4) pair up.
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+            float inv[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float l = 0.f;
+#pragma unroll
+                for (int w = 0; w < NCW; ++w) l += sLS[w * 32 + n * 8 + 2 * t + j];
+                inv[j] = l > 0.f ? 1.f / l : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float e[4] = {o[m][n][0] * inv[0], o[m][n][1] * inv[1], o[m][n][2] * inv[0], o[m][n][3] * inv[1]};
+                float nb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nb[i] = __shfl_down_sync(0xffffffffu, e[i], 4);
+                if (!(g & 1)) {
+                    const int d0 = warp * 32 + m * 16 + g;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int r = row_base + n * 8 + 2 * t + j;
+                        if (r < rows) {
+                            const int head = r / H, tok = r % H;
+                            bf16 *dst = p.out + (long)b * p.out_batch_stride + (long)tok * p.out_row_stride + head * 256;
+                            *reinterpret_cast<uint32_t *>(dst + d0) = pack_bf16x2(e[j], nb[j]);
+                            *reinterpret_cast<uint32_t *>(dst + d0 + 8) = pack_bf16x2(e[2 + j], nb[2 + j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------- host side ----
@@ -1368,5 +1615,39 @@ int launch_denoise_mega3(const pz_config &c, const pz_weights &w, const pz_mix_l
         return PZ_ERR_CUDA;
     }
     count_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------- stand-alone decode attention (host) ----
+int decode_attention2_supported(const pz_config &c) {
+    static const bool off = [] { const char *e = getenv("PZ_DECODE_ATTN2"); return e && e[0] == '0'; }();
+    return !off && c.dtype == PZ_BF16 && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && c.head_dim == 256 && c.n_kv_heads == 1 &&
+           c.n_heads * c.horizon <= 32 && c.horizon <= 8 && c.s_vlm + c.cond_steps + c.horizon <= KEYS;
+}
+
+int launch_decode_attention2(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache, const void *vcache,
+                             int batch_total, const int32_t *valid_len, int layer, int B, void *out, long out_batch_stride,
+                             int out_row_stride, cudaStream_t st) {
+    constexpr int smem = DA2Smem::END + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    // few samples: two CTAs per sample (16 query rows each) so that more SMs share the work
+    const int device_sms = device_sm_count();
+    const bool two = c.n_heads * c.horizon > 16 && 2 * B <= device_sms;
+    static PerDeviceOnce attr_once[2];
+    if (attr_once[two ? 1 : 0].need() &&
+        cudaFuncSetAttribute(two ? decode_attn2_kernel<2> : decode_attn2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess)
+        return PZ_ERR_CUDA;
+    DA2Params p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = c.horizon; p.nh = c.n_heads; p.S_v = c.s_vlm; p.S_p = c.cond_steps; p.S_c = c.s_vlm + c.cond_steps;
+    p.layer = layer; p.batch_total = batch_total; p.qkvw = (c.n_heads + 2) * 256;
+    p.qkv = (const bf16 *)qkv; p.rope_cos = w.rope_act_cos; p.rope_sin = w.rope_act_sin; p.valid_len = valid_len;
+    p.out = (bf16 *)out; p.out_batch_stride = out_batch_stride; p.out_row_stride = out_row_stride;
+    CUtensorMap kmap, vmap;
+    const long slabs = (long)c.n_layers * batch_total;
+    if (!make_kv_map(&kmap, kcache, p.S_c, slabs) || !make_kv_map(&vmap, vcache, p.S_c, slabs)) return PZ_ERR_CUDA;
+    if (two) launch_k(decode_attn2_kernel<2>, dim3(2 * B), dim3(NCT), (size_t)smem, st, p, kmap, vmap);
+    else launch_k(decode_attn2_kernel<4>, dim3(B), dim3(NCT), (size_t)smem, st, p, kmap, vmap);
     return 0;
 }

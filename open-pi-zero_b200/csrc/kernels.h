@@ -118,3 +118,8 @@ int launch_decode_attention(const pz_config &c, const pz_weights &w, const void 
                             const void *vcache, int batch_total, const int32_t *valid_len, float *partials, int layer,
                             int B, void *out, long out_batch_stride, int out_row_stride, cudaStream_t st);
 int launch_attn_combine(const AttnArgs &a, int n_splits, cudaStream_t st);
+// one CTA per sample, K and V read once, no split-key partials (denoise_mega3.cu)
+int decode_attention2_supported(const pz_config &c);
+int launch_decode_attention2(const pz_config &c, const pz_weights &w, const void *qkv, const void *kcache, const void *vcache,
+                             int batch_total, const int32_t *valid_len, int layer, int B, void *out, long out_batch_stride,
+                             int out_row_stride, cudaStream_t st);
