@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 5
+#define PZ_ABI_VERSION 6
 
 typedef enum pz_status {
     PZ_OK = 0,
@@ -110,6 +110,10 @@ typedef struct pz_weights {
     const void  *enc_w2t;               /* action_encoder.linear_2.weight[:, :A] -> [A, A] (time half) */
     const float *enc_b2;                /* action_encoder.linear_2.bias [A] */
     const float *time_freq;             /* [A/2] fp32: exp(-i ln(time_max_period) / (A/2 - 1)), vla/modules.py:15-19 */
+    /* ABI 6: optional text output (pizero.py:105-112, 559-593); NULL / 0 when the model has no lm_head */
+    const float *vlm_final_norm;        /* joint_model.mixtures.vlm.norm.weight [H] (mixture.vlm.use_final_norm) */
+    const void  *lm_head;               /* [vocab, H], usually the embed pointer (tied, pizero.py:112) */
+    int32_t rope_vlm_rows;              /* rows of rope_vlm_cos / _sin (0 = s_vlm): decode steps need positions > s_vlm */
 } pz_weights;
 
 /* Optional capture taps for per-layer parity tests (all fp32 device buffers,
@@ -242,6 +246,19 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *d_input_ids, const void *
                           const int32_t *d_valid_len, const float *d_proprio, const float *d_actions,
                           const float *d_noise, const float *d_t, float sig_min, float *d_loss, float *d_v_psi,
                           void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+
+/* Text output, replaces PiZero.infer_text (pizero.py:559-593; only the vlm mixture, all layers, final norm, lm_head).
+ * pz_text_prefill runs AFTER pz_embed_prefix on the same workspace (it consumes the merged embeddings) and fills the
+ * caller-owned text cache d_kcache / d_vcache [n_layers][batch][cache_rows][head_dim] (model dtype; K post-RoPE).
+ * Prompts are not padded (pizero.py:346-357): q_len valid tokens per sample, d_valid_len[b] = q_len.
+ *   d_logits  fp32 [batch, s_vlm, vocab] (rows >= q_len are meaningless), or [batch, vocab] = the last prompt token with
+ *             last_only != 0, or NULL (cache only)
+ * pz_text_decode appends ONE token per sample at cache row cur_len (position cur_len + 1, `cache_mode="append"`,
+ * joint_model.py:164-240): d_x fp32 [batch, H] = embedding * sqrt(H); d_valid_len1[b] = cur_len + 1; d_logits [batch, vocab]. */
+int pz_text_prefill(pz_handle *h, const int32_t *d_valid_len, void *d_kcache, void *d_vcache, int cache_rows, int q_len,
+                    float *d_logits, int last_only, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+int pz_text_decode(pz_handle *h, const float *d_x, const int32_t *d_valid_len1, int cur_len, void *d_kcache, void *d_vcache,
+                   int cache_rows, float *d_logits, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);

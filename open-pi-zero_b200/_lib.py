@@ -44,7 +44,8 @@ class PzWeights(C.Structure):
                 ("dec_w", vp), ("dec_b", vp),
                 ("rope_vlm_cos", vp), ("rope_vlm_sin", vp), ("rope_act_cos", vp),
                 ("rope_act_sin", vp), ("small_k_pad", C.c_int32),
-                ("enc_w2t", vp), ("enc_b2", vp), ("time_freq", vp)]
+                ("enc_w2t", vp), ("enc_b2", vp), ("time_freq", vp),
+                ("vlm_final_norm", vp), ("lm_head", vp), ("rope_vlm_rows", C.c_int32)]
 
 
 class PzCapture(C.Structure):
@@ -53,7 +54,7 @@ class PzCapture(C.Structure):
                                   "action_preclip")]
 
 
-PZ_ABI_VERSION = 5
+PZ_ABI_VERSION = 6
 PZ_F32, PZ_BF16 = 0, 1
 PZ_FLAG_SIMPLE_KERNELS = 1
 PZ_FLAG_ALLOW_FALLBACK = 2
@@ -63,7 +64,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_sampler_stream_bytes", "pz_sampler_pack", "pz_set_sampler", "pz_infer_action", "pz_embed_prefix",
-           "pz_prefill", "pz_denoise", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss",
+           "pz_prefill", "pz_denoise", "pz_text_prefill", "pz_text_decode", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss",
            "pz_launch_count", "pz_fallback_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
 
 _lib = None
@@ -112,6 +113,8 @@ def load(build_if_needed: bool = True):
     lib.pz_joint_action.argtypes = [hp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_velocity.argtypes = [hp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_flow_matching_loss.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_text_prefill.argtypes = [hp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_text_decode.argtypes = [hp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_launch_count.argtypes = [hp]
     lib.pz_launch_count.restype = C.c_int64
     lib.pz_fallback_count.argtypes = [hp]

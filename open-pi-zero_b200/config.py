@@ -33,6 +33,8 @@ BRIDGE_DIMS = dict(
     # SigLIP-So400m/14 (bridge.yaml:136-145)
     vit_hidden=1152, vit_inter=4304, vit_layers=27, vit_heads=16,
     image_size=224, patch_size=14,
+    # optional text output (pizero.py:37,105-112; the reference's --text_only run sets both, pizero.py:712-714)
+    use_lm_head=False, vlm_use_final_norm=False,
 )
 
 # Pi0-paper shape (BASELINE.json configs[3]): 3 images, 48 text tokens, chunk 50.
@@ -76,7 +78,7 @@ def cfg_from_dims(d: dict) -> AttrDict:
                     rope_theta=theta)
 
     mixture = dict(
-        vlm=mix(d["vlm_hidden"], d["vlm_inter"], False, True, d["vlm_rope_theta"]),
+        vlm=mix(d["vlm_hidden"], d["vlm_inter"], bool(d.get("vlm_use_final_norm", False)), True, d["vlm_rope_theta"]),
         proprio=mix(d["act_hidden"], d["act_inter"], True, True, d["act_rope_theta"]),
         action=mix(d["act_hidden"], d["act_inter"], True, False, d["act_rope_theta"]),
     )
@@ -90,6 +92,7 @@ def cfg_from_dims(d: dict) -> AttrDict:
         action_expert_adaptive_mode=None, time_hidden_size=256,
         time_max_period=d["time_max_period"], num_images=d.get("num_images", 1),
         flow_sig_min=d.get("flow_sig_min", 0.001),
+        use_lm_head=bool(d.get("use_lm_head", False)),
         mixture=mixture,
         vision=dict(config=dict(hidden_size=d["vit_hidden"], intermediate_size=d["vit_inter"],
                                 num_hidden_layers=d["vit_layers"],
@@ -157,4 +160,6 @@ def dims_from_cfg(cfg) -> dict:
         vit_hidden=vis["hidden_size"], vit_inter=vis["intermediate_size"],
         vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"],
         image_size=vis["image_size"], patch_size=vis["patch_size"],
+        use_lm_head=bool(_g(cfg, "use_lm_head", False)),
+        vlm_use_final_norm=bool(_g(mixture["vlm"], "use_final_norm", False)),
     )

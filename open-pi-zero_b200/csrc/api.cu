@@ -642,6 +642,110 @@ static int run_flow_loss(pz_handle *h, const int32_t *valid_len, const float *ac
     return 0;
 }
 
+// --------------------------------------------- text output (PiZero.infer_text, pizero.py:559-593) ------
+// Only the vlm mixture is active, ALL layers run to the end (`final_layer_post_attn_skip_names=[]`), the final norm of the
+// vlm mixture and the (tied) lm_head follow.  K / V go to a caller-owned text cache [layers][B][cache_rows][head_dim]
+// that later decode steps append to (`cache_mode="append"`, joint_model.py:164-240).  Prompts are not padded
+// (pizero.py:346-357 "assume no padding"): every sample has q_len valid tokens, positions 1 .. q_len.
+template <typename T>
+static int run_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache, void *vcache, int cache_rows, int q_len,
+                            float *logits, int last_only, void *wsp, int B, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    if (!w.vlm_final_norm || !w.lm_head) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head (use_lm_head / mixture.vlm.use_final_norm)");
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int H = c.vlm_hidden, hd = c.head_dim, nh = c.n_heads, S_v = c.s_vlm;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)cache_rows * hd;
+    if (q_len < 1 || q_len > S_v || cache_rows < S_v) return fail(h, PZ_ERR_INVALID, "text prefill: 1 <= q_len <= max_image_text_tokens <= cache_rows");
+    for (int b0 = 0; b0 < B; b0 += h->prefix_chunk) {
+        const int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
+        const int M = nb * S_v;
+        float *x = ws.x + (size_t)b0 * S_v * H;
+        for (int l = 0; l < c.n_layers; ++l) {
+            T *Kc = (T *)kcache + ((size_t)l * B + b0) * kv_bs;
+            T *Vc = (T *)vcache + ((size_t)l * B + b0) * kv_bs;
+            launch_rmsnorm<T>(x, h->vlm[l].norm_in, (T *)ws.h, M, H, 1e-6f, st);
+            if (std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && hd == 256 && H % 8 == 0) {
+                const char *e = nullptr;
+                int rc = launch_qkv_rope_tc(ws.h, H, h->vlm[l].w_qkv, ws.q, Kc, Vc, kv_bs, w.rope_vlm_cos, w.rope_vlm_sin, M, H, nh,
+                                            S_v, st, &e);
+                if (rc) return fail(h, rc, e ? e : "fused qkv+rope launch failed");
+            } else {
+                PZ_TRY(Ops<T>::linear(h, lin(ws.h, H, h->vlm[l].w_qkv, nullptr, ws.qkv, qkvd, M, qkvd, H), st));
+                launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)S_v * qd, Kc, Vc, kv_bs, w.rope_vlm_cos,
+                                     w.rope_vlm_sin, nb, S_v, 0, nh, hd, st);
+            }
+            AttnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.K = Kc; a.V = Vc; a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+            a.valid_len = valid_len + b0;
+            a.batch = nb; a.n_heads = nh; a.head_dim = hd; a.s_cache = cache_rows; a.s_vlm = S_v; a.n_fresh = 0;
+            a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+            a.q_row_stride = qd; a.q_head_stride = hd; a.o_row_stride = qd; a.o_head_stride = hd;
+            a.Q = ws.q; a.q_batch_stride = (long)S_v * qd; a.O = ws.att; a.o_batch_stride = (long)S_v * qd;
+            a.q_rows = S_v; a.q_row0 = 0;
+            PZ_TRY(Ops<T>::attention(h, a, st));
+            PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, M, H, c.vlm_inter, st));
+        }
+        if (!logits) continue;
+        if (last_only) {
+            // logits of the last prompt token only: [B, vocab]
+            float *xg = (float *)ws.mlp;   // idle now
+            cudaMemcpy2DAsync(xg, (size_t)H * 4, x + (size_t)(q_len - 1) * H, (size_t)S_v * H * 4, (size_t)H * 4, nb,
+                              cudaMemcpyDeviceToDevice, st);
+            PZ_TRY(norm_linear<T>(h, xg, w.vlm_final_norm, ws.h,
+                                  lin(nullptr, H, w.lm_head, nullptr, logits + (size_t)b0 * c.vocab_size, c.vocab_size, nb,
+                                      c.vocab_size, H, LIN_OUT_F32), H, st));
+        } else {
+            launch_rmsnorm<T>(x, w.vlm_final_norm, (T *)ws.h, M, H, 1e-6f, st);
+            PZ_TRY(Ops<T>::linear(h, lin(ws.h, H, w.lm_head, nullptr, logits + (size_t)b0 * S_v * c.vocab_size, c.vocab_size, M,
+                                         c.vocab_size, H, LIN_OUT_F32), st));
+        }
+    }
+    return 0;
+}
+
+// One decode step: the embedding of one new token per sample (already scaled by sqrt(hidden), joint_model.py:355) at row
+// `cur_len` of the cache, position cur_len + 1; attends rows 0 .. cur_len (no padding).  logits: [B, vocab].
+template <typename T>
+static int run_text_decode(pz_handle *h, const float *x_in, const int32_t *valid_len1, int cur_len, void *kcache, void *vcache,
+                           int cache_rows, float *logits, void *wsp, int B, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    if (!w.vlm_final_norm || !w.lm_head) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head");
+    if (cur_len < 1 || cur_len >= cache_rows || cur_len >= (w.rope_vlm_rows > 0 ? w.rope_vlm_rows : c.s_vlm)) return fail(h, PZ_ERR_INVALID, "text decode: cache / RoPE table exhausted");
+    Workspace ws = carve(c, B, h->prefix_chunk, wsp);
+    const int H = c.vlm_hidden, hd = c.head_dim, nh = c.n_heads;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)cache_rows * hd;
+    float *x = ws.x;   // [B, H] fp32 residual stream of the new tokens
+    copy_f32(x, x_in, (size_t)B * H, st);
+    for (int l = 0; l < c.n_layers; ++l) {
+        T *Kc = (T *)kcache + (size_t)l * B * kv_bs;
+        T *Vc = (T *)vcache + (size_t)l * B * kv_bs;
+        PZ_TRY(norm_linear<T>(h, x, h->vlm[l].norm_in, ws.h, lin(nullptr, H, h->vlm[l].w_qkv, nullptr, ws.qkv, qkvd, B, qkvd, H), H, st));
+        // rotate q and k at position cur_len + 1 (table row cur_len); k, v -> cache row cur_len
+        launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q, (long)qd, Kc + (size_t)cur_len * hd, Vc + (size_t)cur_len * hd, kv_bs,
+                             w.rope_vlm_cos, w.rope_vlm_sin, B, 1, cur_len, nh, hd, st);
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.K = Kc; a.V = Vc; a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+        a.valid_len = valid_len1;   // cur_len + 1 for every sample
+        a.batch = B; a.n_heads = nh; a.head_dim = hd; a.s_cache = cur_len + 1; a.s_vlm = cur_len + 1; a.n_fresh = 0;
+        a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+        a.q_row_stride = qd; a.q_head_stride = hd; a.o_row_stride = qd; a.o_head_stride = hd;
+        a.Q = ws.q; a.q_batch_stride = (long)qd; a.O = ws.att; a.o_batch_stride = (long)qd;
+        a.q_rows = 1; a.q_row0 = cur_len;
+        a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
+        PZ_TRY(Ops<T>::attention(h, a, st));
+        PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, B, H, c.vlm_inter, st));
+    }
+    PZ_TRY(norm_linear<T>(h, x, w.vlm_final_norm, ws.h,
+                          lin(nullptr, H, w.lm_head, nullptr, logits, c.vocab_size, B, c.vocab_size, H, LIN_OUT_F32), H, st));
+    return 0;
+}
+
 // ------------------------------------------------------------------- ABI ----
 extern "C" {
 
@@ -866,6 +970,29 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *ids, const void *pixels, 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->cfg.dtype == PZ_BF16 ? run_flow_loss<bf16>(h, valid_len, actions, noise, t, sig_min, loss, v_psi, ws, B, st)
                                      : run_flow_loss<float>(h, valid_len, actions, noise, t, sig_min, loss, v_psi, ws, B, st);
+    return finish(h, rc);
+}
+
+int pz_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache, void *vcache, int cache_rows, int q_len,
+                    float *logits, int last_only, void *ws, size_t ws_bytes, int B, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!valid_len || !kcache || !vcache) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16
+                 ? run_text_prefill<bf16>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, ws, B, st)
+                 : run_text_prefill<float>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, ws, B, st);
+    return finish(h, rc);
+}
+
+int pz_text_decode(pz_handle *h, const float *x, const int32_t *valid_len1, int cur_len, void *kcache, void *vcache,
+                   int cache_rows, float *logits, void *ws, size_t ws_bytes, int B, void *stream) {
+    PZ_TRY(precheck(h, ws, ws_bytes, B));
+    if (!x || !valid_len1 || !kcache || !vcache || !logits) return fail(h, PZ_ERR_INVALID, "null input");
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16 ? run_text_decode<bf16>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, ws, B, st)
+                                     : run_text_decode<float>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, ws, B, st);
     return finish(h, rc);
 }
 

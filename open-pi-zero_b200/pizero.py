@@ -81,6 +81,36 @@ class KVCache:
         raise PzError("the prefix KV cache is written by the prefill kernels, not from Python")
 
 
+class TextKVCache:
+    """KV cache of `PiZero.infer_text`: one `[layers, B, capacity, head_dim]` tensor per K (post-RoPE) and V that decode
+    steps append to in place (`cache_mode="append"`, joint_model.py:164-240; the reference grows Python lists with
+    `torch.cat`, kv_cache.py:6-46).  Same accessors as the reference's `KVCache`."""
+
+    def __init__(self):
+        self.k = self.v = None
+        self.length = 0          # tokens per sample held so far (prompts are not padded, pizero.py:346-357)
+        self.n_layers = 0
+
+    def _allocate(self, n_layers, batch, capacity, head_dim, dtype, device):
+        self.k = torch.zeros((n_layers, batch, capacity, head_dim), dtype=dtype, device=device)
+        self.v = torch.zeros_like(self.k)
+        self.n_layers, self.length = n_layers, 0
+
+    @property
+    def capacity(self) -> int:
+        return 0 if self.k is None else self.k.shape[2]
+
+    def has_item(self, layer_idx) -> bool:
+        return self.k is not None and self.length > 0 and layer_idx < self.n_layers
+
+    def num_items(self) -> int:
+        return self.length
+
+    def get(self, layer_idx):
+        """(K, V) of one layer as `[B, 1, length, head_dim]` views (kv_cache.py:28-33)."""
+        return self.k[layer_idx, :, None, : self.length], self.v[layer_idx, :, None, : self.length]
+
+
 class JointModel(_Holder):
     """Holds `mixtures.{vlm,proprio,action}` parameters and mirrors the reference's
     `JointModel` surface (`joint_model.py:308-383`): attributes, `build_mixture_caches`
@@ -223,16 +253,23 @@ class PiZero(nn.Module):
         import weakref
         self.joint_model._owner = weakref.ref(self)
         dtype = dtype or torch.float32
+        tied_keys = {k: kind[5:] for k, _, kind, _ in state_dict_spec(d) if kind.startswith("tied:")}
         if init == "reference":
             from .synth import init_state_dict
             sd = init_state_dict(d, seed=int(torch.initial_seed() % (2 ** 31)), tie_proprio=False)
             for k, t in sd.items():
-                _attach(self, k, t.to(device=device, dtype=dtype))
+                if k not in tied_keys:
+                    _attach(self, k, t.to(device=device, dtype=dtype))
         elif init == "empty":
-            for k, shape, _, _ in state_dict_spec(d):
-                _attach(self, k, torch.empty(shape, device=device, dtype=dtype))
+            for k, shape, kind, _ in state_dict_spec(d):
+                if k not in tied_keys:
+                    _attach(self, k, torch.empty(shape, device=device, dtype=dtype))
         else:
             raise ValueError(f"init must be 'reference' or 'empty', got {init!r}")
+        self.use_lm_head = bool(d.get("use_lm_head", False))
+        if self.use_lm_head:   # pizero.py:105-112: lm_head.weight IS embed_tokens.weight
+            self.add_module("lm_head", _Holder())
+            self.lm_head.weight = self.embed_tokens.weight
         self._tied = False
         self._max_batch = max_batch
         self._handle = None
@@ -249,6 +286,7 @@ class PiZero(nn.Module):
         self._sampler_mode = int(os.environ.get("PZ_SAMPLER", "0"))
         self._sampler_pack_batches = tuple(int(b) for b in os.environ.get("PZ_SAMPLER_BATCHES", "1,2").split(",") if b)
         self._sampler_batches = []
+        self.text_max_new_tokens = int(os.environ.get("PZ_TEXT_MAX_NEW_TOKENS", "256"))   # capacity of a text KV cache / RoPE table
         self.max_graphs = int(os.environ.get("PZ_MAX_GRAPHS", "8"))
         # dtype of the action chunk infer_action returns: None = the reference's (the dtype of the pixel values, i.e. the
         # model dtype, pizero.py:454-456,484-490); torch.float32 = the sampler's own fp32 state, unrounded
@@ -462,11 +500,19 @@ class PiZero(nn.Module):
             fr = torch.arange(1, n_pos + 1, dtype=torch.float32)[:, None] * inv[None, :]
             return fr.cos().to(dev).contiguous(), fr.sin().to(dev).contiguous()
 
-        c1, s1 = rope(d["vlm_rope_theta"], d["max_image_text_tokens"])
+        # text decode steps run past the prompt: positions up to max_image_text_tokens + text_max_new_tokens
+        vlm_rope_rows = d["max_image_text_tokens"] + (self.text_max_new_tokens if self.use_lm_head else 0)
+        c1, s1 = rope(d["vlm_rope_theta"], vlm_rope_rows)
         c2, s2 = rope(d["act_rope_theta"], d["cond_steps"] + d["horizon_steps"])
         w.rope_vlm_cos, w.rope_vlm_sin = own(c1), own(s1)
         w.rope_act_cos, w.rope_act_sin = own(c2), own(s2)
         w.small_k_pad = skp
+        w.rope_vlm_rows = vlm_rope_rows
+        if "joint_model.mixtures.vlm.norm.weight" in sd:
+            w.vlm_final_norm = own(f32(sd["joint_model.mixtures.vlm.norm.weight"]))
+        if self.use_lm_head:
+            lm = sd["lm_head.weight"]
+            w.lm_head = w.embed if lm.data_ptr() == sd["embed_tokens.weight"].data_ptr() else own(mat(lm))
 
         cfg = _lib.PzConfig()
         cfg.dtype = _lib.PZ_BF16 if T == torch.bfloat16 else _lib.PZ_F32
@@ -670,6 +716,119 @@ class PiZero(nn.Module):
         # keep the inputs alive until the stream has consumed them
         self._inflight = (ids, pix, prop, vlen, nz)
         return out.to(out_dtype)
+
+    # ------------------------------------------------------------- text output
+    def build_causal_mask_and_position_ids_for_text(self, q_len: int, attention_mask: torch.Tensor, kv_cache=None):
+        """pizero.py:338-372 with the batch size taken from `attention_mask` (the reference reads an undefined `bsz`,
+        SURVEY F11): nothing is masked (no padding), positions = running count of the mask, 1 for pad tokens."""
+        dtype, device = attention_mask.dtype, attention_mask.device
+        bsz = attention_mask.shape[0]
+        if kv_cache is None or kv_cache.num_items() == 0:
+            causal_mask = torch.full((bsz, q_len, q_len), 0, dtype=dtype, device=device)
+        else:
+            assert q_len == 1, "Using KV cache so should only use one single token"
+            causal_mask = torch.full((bsz, q_len, kv_cache.num_items() + q_len), 0, dtype=dtype, device=device)
+        causal_mask = causal_mask.unsqueeze(1)
+        if kv_cache is not None and kv_cache.num_items() > 0:
+            position_ids = attention_mask.cumsum(-1)[:, -1:]
+        else:
+            position_ids = (attention_mask.cumsum(-1)).masked_fill_((attention_mask == 0), 1)
+        return causal_mask, position_ids
+
+    @torch.no_grad()
+    def infer_text(self, input_ids: torch.LongTensor, pixel_values: torch.FloatTensor, attention_mask: torch.Tensor,
+                   kv_cache: Optional[TextKVCache] = None, *, last_token_only: bool = False) -> dict:
+        """pizero.py:559-593: image + text through the vlm mixture alone (all layers, final norm) and the tied lm_head.
+        Needs `use_lm_head` and `mixture.vlm.use_final_norm` in the config (what the reference's `--text_only` run sets,
+        pizero.py:712-714).  First call (no cache, or an empty `TextKVCache`): the whole prompt, `q_len <=
+        max_image_text_tokens` unpadded tokens per sample; `logits` is `[B, q_len, vocab]` fp32 (or `[B, 1, vocab]`, the
+        last prompt token, with `last_token_only=True`: 1 GB less of lm_head output per sample at the full vocabulary).
+        Later calls: ONE new token per sample (`input_ids [B, 1]`, `attention_mask` covering prompt + generated tokens),
+        appended to the cache in place; `logits [B, 1, vocab]`.  Returns {"logits": ..., "kv_cache": ...} (the cache only
+        when one was passed, like the reference)."""
+        if not self.use_lm_head or "joint_model.mixtures.vlm.norm.weight" not in dict(self.named_parameters()):
+            raise PzError("infer_text needs use_lm_head=True and mixture.vlm.use_final_norm=True in the config")
+        if kv_cache is not None and not isinstance(kv_cache, TextKVCache):
+            raise TypeError("kv_cache must be an open_pi_zero_b200 TextKVCache (or None)")
+        self.pack()
+        lib = _lib.load()
+        d = self.dims
+        dev = self._packed[0][0].device
+        B, q_len = input_ids.shape
+        Sv, Hd, V = self.max_image_text_tokens, d["vlm_hidden"], d["vocab_size"]
+        ws, ws_bytes = self._ensure_workspace(B)
+        cache = kv_cache
+        if cache is None or cache.num_items() == 0:
+            if q_len > Sv:
+                raise ValueError(f"the prompt has {q_len} tokens, max_image_text_tokens is {Sv}")
+            if not bool((attention_mask != 0).all()):
+                raise ValueError("infer_text assumes unpadded prompts (pizero.py:346-357)")
+            if cache is None:
+                cache = TextKVCache()
+            cap = Sv + self.text_max_new_tokens
+            if cache.capacity < cap or cache.k.shape[1] != B or cache.k.dtype != self._T:
+                cache._allocate(d["num_layers"], B, cap, d["head_dim"], self._T, dev)
+            ids = torch.full((B, Sv), self.pad_token_id, dtype=torch.int64, device=dev)
+            ids[:, :q_len] = input_ids.to(dev)
+            u8 = pixel_values.dtype == torch.uint8
+            pix = pixel_values.to(device=dev).contiguous() if u8 else pixel_values.to(device=dev, dtype=self._T).contiguous()
+            vlen = torch.full((B,), q_len, dtype=torch.int32, device=dev)
+            logits = torch.empty((B, 1 if last_token_only else Sv, V), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                lib.pz_set_pixel_format(self._handle, 1 if u8 else 0)
+                rc = lib.pz_embed_prefix(self._handle, ids.data_ptr(), pix.data_ptr(), ws, ws_bytes, B, None, stream)
+                if rc == 0:
+                    rc = lib.pz_text_prefill(self._handle, vlen.data_ptr(), cache.k.data_ptr(), cache.v.data_ptr(), cache.capacity,
+                                             q_len, logits.data_ptr(), 1 if last_token_only else 0, ws, ws_bytes, B, stream)
+            if rc != 0:
+                raise PzError(f"infer_text prefill failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
+            cache.length = q_len
+            self._inflight = (ids, pix, vlen)
+            out = {"logits": logits if last_token_only else logits[:, :q_len]}
+        else:
+            if q_len != 1:
+                raise ValueError("Using KV cache so should only use one single token")
+            cur = cache.num_items()
+            if cur + 1 > cache.capacity:
+                raise PzError(f"the text KV cache is full ({cache.capacity} rows): raise PZ_TEXT_MAX_NEW_TOKENS / text_max_new_tokens")
+            # joint_model.py:348-355: embedding scaled by sqrt(hidden) (rounded to the model dtype like the reference)
+            emb = self.embed_tokens.weight[input_ids[:, 0].to(dev)]
+            x = (emb * torch.tensor(Hd ** 0.5, dtype=emb.dtype, device=dev)).to(torch.float32).contiguous()
+            vlen1 = torch.full((B,), cur + 1, dtype=torch.int32, device=dev)
+            logits = torch.empty((B, 1, V), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = lib.pz_text_decode(self._handle, x.data_ptr(), vlen1.data_ptr(), cur, cache.k.data_ptr(), cache.v.data_ptr(),
+                                        cache.capacity, logits.data_ptr(), ws, ws_bytes, B, stream)
+            if rc != 0:
+                raise PzError(f"infer_text decode failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
+            cache.length = cur + 1
+            self._inflight = (x, vlen1)
+            out = {"logits": logits}
+        self.last_launch_count = int(lib.pz_launch_count(self._handle))
+        if kv_cache is not None:
+            out["kv_cache"] = cache
+        else:
+            out["_cache"] = cache   # not in the reference's dict: lets a caller continue decoding without pre-building a cache
+        return out
+
+    @torch.no_grad()
+    def generate_text(self, input_ids, pixel_values, attention_mask, max_new_tokens: int = 16, eos_token_id: Optional[int] = None):
+        """Greedy decoding on top of infer_text (the loop of the reference's `--text_only` run, pizero.py:770-800):
+        returns the generated ids `[B, n]`."""
+        cache = TextKVCache()
+        out = self.infer_text(input_ids, pixel_values, attention_mask, cache, last_token_only=True)
+        mask = attention_mask
+        new = []
+        for _ in range(max_new_tokens):
+            nxt = out["logits"][:, -1].argmax(-1, keepdim=True)
+            new.append(nxt)
+            if eos_token_id is not None and bool((nxt == eos_token_id).all()):
+                break
+            mask = torch.cat([mask, torch.ones_like(mask[:, :1])], dim=-1)
+            out = self.infer_text(nxt, pixel_values, mask, cache)
+        return torch.cat(new, dim=1)
 
     @torch.no_grad()
     def infer_action_naive(

@@ -67,13 +67,15 @@ def state_dict_spec(d: dict) -> list:
             lin(p + "mlp.down_proj", hid, inter, False)
             spec.append((p + "input_layernorm.weight", (hid,), "rms", None))
             spec.append((p + "post_attention_layernorm.weight", (hid,), "rms", None))
-        if name != "vlm":
+        if name != "vlm" or d.get("vlm_use_final_norm", False):
             spec.append((f"joint_model.mixtures.{name}.norm.weight", (hid,), "rms", None))
     lin("action_encoder.linear_1", A, d["action_dim"], True)
     lin("action_encoder.linear_2", A, 2 * A, True)
     lin("action_encoder.linear_3", A, A, True)
     lin("proprio_encoder", A, d["proprio_dim"], True)
     lin("action_decoder", d["action_dim"], A, True)
+    if d.get("use_lm_head", False):   # tied to embed_tokens.weight (pizero.py:105-112): the same tensor under a second key
+        spec.append(("lm_head.weight", (d["vocab_size"], H), "tied:embed_tokens.weight", None))
     return spec
 
 
@@ -103,6 +105,9 @@ def init_state_dict(d: dict, seed: int = 42, randomize_norms: bool = False,
             t = torch.zeros(shape)
             if randomize_norms:
                 t = 0.1 * torch.randn(shape, generator=g)
+        elif kind.startswith("tied:"):
+            sd[key] = sd[kind[5:]]
+            continue
         else:
             raise ValueError(kind)
         sd[key] = t.to(dtype)

@@ -299,6 +299,56 @@ def infer_action(sd, dims, input_ids, pixel_values, attention_mask, proprios, no
     return action
 
 
+# --------------------------------------------------------------------------
+# text output
+# --------------------------------------------------------------------------
+@torch.no_grad()
+def infer_text(sd, dims, input_ids, pixel_values, attention_mask, kv_cache=None):
+    """pizero.py:559-593 (`infer_text`) with its mask / position builder (:338-372; the batch size it needs is taken from
+    `attention_mask` -- the reference reads an undefined global `bsz`; tests/golden/text_tiny.pt was produced
+    by the unmodified reference with that one name injected into its module).  Only the vlm mixture is active, in
+    `cache_mode="append"` (joint_model.py:164-240): nothing is masked, every layer runs to the end
+    (`final_layer_post_attn_skip_names=[]`), then the vlm mixture's final norm and the tied lm_head.
+    `kv_cache`: None, or a list of per-layer (K, V) `[B, 1, S, hd]` that is extended in place.  Returns {"logits"}."""
+    L, nh, nkv, hd = dims["num_layers"], dims["num_heads"], dims["num_kv_heads"], dims["head_dim"]
+    B, q_len = input_ids.shape
+    cached = kv_cache is not None and len(kv_cache) > 0
+    if cached:
+        assert q_len == 1, "Using KV cache so should only use one single token"
+        position_ids = attention_mask.cumsum(-1)[:, -1:]
+    else:
+        position_ids = attention_mask.cumsum(-1).masked_fill(attention_mask == 0, 1)
+    embeds = embed_prefix(sd, dims, input_ids, pixel_values)      # pizero.py:569 (no image token in a decode step: token embedding)
+    x = embeds * torch.tensor(embeds.shape[-1] ** 0.5, dtype=embeds.dtype)   # joint_model.py:348-355
+    for li in range(L):
+        p = "joint_model.mixtures.vlm.layers.%d." % li
+        h = gemma_rms_norm(x, sd[p + "input_layernorm.weight"])
+        q = F.linear(h, sd[p + "self_attn.q_proj.weight"]).view(B, q_len, nh, hd).transpose(1, 2)
+        k = F.linear(h, sd[p + "self_attn.k_proj.weight"]).view(B, q_len, nkv, hd).transpose(1, 2)
+        v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(B, q_len, nkv, hd).transpose(1, 2)
+        cos, sin = rope_cos_sin(position_ids, hd, dims["vlm_rope_theta"], h.dtype)
+        k = apply_rope(k, cos, sin)
+        q = apply_rope(q, cos, sin)
+        if kv_cache is not None:                                   # joint_model.py:195-240: append, then use old + new
+            if len(kv_cache) > li:
+                k = torch.cat((kv_cache[li][0], k), dim=-2)
+                v = torch.cat((kv_cache[li][1], v), dim=-2)
+                kv_cache[li] = (k, v)
+            else:
+                kv_cache.append((k, v))
+        rep = nh // nkv
+        K, V = k.repeat_interleave(rep, dim=1), v.repeat_interleave(rep, dim=1)
+        w = torch.matmul(q, K.transpose(2, 3)) / math.sqrt(hd)
+        w = torch.tanh(w / ATTN_SOFTCAP) * ATTN_SOFTCAP
+        w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)  # the text mask is all zeros
+        o = torch.matmul(w, V).transpose(1, 2).reshape(B, q_len, nh * hd)
+        x1 = x + F.linear(o, sd[p + "self_attn.o_proj.weight"])
+        h2 = gemma_rms_norm(x1, sd[p + "post_attention_layernorm.weight"])
+        x = x1 + gemma_mlp(h2, sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"], sd[p + "mlp.down_proj.weight"])
+    out = gemma_rms_norm(x, sd["joint_model.mixtures.vlm.norm.weight"])
+    return {"logits": F.linear(out, sd.get("lm_head.weight", sd["embed_tokens.weight"]))}
+
+
 @torch.no_grad()
 def infer_action_naive(sd, dims, input_ids, pixel_values, attention_mask, proprios, noise):
     """pizero.py:492-557 -- no KV cache: every Euler step re-runs the whole

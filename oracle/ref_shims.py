@@ -105,7 +105,7 @@ def reference_cfg(dims: dict) -> RefCfg:
     d = dims
     mixture = {
         "vlm": dict(hidden_size=d["vlm_hidden"], intermediate_size=d["vlm_inter"],
-                    use_final_norm=False, cache=True, use_quantize=False, use_lora=False,
+                    use_final_norm=bool(d.get("vlm_use_final_norm", False)), cache=True, use_quantize=False, use_lora=False,
                     adaptive_mode=None, rope_theta=d["vlm_rope_theta"]),
         "proprio": dict(hidden_size=d["act_hidden"], intermediate_size=d["act_inter"],
                         use_final_norm=True, cache=True, use_quantize=False, use_lora=False,
@@ -121,7 +121,8 @@ def reference_cfg(dims: dict) -> RefCfg:
         cond_steps=d["cond_steps"], horizon_steps=d["horizon_steps"],
         num_inference_steps=d["num_inference_steps"], action_dim=d["action_dim"],
         proprio_dim=d["proprio_dim"], final_action_clip_value=d["final_action_clip_value"],
-        flow_sig_min=0.001, action_expert_adaptive_mode=None, time_hidden_size=256,
+        flow_sig_min=0.001, use_lm_head=bool(d.get("use_lm_head", False)),
+        action_expert_adaptive_mode=None, time_hidden_size=256,
         time_max_period=d["time_max_period"], mixture=mixture,
         vision=dict(_target_="src.model.paligemma.siglip.SiglipVisionModel",
                     config=dict(hidden_size=d["vit_hidden"], intermediate_size=d["vit_inter"],

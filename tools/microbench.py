@@ -40,6 +40,18 @@ def bench_linear(impl, M, N, K, flags, iters=200, nbuf=8):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("floor",):   # what a launch costs when there is next to nothing to compute
+        bench_linear(1, 128, 128, 64, 0)
+        bench_linear(1, 128, 128, 64, OUT_F32 | ACCUM)
+        bench_linear(1, 128, 256, 512, 0)
+        bench_linear(1, 256, 2560, 1024, 0)
+        bench_linear(1, 256, 1024, 2048, OUT_F32 | ACCUM)
+        bench_linear(1, 256, 8192, 1024, GEGLU)
+        bench_linear(1, 256, 1024, 4096, OUT_F32 | ACCUM)
+        bench_linear(1, 276, 2560, 2048, 0, iters=50)
+        bench_linear(1, 276, 2048, 2048, OUT_F32 | ACCUM, iters=50)
+        bench_linear(1, 276, 32768, 2048, GEGLU, iters=20)
+        bench_linear(1, 276, 2048, 16384, OUT_F32 | ACCUM, iters=20)
     if which in ("all", "tc"):
         for M in (256,):
             bench_linear(1, M, 2560, 1024, 0)
