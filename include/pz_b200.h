@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 6
+#define PZ_ABI_VERSION 7
 
 typedef enum pz_status {
     PZ_OK = 0,
@@ -259,6 +259,25 @@ int pz_text_prefill(pz_handle *h, const int32_t *d_valid_len, void *d_kcache, vo
                     float *d_logits, int last_only, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 int pz_text_decode(pz_handle *h, const float *d_x, const int32_t *d_valid_len1, int cur_len, void *d_kcache, void *d_vcache,
                    int cache_rows, float *d_logits, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+
+/* The flow-matching training step, replaces PiZero.forward + loss.backward() (pizero.py:607-661, train.py:350-368):
+ * forward with the activations kept in the training workspace, then the backward (statement: oracle/pizero_backward.py).
+ *   d_actions, d_noise  fp32 [batch, horizon, action_dim];  d_t fp32 [batch] (TrainAgent.sample_fm_time, train.py:239-247)
+ *   grads     NULL = loss only; else the SAME structs as the weights with every non-NULL pointer an fp32 device buffer of
+ *             the packed shape of that weight (fused q|k|v rows, gate|up blocks of PZ_GU_BLOCK, padded small matrices,
+ *             dec_b [8]); d loss / d weight * loss_scale is ACCUMULATED into them (micro-batches add up, as under DDP
+ *             no_sync, train.py:350-356).  Fields without a gradient (embed: frozen, pizero.py:243-249; RoPE / time tables)
+ *             are ignored.  If the proprio table aliases the action table (tied weights) both gradients land in one buffer.
+ *   d_loss    fp32 [1]: mean squared error of this batch (unscaled)
+ *   flags     PZ_TRAIN_FREEZE_VISION: stop at the projector output (no SigLIP / projector gradients)
+ * Image tokens must be the first n_images * n_img_tokens positions of every sequence (what VLAProcessor builds,
+ * processing.py:63-136).  Workspace: pz_train_workspace_bytes(batch), 1 KiB aligned. */
+#define PZ_TRAIN_FREEZE_VISION 1
+size_t pz_train_workspace_bytes(const pz_handle *h, int batch);
+int pz_flow_matching_step(pz_handle *h, const int64_t *d_input_ids, const void *d_pixels, const int32_t *d_valid_len,
+                          const float *d_proprio, const float *d_actions, const float *d_noise, const float *d_t, float sig_min,
+                          const pz_weights *grads, float loss_scale, float *d_loss, void *d_workspace, size_t workspace_bytes,
+                          int batch, int flags, void *stream);
 
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);

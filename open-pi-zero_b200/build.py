@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpz_b200.so")
-SOURCES = ["api.cu", "simple.cu", "elementwise.cu", "gemm_tc.cu", "skinny.cu", "attn_mma.cu", "attn_tc.cu",
+SOURCES = ["api.cu", "train.cu", "simple.cu", "elementwise.cu", "gemm_tc.cu", "skinny.cu", "attn_mma.cu", "attn_tc.cu",
            "denoise_mega.cu", "denoise_mega3.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared"]
@@ -38,9 +38,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    for src in _sources():   # compile translation units in parallel
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(HERE, "..", "include", "pz_b200.h"))
+    hdr_t = max(os.path.getmtime(f) for f in hdrs)
+    tag = os.path.join(HERE, "build", "flags.txt")
+    same_flags = os.path.exists(tag) and open(tag).read() == " ".join(flags)
+    for src in _sources():   # compile translation units in parallel; objects newer than their source and every header are kept
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         objs.append(obj)
+        if (not force and same_flags and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                and os.path.getmtime(obj) > hdr_t):
+            continue
         cmd = [nvcc] + [f for f in flags if f != "-shared"] + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -51,6 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out, file=sys.stderr)
+    with open(tag, "w") as fh:
+        fh.write(" ".join(flags))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:

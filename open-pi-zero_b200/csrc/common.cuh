@@ -152,6 +152,14 @@ static inline int device_sm_count() {
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter *g_launch_counter;
 extern int g_pdl_enabled;
+// > 0: launch without the PDL attribute (griddepcontrol.wait is then a no-op and plain stream order holds).  The GEMM and
+// skinny kernels fetch their WEIGHT operand before griddepcontrol.wait -- correct for weights, wrong when that operand was
+// written by the kernel just in front (the transposed operands of the training step's backward, train.cu).
+extern thread_local int g_pdl_off;
+struct PdlOff {
+    PdlOff() { ++g_pdl_off; }
+    ~PdlOff() { --g_pdl_off; }
+};
 static inline void count_launch() { if (g_launch_counter) g_launch_counter->n++; }
 
 template <typename... KArgs, typename... Args>
@@ -162,7 +170,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (g_pdl_enabled && !g_pdl_off) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
     count_launch();
 }

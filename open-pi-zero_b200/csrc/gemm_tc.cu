@@ -517,7 +517,7 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
     lc.gridDim = dim3(workers * CG); lc.blockDim = dim3(NUM_THREADS2); lc.dynamicSmemBytes = cfg::SMEM_BYTES; lc.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (g_pdl_enabled) {
+    if (g_pdl_enabled && !g_pdl_off) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

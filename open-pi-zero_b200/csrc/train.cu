@@ -1,0 +1,1062 @@
+// train.cu -- the flow-matching training step (reference: PiZero.forward, src/model/vla/pizero.py:607-661, followed by
+// loss.backward(), src/agent/train.py:350-368): forward with every activation the backward needs kept in HBM, then the
+// backward written out op by op (statement: oracle/pizero_backward.py, which is pinned to the unmodified reference's
+// autograd on all parameter tensors).  Gradients are accumulated in fp32, in the PACKED layouts the forward kernels read
+// (fused q|k|v rows, gate|up blocks of 128, padded small matrices), so that an optimizer can update the kernel-side
+// weights in place.
+//
+// B200 plan: every matrix product of the backward runs through the same tcgen05 GEMM as the forward,
+//   dX[M,K] = dY[M,N] . W[N,K]           -> gemm(A = dY,   W' = W^T [K,N])
+//   dW[N,K] = dY[M,N]^T . X[M,K]         -> gemm(A = dY^T, W' = X^T [K,M]), fp32 TMA reduce-add into the gradient
+// on K-major operands produced by a tiled transpose (HBM-bound, ~2 % of the step); nothing is recomputed except the
+// normalised activations (one norm kernel each); 180 GB of HBM hold the ~30 GB of saved activations at 32 samples.
+// The attention backward is one SIMT kernel for both the joint block-masked soft-capped MQA attention and SigLIP's.
+#include "api_internal.cuh"
+
+namespace {
+
+inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+
+// ============================================================== kernels ====
+// out[c][r] = in[r][c]; out has row stride ld_out >= R, columns R .. ld_out-1 are zero-filled (they are the K padding of
+// the GEMM that consumes `out`).  32 x 32 tiles through shared memory, block (32, 8).
+template <typename T>
+__global__ void transpose_kernel(const T *__restrict__ in, int ld_in, T *__restrict__ out, int ld_out, int R, int C) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ T tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < R && c < C) ? in[(long)r * ld_in + c] : from_f32<T>(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < C && r < ld_out) out[(long)c * ld_out + r] = tile[tx][i];
+    }
+}
+template <typename T>
+void transpose(const T *in, int ld_in, T *out, int ld_out, int R, int C, cudaStream_t st) {
+    launch_k(transpose_kernel<T>, dim3((C + 31) / 32, (ld_out + 31) / 32), dim3(32, 8), 0, st, in, ld_in, out, ld_out, R, C);
+}
+
+// dst = T(scale * src)
+template <typename T>
+__global__ void cast_scale_kernel(const float *__restrict__ src, T *__restrict__ dst, long n, float scale) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        dst[i] = from_f32<T>(src[i] * scale);
+}
+template <typename T>
+void cast_scale(const float *src, T *dst, long n, float scale, cudaStream_t st) {
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_k(cast_scale_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, st, src, dst, n, scale);
+}
+
+PZ_DEVINL float gelu_tanh_grad(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float th = tanhf(k0 * (x + k1 * x * x * x));
+    return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * k0 * (1.f + 3.f * k1 * x * x);
+}
+
+// GeGLU on the packed gate|up layout (blocks of PZ_GU_BLOCK gate columns then PZ_GU_BLOCK up columns):
+// m = gelu_tanh(g) * u (paligemma/modules.py:86-95)
+template <typename T>
+__global__ void geglu_fwd_kernel(const T *__restrict__ gu, T *__restrict__ m, long total, int inter) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / inter;
+        const int c = (int)(i % inter);
+        const long o = r * 2 * inter + (long)(c / PZ_GU_BLOCK) * 2 * PZ_GU_BLOCK + (c % PZ_GU_BLOCK);
+        m[i] = from_f32<T>(gelu_tanh(to_f32<T>(gu[o])) * to_f32<T>(gu[o + PZ_GU_BLOCK]));
+    }
+}
+// dg = dm u gelu'(g), du = dm gelu(g), written in the same packed layout
+template <typename T>
+__global__ void geglu_bwd_kernel(const T *__restrict__ gu, const T *__restrict__ dm, T *__restrict__ dgu, long total, int inter) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / inter;
+        const int c = (int)(i % inter);
+        const long o = r * 2 * inter + (long)(c / PZ_GU_BLOCK) * 2 * PZ_GU_BLOCK + (c % PZ_GU_BLOCK);
+        const float g = to_f32<T>(gu[o]), u = to_f32<T>(gu[o + PZ_GU_BLOCK]), d = to_f32<T>(dm[i]);
+        dgu[o] = from_f32<T>(d * u * gelu_tanh_grad(g));
+        dgu[o + PZ_GU_BLOCK] = from_f32<T>(d * gelu_tanh(g));
+    }
+}
+inline unsigned ew_blocks(long total) {
+    long b = (total + 255) / 256;
+    return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+// act = gelu_tanh(pre) (SigLIP MLP, siglip.py:188-192); the pre-activation is kept for the backward
+template <typename T>
+__global__ void gelu_fwd_kernel(const T *__restrict__ pre, T *__restrict__ out, long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        out[i] = from_f32<T>(gelu_tanh(to_f32<T>(pre[i])));
+}
+// dpre = dpost * act'(pre)
+template <typename T>
+__global__ void gelu_bwd_kernel(const T *__restrict__ pre, const T *__restrict__ dpost, T *__restrict__ dpre, long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        dpre[i] = from_f32<T>(to_f32<T>(dpost[i]) * gelu_tanh_grad(to_f32<T>(pre[i])));
+}
+// action encoder: z = silu(zpre + bias[sample]); dzpre = dz * silu'(.)
+template <typename T>
+__global__ void silu_bwd_kernel(const float *__restrict__ zpre, const float *__restrict__ bias, const float *__restrict__ dz,
+                                T *__restrict__ out, long total, int cols, int rows_per_sample) {
+    pdl_trigger();
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols;
+        const int c = (int)(i % cols);
+        const float x = zpre[i] + bias[(r / rows_per_sample) * cols + c];
+        const float s = 1.f / (1.f + __expf(-x));
+        out[i] = from_f32<T>(dz[i] * s * (1.f + x * (1.f - s)));
+    }
+}
+
+// Gemma RMSNorm backward (paligemma/modules.py:13-21): y = x r (1 + w), r = (mean x^2 + eps)^-1/2
+//   dx += r (1+w) dy - x r^3 mean(x (1+w) dy);   dw += sum_rows dy x r
+// One CTA walks rows blockIdx.x, + gridDim.x, ...; a thread owns columns tid + 256 k (cols <= 2048) and keeps its dw
+// partials in registers until the end (one atomicAdd per column and CTA).
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                          const float *__restrict__ dy, float *__restrict__ dx,
+                                                          float *__restrict__ dw, long rows, int cols, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    float dwl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        float xv[8], gy[8];
+        float ss = 0.f, dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            xv[k] = gy[k] = 0.f;
+            if (c < cols) {
+                xv[k] = x[r * cols + c];
+                gy[k] = dy[r * cols + c];
+                ss += xv[k] * xv[k];
+                dot += xv[k] * gy[k] * (1.f + w[c]);
+            }
+        }
+        ss = block_sum(ss, red);
+        dot = block_sum(dot, red);
+        const float rr = rsqrtf(ss / cols + eps);
+        const float k3 = rr * rr * rr * dot / cols;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            if (c < cols) {
+                dx[r * cols + c] += rr * gy[k] * (1.f + w[c]) - xv[k] * k3;
+                dwl[k] += gy[k] * xv[k] * rr;
+            }
+        }
+    }
+    if (dw) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            if (c < cols) atomicAdd(dw + c, dwl[k]);
+        }
+    }
+}
+void rmsnorm_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, long rows, int cols, cudaStream_t st) {
+    unsigned blocks = (unsigned)(rows < 148 * 4 ? rows : 148 * 4);
+    launch_k(rmsnorm_bwd_kernel, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, rows, cols, 1e-6f);
+}
+
+// LayerNorm backward (siglip.py:211,217,298): y = xh w + b, xh = (x - mean) rstd
+//   dx += rstd (g - mean g - xh mean(g xh)), g = dy w;   dw += sum dy xh;   db += sum dy
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ dy, float *__restrict__ dx,
+                                                            float *__restrict__ dw, float *__restrict__ db, long rows, int cols,
+                                                            float eps) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    float dwl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dbl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        float xv[8], gy[8];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            xv[k] = gy[k] = 0.f;
+            if (c < cols) { xv[k] = x[r * cols + c]; gy[k] = dy[r * cols + c]; s += xv[k]; }
+        }
+        const float mean = block_sum(s, red) / cols;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (threadIdx.x + k * 256 < cols) { const float d = xv[k] - mean; q += d * d; }
+        const float rstd = rsqrtf(block_sum(q, red) / cols + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            if (c < cols) {
+                xv[k] = (xv[k] - mean) * rstd;   // xh
+                const float g = gy[k] * w[c];
+                sg += g; sgx += g * xv[k];
+            }
+        }
+        sg = block_sum(sg, red) / cols;
+        sgx = block_sum(sgx, red) / cols;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = threadIdx.x + k * 256;
+            if (c < cols) {
+                dx[r * cols + c] += rstd * (gy[k] * w[c] - sg - xv[k] * sgx);
+                dwl[k] += gy[k] * xv[k];
+                dbl[k] += gy[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < cols) {
+            if (dw) atomicAdd(dw + c, dwl[k]);
+            if (db) atomicAdd(db + c, dbl[k]);
+        }
+    }
+}
+void layernorm_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, float *db, long rows, int cols,
+                   cudaStream_t st) {
+    unsigned blocks = (unsigned)(rows < 148 * 4 ? rows : 148 * 4);
+    launch_k(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, db, rows, cols, 1e-6f);
+}
+
+// out[c] += sum_r in[r][c] (bias gradients); block (32, 8), grid (column tiles, row slabs)
+template <typename T>
+__global__ void colsum_kernel(const T *__restrict__ in, int ld, float *__restrict__ out, long rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (c < cols)
+        for (long r = (long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) acc += to_f32<T>(in[r * ld + c]);
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+template <typename T>
+void colsum(const T *in, int ld, float *out, long rows, int cols, cudaStream_t st) {
+    if (!out) return;
+    long slabs = (rows + 255) / 256;
+    if (slabs > 64) slabs = 64;
+    if (slabs < 1) slabs = 1;
+    launch_k(colsum_kernel<T>, dim3((cols + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, st, in, ld, out, rows, cols);
+}
+
+// out[g][c] = sum_{r < group} in[g * group + r][c] (T -> T): the time half of the action encoder sees one row per sample
+template <typename T>
+__global__ void group_sum_kernel(const T *__restrict__ in, T *__restrict__ out, long total, int cols, int group) {
+    pdl_trigger();
+    pdl_wait();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long g = i / cols;
+    const int c = (int)(i % cols);
+    float s = 0.f;
+    for (int r = 0; r < group; ++r) s += to_f32<T>(in[(g * group + r) * cols + c]);
+    out[i] = from_f32<T>(s);
+}
+// out[p][c] += sum_img in[img * period + p][c] (fp32): position-embedding gradient
+__global__ void period_sum_kernel(const float *__restrict__ in, float *__restrict__ out, long total, int cols, int period, int n) {
+    pdl_trigger();
+    pdl_wait();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s = 0.f;
+    for (int k = 0; k < n; ++k) s += in[(long)k * period * cols + i];
+    out[i] += s;
+}
+
+// d loss / d v of mean((v - (x1 - (1 - sig) x0))^2) (pizero.py:658-661), as a [rows, 8] matrix (pad columns zero)
+template <typename T>
+__global__ void loss_bwd_kernel(const float *__restrict__ vel, int vel_ld, const float *__restrict__ x0, const float *__restrict__ x1,
+                                T *__restrict__ dv, long rows, int adim, float sig_min, float loss_scale) {
+    pdl_trigger();
+    pdl_wait();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 8) return;
+    const long r = i / 8;
+    const int c = (int)(i % 8);
+    float g = 0.f;
+    if (c < adim) {
+        const long j = r * adim + c;
+        g = 2.f * (vel[r * vel_ld + c] - (x1[j] - (1.f - sig_min) * x0[j])) / (float)(rows * adim) * loss_scale;
+    }
+    dv[i] = from_f32<T>(g);
+}
+
+// Backward of RoPE + the Q/K/V split (model/utils.py:4-16): y1 = x1 c - x2 s, y2 = x2 c + x1 s  =>
+// dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s.  Assembles the gradient of the raw fused projection [q | k | v] of one
+// mixture from dq [M, nh*hd] (fp32, may be null = zero) and the rows `row_off ..` of the joint dK / dV [B][S_all][hd].
+template <typename T>
+__global__ void rope_bwd_merge_kernel(const float *__restrict__ dq, const float *__restrict__ dK, const float *__restrict__ dV,
+                                      long dkv_bs, int row_off, const float *__restrict__ cos_t, const float *__restrict__ sin_t,
+                                      int pos0, T *__restrict__ out, int s_x, int nh, int hd) {
+    pdl_trigger();
+    pdl_wait();
+    const long row = blockIdx.x;
+    const int b = (int)(row / s_x), s = (int)(row % s_x);
+    const int half = hd >> 1, qkvd = (nh + 2) * hd;
+    const float *cs = cos_t + (long)(pos0 + s) * half, *sn = sin_t + (long)(pos0 + s) * half;
+    const float *gk = dK + (long)b * dkv_bs + (long)(row_off + s) * hd;
+    const float *gv = dV + (long)b * dkv_bs + (long)(row_off + s) * hd;
+    T *o = out + row * qkvd;
+    for (int i = threadIdx.x; i < (nh + 1) * half; i += blockDim.x) {
+        const int h = i / half, d = i % half;
+        const float *g = h < nh ? (dq ? dq + row * nh * hd + (long)h * hd : nullptr) : gk;
+        const float g1 = g ? g[d] : 0.f, g2 = g ? g[d + half] : 0.f;
+        o[h * hd + d] = from_f32<T>(g1 * cs[d] + g2 * sn[d]);
+        o[h * hd + d + half] = from_f32<T>(g2 * cs[d] - g1 * sn[d]);
+    }
+    for (int i = threadIdx.x; i < hd; i += blockDim.x) o[(nh + 1) * hd + i] = from_f32<T>(gv[i]);
+}
+
+// eight consecutive elements as fp32 (16-byte load for bf16 when the address allows it)
+template <typename T> PZ_DEVINL void load8(const T *p, float *o);
+template <> PZ_DEVINL void load8<float>(const float *p, float *o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = p[i];
+}
+template <> PZ_DEVINL void load8<bf16>(const bf16 *p, float *o) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        o[0] = bf16lo(v.x); o[1] = bf16hi(v.x); o[2] = bf16lo(v.y); o[3] = bf16hi(v.y);
+        o[4] = bf16lo(v.z); o[5] = bf16hi(v.z); o[6] = bf16lo(v.w); o[7] = bf16hi(v.w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __bfloat162float(p[i]);
+    }
+}
+
+// --------------------------------------------------- attention backward ----
+// o = P V, P = softmax(cap tanh(s / cap) + mask), s = scale q k^T (joint_model.py:255-283; cap = 0: SigLIP, siglip.py:133-152).
+// A CTA owns 32 (query row, head) pairs that share their keys: 4 rows x 8 heads on the single K/V head of the joint
+// model (MQA), 32 rows of one head for SigLIP.  Phase 1: logits of the 32 pairs against every key (thread = key);
+// phase 2: softmax statistics (warp = 4 pairs); phase 3 (thread = key): dP = dO V^T, dS = P (dP - D) (1 - tanh^2) scale,
+// dV_j += sum_p P dO_p and dK_j += sum_p dS q_p as fp32 atomics (the other row tiles add to the same key rows);
+// phase 4 (thread = feature): dQ_p = sum_j dS_pj K_j, owned by this CTA.  Rows of a tile never straddle a segment
+// (vlm | proprio | action), so key visibility is uniform across the tile (block mask, pizero.py:271-310).
+struct AttnBwdArgs {
+    int n_seg;
+    int seg_rows[3];
+    int seg_active[3];
+    const void *Q[3], *dO[3], *O[3];   // T
+    float *dQ[3];                      // fp32, geometry (dq_rs, head stride hd)
+    int q_rs, o_rs, dq_rs;             // row strides in elements
+    const void *K, *V;                 // T
+    long kv_bs; int kv_rs, kv_hs;
+    float *dK, *dV;                    // fp32
+    long dkv_bs; int dkv_rs, dkv_hs;
+    const int32_t *valid_len;
+    int s_v, s_p;                      // mask boundaries (valid_len != null)
+    int n_keys, batch, n_heads, hd, hpc;   // hpc: heads per CTA (n_heads when kv_hs == 0 and n_heads divides 32, else 1)
+    float scale, softcap;
+    int sp;                            // padded key count of the shared-memory score rows (multiple of 4)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float smf[];
+    const int hd = a.hd, SP = a.sp;
+    float *qs = smf;                    // [32][hd]
+    float *dos = qs + 32 * hd;          // [32][hd]
+    float *sb = dos + 32 * hd;          // [32][SP]
+    float *Dp = sb + 32 * SP;           // [32]
+    float *mx = Dp + 32, *inv = mx + 32, *actf = inv + 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int QT = 32 / a.hpc;
+    // which segment / row tile
+    int seg = 0, tile = blockIdx.x, seg_off = 0;
+    for (;;) {
+        int tiles = a.seg_active[seg] ? (a.seg_rows[seg] + QT - 1) / QT : 0;
+        if (tile < tiles) break;
+        tile -= tiles; seg_off += a.seg_rows[seg]; ++seg;
+        if (seg >= a.n_seg) return;
+    }
+    const int b = blockIdx.z, head0 = blockIdx.y * a.hpc;
+    const int rows = a.seg_rows[seg];
+    const int vl = a.valid_len ? a.valid_len[b] : (1 << 30);
+    const T *Qp = (const T *)a.Q[seg], *dOp = (const T *)a.dO[seg], *Op = (const T *)a.O[seg];
+    // ---- load q, dO (fp32 in shared memory), D = dO . O, active flags
+    for (int p = warp * 4; p < warp * 4 + 4; ++p) {
+        const int hi = p / QT, ri = p % QT;
+        const int row = tile * QT + ri, head = head0 + hi;
+        const bool act = row < rows && !(a.valid_len && seg_off + row < a.s_v && seg_off + row >= vl);
+        float dsum = 0.f;
+        for (int d = lane; d < hd; d += 32) {
+            float qv = 0.f, gv = 0.f, ov = 0.f;
+            if (act) {
+                const long r = (long)b * rows + row;
+                qv = to_f32<T>(Qp[r * a.q_rs + head * hd + d]);
+                gv = to_f32<T>(dOp[r * a.o_rs + head * hd + d]);
+                ov = to_f32<T>(Op[r * a.o_rs + head * hd + d]);
+            }
+            qs[p * hd + d] = qv; dos[p * hd + d] = gv;
+            dsum += gv * ov;
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) { Dp[p] = dsum; actf[p] = act ? 1.f : 0.f; }
+    }
+    __syncthreads();
+    const T *Kb = (const T *)a.K + (long)b * a.kv_bs + (long)head0 * a.kv_hs;
+    const T *Vb = (const T *)a.V + (long)b * a.kv_bs + (long)head0 * a.kv_hs;
+    auto visible = [&](int j) -> bool {
+        if (!a.valid_len) return true;
+        if (j < a.s_v) return j < vl;
+        if (j < a.s_v + a.s_p) return seg >= 1;
+        return seg >= 2;
+    };
+    // ---- phase 1: logits
+    for (int j = tid; j < SP; j += 256) {
+        if (j >= a.n_keys || !visible(j)) {
+            for (int p = 0; p < 32; ++p) sb[p * SP + j] = -INFINITY;
+            continue;
+        }
+        float acc[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) acc[p] = 0.f;
+        const T *kr = Kb + (long)j * a.kv_rs;
+        for (int c = 0; c < hd; c += 8) {
+            float kv[8];
+            load8<T>(kr + c, kv);
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const float4 q0 = *reinterpret_cast<const float4 *>(qs + p * hd + c);
+                const float4 q1 = *reinterpret_cast<const float4 *>(qs + p * hd + c + 4);
+                acc[p] += kv[0] * q0.x + kv[1] * q0.y + kv[2] * q0.z + kv[3] * q0.w + kv[4] * q1.x + kv[5] * q1.y + kv[6] * q1.z +
+                          kv[7] * q1.w;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const float s = acc[p] * a.scale;
+            sb[p * SP + j] = a.softcap > 0.f ? a.softcap * tanhf(s / a.softcap) : s;
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: softmax statistics
+    for (int p = warp * 4; p < warp * 4 + 4; ++p) {
+        float m = -INFINITY;
+        for (int j = lane; j < a.n_keys; j += 32) m = fmaxf(m, sb[p * SP + j]);
+        m = warp_max(m);
+        float s = 0.f;
+        if (m > -INFINITY)
+            for (int j = lane; j < a.n_keys; j += 32) s += __expf(sb[p * SP + j] - m);
+        s = warp_sum(s);
+        if (lane == 0) { mx[p] = m; inv[p] = (s > 0.f && actf[p] > 0.f) ? 1.f / s : 0.f; }
+    }
+    __syncthreads();
+    // ---- phase 3: dP, dS; dV and dK
+    for (int j = tid; j < SP; j += 256) {
+        if (j >= a.n_keys || !visible(j)) {
+            for (int p = 0; p < 32; ++p) sb[p * SP + j] = 0.f;
+            continue;
+        }
+        float acc[32], pr[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) acc[p] = 0.f;
+        const T *vr = Vb + (long)j * a.kv_rs;
+        for (int c = 0; c < hd; c += 8) {
+            float vv[8];
+            load8<T>(vr + c, vv);
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const float4 g0 = *reinterpret_cast<const float4 *>(dos + p * hd + c);
+                const float4 g1 = *reinterpret_cast<const float4 *>(dos + p * hd + c + 4);
+                acc[p] += vv[0] * g0.x + vv[1] * g0.y + vv[2] * g0.z + vv[3] * g0.w + vv[4] * g1.x + vv[5] * g1.y + vv[6] * g1.z +
+                          vv[7] * g1.w;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const float lg = sb[p * SP + j];
+            const float pv = inv[p] > 0.f ? __expf(lg - mx[p]) * inv[p] : 0.f;
+            const float th = a.softcap > 0.f ? lg / a.softcap : 0.f;
+            pr[p] = pv;
+            acc[p] = pv * (acc[p] - Dp[p]) * (1.f - th * th) * a.scale;   // dS
+            sb[p * SP + j] = acc[p];
+        }
+        // MQA: all heads of the tile add into the same key row; SigLIP: hpc == 1
+        float *dVr = a.dV + (long)b * a.dkv_bs + (long)j * a.dkv_rs + (long)head0 * a.dkv_hs;
+        float *dKr = a.dK + (long)b * a.dkv_bs + (long)j * a.dkv_rs + (long)head0 * a.dkv_hs;
+        for (int c = 0; c < hd; c += 8) {
+            float av[8], ak[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = ak[i] = 0.f;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const float4 g0 = *reinterpret_cast<const float4 *>(dos + p * hd + c);
+                const float4 g1 = *reinterpret_cast<const float4 *>(dos + p * hd + c + 4);
+                const float4 q0 = *reinterpret_cast<const float4 *>(qs + p * hd + c);
+                const float4 q1 = *reinterpret_cast<const float4 *>(qs + p * hd + c + 4);
+                av[0] += pr[p] * g0.x; av[1] += pr[p] * g0.y; av[2] += pr[p] * g0.z; av[3] += pr[p] * g0.w;
+                av[4] += pr[p] * g1.x; av[5] += pr[p] * g1.y; av[6] += pr[p] * g1.z; av[7] += pr[p] * g1.w;
+                ak[0] += acc[p] * q0.x; ak[1] += acc[p] * q0.y; ak[2] += acc[p] * q0.z; ak[3] += acc[p] * q0.w;
+                ak[4] += acc[p] * q1.x; ak[5] += acc[p] * q1.y; ak[6] += acc[p] * q1.z; ak[7] += acc[p] * q1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { atomicAdd(dVr + c + i, av[i]); atomicAdd(dKr + c + i, ak[i]); }
+        }
+    }
+    __syncthreads();
+    // ---- phase 4: dQ
+    if (tid < hd) {
+        float acc[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) acc[p] = 0.f;
+        const T *kc = Kb + tid;
+        for (int j = 0; j < a.n_keys; j += 4) {
+            float k4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) k4[i] = (j + i < a.n_keys) ? to_f32<T>(kc[(long)(j + i) * a.kv_rs]) : 0.f;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(sb + p * SP + j);
+                acc[p] += s4.x * k4[0] + s4.y * k4[1] + s4.z * k4[2] + s4.w * k4[3];
+            }
+        }
+        float *dQp = a.dQ[seg];
+        for (int p = 0; p < 32; ++p) {
+            const int hi = p / QT, ri = p % QT;
+            const int row = tile * QT + ri;
+            if (row < rows) dQp[((long)b * rows + row) * a.dq_rs + (head0 + hi) * hd + tid] = acc[p];
+        }
+    }
+}
+
+template <typename T>
+int attn_bwd(AttnBwdArgs a, cudaStream_t st, const char **err) {
+    if (a.hd % 8 || a.hd > 256) { *err = "attention backward: head_dim must be a multiple of 8, <= 256"; return PZ_ERR_INVALID; }
+    a.hpc = (a.kv_hs == 0 && 32 % a.n_heads == 0) ? a.n_heads : 1;
+    a.sp = rup(a.n_keys, 4);
+    const int QT = 32 / a.hpc;
+    int tiles = 0;
+    for (int s = 0; s < a.n_seg; ++s) if (a.seg_active[s]) tiles += (a.seg_rows[s] + QT - 1) / QT;
+    if (!tiles) return 0;
+    size_t smem = (size_t)(64 * a.hd + 32 * a.sp + 128) * sizeof(float);
+    if (smem > 220 * 1024) { *err = "attention backward: too many keys for the shared-memory score tile"; return PZ_ERR_INVALID; }
+    static PerDeviceOnce once;
+    if (once.need()) cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    launch_k(attn_bwd_kernel<T>, dim3(tiles, a.n_heads / a.hpc, a.batch), dim3(256), smem, st, a);
+    return 0;
+}
+
+// ========================================================= host helpers ====
+// one linear layer of the training step: the tensor-core / skinny kernels where the shape has one, otherwise the SIMT
+// kernel (the 7- and 8-wide matrices of the action heads and the fp32 build)
+template <typename T>
+int tlin(pz_handle *h, const LinearArgs &a, cudaStream_t st) {
+    if (std::is_same<T, bf16>::value && !(h->cfg.flags & PZ_FLAG_SIMPLE_KERNELS)) {
+        if (skinny_supported(a)) return launch_linear_skinny(a, st);
+        if (gemm_tc_supported(a)) {
+            const char *e = nullptr;
+            int rc = launch_linear_tc(a, st, &e);
+            if (rc) return fail(h, rc, e ? e : "tcgen05 gemm launch failed");
+            return 0;
+        }
+    }
+    launch_linear_simple<T>(a, st);
+    return 0;
+}
+
+struct Scratch {          // transposed operands of one backward linear layer
+    void *tA, *tB, *wT;
+};
+
+// Backward of y = x W^T (bias handled by the caller through colsum):
+//   dX [M,K] (fp32 `dx_flags` = LIN_OUT_F32 [| LIN_ACCUM], or T with 0) = dY . W
+//   dW [N,K] fp32 += dY^T . X
+// dY: T [M,N] (ld ldy); X: T [M,K] (ld ldx); W: T [N,K].
+template <typename T>
+int linear_bwd(pz_handle *h, const void *dY, int ldy, const void *X, int ldx, const void *W, void *dX, int ld_dx,
+               int dx_flags, float *dW, int M, int N, int K, const Scratch &sc, cudaStream_t st) {
+    PdlOff no_pdl;   // the "weight" operand of both products is written by the transpose right in front of them
+    if (dX) {
+        transpose<T>((const T *)W, K, (T *)sc.wT, rup(N, 8), N, K, st);            // W^T: [K][N]
+        LinearArgs a = lin(dY, ldy, sc.wT, nullptr, dX, ld_dx, M, K, rup(N, 8), dx_flags);
+        if (rup(N, 8) != N && ldy < rup(N, 8)) return fail(h, PZ_ERR_INVALID, "linear_bwd: dY row stride smaller than the padded width");
+        PZ_TRY(tlin<T>(h, a, st));
+    }
+    if (dW) {
+        const int Mp = rup(M, 8);
+        transpose<T>((const T *)dY, ldy, (T *)sc.tA, Mp, M, N, st);               // dY^T: [N][Mp]
+        transpose<T>((const T *)X, ldx, (T *)sc.tB, Mp, M, K, st);                // X^T : [K][Mp]
+        PZ_TRY(tlin<T>(h, lin(sc.tA, Mp, sc.tB, nullptr, dW, K, N, K, Mp, LIN_OUT_F32 | LIN_ACCUM), st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------ workspace ----
+struct MixDims { int rows, hidden, inter; };   // rows per sample
+
+struct TrainWs {
+    // saved by the forward
+    void *patches;                              // T [Mv, kp]
+    std::vector<float *> xv;                    // [LV + 1] fp32 [Mv, V]: SigLIP residual stream entering layer i
+    std::vector<float *> xv_mid;                // [LV] after attention
+    std::vector<void *> qkvv, av, f1, actv;     // [LV] T
+    void *hv_post;                              // T [Mv, V] post layernorm output
+    float *feats;                               // fp32 [Mv, H]
+    std::vector<float *> xin[3];                // [L + 1] fp32 [M_m, H_m]
+    std::vector<float *> x1[3];                 // [L]
+    std::vector<void *> q[3], att[3], gu[3], mm[3];   // [L] T
+    std::vector<void *> K, V;                   // [L] T [B][S_all][hd]
+    void *a_in, *e1, *temb, *z, *pp, *hfin;     // T
+    float *tbias, *zpre, *vel, *psi;
+    // scratch
+    void *h, *qkv, *tA, *tB, *wT, *dyb, *d_m, *dgu, *dqkv;
+    void *datt[3];
+    float *dx[3], *dq[3], *dh, *dK, *dV;
+    float *att_scratch; size_t att_scratch_bytes;
+    size_t total;
+};
+
+TrainWs carve_train(const pz_config &c, int B, void *base) {
+    TrainWs w;
+    Bump b;
+    b.base = (char *)base;
+    const size_t es = c.dtype == PZ_BF16 ? 2 : 4;
+    const int L = c.n_layers, LV = c.vit_layers;
+    const int S_all = c.s_vlm + c.cond_steps + c.horizon;
+    const size_t qd = (size_t)c.n_heads * c.head_dim, qkvd = (size_t)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+    const size_t Mv = (size_t)B * c.n_images * c.n_img_tokens;
+    const int V = c.vit_hidden, VI = c.vit_inter, H = c.vlm_hidden, A = c.act_hidden;
+    const MixDims md[3] = {{c.s_vlm, H, c.vlm_inter}, {c.cond_steps, A, c.act_inter}, {c.horizon, A, c.act_inter}};
+    w.patches = b.take<void>(Mv * c.patch_k_pad * es);
+    w.xv.resize(LV + 1); w.xv_mid.resize(LV); w.qkvv.resize(LV); w.av.resize(LV); w.f1.resize(LV); w.actv.resize(LV);
+    for (int i = 0; i <= LV; ++i) w.xv[i] = b.take<float>(Mv * V * 4);
+    for (int i = 0; i < LV; ++i) {
+        w.xv_mid[i] = b.take<float>(Mv * V * 4);
+        w.qkvv[i] = b.take<void>(Mv * 3 * V * es);
+        w.av[i] = b.take<void>(Mv * V * es);
+        w.f1[i] = b.take<void>(Mv * VI * es);
+        w.actv[i] = b.take<void>(Mv * VI * es);
+    }
+    w.hv_post = b.take<void>(Mv * V * es);
+    w.feats = b.take<float>(Mv * H * 4);
+    size_t Mmax = 0, MHmax = 0, MImax = 0;
+    for (int m = 0; m < 3; ++m) {
+        const size_t M = (size_t)B * md[m].rows;
+        Mmax = M > Mmax ? M : Mmax;
+        MHmax = M * md[m].hidden > MHmax ? M * md[m].hidden : MHmax;
+        MImax = M * md[m].inter > MImax ? M * md[m].inter : MImax;
+        w.xin[m].resize(L + 1); w.x1[m].resize(L); w.q[m].resize(L); w.att[m].resize(L); w.gu[m].resize(L); w.mm[m].resize(L);
+        for (int l = 0; l <= L; ++l) w.xin[m][l] = b.take<float>(M * md[m].hidden * 4);
+        for (int l = 0; l < L; ++l) {
+            w.x1[m][l] = b.take<float>(M * md[m].hidden * 4);
+            w.q[m][l] = b.take<void>(M * qd * es);
+            w.att[m][l] = b.take<void>(M * qd * es);
+            w.gu[m][l] = b.take<void>(M * 2 * md[m].inter * es);
+            w.mm[m][l] = b.take<void>(M * md[m].inter * es);
+        }
+        w.datt[m] = b.take<void>(M * qd * es);
+        w.dx[m] = b.take<float>(M * md[m].hidden * 4);
+        w.dq[m] = b.take<float>(M * qd * 4);
+    }
+    w.K.resize(L); w.V.resize(L);
+    for (int l = 0; l < L; ++l) {
+        w.K[l] = b.take<void>((size_t)B * S_all * c.head_dim * es);
+        w.V[l] = b.take<void>((size_t)B * S_all * c.head_dim * es);
+    }
+    const size_t Ma = (size_t)B * c.horizon, Mp = (size_t)B * c.cond_steps;
+    w.a_in = b.take<void>(Ma * 64 * es);
+    w.e1 = b.take<void>(Ma * A * es);
+    w.temb = b.take<void>((size_t)rup(B, 8) * A * es);
+    w.z = b.take<void>(Ma * A * es);
+    w.pp = b.take<void>(Mp * 64 * es);
+    w.hfin = b.take<void>(Ma * A * es);
+    w.tbias = b.take<float>((size_t)B * A * 4);
+    w.zpre = b.take<float>(Ma * A * 4);
+    w.vel = b.take<float>(Ma * 8 * 4);
+    w.psi = b.take<float>(Ma * c.action_dim * 4);
+    // scratch: sized for the widest operand of any backward linear layer (SigLIP rows included)
+    size_t rows_max = Mmax > Mv ? Mmax : Mv;
+    size_t wide = qkvd;                                  // widest dY / X feature count
+    const size_t cand[] = {(size_t)2 * c.vlm_inter, (size_t)2 * c.act_inter, (size_t)3 * V, (size_t)VI, (size_t)H, (size_t)c.patch_k_pad, qd};
+    for (size_t v : cand) wide = v > wide ? v : wide;
+    const size_t t_elems = wide * (rows_max + 8);
+    size_t w_elems = (size_t)2 * c.vlm_inter * H;
+    const size_t wc[] = {(size_t)2 * c.act_inter * A, (size_t)3 * V * V, (size_t)VI * V, qkvd * H, qd * H, (size_t)H * V, (size_t)V * c.patch_k_pad};
+    for (size_t v : wc) w_elems = v > w_elems ? v : w_elems;
+    w.tA = b.take<void>(t_elems * es);
+    w.tB = b.take<void>(t_elems * es);
+    w.wT = b.take<void>((w_elems + 8 * wide) * es);
+    size_t hmax = MHmax > Mv * V ? MHmax : Mv * V;
+    w.h = b.take<void>(hmax * es);
+    w.dyb = b.take<void>((hmax > Mv * (size_t)H ? hmax : Mv * (size_t)H) * es);
+    w.dh = b.take<float>((hmax > Mv * (size_t)3 * V ? hmax : Mv * (size_t)3 * V) * 4);
+    w.qkv = b.take<void>((Mmax * qkvd > Mv * 3 * V ? Mmax * qkvd : Mv * 3 * V) * es);
+    w.dqkv = b.take<void>((Mmax * qkvd > Mv * 3 * V ? Mmax * qkvd : Mv * 3 * V) * es);
+    size_t imax = MImax > Mv * VI ? MImax : Mv * VI;
+    w.d_m = b.take<void>(imax * es);
+    w.dgu = b.take<void>(2 * imax * es);
+    w.dK = b.take<float>((size_t)B * S_all * c.head_dim * 4);
+    w.dV = b.take<float>((size_t)B * S_all * c.head_dim * 4);
+    {
+        size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
+        size_t tiles = (S_all + 63) / 64;
+        w.att_scratch_bytes = rows <= 64 ? (size_t)B * tiles * rows * (c.head_dim + 2) * 4 : 0;
+        w.att_scratch = b.take<float>(w.att_scratch_bytes);
+    }
+    w.total = (b.off + 1023) & ~(size_t)1023;
+    return w;
+}
+
+// the gradient buffers: the same structs as the weights, every non-null pointer an fp32 buffer of the packed shape
+struct Grads {
+    pz_weights g;
+    std::vector<pz_vit_layer> vit;
+    std::vector<pz_mix_layer> mix[3];
+};
+inline float *G(const void *p) { return (float *)const_cast<void *>(p); }
+
+template <typename T>
+int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len, const float *proprio,
+                     const float *actions, const float *noise, const float *t, float sig_min, const Grads *gr, float *loss,
+                     float loss_scale, void *wsp, int B, int flags, cudaStream_t st) {
+    const pz_config &c = h->cfg;
+    const pz_weights &w = h->w;
+    if (!w.enc_w2t || !w.enc_b2 || !w.time_freq) return fail(h, PZ_ERR_UNBOUND, "enc_w2t / enc_b2 / time_freq not bound");
+    TrainWs ws = carve_train(c, B, wsp);
+    const int L = c.n_layers, LV = c.vit_layers;
+    const int H = c.vlm_hidden, A = c.act_hidden, hd = c.head_dim, nh = c.n_heads;
+    const int S_v = c.s_vlm, S_p = c.cond_steps, Hz = c.horizon, S_c = S_v + S_p, S_all = S_c + Hz;
+    const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
+    const long kv_bs = (long)S_all * hd;
+    const int V = c.vit_hidden, VI = c.vit_inter, P = c.n_img_tokens, hdv = V / c.vit_heads;
+    const int n_img = B * c.n_images, Mv = n_img * P;
+    const MixDims md[3] = {{S_v, H, c.vlm_inter}, {S_p, A, c.act_inter}, {Hz, A, c.act_inter}};
+    const pz_mix_layer *mixw[3] = {h->vlm.data(), h->proprio.data(), h->action.data()};
+    const int row_off[3] = {0, S_v, S_c};
+    const float *rc_[3] = {w.rope_vlm_cos, w.rope_act_cos, w.rope_act_cos};
+    const float *rs_[3] = {w.rope_vlm_sin, w.rope_act_sin, w.rope_act_sin};
+    const int pos0[3] = {0, 0, S_p};
+    const int Ma = B * Hz, Mp = B * S_p;
+    const int skp = w.small_k_pad;
+    const bool want_grads = gr != nullptr;
+    const bool vit_grads = want_grads && !(flags & PZ_TRAIN_FREEZE_VISION);
+    Scratch sc{ws.tA, ws.tB, ws.wT};
+    const char *err = nullptr;
+
+    // ================================================================ forward
+    // ---- SigLIP (siglip.py:59-78, 220-238, 298) with the residual stream and the GEMM inputs of every layer kept
+    if (h->pixel_format == PZ_PIXELS_U8) launch_im2col_u8<T>((const uint8_t *)pixels, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+    else launch_im2col<T>((const T *)pixels, (T *)ws.patches, n_img, c.image_size, c.patch_size, c.patch_k_pad, st);
+    launch_bcast_rows(ws.xv[0], w.pos_emb, Mv, V, P, st);
+    PZ_TRY(tlin<T>(h, lin(ws.patches, c.patch_k_pad, w.patch_w, w.patch_b, ws.xv[0], V, Mv, V, c.patch_k_pad, LIN_OUT_F32 | LIN_ACCUM), st));
+    for (int i = 0; i < LV; ++i) {
+        const pz_vit_layer &Lw = h->vit[i];
+        launch_layernorm<T>(ws.xv[i], Lw.ln1_w, Lw.ln1_b, (T *)ws.h, Mv, V, 1e-6f, st);
+        PZ_TRY(tlin<T>(h, lin(ws.h, V, Lw.w_qkv, Lw.b_qkv, ws.qkvv[i], 3 * V, Mv, 3 * V, V), st));
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.Q = ws.qkvv[i]; a.q_batch_stride = (long)P * 3 * V; a.q_row_stride = 3 * V; a.q_head_stride = hdv;
+        a.K = (const T *)ws.qkvv[i] + V; a.V = (const T *)ws.qkvv[i] + 2 * V;
+        a.kv_batch_stride = (long)P * 3 * V; a.kv_row_stride = 3 * V; a.kv_head_stride = hdv;
+        a.O = ws.av[i]; a.o_batch_stride = (long)P * V; a.o_row_stride = V; a.o_head_stride = hdv;
+        a.batch = n_img; a.n_heads = c.vit_heads; a.head_dim = hdv; a.q_rows = P; a.q_row0 = 0;
+        a.s_cache = P; a.s_vlm = P; a.n_fresh = 0;
+        a.scale = 1.0f / sqrtf((float)hdv); a.softcap = 0.f;
+        PZ_TRY(Ops<T>::attention(h, a, st));
+        copy_f32(ws.xv_mid[i], ws.xv[i], (size_t)Mv * V, st);
+        PZ_TRY(tlin<T>(h, lin(ws.av[i], V, Lw.w_o, Lw.b_o, ws.xv_mid[i], V, Mv, V, V, LIN_OUT_F32 | LIN_ACCUM), st));
+        launch_layernorm<T>(ws.xv_mid[i], Lw.ln2_w, Lw.ln2_b, (T *)ws.h, Mv, V, 1e-6f, st);
+        PZ_TRY(tlin<T>(h, lin(ws.h, V, Lw.w_fc1, Lw.b_fc1, ws.f1[i], VI, Mv, VI, V), st));
+        launch_k(gelu_fwd_kernel<T>, dim3(ew_blocks((long)Mv * VI)), dim3(256), 0, st, (const T *)ws.f1[i], (T *)ws.actv[i], (long)Mv * VI);
+        copy_f32(ws.xv[i + 1], ws.xv_mid[i], (size_t)Mv * V, st);
+        PZ_TRY(tlin<T>(h, lin(ws.actv[i], VI, Lw.w_fc2, Lw.b_fc2, ws.xv[i + 1], V, Mv, V, VI, LIN_OUT_F32 | LIN_ACCUM), st));
+    }
+    launch_layernorm<T>(ws.xv[LV], w.post_ln_w, w.post_ln_b, (T *)ws.hv_post, Mv, V, 1e-6f, st);
+    PZ_TRY(tlin<T>(h, lin(ws.hv_post, V, w.proj_w, w.proj_b, ws.feats, H, Mv, H, V, LIN_OUT_F32), st));
+    launch_embed_merge<T>(ids, (const T *)w.embed, ws.feats, ws.xin[0][0], B, S_v, H, c.n_images * P, c.image_token_index,
+                          c.pad_token_id, sqrtf((float)H), st);
+    // ---- proprio encoder, time embedding, action encoder (pizero.py:597-639, vla/modules.py:9-53)
+    launch_cast_pad<T>(proprio, (T *)ws.pp, Mp, c.proprio_dim, skp, st);
+    PZ_TRY(tlin<T>(h, lin(ws.pp, skp, w.prop_w, w.prop_b, ws.xin[1][0], A, Mp, A, skp, LIN_OUT_F32, sqrtf((float)A)), st));
+    launch_psi(noise, actions, t, ws.psi, B, Hz * c.action_dim, sig_min, st);
+    cudaMemsetAsync(ws.temb, 0, (size_t)rup(B, 8) * A * sizeof(T), st);
+    launch_time_embed<T>(t, w.time_freq, (T *)ws.temb, B, A / 2, st);
+    PZ_TRY(tlin<T>(h, lin(ws.temb, A, w.enc_w2t, w.enc_b2, ws.tbias, A, B, A, A, LIN_OUT_F32), st));
+    launch_cast_pad<T>(ws.psi, (T *)ws.a_in, Ma, c.action_dim, skp, st);
+    PZ_TRY(tlin<T>(h, lin(ws.a_in, skp, w.enc_w1, w.enc_b1, ws.e1, A, Ma, A, skp), st));
+    PZ_TRY(tlin<T>(h, lin(ws.e1, A, w.enc_w2a, nullptr, ws.zpre, A, Ma, A, A, LIN_OUT_F32), st));
+    launch_rowbias_silu<T>(ws.zpre, ws.tbias, (T *)ws.z, Ma, A, Hz, st);
+    PZ_TRY(tlin<T>(h, lin(ws.z, A, w.enc_w3, w.enc_b3, ws.xin[2][0], A, Ma, A, A, LIN_OUT_F32, sqrtf((float)A)), st));
+    // ---- joint model, all three mixtures active, no cache (joint_model.py:24-127, 243-305)
+    for (int l = 0; l < L; ++l) {
+        const bool last = l == L - 1;
+        T *Kl = (T *)ws.K[l], *Vl = (T *)ws.V[l];
+        for (int m = 0; m < 3; ++m) {
+            const int M = B * md[m].rows, Hm = md[m].hidden;
+            const pz_mix_layer &Lw = mixw[m][l];
+            launch_rmsnorm<T>(ws.xin[m][l], Lw.norm_in, (T *)ws.h, M, Hm, 1e-6f, st);
+            PZ_TRY(tlin<T>(h, lin(ws.h, Hm, Lw.w_qkv, nullptr, ws.qkv, qkvd, M, qkvd, Hm), st));
+            launch_rope_split<T>((const T *)ws.qkv, qkvd, (T *)ws.q[m][l], (long)md[m].rows * qd, Kl + (size_t)row_off[m] * hd,
+                                 Vl + (size_t)row_off[m] * hd, kv_bs, rc_[m], rs_[m], B, md[m].rows, pos0[m], nh, hd, st);
+        }
+        for (int m = 0; m < 3; ++m) {
+            if (last && m < 2) continue;   // joint_model.py:297-299: the vlm / proprio halves of the last layer are dropped
+            AttnArgs a;
+            memset(&a, 0, sizeof(a));
+            a.K = Kl; a.V = Vl; a.kv_batch_stride = kv_bs; a.kv_row_stride = hd; a.kv_head_stride = 0;
+            a.valid_len = valid_len;
+            a.batch = B; a.n_heads = nh; a.head_dim = hd; a.s_cache = S_c; a.s_vlm = S_v;
+            a.scale = 1.0f / sqrtf((float)hd); a.softcap = 50.f;
+            a.q_row_stride = qd; a.q_head_stride = hd; a.o_row_stride = qd; a.o_head_stride = hd;
+            a.Q = ws.q[m][l]; a.q_batch_stride = (long)md[m].rows * qd;
+            a.O = ws.att[m][l]; a.o_batch_stride = (long)md[m].rows * qd;
+            a.q_rows = md[m].rows; a.q_row0 = row_off[m];
+            a.scratch = ws.att_scratch; a.scratch_bytes = ws.att_scratch_bytes;
+            // rows >= valid_len are skipped by the attention kernels: give them a defined (zero) output -- the backward
+            // multiplies every saved row by a gradient row, and 0 * uninitialised is not 0
+            if (m == 0) cudaMemsetAsync(ws.att[m][l], 0, (size_t)B * md[m].rows * qd * sizeof(T), st);
+            if (m == 2) {
+                a.n_fresh = Hz;
+                a.K2 = Kl + (size_t)S_c * hd; a.V2 = Vl + (size_t)S_c * hd; a.kv2_batch_stride = kv_bs; a.kv2_row_stride = hd;
+            }
+            PZ_TRY(Ops<T>::attention(h, a, st));
+        }
+        for (int m = 0; m < 3; ++m) {
+            if (last && m < 2) continue;
+            const int M = B * md[m].rows, Hm = md[m].hidden, Im = md[m].inter;
+            const pz_mix_layer &Lw = mixw[m][l];
+            copy_f32(ws.x1[m][l], ws.xin[m][l], (size_t)M * Hm, st);
+            PZ_TRY(tlin<T>(h, lin(ws.att[m][l], qd, Lw.w_o, nullptr, ws.x1[m][l], Hm, M, Hm, qd, LIN_OUT_F32 | LIN_ACCUM), st));
+            launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
+            PZ_TRY(tlin<T>(h, lin(ws.h, Hm, Lw.w_gate_up, nullptr, ws.gu[m][l], 2 * Im, M, 2 * Im, Hm), st));
+            launch_k(geglu_fwd_kernel<T>, dim3(ew_blocks((long)M * Im)), dim3(256), 0, st, (const T *)ws.gu[m][l], (T *)ws.mm[m][l],
+                     (long)M * Im, Im);
+            copy_f32(ws.xin[m][l + 1], ws.x1[m][l], (size_t)M * Hm, st);
+            PZ_TRY(tlin<T>(h, lin(ws.mm[m][l], Im, Lw.w_down, nullptr, ws.xin[m][l + 1], Hm, M, Hm, Im, LIN_OUT_F32 | LIN_ACCUM), st));
+        }
+    }
+    // ---- final norm, action decoder, loss (joint_model.py:375-380, pizero.py:657-661)
+    launch_rmsnorm<T>(ws.xin[2][L], w.action_final_norm, (T *)ws.hfin, Ma, A, 1e-6f, st);
+    PZ_TRY(tlin<T>(h, lin(ws.hfin, A, w.dec_w, w.dec_b, ws.vel, 8, Ma, c.action_dim, A, LIN_OUT_F32), st));
+    launch_fm_loss(ws.vel, 8, noise, actions, loss, nullptr, Ma, c.action_dim, sig_min, st);
+    if (!want_grads) return 0;
+
+    // =============================================================== backward
+    const pz_weights &g = gr->g;
+    const pz_mix_layer *mixg[3] = {gr->mix[0].data(), gr->mix[1].data(), gr->mix[2].data()};
+    // ---- loss -> action decoder -> final norm
+    T *dv = (T *)ws.dyb;
+    launch_k(loss_bwd_kernel<T>, dim3((Ma * 8 + 255) / 256), dim3(256), 0, st, (const float *)ws.vel, 8, noise, actions, dv, (long)Ma,
+             c.action_dim, sig_min, loss_scale);
+    colsum<T>(dv, 8, G(g.dec_b), Ma, c.action_dim, st);
+    PZ_TRY(linear_bwd<T>(h, dv, 8, ws.hfin, A, w.dec_w, ws.dh, A, LIN_OUT_F32, G(g.dec_w), Ma, 8, A, sc, st));
+    for (int m = 0; m < 3; ++m) cudaMemsetAsync(ws.dx[m], 0, (size_t)B * md[m].rows * md[m].hidden * 4, st);
+    rmsnorm_bwd(ws.xin[2][L], w.action_final_norm, ws.dh, ws.dx[2], G(g.action_final_norm), Ma, A, st);
+    // ---- layers, last to first
+    for (int l = L - 1; l >= 0; --l) {
+        const bool last = l == L - 1;
+        for (int m = 0; m < 3; ++m) {
+            if (last && m < 2) continue;
+            const int M = B * md[m].rows, Hm = md[m].hidden, Im = md[m].inter;
+            const pz_mix_layer &Lw = mixw[m][l];
+            const pz_mix_layer &Lg = mixg[m][l];
+            // MLP: x_out = x1 + down(gelu(g) u)
+            cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
+            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.mm[m][l], Im, Lw.w_down, ws.d_m, Im, 0, G(Lg.w_down), M, Hm, Im, sc, st));
+            launch_k(geglu_bwd_kernel<T>, dim3(ew_blocks((long)M * Im)), dim3(256), 0, st, (const T *)ws.gu[m][l], (const T *)ws.d_m,
+                     (T *)ws.dgu, (long)M * Im, Im);
+            launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
+            PZ_TRY(linear_bwd<T>(h, ws.dgu, 2 * Im, ws.h, Hm, Lw.w_gate_up, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_gate_up), M, 2 * Im, Hm, sc, st));
+            rmsnorm_bwd(ws.x1[m][l], Lw.norm_post, ws.dh, ws.dx[m], G(Lg.norm_post), M, Hm, st);   // dx is now d / d x1
+            // attention output projection: x1 = x + o_proj(att)
+            cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
+            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.att[m][l], qd, Lw.w_o, ws.datt[m], qd, 0, G(Lg.w_o), M, Hm, qd, sc, st));
+        }
+        // attention
+        cudaMemsetAsync(ws.dK, 0, (size_t)B * S_all * hd * 4, st);
+        cudaMemsetAsync(ws.dV, 0, (size_t)B * S_all * hd * 4, st);
+        AttnBwdArgs ab;
+        memset(&ab, 0, sizeof(ab));
+        ab.n_seg = 3;
+        for (int m = 0; m < 3; ++m) {
+            ab.seg_rows[m] = md[m].rows;
+            ab.seg_active[m] = !(last && m < 2);
+            ab.Q[m] = ws.q[m][l]; ab.dO[m] = ws.datt[m]; ab.O[m] = ws.att[m][l]; ab.dQ[m] = ws.dq[m];
+        }
+        ab.q_rs = ab.o_rs = ab.dq_rs = qd;
+        ab.K = ws.K[l]; ab.V = ws.V[l]; ab.kv_bs = kv_bs; ab.kv_rs = hd; ab.kv_hs = 0;
+        ab.dK = ws.dK; ab.dV = ws.dV; ab.dkv_bs = kv_bs; ab.dkv_rs = hd; ab.dkv_hs = 0;
+        ab.valid_len = valid_len; ab.s_v = S_v; ab.s_p = S_p;
+        ab.n_keys = S_all; ab.batch = B; ab.n_heads = nh; ab.hd = hd;
+        ab.scale = 1.0f / sqrtf((float)hd); ab.softcap = 50.f;
+        {
+            int rc = attn_bwd<T>(ab, st, &err);
+            if (rc) return fail(h, rc, err ? err : "attention backward failed");
+        }
+        // q / k / v projections and the input norm
+        for (int m = 0; m < 3; ++m) {
+            const int M = B * md[m].rows, Hm = md[m].hidden;
+            const pz_mix_layer &Lw = mixw[m][l];
+            const pz_mix_layer &Lg = mixg[m][l];
+            launch_k(rope_bwd_merge_kernel<T>, dim3(M), dim3(256), 0, st, (const float *)((last && m < 2) ? nullptr : ws.dq[m]),
+                     (const float *)ws.dK, (const float *)ws.dV, kv_bs, row_off[m], rc_[m], rs_[m], pos0[m], (T *)ws.dqkv, md[m].rows, nh, hd);
+            launch_rmsnorm<T>(ws.xin[m][l], Lw.norm_in, (T *)ws.h, M, Hm, 1e-6f, st);
+            PZ_TRY(linear_bwd<T>(h, ws.dqkv, qkvd, ws.h, Hm, Lw.w_qkv, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_qkv), M, qkvd, Hm, sc, st));
+            rmsnorm_bwd(ws.xin[m][l], Lw.norm_in, ws.dh, ws.dx[m], G(Lg.norm_in), M, Hm, st);
+        }
+    }
+    // ---- action encoder (vla/modules.py:39-53); dx[2] = d / d (sqrt(A) * linear_3(z))
+    {
+        T *dy3 = (T *)ws.dyb;
+        cast_scale<T>(ws.dx[2], dy3, (long)Ma * A, sqrtf((float)A), st);
+        colsum<T>(dy3, A, G(g.enc_b3), Ma, A, st);
+        PZ_TRY(linear_bwd<T>(h, dy3, A, ws.z, A, w.enc_w3, ws.dh, A, LIN_OUT_F32, G(g.enc_w3), Ma, A, A, sc, st));
+        T *dzp = (T *)ws.dqkv;
+        launch_k(silu_bwd_kernel<T>, dim3(ew_blocks((long)Ma * A)), dim3(256), 0, st, (const float *)ws.zpre, (const float *)ws.tbias,
+                 (const float *)ws.dh, dzp, (long)Ma * A, A, Hz);
+        colsum<T>(dzp, A, G(g.enc_b2), Ma, A, st);
+        T *de1 = (T *)ws.d_m;
+        PZ_TRY(linear_bwd<T>(h, dzp, A, ws.e1, A, w.enc_w2a, de1, A, 0, G(g.enc_w2a), Ma, A, A, sc, st));
+        // time half: one input row per sample, its gradient is the sum over the sample's action tokens
+        T *dzs = (T *)ws.dgu;
+        launch_k(group_sum_kernel<T>, dim3((B * A + 255) / 256), dim3(256), 0, st, (const T *)dzp, dzs, (long)B * A, A, Hz);
+        PZ_TRY(linear_bwd<T>(h, dzs, A, ws.temb, A, w.enc_w2t, nullptr, 0, 0, G(g.enc_w2t), B, A, A, sc, st));
+        colsum<T>(de1, A, G(g.enc_b1), Ma, A, st);
+        PZ_TRY(linear_bwd<T>(h, de1, A, ws.a_in, skp, w.enc_w1, nullptr, 0, 0, G(g.enc_w1), Ma, A, skp, sc, st));
+    }
+    // ---- proprio encoder (pizero.py:630)
+    {
+        T *dyp = (T *)ws.dyb;
+        cast_scale<T>(ws.dx[1], dyp, (long)Mp * A, sqrtf((float)A), st);
+        colsum<T>(dyp, A, G(g.prop_b), Mp, A, st);
+        PZ_TRY(linear_bwd<T>(h, dyp, A, ws.pp, skp, w.prop_w, nullptr, 0, 0, G(g.prop_w), Mp, A, skp, sc, st));
+    }
+    if (!vit_grads) return 0;
+    // ---- embedding merge (pizero.py:376-414): image rows of the merged sequence are the projector output (the
+    // 1/sqrt(H) of the merge and the sqrt(H) of the joint model cancel); token embeddings are frozen (pizero.py:243-249)
+    const int n_feat = c.n_images * P;
+    float *dfe = ws.dh;   // fp32 [Mv, H]
+    cudaMemcpy2DAsync(dfe, (size_t)n_feat * H * 4, ws.dx[0], (size_t)S_v * H * 4, (size_t)n_feat * H * 4, B, cudaMemcpyDeviceToDevice, st);
+    T *dfb = (T *)ws.dyb;
+    cast_scale<T>(dfe, dfb, (long)Mv * H, 1.f, st);
+    colsum<T>(dfb, H, G(g.proj_b), Mv, H, st);
+    float *dxv = ws.feats;   // the forward's projector output is no longer needed: fp32 [Mv, H] >= [Mv, V]
+    PZ_TRY(linear_bwd<T>(h, dfb, H, ws.hv_post, V, w.proj_w, ws.dh, V, LIN_OUT_F32, G(g.proj_w), Mv, H, V, sc, st));
+    cudaMemsetAsync(dxv, 0, (size_t)Mv * V * 4, st);
+    layernorm_bwd(ws.xv[LV], w.post_ln_w, ws.dh, dxv, G(g.post_ln_w), G(g.post_ln_b), Mv, V, st);
+    for (int i = LV - 1; i >= 0; --i) {
+        const pz_vit_layer &Lw = h->vit[i];
+        const pz_vit_layer &Lg = gr->vit[i];
+        // MLP
+        cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
+        colsum<T>((const T *)ws.dyb, V, G(Lg.b_fc2), Mv, V, st);
+        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.actv[i], VI, Lw.w_fc2, ws.d_m, VI, 0, G(Lg.w_fc2), Mv, V, VI, sc, st));
+        launch_k(gelu_bwd_kernel<T>, dim3(ew_blocks((long)Mv * VI)), dim3(256), 0, st, (const T *)ws.f1[i], (const T *)ws.d_m, (T *)ws.dgu,
+                 (long)Mv * VI);
+        colsum<T>((const T *)ws.dgu, VI, G(Lg.b_fc1), Mv, VI, st);
+        launch_layernorm<T>(ws.xv_mid[i], Lw.ln2_w, Lw.ln2_b, (T *)ws.h, Mv, V, 1e-6f, st);
+        PZ_TRY(linear_bwd<T>(h, ws.dgu, VI, ws.h, V, Lw.w_fc1, ws.dh, V, LIN_OUT_F32, G(Lg.w_fc1), Mv, VI, V, sc, st));
+        layernorm_bwd(ws.xv_mid[i], Lw.ln2_w, ws.dh, dxv, G(Lg.ln2_w), G(Lg.ln2_b), Mv, V, st);
+        // attention
+        cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
+        colsum<T>((const T *)ws.dyb, V, G(Lg.b_o), Mv, V, st);
+        T *dav = (T *)ws.d_m;
+        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.av[i], V, Lw.w_o, dav, V, 0, G(Lg.w_o), Mv, V, V, sc, st));
+        float *dqkv32 = ws.dh;   // fp32 [Mv, 3V]: dq | dk | dv
+        cudaMemsetAsync(dqkv32, 0, (size_t)Mv * 3 * V * 4, st);
+        AttnBwdArgs ab;
+        memset(&ab, 0, sizeof(ab));
+        ab.n_seg = 1; ab.seg_rows[0] = P; ab.seg_active[0] = 1;
+        ab.Q[0] = ws.qkvv[i]; ab.dO[0] = dav; ab.O[0] = ws.av[i]; ab.dQ[0] = dqkv32;
+        ab.q_rs = 3 * V; ab.o_rs = V; ab.dq_rs = 3 * V;
+        ab.K = (const T *)ws.qkvv[i] + V; ab.V = (const T *)ws.qkvv[i] + 2 * V; ab.kv_bs = (long)P * 3 * V; ab.kv_rs = 3 * V; ab.kv_hs = hdv;
+        ab.dK = dqkv32 + V; ab.dV = dqkv32 + 2 * V; ab.dkv_bs = (long)P * 3 * V; ab.dkv_rs = 3 * V; ab.dkv_hs = hdv;
+        ab.valid_len = nullptr; ab.n_keys = P; ab.batch = n_img; ab.n_heads = c.vit_heads; ab.hd = hdv;
+        ab.scale = 1.0f / sqrtf((float)hdv); ab.softcap = 0.f;
+        {
+            int rc = attn_bwd<T>(ab, st, &err);
+            if (rc) return fail(h, rc, err ? err : "attention backward failed");
+        }
+        cast_scale<T>(dqkv32, (T *)ws.dqkv, (long)Mv * 3 * V, 1.f, st);
+        colsum<T>((const T *)ws.dqkv, 3 * V, G(Lg.b_qkv), Mv, 3 * V, st);
+        launch_layernorm<T>(ws.xv[i], Lw.ln1_w, Lw.ln1_b, (T *)ws.h, Mv, V, 1e-6f, st);
+        PZ_TRY(linear_bwd<T>(h, ws.dqkv, 3 * V, ws.h, V, Lw.w_qkv, ws.dh, V, LIN_OUT_F32, G(Lg.w_qkv), Mv, 3 * V, V, sc, st));
+        layernorm_bwd(ws.xv[i], Lw.ln1_w, ws.dh, dxv, G(Lg.ln1_w), G(Lg.ln1_b), Mv, V, st);
+    }
+    // ---- patch embedding (the convolution as a matrix product over unfolded patches) and the position table
+    if (g.pos_emb) launch_k(period_sum_kernel, dim3((P * V + 255) / 256), dim3(256), 0, st, (const float *)dxv, G(g.pos_emb), (long)P * V, V, P, n_img);
+    cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
+    colsum<T>((const T *)ws.dyb, V, G(g.patch_b), Mv, V, st);
+    PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.patches, c.patch_k_pad, w.patch_w, nullptr, 0, 0, G(g.patch_w), Mv, V, c.patch_k_pad, sc, st));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------- ABI ----
+extern "C" {
+
+size_t pz_train_workspace_bytes(const pz_handle *h, int batch) {
+    if (!h || batch < 1) return 0;
+    return carve_train(h->cfg, batch, nullptr).total;
+}
+
+int pz_flow_matching_step(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len, const float *proprio,
+                          const float *actions, const float *noise, const float *t, float sig_min, const pz_weights *grads,
+                          float loss_scale, float *loss, void *ws, size_t ws_bytes, int B, int flags, void *stream) {
+    if (!h) return PZ_ERR_INVALID;
+    if (!h->bound) return fail(h, PZ_ERR_UNBOUND, "pz_bind_weights has not been called");
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, PZ_ERR_INVALID, "batch out of range (1..max_batch)");
+    if (!ids || !pixels || !valid_len || !proprio || !actions || !noise || !t || !loss) return fail(h, PZ_ERR_INVALID, "null input");
+    if (!ws || ws_bytes < pz_train_workspace_bytes(h, B)) return fail(h, PZ_ERR_WORKSPACE, "training workspace too small");
+    if (((uintptr_t)ws) & 1023) return fail(h, PZ_ERR_WORKSPACE, "workspace must be 1 KiB aligned");
+    if (h->cfg.vlm_hidden > 2048 || h->cfg.act_hidden > 2048 || h->cfg.vit_hidden > 2048)
+        return fail(h, PZ_ERR_INVALID, "training step: hidden sizes up to 2048");
+    Grads gr;
+    if (grads) {
+        if (!grads->vit || !grads->vlm || !grads->proprio || !grads->action) return fail(h, PZ_ERR_INVALID, "gradient layer tables missing");
+        gr.g = *grads;
+        gr.vit.assign(grads->vit, grads->vit + h->cfg.vit_layers);
+        gr.mix[0].assign(grads->vlm, grads->vlm + h->cfg.n_layers);
+        gr.mix[1].assign(grads->proprio, grads->proprio + h->cfg.n_layers);
+        gr.mix[2].assign(grads->action, grads->action + h->cfg.n_layers);
+    }
+    h->lc.n = 0;
+    g_launch_counter = &h->lc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->cfg.dtype == PZ_BF16
+                 ? forward_backward<bf16>(h, ids, pixels, valid_len, proprio, actions, noise, t, sig_min, grads ? &gr : nullptr, loss,
+                                          loss_scale, ws, B, flags, st)
+                 : forward_backward<float>(h, ids, pixels, valid_len, proprio, actions, noise, t, sig_min, grads ? &gr : nullptr, loss,
+                                           loss_scale, ws, B, flags, st);
+    g_launch_counter = nullptr;
+    if (rc) return rc;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, PZ_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    return PZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""GPU parity of the flow-matching TRAINING STEP (`PiZero.forward` + `loss.backward()`, reference pizero.py:607-661 /
+train.py:350-368) through the C ABI (`pz_flow_matching_step`): loss and d loss / d parameter for every trainable tensor.
+
+Checkers: (1) `oracle.pizero_backward.flow_matching_backward_full` (the hand-written backward, itself pinned to the
+unmodified reference's autograd in tests/test_flow_matching.py) on the kernels' small shape; (2) the gradient norms and
+leading rows the UNMODIFIED reference's `loss.backward()` produced at the real widths (tests/golden/fm_width2.pt,
+oracle/make_golden_fm.py).  Tolerances, per tensor, relative Frobenius error: fp32 <= 2e-3; bf16 <= 6e-2 (bf16 operands
+in every product of a 2 x (27 + 18)-layer backward chain; the loss itself <= 2e-2)."""
+import os
+
+import pytest
+import torch
+
+from helpers import SMALL, max_abs, pz, rel_err
+from oracle import pizero_backward as Bk
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(d, sd, dtype):
+    from open_pi_zero_b200.pizero import PiZero
+    m = PiZero(pz.cfg_from_dims(d), init="empty")
+    m.load_state_dict(sd, strict=True)
+    return m.to(dtype).to("cuda")
+
+
+def _targets(d, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    actions = torch.rand((B, d["horizon_steps"], d["action_dim"]), generator=g) * 2 - 1
+    noise = torch.randn((B, d["horizon_steps"], d["action_dim"]), generator=g)
+    t = torch.rand((B,), generator=g)
+    return actions, noise, t
+
+
+def _step(m, inp, actions, noise, t, grads, **kw):
+    from open_pi_zero_b200.train import flow_matching_step
+    dt = next(m.parameters()).dtype
+    loss = flow_matching_step(m, inp["input_ids"].cuda(), inp["pixel_values"].cuda().to(dt), inp["proprios"].cuda(),
+                              actions.cuda(), t.cuda(), noise=noise.cuda(), valid_len=inp["valid_len"].cuda(), grads=grads, **kw)
+    torch.cuda.synchronize()
+    return loss
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 6e-2)])
+def test_small_every_gradient_vs_oracle(dtype, tol):
+    from open_pi_zero_b200.train import GradBuffer
+    d = SMALL
+    B = 3
+    sd = pz.init_state_dict(d, seed=13, randomize_norms=True, tie_proprio=False)
+    inp = pz.make_inputs(d, B, seed=31, min_text=0)
+    actions, noise, t = _targets(d, B, 5)
+    want_loss, want = Bk.flow_matching_backward_full(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                                                     inp["proprios"], actions, t, noise)
+    m = _model(d, sd, dtype)
+    gb = GradBuffer(m)
+    assert not gb.tied
+    loss = _step(m, inp, actions, noise, t, gb)
+    assert abs(float(loss) - float(want_loss)) < (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, float(want_loss))
+    got = gb.unpack()
+    worst, worst_key, checked, errs = 0.0, None, 0, {}
+    for k, g in want.items():
+        if k == "embed_tokens.weight":      # frozen in the reference's training (pizero.py:243-249); not produced
+            continue
+        assert k in got, k
+        assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
+        if float(g.abs().max()) == 0.0:     # the discarded last-layer vlm / proprio half
+            assert float(got[k].abs().max()) == 0.0, k
+            continue
+        if k.endswith("self_attn.k_proj.bias"):
+            # softmax is invariant to a constant added to every key: this gradient is zero in exact arithmetic and what is
+            # left is rounding noise -- compare it with the scale of the q bias gradient instead of with itself
+            scale = float(want[k.replace("k_proj", "q_proj")].norm())
+            assert float(g.norm()) < 1e-3 * scale and float(got[k].norm()) < (1e-3 if dtype == torch.float32 else 5e-2) * scale, k
+            continue
+        e = rel_err(got[k], g)
+        errs[k] = e
+        if e > worst:
+            worst, worst_key = e, k
+        checked += 1
+    print(f"[train step small {dtype}] loss {float(loss):.6f} vs {float(want_loss):.6f}; {checked} gradient tensors, worst "
+          f"relative error {worst:.3e} ({worst_key}); launches {m.last_launch_count}")
+    bad = {k: round(e, 5) for k, e in errs.items() if not e < tol}
+    assert checked >= 90
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 6e-2)])
+def test_width2_gradients_vs_reference_autograd(golden_dir, dtype, tol):
+    """Real widths (2048 / 16384, 1024 / 4096, 1152 / 4304, head_dim 256; 2 + 2 layers): gradient norms and leading rows
+    of the UNMODIFIED reference's loss.backward()."""
+    from open_pi_zero_b200.train import GradBuffer
+    path = os.path.join(golden_dir, "fm_width2.pt")
+    if not os.path.exists(path):
+        pytest.skip("fm_width2.pt missing")
+    fx = torch.load(path, weights_only=False)
+    if "grad_norms" not in fx["ref"]:
+        pytest.skip("fixture predates the gradient capture")
+    d = fx["dims"]
+    sd = pz.init_state_dict(d, seed=fx["seed"], randomize_norms=fx["randomize_norms"], tie_proprio=fx["tie_proprio"])
+    inp = pz.make_inputs(d, fx["batch"], seed=fx["inputs_seed"])
+    m = _model(d, sd, dtype)
+    del sd
+    gb = GradBuffer(m)
+    loss = _step(m, inp, fx["actions"], fx["noise"], fx["t"], gb)
+    ref = fx["ref"]
+    assert abs(float(loss) - float(ref["loss"])) < (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, float(ref["loss"]))
+    got = gb.unpack()
+    worst_n, worst_h, checked = 0.0, 0.0, 0
+    for k, want_n in ref["grad_norms"].items():
+        want_n = float(want_n)
+        if k not in got:   # frozen embedding (pizero.py:243-249) or a parameter the loss does not depend on (proprio final norm)
+            assert k in ("embed_tokens.weight", "lm_head.weight") or want_n == 0.0, k
+            continue
+        g = got[k]
+        if want_n == 0.0:
+            if ".17." in k or f".{d['num_layers'] - 1}." in k:
+                assert float(g.abs().max()) == 0.0, k
+            continue
+        if k.endswith("self_attn.k_proj.bias"):   # zero in exact arithmetic (see above): rounding noise on both sides
+            scale = float(ref["grad_norms"][k.replace("k_proj", "q_proj")])
+            assert want_n < 1e-3 * scale and float(g.norm()) < (1e-3 if dtype == torch.float32 else 5e-2) * scale, k
+            continue
+        en = abs(float(g.double().norm()) - want_n) / want_n
+        head = g.reshape(g.shape[0], -1)[:4, :64] if g.dim() > 1 else g[:64]
+        want_h = ref["grad_heads"][k]
+        eh = max_abs(head, want_h) / max(float(want_h.abs().max()), want_n / g.numel() ** 0.5)
+        worst_n, worst_h = max(worst_n, en), max(worst_h, eh)
+        assert en < tol and eh < 4 * tol, (k, en, eh)   # (NaN fails both)
+        checked += 1
+    print(f"[train step width2 {dtype}] loss {float(loss):.6f} vs reference {float(ref['loss']):.6f}; {checked} tensors; worst norm "
+          f"error {worst_n:.3e}, worst leading-rows error {worst_h:.3e}")
+    assert checked >= 80
+
+
+def test_accumulation_loss_scale_and_frozen_vision():
+    """Two calls at loss_scale 0.5 accumulate to one call at 1 (micro-batches under no_sync, train.py:350-356);
+    `freeze_vision` leaves the SigLIP / projector gradients untouched and everything else unchanged."""
+    from open_pi_zero_b200.train import GradBuffer
+    d = SMALL
+    B = 2
+    sd = pz.init_state_dict(d, seed=3, randomize_norms=True, tie_proprio=True)
+    inp = pz.make_inputs(d, B, seed=7)
+    actions, noise, t = _targets(d, B, 9)
+    m = _model(d, sd, torch.float32)
+    m.tie_action_proprio_weights()
+    a, b, c = GradBuffer(m), GradBuffer(m), GradBuffer(m)
+    assert a.tied
+    l1 = _step(m, inp, actions, noise, t, a)
+    _step(m, inp, actions, noise, t, b, loss_scale=0.5)
+    _step(m, inp, actions, noise, t, b, loss_scale=0.5)
+    assert rel_err(b.flat, a.flat) < 1e-4      # fp32 atomics: not bit-equal
+    l3 = _step(m, inp, actions, noise, t, c, freeze_vision=True)
+    assert float(l1) == float(l3)
+    ga, gc = a.unpack(), c.unpack()
+    for k in ga:
+        if k.startswith("vision_tower.") or k.startswith("multi_modal_projector."):
+            assert float(gc[k].abs().max()) == 0.0, k
+        else:
+            assert rel_err(gc[k], ga[k]) < 1e-4 or float(ga[k].abs().max()) == 0.0, k
+    # loss only
+    l4 = _step(m, inp, actions, noise, t, None)
+    assert float(l4) == float(l1)
