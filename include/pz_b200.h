@@ -279,6 +279,21 @@ int pz_flow_matching_step(pz_handle *h, const int64_t *d_input_ids, const void *
                           const pz_weights *grads, float loss_scale, float *d_loss, void *d_workspace, size_t workspace_bytes,
                           int batch, int flags, void *stream);
 
+/* Optimizer step on the flat gradient buffer (replaces clip_grad_norm_ + AdamW8bit.step, train.py:371-379; the reference's
+ * 8-bit AdamW is the third-party bitsandbytes 0.4x optimizer, absent from /root/reference -- the update rule here is
+ * torch.optim.AdamW's on fp32 master weights and fp32 moments).
+ * pz_grad_sumsq: *d_out = sum of squares of d_grad[0..n).
+ * pz_adamw_step: elements [begin, end) (one parameter group; begin a multiple of 256) of the flat master / grad / m / v buffers;
+ *   g = grad * grad_scale * min(1, max_grad_norm / (sqrt(*d_sumsq) * grad_scale + 1e-6))   (d_sumsq NULL = no clipping)
+ *   and the updated weight is written, rounded to dst_dtype, into the packed weight tensor of its entry:
+ *   entry e covers flat elements [d_entry_off[e], d_entry_off[e] + d_entry_n[e]) -> d_entry_dst[e][0 .. d_entry_n[e]);
+ *   entry offsets are multiples of 256.  zero_grad != 0 clears the gradient elements it consumed.  step counts from 1. */
+int pz_grad_sumsq(const float *d_grad, size_t n, float *d_out, void *stream);
+int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t begin, size_t end, const long long *d_entry_off,
+                  void *const *d_entry_dst, const long long *d_entry_n, int n_entries, int dst_dtype, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float *d_sumsq, float max_grad_norm,
+                  float grad_scale, int zero_grad, void *stream);
+
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);
 

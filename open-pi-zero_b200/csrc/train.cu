@@ -566,6 +566,71 @@ int attn_bwd(AttnBwdArgs a, cudaStream_t st, const char **err) {
     return 0;
 }
 
+
+// ------------------------------------------------------------ optimizer ----
+// sum of squares of a flat fp32 gradient buffer (clip_grad_norm_, train.py:371): per-CTA partial, one atomicAdd each
+__global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    float acc = 0.f;
+    const size_t n4 = n / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x4[i];
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments) on fp32 master weights laid out like
+// the gradient buffer, with the global-norm clip folded in and the updated value written straight into the PACKED weight
+// tensor the kernels read (model dtype).  A CTA's 256 consecutive elements lie inside one entry (entries start on
+// multiples of 256), found by bisection over the entry offsets.
+struct AdamWArgs {
+    float *master, *m, *v, *grad;
+    size_t begin, end;                 // element range of this parameter group
+    const long long *entry_off;        // [n_entries + 1]
+    void *const *entry_dst;            // [n_entries] packed weight tensors
+    const long long *entry_n;          // [n_entries] elements of each
+    int n_entries, dst_bf16;
+    float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+    const float *sumsq;                // device scalar: sum of squares of the (scaled) gradients, or null = no clipping
+    float max_norm, grad_scale;
+    int zero_grad;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t base = a.begin + (size_t)blockIdx.x * 256;
+    if (base >= a.end) return;
+    int lo = 0, hi = a.n_entries;      // last entry with off <= base
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((size_t)a.entry_off[mid] <= base) lo = mid; else hi = mid;
+    }
+    const size_t i = base + threadIdx.x;
+    const size_t local = i - (size_t)a.entry_off[lo];
+    if (i >= a.end || local >= (size_t)a.entry_n[lo]) return;
+    float gs = a.grad_scale;
+    if (a.sumsq) {
+        const float norm = sqrtf(*a.sumsq) * a.grad_scale;
+        gs *= fminf(1.f, a.max_norm / (norm + 1e-6f));
+    }
+    const float g = a.grad[i] * gs;
+    if (a.zero_grad) a.grad[i] = 0.f;
+    float p = a.master[i] * (1.f - a.lr * a.wd);
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m; a.v[i] = v;
+    p -= (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+    a.master[i] = p;
+    if (a.dst_bf16) ((bf16 *)a.entry_dst[lo])[local] = __float2bfloat16_rn(p);
+    else ((float *)a.entry_dst[lo])[local] = p;
+}
+
 // ========================================================= host helpers ====
 // one linear layer of the training step: the tensor-core / skinny kernels where the shape has one, otherwise the SIMT
 // kernel (the 7- and 8-wide matrices of the action heads and the fp32 build)
@@ -1057,6 +1122,39 @@ int pz_flow_matching_step(pz_handle *h, const int64_t *ids, const void *pixels, 
         return fail(h, PZ_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
     }
     return PZ_OK;
+}
+
+
+int pz_grad_sumsq(const float *d_grad, size_t n, float *d_out, void *stream) {
+    if (!d_grad || !d_out) return PZ_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(d_out, 0, sizeof(float), st);
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, d_grad, n, d_out);
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
+int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t begin, size_t end, const long long *d_entry_off,
+                  void *const *d_entry_dst, const long long *d_entry_n, int n_entries, int dst_dtype, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float *d_sumsq, float max_grad_norm,
+                  float grad_scale, int zero_grad, void *stream) {
+    if (!d_master || !d_grad || !d_m || !d_v || !d_entry_off || !d_entry_dst || !d_entry_n || n_entries < 1 || step < 1 || end < begin ||
+        (begin & 255))
+        return PZ_ERR_INVALID;
+    if (end == begin) return PZ_OK;
+    AdamWArgs a;
+    a.master = d_master; a.m = d_m; a.v = d_v; a.grad = d_grad; a.begin = begin; a.end = end;
+    a.entry_off = d_entry_off; a.entry_dst = d_entry_dst; a.entry_n = d_entry_n; a.n_entries = n_entries;
+    a.dst_bf16 = dst_dtype == PZ_BF16;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    a.bc1 = 1.f - powf(beta1, (float)step);
+    a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    a.sumsq = d_sumsq; a.max_norm = max_grad_norm; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
+    const size_t blocks = (end - begin + 255) / 256;
+    launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -17,8 +17,12 @@ from . import _lib
 
 VIT_FIELDS = ("ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_w", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2")
 MIX_FIELDS = ("norm_in", "w_qkv", "w_o", "norm_post", "w_gate_up", "w_down")
-TOP_FIELDS = ("patch_w", "patch_b", "pos_emb", "post_ln_w", "post_ln_b", "proj_w", "proj_b", "action_final_norm",
-              "enc_w1", "enc_b1", "enc_w2a", "enc_w2t", "enc_b2", "enc_w3", "enc_b3", "prop_w", "prop_b", "dec_w", "dec_b")
+# flat order = the reference's two optimizer groups (pizero.py:114-129, train.py:171-199): [vision tower, projector, vlm
+# mixture] then [action encoder / decoder, proprio encoder, action (and proprio) mixture]
+TOP_VLM = ("patch_w", "patch_b", "pos_emb", "post_ln_w", "post_ln_b", "proj_w", "proj_b")
+TOP_ACTION = ("action_final_norm", "enc_w1", "enc_b1", "enc_w2a", "enc_w2t", "enc_b2", "enc_w3", "enc_b3", "prop_w", "prop_b",
+              "dec_w", "dec_b")
+TOP_FIELDS = TOP_VLM + TOP_ACTION
 
 
 def _ptr(v) -> int:
@@ -42,24 +46,37 @@ class GradBuffer:
         self._index: Dict[tuple, Tuple[int, tuple]] = {}
         off = 0
 
+        self._ptrs: Dict[tuple, int] = {}
+
         def add(key, ptr):
             nonlocal off
             t = by_ptr[ptr]
+            self._ptrs[key] = ptr
             self.entries.append((key, off, tuple(t.shape)))
             self._index[key] = (off, tuple(t.shape))
             off += (t.numel() + 255) // 256 * 256      # 1 KiB-aligned fp32 slices
 
-        for f in TOP_FIELDS:
-            add(("top", f), _ptr(getattr(w, f)))
-        for i in range(d["vit_layers"]):
-            for f in VIT_FIELDS:
-                add(("vit", i, f), _ptr(getattr(w.vit[i], f)))
-        self.tied = C.addressof(w.proprio.contents) == C.addressof(w.action.contents)
-        for name in ("vlm", "action") + (() if self.tied else ("proprio",)):
+        def add_mixture(name):
             arr = getattr(w, name)
             for i in range(d["num_layers"]):
                 for f in MIX_FIELDS:
                     add((name, i, f), _ptr(getattr(arr[i], f)))
+
+        for f in TOP_VLM:
+            add(("top", f), _ptr(getattr(w, f)))
+        for i in range(d["vit_layers"]):
+            for f in VIT_FIELDS:
+                add(("vit", i, f), _ptr(getattr(w.vit[i], f)))
+        add_mixture("vlm")
+        self.action_begin = off                      # first element of the action-expert group
+        for f in TOP_ACTION:
+            add(("top", f), _ptr(getattr(w, f)))
+        self.tied = C.addressof(w.proprio.contents) == C.addressof(w.action.contents)
+        add_mixture("action")
+        if not self.tied:
+            add_mixture("proprio")
+        self.numel = off
+        self.packed = {key: by_ptr[p] for key, p in self._ptrs.items()}   # key -> packed weight tensor (model dtype)
         dev = keep[0].device
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         base = self.flat.data_ptr()
@@ -88,21 +105,24 @@ class GradBuffer:
         self.flat.zero_()
         return self
 
-    def view(self, key) -> torch.Tensor:
+    def view(self, key, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
         off, shape = self._index[key]
         n = 1
         for s in shape:
             n *= s
-        return self.flat[off:off + n].view(shape)
+        return (self.flat if flat is None else flat)[off:off + n].view(shape)
 
-    def unpack(self) -> Dict[str, torch.Tensor]:
-        """Gradients under the reference's parameter names / shapes (fp32 views or small copies of `.flat`)."""
+    def unpack(self, flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """The buffer (default: the gradients; any flat tensor of the same layout, e.g. the optimizer's master weights)
+        under the reference's parameter names / shapes (fp32 views or small copies)."""
         d = self.model.dims
+        _view = self.view
+        self_view = lambda key: _view(key, flat)   # noqa: E731
         out: Dict[str, torch.Tensor] = {}
         V, ps = d["vit_hidden"], d["patch_size"]
         A, adim, pdim = d["act_hidden"], d["action_dim"], d["proprio_dim"]
         vp = "vision_tower.vision_model."
-        top = lambda f: self.view(("top", f))   # noqa: E731
+        top = lambda f: self_view(("top", f))   # noqa: E731
         out[vp + "embeddings.patch_embedding.weight"] = top("patch_w")[:, :3 * ps * ps].reshape(V, 3, ps, ps)
         out[vp + "embeddings.patch_embedding.bias"] = top("patch_b")
         out[vp + "embeddings.position_embedding.weight"] = top("pos_emb")
@@ -110,7 +130,7 @@ class GradBuffer:
         out["multi_modal_projector.linear.weight"], out["multi_modal_projector.linear.bias"] = top("proj_w"), top("proj_b")
         for i in range(d["vit_layers"]):
             q = vp + f"encoder.layers.{i}."
-            g = lambda f: self.view(("vit", i, f))   # noqa: E731
+            g = lambda f: self_view(("vit", i, f))   # noqa: E731
             out[q + "layer_norm1.weight"], out[q + "layer_norm1.bias"] = g("ln1_w"), g("ln1_b")
             out[q + "layer_norm2.weight"], out[q + "layer_norm2.bias"] = g("ln2_w"), g("ln2_b")
             wq, bq = g("w_qkv"), g("b_qkv")
@@ -125,7 +145,7 @@ class GradBuffer:
             src = "action" if (name == "proprio" and self.tied) else name
             for i in range(d["num_layers"]):
                 p = f"joint_model.mixtures.{name}.layers.{i}."
-                g = lambda f: self.view((src, i, f))   # noqa: E731
+                g = lambda f: self_view((src, i, f))   # noqa: E731
                 out[p + "input_layernorm.weight"] = g("norm_in")
                 out[p + "post_attention_layernorm.weight"] = g("norm_post")
                 wq = g("w_qkv")
@@ -200,3 +220,97 @@ def flow_matching_step(model, input_ids, pixel_values, proprios, actions, t, *, 
     model.last_launch_count = int(lib.pz_launch_count(model._handle))
     model._inflight = (ids, pix, prop, vlen, x1, x0, tt)
     return loss
+
+
+class FusedAdamW:
+    """clip_grad_norm_ + the two AdamW optimizers of the reference's training loop (train.py:171-199, 371-379) as ONE fused
+    pass per parameter group over the flat buffers: fp32 master weights and moments in the GradBuffer layout, the updated
+    weights written straight into the packed tensors the forward kernels read (no re-pack after a step).  The update rule
+    is `torch.optim.AdamW`'s (the reference's bitsandbytes AdamW8bit keeps 8-bit moments)."""
+
+    def __init__(self, grads: GradBuffer, action_lr: float = 5e-5, vlm_lr: float = 5e-5, action_weight_decay: float = 0.0,
+                 vlm_weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: Optional[float] = 1.0,
+                 train_vlm: bool = True):
+        self.grads = grads
+        self.model = grads.model
+        dev = grads.flat.device
+        self.master = torch.zeros_like(grads.flat)
+        for key, _, _ in grads.entries:     # master weights <- the packed weights (exact for an fp32 model)
+            grads.view(key, self.master).copy_(grads.packed[key].to(torch.float32))
+        self.m = torch.zeros_like(grads.flat)
+        self.v = torch.zeros_like(grads.flat)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        offs = [off for _, off, _ in grads.entries] + [grads.numel]
+        self._off = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self._n = torch.tensor([grads.packed[k].numel() for k, _, _ in grads.entries], dtype=torch.int64, device=dev)
+        self._dst = torch.tensor([grads.packed[k].data_ptr() for k, _, _ in grads.entries], dtype=torch.int64, device=dev)
+        self.groups = {"vlm": dict(begin=0, end=grads.action_begin, lr=vlm_lr, weight_decay=vlm_weight_decay),
+                       "action": dict(begin=grads.action_begin, end=grads.numel, lr=action_lr, weight_decay=action_weight_decay)}
+        self.betas, self.eps, self.max_grad_norm, self.train_vlm = betas, eps, max_grad_norm, train_vlm
+        self.step_count = 0
+        self._packed_owner = self.model._packed     # the dst pointers are only valid for this packing
+
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = True):
+        """One update from the accumulated gradients.  `grad_scale` multiplies every gradient first (1 / world_size after a
+        sum all-reduce).  The gradient norm is measured over the trained parameters (train.py:371)."""
+        from .pizero import PzError
+        if self.model._packed is not self._packed_owner:
+            raise PzError("the model was re-packed since this optimizer was built (parameters edited outside of it)")
+        lib = _lib.load()
+        g = self.grads
+        dev = g.flat.device
+        self.step_count += 1
+        names = ("vlm", "action") if self.train_vlm else ("action",)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            lo = 0 if self.train_vlm else g.action_begin
+            sumsq = None
+            if self.max_grad_norm is not None:
+                rc = lib.pz_grad_sumsq(g.flat.data_ptr() + 4 * lo, g.numel - lo, self.sumsq.data_ptr(), st)
+                if rc != 0:
+                    raise PzError(f"pz_grad_sumsq failed ({rc})")
+                sumsq = self.sumsq.data_ptr()
+            for name in names:
+                grp = self.groups[name]
+                rc = lib.pz_adamw_step(self.master.data_ptr(), g.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), grp["begin"],
+                                       grp["end"], self._off.data_ptr(), self._dst.data_ptr(), self._n.data_ptr(), len(g.entries),
+                                       _lib.PZ_BF16 if self.model._T == torch.bfloat16 else _lib.PZ_F32, float(grp["lr"]),
+                                       float(self.betas[0]), float(self.betas[1]), float(self.eps), float(grp["weight_decay"]),
+                                       self.step_count, sumsq, float(self.max_grad_norm or 0.0), float(grad_scale),
+                                       1 if zero_grad else 0, st)
+                if rc != 0:
+                    raise PzError(f"pz_adamw_step failed ({rc})")
+        self.model._graphs = {}     # captured graphs replay kernels on the same packed tensors: still valid, but drop for safety
+        self._params_stale = True
+
+    def grad_norm(self) -> torch.Tensor:
+        """sqrt of the last measured sum of squares (before grad_scale): the value clip_grad_norm_ returns."""
+        return self.sumsq.sqrt()
+
+    @torch.no_grad()
+    def sync_parameters(self):
+        """Copy the master weights back into the reference-layout nn.Parameters (for state_dict() / checkpoints / EMA,
+        train.py:390-403).  Not needed between steps: the kernels read the packed tensors the optimizer updates."""
+        named = dict(self.model.named_parameters())
+        for k, t in self.grads.unpack(self.master).items():
+            if k in named:
+                named[k].copy_(t.to(named[k].dtype))
+        self.model._packed_key = self.model._param_key()      # the packed weights already hold these values
+        self._params_stale = False
+
+
+def allreduce_gradients(grads: GradBuffer, bucket_mb: int = 256, group=None, async_op: bool = False):
+    """Sum the flat gradient buffer over the data-parallel ranks in buckets of `bucket_mb` (DDP's C1, train.py:119-126,
+    350-368; NCCL over NVLink / NVSwitch on the GPU box, gloo in the CPU tests).  Divide by the world size through
+    `FusedAdamW.step(grad_scale=1 / world_size)`.  Returns the work handles when `async_op`."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return []
+    n = grads.flat.numel()
+    step = max(1, bucket_mb * (1 << 20) // 4)
+    works = []
+    for lo in range(0, n, step):
+        w = dist.all_reduce(grads.flat[lo:lo + step], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works

@@ -160,3 +160,51 @@ def test_accumulation_loss_scale_and_frozen_vision():
     # loss only
     l4 = _step(m, inp, actions, noise, t, None)
     assert float(l4) == float(l1)
+
+
+def test_fused_adamw_matches_torch_adamw_and_updates_the_packed_weights():
+    """Two optimizer steps (global-norm clip + AdamW, two parameter groups) against torch.optim.AdamW +
+    clip_grad_norm_ applied to the unpacked gradients in the reference's layout (train.py:371-379); the loss of the next
+    forward must see the new weights without a re-pack; sync_parameters() writes them back under the reference's names."""
+    from open_pi_zero_b200.train import FusedAdamW, GradBuffer
+    d = SMALL
+    B = 2
+    sd = pz.init_state_dict(d, seed=21, randomize_norms=True, tie_proprio=False)
+    inp = pz.make_inputs(d, B, seed=2)
+    actions, noise, t = _targets(d, B, 4)
+    m = _model(d, sd, torch.float32)
+    gb = GradBuffer(m)
+    opt = FusedAdamW(gb, action_lr=3e-3, vlm_lr=1e-3, action_weight_decay=0.1, vlm_weight_decay=0.0, max_grad_norm=0.5)
+    ref_params = {k: v.detach().clone().float().cuda().requires_grad_(True) for k, v in sd.items()}
+    act_keys = [k for k in ref_params if k.startswith(("action_encoder.", "action_decoder.", "proprio_encoder.",
+                                                       "joint_model.mixtures.action.", "joint_model.mixtures.proprio."))]
+    vlm_keys = [k for k in ref_params if k not in act_keys and k != "embed_tokens.weight"]
+    topt = torch.optim.AdamW([dict(params=[ref_params[k] for k in vlm_keys], lr=1e-3, weight_decay=0.0),
+                              dict(params=[ref_params[k] for k in act_keys], lr=3e-3, weight_decay=0.1)], betas=(0.9, 0.999), eps=1e-8)
+    losses = []
+    for it in range(2):
+        losses.append(float(_step(m, inp, actions, noise, t, gb)))
+        got = gb.unpack()
+        for k, p in ref_params.items():
+            p.grad = got[k].detach().clone() if k in got else None
+        trained = [ref_params[k] for k in vlm_keys + act_keys if ref_params[k].grad is not None]
+        tn = torch.nn.utils.clip_grad_norm_(trained, max_norm=0.5)
+        topt.step()
+        opt.step()
+        torch.cuda.synchronize()
+        assert abs(float(opt.grad_norm()) - float(tn)) < 1e-4 * float(tn)
+        assert float(gb.flat.abs().max()) == 0.0          # zero_grad fused into the update
+    l3 = float(_step(m, inp, actions, noise, t, None))
+    assert l3 < losses[0]                                    # the kernels read the updated packed weights
+    opt.sync_parameters()
+    now = dict(m.named_parameters())
+    worst = 0.0
+    for k in vlm_keys + act_keys:
+        if ref_params[k].grad is None:
+            continue
+        worst = max(worst, max_abs(now[k], ref_params[k]) / max(1e-6, float(ref_params[k].abs().max())))
+    print(f"[fused AdamW] losses {losses} -> {l3:.6f}; worst relative parameter difference vs torch.optim.AdamW {worst:.3e}")
+    assert worst < 1e-5
+    # after the sync the packed weights are not rebuilt and the loss is unchanged
+    packed = m._packed
+    assert abs(float(_step(m, inp, actions, noise, t, None)) - l3) < 1e-6 and m._packed is packed
