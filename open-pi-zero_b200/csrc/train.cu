@@ -37,8 +37,55 @@ __global__ void transpose_kernel(const T *__restrict__ in, int ld_in, T *__restr
         if (c < C && r < ld_out) out[(long)c * ld_out + r] = tile[tx][i];
     }
 }
+// bf16 fast path: 64 x 64 tiles, 16-byte global accesses on both sides (needs 16-byte aligned bases and row strides)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16 *__restrict__ in, int ld_in, bf16 *__restrict__ out,
+                                                             int ld_out, int R, int C) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ unsigned short tile[64][66];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int r = pass * 32 + (t >> 3), cs = (t & 7) * 8;
+        const int gr = r0 + r, gc = c0 + cs;
+        unsigned short v[8];
+        if (gr < R && gc + 8 <= C) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(in + (long)gr * ld_in + gc);
+            v[0] = x.x & 0xffff; v[1] = x.x >> 16; v[2] = x.y & 0xffff; v[3] = x.y >> 16;
+            v[4] = x.z & 0xffff; v[5] = x.z >> 16; v[6] = x.w & 0xffff; v[7] = x.w >> 16;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = (gr < R && gc + k < C) ? reinterpret_cast<const unsigned short *>(in)[(long)gr * ld_in + gc + k] : (unsigned short)0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tile[r][cs + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int c = pass * 32 + (t >> 3), rs = (t & 7) * 8;
+        const int gc = c0 + c, gr = r0 + rs;
+        if (gc < C && gr < ld_out) {
+            unsigned short v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = tile[rs + k][c];
+            uint4 o;
+            o.x = v[0] | ((unsigned)v[1] << 16); o.y = v[2] | ((unsigned)v[3] << 16);
+            o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
+            *reinterpret_cast<uint4 *>(out + (long)gc * ld_out + gr) = o;
+        }
+    }
+}
 template <typename T>
 void transpose(const T *in, int ld_in, T *out, int ld_out, int R, int C, cudaStream_t st) {
+    if (std::is_same<T, bf16>::value && ld_in % 8 == 0 && ld_out % 8 == 0 &&
+        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        launch_k(transpose_bf16_kernel, dim3((C + 63) / 64, (ld_out + 63) / 64), dim3(256), 0, st, (const bf16 *)in, ld_in, (bf16 *)out,
+                 ld_out, R, C);
+        return;
+    }
     launch_k(transpose_kernel<T>, dim3((C + 31) / 32, (ld_out + 31) / 32), dim3(32, 8), 0, st, in, ld_in, out, ld_out, R, C);
 }
 
@@ -65,15 +112,32 @@ PZ_DEVINL float gelu_tanh_grad(float x) {
 
 // GeGLU on the packed gate|up layout (blocks of PZ_GU_BLOCK gate columns then PZ_GU_BLOCK up columns):
 // m = gelu_tanh(g) * u (paligemma/modules.py:86-95)
+template <typename T> PZ_DEVINL void store8(T *p, const float *v);
+template <> PZ_DEVINL void store8<float>(float *p, const float *v) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = v[i];
+}
+template <> PZ_DEVINL void store8<bf16>(bf16 *p, const float *v) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+template <typename T> PZ_DEVINL void load8(const T *p, float *o);
+
+// one thread = 8 consecutive output columns (inside one block of PZ_GU_BLOCK); `total` counts groups of 8
 template <typename T>
 __global__ void geglu_fwd_kernel(const T *__restrict__ gu, T *__restrict__ m, long total, int inter) {
     pdl_trigger();
     pdl_wait();
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / inter;
-        const int c = (int)(i % inter);
+    const int per_row = inter / 8;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 8; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / per_row;
+        const int c = (int)(i % per_row) * 8;
         const long o = r * 2 * inter + (long)(c / PZ_GU_BLOCK) * 2 * PZ_GU_BLOCK + (c % PZ_GU_BLOCK);
-        m[i] = from_f32<T>(gelu_tanh(to_f32<T>(gu[o])) * to_f32<T>(gu[o + PZ_GU_BLOCK]));
+        float g[8], u[8], out[8];
+        load8<T>(gu + o, g);
+        load8<T>(gu + o + PZ_GU_BLOCK, u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = gelu_tanh(g[k]) * u[k];
+        store8<T>(m + r * inter + c, out);
     }
 }
 // dg = dm u gelu'(g), du = dm gelu(g), written in the same packed layout
@@ -81,13 +145,19 @@ template <typename T>
 __global__ void geglu_bwd_kernel(const T *__restrict__ gu, const T *__restrict__ dm, T *__restrict__ dgu, long total, int inter) {
     pdl_trigger();
     pdl_wait();
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / inter;
-        const int c = (int)(i % inter);
+    const int per_row = inter / 8;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 8; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / per_row;
+        const int c = (int)(i % per_row) * 8;
         const long o = r * 2 * inter + (long)(c / PZ_GU_BLOCK) * 2 * PZ_GU_BLOCK + (c % PZ_GU_BLOCK);
-        const float g = to_f32<T>(gu[o]), u = to_f32<T>(gu[o + PZ_GU_BLOCK]), d = to_f32<T>(dm[i]);
-        dgu[o] = from_f32<T>(d * u * gelu_tanh_grad(g));
-        dgu[o + PZ_GU_BLOCK] = from_f32<T>(d * gelu_tanh(g));
+        float g[8], u[8], d[8], dg[8], du[8];
+        load8<T>(gu + o, g);
+        load8<T>(gu + o + PZ_GU_BLOCK, u);
+        load8<T>(dm + r * inter + c, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { dg[k] = d[k] * u[k] * gelu_tanh_grad(g[k]); du[k] = d[k] * gelu_tanh(g[k]); }
+        store8<T>(dgu + o, dg);
+        store8<T>(dgu + o + PZ_GU_BLOCK, du);
     }
 }
 inline unsigned ew_blocks(long total) {
@@ -604,31 +674,62 @@ struct AdamWArgs {
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
     pdl_trigger();
     pdl_wait();
-    const size_t base = a.begin + (size_t)blockIdx.x * 256;
-    if (base >= a.end) return;
-    int lo = 0, hi = a.n_entries;      // last entry with off <= base
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((size_t)a.entry_off[mid] <= base) lo = mid; else hi = mid;
-    }
-    const size_t i = base + threadIdx.x;
-    const size_t local = i - (size_t)a.entry_off[lo];
-    if (i >= a.end || local >= (size_t)a.entry_n[lo]) return;
     float gs = a.grad_scale;
     if (a.sumsq) {
         const float norm = sqrtf(*a.sumsq) * a.grad_scale;
         gs *= fminf(1.f, a.max_norm / (norm + 1e-6f));
     }
-    const float g = a.grad[i] * gs;
-    if (a.zero_grad) a.grad[i] = 0.f;
-    float p = a.master[i] * (1.f - a.lr * a.wd);
-    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
-    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
-    a.m[i] = m; a.v[i] = v;
-    p -= (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
-    a.master[i] = p;
-    if (a.dst_bf16) ((bf16 *)a.entry_dst[lo])[local] = __float2bfloat16_rn(p);
-    else ((float *)a.entry_dst[lo])[local] = p;
+    const float decay = 1.f - a.lr * a.wd, step_size = a.lr / a.bc1, omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
+    // a warp owns 128 consecutive elements per iteration (4 per lane): entries start on multiples of 256, so a warp never
+    // straddles two of them; the entry index only moves forward as the warp walks the buffer
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    int e = -1;
+    for (size_t base = a.begin + warp_id * 128; base < a.end; base += n_warps * 128) {
+        if (e < 0) {
+            int lo = 0, hi = a.n_entries;      // last entry with off <= base
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((size_t)__ldg(a.entry_off + mid) <= base) lo = mid; else hi = mid;
+            }
+            e = lo;
+        } else {
+            while (e + 1 < a.n_entries && (size_t)__ldg(a.entry_off + e + 1) <= base) ++e;
+        }
+        const size_t i = base + 4 * lane;
+        const size_t local = i - (size_t)__ldg(a.entry_off + e);
+        const size_t n_e = (size_t)__ldg(a.entry_n + e);
+        if (i >= a.end || local >= n_e) continue;
+        const float4 g4 = *reinterpret_cast<const float4 *>(a.grad + i);
+        const float4 p4 = *reinterpret_cast<const float4 *>(a.master + i);
+        const float4 m4 = *reinterpret_cast<const float4 *>(a.m + i);
+        const float4 v4 = *reinterpret_cast<const float4 *>(a.v + i);
+        float g[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs}, p[4] = {p4.x, p4.y, p4.z, p4.w};
+        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k] = a.beta1 * m[k] + omb1 * g[k];
+            v[k] = a.beta2 * v[k] + omb2 * g[k] * g[k];
+            p[k] = p[k] * decay - step_size * m[k] / (sqrtf(v[k]) / a.bc2_sqrt + a.eps);
+        }
+        // (the 0 .. 3 pad elements behind an entry's end are updated too: their gradient is 0, they stay 0)
+        *reinterpret_cast<float4 *>(a.master + i) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4 *>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4 *>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
+        if (a.zero_grad) *reinterpret_cast<float4 *>(a.grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int nk = (int)(n_e - local < 4 ? n_e - local : 4);
+        if (a.dst_bf16) {
+            bf16 *dst = (bf16 *)__ldg(reinterpret_cast<const unsigned long long *>(a.entry_dst) + e) + local;
+            if (nk == 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]));
+            } else {
+                for (int k = 0; k < nk; ++k) dst[k] = __float2bfloat16_rn(p[k]);
+            }
+        } else {
+            float *dst = (float *)__ldg(reinterpret_cast<const unsigned long long *>(a.entry_dst) + e) + local;
+            for (int k = 0; k < nk; ++k) dst[k] = p[k];
+        }
+    }
 }
 
 // ========================================================= host helpers ====
@@ -914,7 +1015,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             PZ_TRY(tlin<T>(h, lin(ws.att[m][l], qd, Lw.w_o, nullptr, ws.x1[m][l], Hm, M, Hm, qd, LIN_OUT_F32 | LIN_ACCUM), st));
             launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
             PZ_TRY(tlin<T>(h, lin(ws.h, Hm, Lw.w_gate_up, nullptr, ws.gu[m][l], 2 * Im, M, 2 * Im, Hm), st));
-            launch_k(geglu_fwd_kernel<T>, dim3(ew_blocks((long)M * Im)), dim3(256), 0, st, (const T *)ws.gu[m][l], (T *)ws.mm[m][l],
+            launch_k(geglu_fwd_kernel<T>, dim3(ew_blocks((long)M * Im / 8)), dim3(256), 0, st, (const T *)ws.gu[m][l], (T *)ws.mm[m][l],
                      (long)M * Im, Im);
             copy_f32(ws.xin[m][l + 1], ws.x1[m][l], (size_t)M * Hm, st);
             PZ_TRY(tlin<T>(h, lin(ws.mm[m][l], Im, Lw.w_down, nullptr, ws.xin[m][l + 1], Hm, M, Hm, Im, LIN_OUT_F32 | LIN_ACCUM), st));
@@ -948,7 +1049,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             // MLP: x_out = x1 + down(gelu(g) u)
             cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.mm[m][l], Im, Lw.w_down, ws.d_m, Im, 0, G(Lg.w_down), M, Hm, Im, sc, st));
-            launch_k(geglu_bwd_kernel<T>, dim3(ew_blocks((long)M * Im)), dim3(256), 0, st, (const T *)ws.gu[m][l], (const T *)ws.d_m,
+            launch_k(geglu_bwd_kernel<T>, dim3(ew_blocks((long)M * Im / 8)), dim3(256), 0, st, (const T *)ws.gu[m][l], (const T *)ws.d_m,
                      (T *)ws.dgu, (long)M * Im, Im);
             launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dgu, 2 * Im, ws.h, Hm, Lw.w_gate_up, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_gate_up), M, 2 * Im, Hm, sc, st));
@@ -1152,7 +1253,8 @@ int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t
     a.bc1 = 1.f - powf(beta1, (float)step);
     a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     a.sumsq = d_sumsq; a.max_norm = max_grad_norm; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
-    const size_t blocks = (end - begin + 255) / 256;
+    size_t blocks = (end - begin + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
     launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
     return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
 }
