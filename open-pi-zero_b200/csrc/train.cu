@@ -11,6 +11,8 @@
 // on K-major operands produced by a tiled transpose (HBM-bound, ~2 % of the step); nothing is recomputed except the
 // normalised activations (one norm kernel each); 180 GB of HBM hold the ~30 GB of saved activations at 32 samples.
 // The attention backward is one SIMT kernel for both the joint block-masked soft-capped MQA attention and SigLIP's.
+#include <mma.h>
+
 #include "api_internal.cuh"
 
 namespace {
@@ -637,6 +639,324 @@ int attn_bwd(AttnBwdArgs a, cudaStream_t st, const char **err) {
 }
 
 
+
+// ------------------------------------- attention backward on tensor cores (bf16) ----
+// Two kernels over 2-D views (FlashAttention-2 style split, so that nothing is accumulated with atomics):
+//   attn_bwd_dq_kernel : a CTA owns 64 query rows; pass A walks the key blocks for the softmax statistics (log-sum-exp)
+//                        and D = rowsum(dO o O); pass B recomputes S, forms dS and accumulates dQ = dS K in registers.
+//   attn_bwd_dkv_kernel: a CTA owns 64 keys and walks the query tiles: dV += P^T dO, dK += dS^T Q in registers.
+// "Query rows" are (token, head) pairs: with one K/V head (MQA) the 8 heads of a token are 8 consecutive rows of the
+// [tokens * heads, head_dim] view of the q buffer, so one CTA serves all heads against one copy of K / V; SigLIP (one K/V
+// head per q head) launches one group per head.  All products are 16x16x16 bf16 MMAs (warp-level `wmma`, fp32
+// accumulation) on shared-memory tiles; P and dS are rounded to bf16 for the second product, as the forward rounds P.
+using namespace nvcuda;
+
+struct AttnBwd2Args {
+    const bf16 *Q, *dO, *O;
+    float *dQ;
+    long q_bs, q_gs; int ld_q;
+    long o_bs, o_gs; int ld_o;
+    long dq_bs, dq_gs; int ld_dq;
+    const bf16 *K, *V;
+    long kv_bs, kv_gs; int ld_kv;
+    float *dK, *dV;
+    long dkv_bs, dkv_gs; int ld_dkv;
+    float *lse, *dvec;                 // [batch][groups][NQ]
+    const int32_t *valid_len;
+    int NQ, NK, hd, hpr;               // hpr: query rows per token (heads folded into the rows)
+    int seg, s_v, s_p;                 // segment of the queries (block mask, pizero.py:271-310); valid_len == null: no mask
+    float scale, softcap;
+    int accumulate, groups;
+};
+
+constexpr int SLD = 72;               // row pitch of the 64 x 64 score tiles (floats / bf16s)
+// hardware tanh (rel. error 2^-11; the forward kernels soft-cap with the same instruction)
+PZ_DEVINL float tanh_hw(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// bf16 tiles are [64][HDP + 8]: a row pitch that is an odd multiple of 16 bytes keeps the 8 rows of a fragment load on
+// different banks (a 512-byte pitch put them all on the same ones: measured 27 TFLOP/s)
+template <int HDP>
+PZ_DEVINL void load_rows64(bf16 *dst, const bf16 *src, int ld, int row0, int n_rows, int hd, int hpr, int tok_limit) {
+    // dst[r][0..HDP) <- src[(row0 + r) * ld + 0..hd), zero beyond hd, beyond n_rows and for tokens >= tok_limit
+    constexpr int CH = HDP / 8, LDP = HDP + 8;
+    for (int i = threadIdx.x; i < 64 * CH; i += 256) {
+        const int r = i / CH, c = (i % CH) * 8;
+        const int row = row0 + r;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row < n_rows && c < hd && row / hpr < tok_limit) v = *reinterpret_cast<const uint4 *>(src + (long)row * ld + c);
+        *reinterpret_cast<uint4 *>(dst + r * LDP + c) = v;
+    }
+}
+
+PZ_DEVINL bool key_visible(const AttnBwd2Args &a, int j, int vl) {
+    if (j >= a.NK) return false;
+    if (!a.valid_len) return true;
+    if (j < a.s_v) return j < vl;
+    if (j < a.s_v + a.s_p) return a.seg >= 1;
+    return a.seg >= 2;
+}
+
+// S[64 x 64] = A[64 x HDP] . B[64 x HDP]^T into the fp32 tile `out` (8 warps: 4 row tiles x 2 column halves)
+template <int HDP>
+PZ_DEVINL void mma_qkT(const bf16 *A, const bf16 *B, float *out, int warp) {
+    constexpr int LDP = HDP + 8;
+    const int wr = warp >> 1, wc = warp & 1;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
+    wmma::fill_fragment(acc[0], 0.f);
+    wmma::fill_fragment(acc[1], 0.f);
+#pragma unroll 4
+    for (int k = 0; k < HDP / 16; ++k) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
+        wmma::load_matrix_sync(fa, A + wr * 16 * LDP + k * 16, LDP);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> fb;
+            wmma::load_matrix_sync(fb, B + (wc * 32 + t * 16) * LDP + k * 16, LDP);
+            wmma::mma_sync(acc[t], fa, fb, acc[t]);
+        }
+    }
+    wmma::store_matrix_sync(out + wr * 16 * SLD + wc * 32, acc[0], SLD, wmma::mem_row_major);
+    wmma::store_matrix_sync(out + wr * 16 * SLD + wc * 32 + 16, acc[1], SLD, wmma::mem_row_major);
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(const AttnBwd2Args a) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ uint8_t smraw[];
+    uint8_t *sm = align_smem(smraw, 128);
+    constexpr int LDP = HDP + 8;
+    bf16 *Qs = (bf16 *)sm, *dOs = Qs + 64 * LDP, *Ks = dOs + 64 * LDP, *Vs = Ks + 64 * LDP;
+    float *Sf = (float *)(Vs + 64 * LDP), *Df = Sf + 64 * SLD;
+    bf16 *Pb = (bf16 *)(Df + 64 * SLD);
+    float *sD = (float *)(Pb + 64 * SLD), *sL = sD + 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, g = blockIdx.y, row0 = blockIdx.x * 64;
+    const int vl = a.valid_len ? a.valid_len[b] : (1 << 30);
+    const int tok_limit = (a.valid_len && a.seg == 0) ? vl : (1 << 30);
+    const bf16 *Qg = a.Q + b * a.q_bs + g * a.q_gs, *dOg = a.dO + b * a.o_bs + g * a.o_gs, *Og = a.O + b * a.o_bs + g * a.o_gs;
+    const bf16 *Kg = a.K + b * a.kv_bs + g * a.kv_gs, *Vg = a.V + b * a.kv_bs + g * a.kv_gs;
+    load_rows64<HDP>(Qs, Qg, a.ld_q, row0, a.NQ, a.hd, a.hpr, tok_limit);
+    load_rows64<HDP>(dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
+    __syncthreads();
+    // D = rowsum(dO o O): a warp takes 8 rows
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+        const int row = row0 + r;
+        float acc = 0.f;
+        if (row < a.NQ && row / a.hpr < tok_limit)
+            for (int d = lane; d < a.hd; d += 32) acc += __bfloat162float(dOs[r * LDP + d]) * __bfloat162float(Og[(long)row * a.ld_o + d]);
+        acc = warp_sum(acc);
+        if (lane == 0) sD[r] = acc;
+    }
+    const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
+    const int er = tid >> 2, ec0 = (tid & 3) * 16;      // elementwise mapping: 4 threads per row, 16 columns each
+    const bool row_ok = row0 + er < a.NQ && (row0 + er) / a.hpr < tok_limit;
+    const int n_kb = (a.NK + 63) / 64;
+    // ---- pass A: log-sum-exp of every row
+    float m_run = -INFINITY, s_run = 0.f;
+    for (int kb = 0; kb < n_kb; ++kb) {
+        __syncthreads();
+        load_rows64<HDP>(Ks, Kg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
+        __syncthreads();
+        mma_qkT<HDP>(Qs, Ks, Sf, warp);
+        __syncthreads();
+        float lg[16], mloc = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float sv = Sf[er * SLD + ec0 + c] * a.scale;
+            const float l = a.softcap > 0.f ? a.softcap * tanh_hw(sv * inv_cap) : sv;
+            lg[c] = key_visible(a, kb * 64 + ec0 + c, vl) ? l : -INFINITY;
+            mloc = fmaxf(mloc, lg[c]);
+        }
+        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+        const float m_new = fmaxf(m_run, mloc);
+        float sloc = 0.f;
+        if (m_new > -INFINITY) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sloc += __expf(lg[c] - m_new);
+        }
+        sloc += __shfl_xor_sync(0xffffffffu, sloc, 1);
+        sloc += __shfl_xor_sync(0xffffffffu, sloc, 2);
+        s_run = (m_run > -INFINITY ? s_run * __expf(m_run - m_new) : 0.f) + sloc;
+        m_run = m_new;
+    }
+    const float lse = (row_ok && s_run > 0.f) ? m_run + __logf(s_run) : INFINITY;   // +inf: P = exp(l - lse) = 0
+    __syncthreads();
+    if ((tid & 3) == 0) {
+        sL[er] = lse;
+        if (row0 + er < a.NQ) {
+            const long o = ((long)b * a.groups + g) * a.NQ + row0 + er;
+            a.lse[o] = lse;
+            a.dvec[o] = sD[er];
+        }
+    }
+    // ---- pass B: dQ = sum over key blocks of dS K
+    constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
+    const int wr = warp >> 1, wc = warp & 1;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> accq[HALF];
+#pragma unroll
+    for (int t = 0; t < HALF; ++t) wmma::fill_fragment(accq[t], 0.f);
+    for (int kb = 0; kb < n_kb; ++kb) {
+        __syncthreads();
+        load_rows64<HDP>(Ks, Kg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
+        load_rows64<HDP>(Vs, Vg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
+        __syncthreads();
+        mma_qkT<HDP>(Qs, Ks, Sf, warp);
+        mma_qkT<HDP>(dOs, Vs, Df, warp);
+        __syncthreads();
+        const float Dr = sD[er], Lr = sL[er];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float sv = Sf[er * SLD + ec0 + c] * a.scale;
+            const float l = a.softcap > 0.f ? a.softcap * tanh_hw(sv * inv_cap) : sv;
+            const float th = l * inv_cap;
+            const float pv = key_visible(a, kb * 64 + ec0 + c, vl) ? __expf(l - Lr) : 0.f;
+            Pb[er * SLD + ec0 + c] = __float2bfloat16_rn(pv * (Df[er * SLD + ec0 + c] - Dr) * (1.f - th * th) * a.scale);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
+            wmma::load_matrix_sync(fa, Pb + wr * 16 * SLD + kk * 16, SLD);
+#pragma unroll
+            for (int t = 0; t < HALF; ++t) {
+                const int ct = wc * HALF + t;
+                if (ct < NCT) {
+                    wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
+                    wmma::load_matrix_sync(fb, Ks + kk * 16 * LDP + ct * 16, LDP);
+                    wmma::mma_sync(accq[t], fa, fb, accq[t]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float *stage = (float *)Ks;    // 64 x HDP fp32 = the K and V tiles
+#pragma unroll
+    for (int t = 0; t < HALF; ++t) {
+        const int ct = wc * HALF + t;
+        if (ct < NCT) wmma::store_matrix_sync(stage + wr * 16 * HDP + ct * 16, accq[t], HDP, wmma::mem_row_major);
+    }
+    __syncthreads();
+    float *dQg = a.dQ + b * a.dq_bs + g * a.dq_gs;
+    for (int i = tid; i < 64 * a.hd; i += 256) {
+        const int r = i / a.hd, c = i % a.hd;
+        if (row0 + r < a.NQ) dQg[(long)(row0 + r) * a.ld_dq + c] = stage[r * HDP + c];
+    }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(const AttnBwd2Args a) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ uint8_t smraw[];
+    uint8_t *sm = align_smem(smraw, 128);
+    constexpr int LDP = HDP + 8;
+    bf16 *Qs = (bf16 *)sm, *dOs = Qs + 64 * LDP, *Ks = dOs + 64 * LDP, *Vs = Ks + 64 * LDP;
+    float *Sf = (float *)(Vs + 64 * LDP), *Df = Sf + 64 * SLD;
+    bf16 *Pb = (bf16 *)(Df + 64 * SLD), *dSb = Pb + 64 * SLD;
+    float *sD = (float *)(dSb + 64 * SLD), *sL = sD + 64;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.z, g = blockIdx.y, key0 = blockIdx.x * 64;
+    const int vl = a.valid_len ? a.valid_len[b] : (1 << 30);
+    const int tok_limit = (a.valid_len && a.seg == 0) ? vl : (1 << 30);
+    const bf16 *Qg = a.Q + b * a.q_bs + g * a.q_gs, *dOg = a.dO + b * a.o_bs + g * a.o_gs;
+    const bf16 *Kg = a.K + b * a.kv_bs + g * a.kv_gs, *Vg = a.V + b * a.kv_bs + g * a.kv_gs;
+    load_rows64<HDP>(Ks, Kg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
+    load_rows64<HDP>(Vs, Vg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
+    constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
+    const int kr = warp & 3, wc = warp >> 2;          // 16 keys x one half of the feature tiles per warp
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acck[HALF], accv[HALF];
+#pragma unroll
+    for (int t = 0; t < HALF; ++t) { wmma::fill_fragment(acck[t], 0.f); wmma::fill_fragment(accv[t], 0.f); }
+    const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
+    const int er = tid >> 2, ec0 = (tid & 3) * 16;
+    const int n_qt = (a.NQ + 63) / 64;
+    // keys of this block that any query of this segment sees: skip the block if none
+    bool any = false;
+    for (int j = key0; j < key0 + 64; ++j) any = any || key_visible(a, j, vl);
+    for (int qt = 0; any && qt < n_qt; ++qt) {
+        const int row0 = qt * 64;
+        if (a.valid_len && a.seg == 0 && row0 / a.hpr >= vl) break;      // padded tokens only from here on
+        __syncthreads();
+        load_rows64<HDP>(Qs, Qg, a.ld_q, row0, a.NQ, a.hd, a.hpr, tok_limit);
+        load_rows64<HDP>(dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
+        if (tid < 64) {
+            const long o = ((long)b * a.groups + g) * a.NQ + row0 + tid;
+            const bool ok = row0 + tid < a.NQ;
+            sL[tid] = ok ? a.lse[o] : INFINITY;
+            sD[tid] = ok ? a.dvec[o] : 0.f;
+        }
+        __syncthreads();
+        mma_qkT<HDP>(Qs, Ks, Sf, warp);
+        mma_qkT<HDP>(dOs, Vs, Df, warp);
+        __syncthreads();
+        const float Dr = sD[er], Lr = sL[er];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float sv = Sf[er * SLD + ec0 + c] * a.scale;
+            const float l = a.softcap > 0.f ? a.softcap * tanh_hw(sv * inv_cap) : sv;
+            const float th = l * inv_cap;
+            const float pv = key_visible(a, key0 + ec0 + c, vl) ? __expf(l - Lr) : 0.f;
+            Pb[er * SLD + ec0 + c] = __float2bfloat16_rn(pv);
+            dSb[er * SLD + ec0 + c] = __float2bfloat16_rn(pv * (Df[er * SLD + ec0 + c] - Dr) * (1.f - th * th) * a.scale);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q0 = 0; q0 < 4; ++q0) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fp, fs;   // P^T, dS^T: (key, query) at [query][key]
+            wmma::load_matrix_sync(fp, Pb + q0 * 16 * SLD + kr * 16, SLD);
+            wmma::load_matrix_sync(fs, dSb + q0 * 16 * SLD + kr * 16, SLD);
+#pragma unroll
+            for (int t = 0; t < HALF; ++t) {
+                const int ct = wc * HALF + t;
+                if (ct < NCT) {
+                    wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fo, fq;
+                    wmma::load_matrix_sync(fo, dOs + q0 * 16 * LDP + ct * 16, LDP);
+                    wmma::load_matrix_sync(fq, Qs + q0 * 16 * LDP + ct * 16, LDP);
+                    wmma::mma_sync(accv[t], fp, fo, accv[t]);
+                    wmma::mma_sync(acck[t], fs, fq, acck[t]);
+                }
+            }
+        }
+    }
+    float *stage = (float *)Qs;    // 64 x HDP fp32 = the Q and dO tiles
+    for (int which = 0; which < 2; ++which) {
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) {
+            const int ct = wc * HALF + t;
+            if (ct < NCT) wmma::store_matrix_sync(stage + kr * 16 * HDP + ct * 16, which ? acck[t] : accv[t], HDP, wmma::mem_row_major);
+        }
+        __syncthreads();
+        float *dst = (which ? a.dK : a.dV) + b * a.dkv_bs + g * a.dkv_gs;
+        for (int i = tid; i < 64 * a.hd; i += 256) {
+            const int r = i / a.hd, c = i % a.hd;
+            if (key0 + r < a.NK) {
+                float *p = dst + (long)(key0 + r) * a.ld_dkv + c;
+                *p = (a.accumulate ? *p : 0.f) + stage[r * HDP + c];
+            }
+        }
+    }
+}
+
+template <int HDP>
+int attn_bwd2_launch(const AttnBwd2Args &a, int batch, bool dq, bool dkv, cudaStream_t st) {
+    const size_t smem = (size_t)4 * 64 * (HDP + 8) * 2 + 2 * 64 * SLD * 4 + 2 * 64 * SLD * 2 + 2 * 64 * 4 + 128;
+    static PerDeviceOnce once;
+    if (once.need()) {
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    if (dq) launch_k(attn_bwd_dq_kernel<HDP>, dim3((a.NQ + 63) / 64, a.groups, batch), dim3(256), smem, st, a);
+    if (dkv) launch_k(attn_bwd_dkv_kernel<HDP>, dim3((a.NK + 63) / 64, a.groups, batch), dim3(256), smem, st, a);
+    return 0;
+}
+
 // ------------------------------------------------------------ optimizer ----
 // sum of squares of a flat fp32 gradient buffer (clip_grad_norm_, train.py:371): per-CTA partial, one atomicAdd each
 __global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out) {
@@ -797,7 +1117,7 @@ struct TrainWs {
     // scratch
     void *h, *qkv, *tA, *tB, *wT, *dyb, *d_m, *dgu, *dqkv;
     void *datt[3];
-    float *dx[3], *dq[3], *dh, *dK, *dV;
+    float *dx[3], *dq[3], *dh, *dK, *dV, *lse, *dvec;
     float *att_scratch; size_t att_scratch_bytes;
     size_t total;
 };
@@ -884,6 +1204,11 @@ TrainWs carve_train(const pz_config &c, int B, void *base) {
     w.dK = b.take<float>((size_t)B * S_all * c.head_dim * 4);
     w.dV = b.take<float>((size_t)B * S_all * c.head_dim * 4);
     {
+        size_t nj = (size_t)B * c.s_vlm * c.n_heads, nv = Mv * c.vit_heads;
+        w.lse = b.take<float>((nj > nv ? nj : nv) * 4);
+        w.dvec = b.take<float>((nj > nv ? nj : nv) * 4);
+    }
+    {
         size_t rows = (size_t)c.n_heads * (c.horizon > c.cond_steps ? c.horizon : c.cond_steps);
         size_t tiles = (S_all + 63) / 64;
         w.att_scratch_bytes = rows <= 64 ? (size_t)B * tiles * rows * (c.head_dim + 2) * 4 : 0;
@@ -928,6 +1253,9 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     const bool vit_grads = want_grads && !(flags & PZ_TRAIN_FREEZE_VISION);
     Scratch sc{ws.tA, ws.tB, ws.wT};
     const char *err = nullptr;
+    // bf16: attention backward on the tensor cores (PZ_ATTN_BWD_SIMT=1 keeps the SIMT kernel, the fp32 build's only one)
+    static const bool simt_attn = [] { const char *e = getenv("PZ_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();
+    const bool tc_attn_bwd = std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && !simt_attn;
 
     // ================================================================ forward
     // ---- SigLIP (siglip.py:59-78, 220-238, 298) with the residual stream and the GEMM inputs of every layer kept
@@ -1059,6 +1387,26 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.att[m][l], qd, Lw.w_o, ws.datt[m], qd, 0, G(Lg.w_o), M, Hm, qd, sc, st));
         }
         // attention
+        if (tc_attn_bwd && hd == 256) {
+            AttnBwd2Args b2;
+            memset(&b2, 0, sizeof(b2));
+            b2.K = (const bf16 *)ws.K[l]; b2.V = (const bf16 *)ws.V[l]; b2.kv_bs = kv_bs; b2.ld_kv = hd;
+            b2.dK = ws.dK; b2.dV = ws.dV; b2.dkv_bs = kv_bs; b2.ld_dkv = hd;
+            b2.lse = ws.lse; b2.dvec = ws.dvec; b2.valid_len = valid_len; b2.s_v = S_v; b2.s_p = S_p;
+            b2.NK = S_all; b2.hd = hd; b2.hpr = nh; b2.groups = 1;
+            b2.scale = 1.0f / sqrtf((float)hd); b2.softcap = 50.f;
+            bool first = true;
+            for (int m = 0; m < 3; ++m) {
+                if (last && m < 2) continue;
+                // the [tokens, heads * hd] buffers seen as [tokens * heads, hd]: the heads of a token are consecutive query rows
+                b2.Q = (const bf16 *)ws.q[m][l]; b2.q_bs = (long)md[m].rows * qd; b2.ld_q = hd;
+                b2.dO = (const bf16 *)ws.datt[m]; b2.O = (const bf16 *)ws.att[m][l]; b2.o_bs = (long)md[m].rows * qd; b2.ld_o = hd;
+                b2.dQ = ws.dq[m]; b2.dq_bs = (long)md[m].rows * qd; b2.ld_dq = hd;
+                b2.NQ = md[m].rows * nh; b2.seg = m; b2.accumulate = first ? 0 : 1;
+                attn_bwd2_launch<256>(b2, B, true, true, st);
+                first = false;
+            }
+        } else {
         cudaMemsetAsync(ws.dK, 0, (size_t)B * S_all * hd * 4, st);
         cudaMemsetAsync(ws.dV, 0, (size_t)B * S_all * hd * 4, st);
         AttnBwdArgs ab;
@@ -1078,6 +1426,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         {
             int rc = attn_bwd<T>(ab, st, &err);
             if (rc) return fail(h, rc, err ? err : "attention backward failed");
+        }
         }
         // q / k / v projections and the input norm
         for (int m = 0; m < 3; ++m) {
@@ -1149,6 +1498,19 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         T *dav = (T *)ws.d_m;
         PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.av[i], V, Lw.w_o, dav, V, 0, G(Lg.w_o), Mv, V, V, sc, st));
         float *dqkv32 = ws.dh;   // fp32 [Mv, 3V]: dq | dk | dv
+        if (tc_attn_bwd && hdv == 72) {
+            AttnBwd2Args b2;
+            memset(&b2, 0, sizeof(b2));
+            b2.Q = (const bf16 *)ws.qkvv[i]; b2.q_bs = (long)P * 3 * V; b2.q_gs = hdv; b2.ld_q = 3 * V;
+            b2.dO = (const bf16 *)dav; b2.O = (const bf16 *)ws.av[i]; b2.o_bs = (long)P * V; b2.o_gs = hdv; b2.ld_o = V;
+            b2.dQ = dqkv32; b2.dq_bs = (long)P * 3 * V; b2.dq_gs = hdv; b2.ld_dq = 3 * V;
+            b2.K = (const bf16 *)ws.qkvv[i] + V; b2.V = (const bf16 *)ws.qkvv[i] + 2 * V; b2.kv_bs = (long)P * 3 * V; b2.kv_gs = hdv; b2.ld_kv = 3 * V;
+            b2.dK = dqkv32 + V; b2.dV = dqkv32 + 2 * V; b2.dkv_bs = (long)P * 3 * V; b2.dkv_gs = hdv; b2.ld_dkv = 3 * V;
+            b2.lse = ws.lse; b2.dvec = ws.dvec; b2.valid_len = nullptr;
+            b2.NQ = P; b2.NK = P; b2.hd = hdv; b2.hpr = 1; b2.groups = c.vit_heads;
+            b2.scale = 1.0f / sqrtf((float)hdv); b2.softcap = 0.f; b2.accumulate = 0;
+            attn_bwd2_launch<80>(b2, n_img, true, true, st);
+        } else {
         cudaMemsetAsync(dqkv32, 0, (size_t)Mv * 3 * V * 4, st);
         AttnBwdArgs ab;
         memset(&ab, 0, sizeof(ab));
@@ -1162,6 +1524,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         {
             int rc = attn_bwd<T>(ab, st, &err);
             if (rc) return fail(h, rc, err ? err : "attention backward failed");
+        }
         }
         cast_scale<T>(dqkv32, (T *)ws.dqkv, (long)Mv * 3 * V, 1.f, st);
         colsum<T>((const T *)ws.dqkv, 3 * V, G(Lg.b_qkv), Mv, 3 * V, st);
