@@ -270,6 +270,10 @@ int pz_text_decode(pz_handle *h, const float *d_x, const int32_t *d_valid_len1, 
  *             are ignored.  If the proprio table aliases the action table (tied weights) both gradients land in one buffer.
  *   d_loss    fp32 [1]: mean squared error of this batch (unscaled)
  *   flags     PZ_TRAIN_FREEZE_VISION: stop at the projector output (no SigLIP / projector gradients)
+ *   events    optional array of cudaEvent_t (NULL entries skipped) recorded on `stream` when a group of gradients is final, so
+ *             that a data-parallel caller can all-reduce that slice on another stream while the backward goes on (DDP bucket
+ *             overlap, train.py:121): [l] joint layer l (vlm / action / proprio entries of that layer), [n_layers] the encoder /
+ *             decoder heads and the final norm, [n_layers + 1 + i] SigLIP layer i, [n_layers + 1 + vit_layers] the rest
  * Image tokens must be the first n_images * n_img_tokens positions of every sequence (what VLAProcessor builds,
  * processing.py:63-136).  Workspace: pz_train_workspace_bytes(batch), 1 KiB aligned. */
 #define PZ_TRAIN_FREEZE_VISION 1
@@ -277,17 +281,19 @@ size_t pz_train_workspace_bytes(const pz_handle *h, int batch);
 int pz_flow_matching_step(pz_handle *h, const int64_t *d_input_ids, const void *d_pixels, const int32_t *d_valid_len,
                           const float *d_proprio, const float *d_actions, const float *d_noise, const float *d_t, float sig_min,
                           const pz_weights *grads, float loss_scale, float *d_loss, void *d_workspace, size_t workspace_bytes,
-                          int batch, int flags, void *stream);
+                          int batch, int flags, void *const *events, int n_events, void *stream);
 
 /* Optimizer step on the flat gradient buffer (replaces clip_grad_norm_ + AdamW8bit.step, train.py:371-379; the reference's
  * 8-bit AdamW is the third-party bitsandbytes 0.4x optimizer, absent from /root/reference -- the update rule here is
  * torch.optim.AdamW's on fp32 master weights and fp32 moments).
- * pz_grad_sumsq: *d_out = sum of squares of d_grad[0..n).
+ * pz_grad_sumsq: d_out[0] = sum of squares of d_grad[0..n), summed in a fixed order (bit-reproducible across replicas);
+ *   d_out must hold 1 + PZ_SUMSQ_SCRATCH floats (the per-CTA partials live behind the result).
  * pz_adamw_step: elements [begin, end) (one parameter group; begin a multiple of 256) of the flat master / grad / m / v buffers;
  *   g = grad * grad_scale * min(1, max_grad_norm / (sqrt(*d_sumsq) * grad_scale + 1e-6))   (d_sumsq NULL = no clipping)
  *   and the updated weight is written, rounded to dst_dtype, into the packed weight tensor of its entry:
  *   entry e covers flat elements [d_entry_off[e], d_entry_off[e] + d_entry_n[e]) -> d_entry_dst[e][0 .. d_entry_n[e]);
  *   entry offsets are multiples of 256.  zero_grad != 0 clears the gradient elements it consumed.  step counts from 1. */
+#define PZ_SUMSQ_SCRATCH 1184
 int pz_grad_sumsq(const float *d_grad, size_t n, float *d_out, void *stream);
 int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t begin, size_t end, const long long *d_entry_off,
                   void *const *d_entry_dst, const long long *d_entry_n, int n_entries, int dst_dtype, float lr, float beta1,

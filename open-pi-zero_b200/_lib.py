@@ -115,7 +115,7 @@ def load(build_if_needed: bool = True):
     lib.pz_flow_matching_loss.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_train_workspace_bytes.argtypes = [hp, C.c_int]
     lib.pz_train_workspace_bytes.restype = C.c_size_t
-    lib.pz_flow_matching_step.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, C.c_float, vp, vp, C.c_size_t, C.c_int, C.c_int, vp]
+    lib.pz_flow_matching_step.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, C.c_float, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, vp]
     lib.pz_grad_sumsq.argtypes = [vp, C.c_size_t, vp, vp]
     lib.pz_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int, vp, C.c_float, C.c_float, C.c_int, vp]

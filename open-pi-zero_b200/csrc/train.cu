@@ -958,8 +958,10 @@ int attn_bwd2_launch(const AttnBwd2Args &a, int batch, bool dq, bool dkv, cudaSt
 }
 
 // ------------------------------------------------------------ optimizer ----
-// sum of squares of a flat fp32 gradient buffer (clip_grad_norm_, train.py:371): per-CTA partial, one atomicAdd each
-__global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out) {
+// sum of squares of a flat fp32 gradient buffer (clip_grad_norm_, train.py:371).  Deterministic: every CTA writes its
+// partial, a second one-CTA pass adds them in a fixed order -- data-parallel replicas must compute bit-identical clip
+// factors from their bit-identical all-reduced gradients, or their weights drift apart.
+__global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ x, size_t n, float *__restrict__ partial) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[32];
@@ -972,7 +974,16 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ x,
     }
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float *__restrict__ partial, int n, float *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) *out = acc;
 }
 
 // AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments) on fp32 master weights laid out like
@@ -1229,7 +1240,7 @@ inline float *G(const void *p) { return (float *)const_cast<void *>(p); }
 template <typename T>
 int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len, const float *proprio,
                      const float *actions, const float *noise, const float *t, float sig_min, const Grads *gr, float *loss,
-                     float loss_scale, void *wsp, int B, int flags, cudaStream_t st) {
+                     float loss_scale, void *wsp, int B, int flags, void *const *events, int n_events, cudaStream_t st) {
     const pz_config &c = h->cfg;
     const pz_weights &w = h->w;
     if (!w.enc_w2t || !w.enc_b2 || !w.time_freq) return fail(h, PZ_ERR_UNBOUND, "enc_w2t / enc_b2 / time_freq not bound");
@@ -1253,6 +1264,9 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     const bool vit_grads = want_grads && !(flags & PZ_TRAIN_FREEZE_VISION);
     Scratch sc{ws.tA, ws.tB, ws.wT};
     const char *err = nullptr;
+    // "these gradients are final" marks for the caller's bucketed all-reduce: [0, L) joint layer l, L the encoder / decoder
+    // heads, L + 1 + i SigLIP layer i, L + 1 + LV everything else (projector, patch embedding, position table)
+    auto mark = [&](int idx) { if (events && idx < n_events && events[idx]) cudaEventRecord((cudaEvent_t)events[idx], st); };
     // bf16: attention backward on the tensor cores (PZ_ATTN_BWD_SIMT=1 keeps the SIMT kernel, the fp32 build's only one)
     static const bool simt_attn = [] { const char *e = getenv("PZ_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();
     const bool tc_attn_bwd = std::is_same<T, bf16>::value && !(c.flags & PZ_FLAG_SIMPLE_KERNELS) && !simt_attn;
@@ -1439,6 +1453,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             PZ_TRY(linear_bwd<T>(h, ws.dqkv, qkvd, ws.h, Hm, Lw.w_qkv, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_qkv), M, qkvd, Hm, sc, st));
             rmsnorm_bwd(ws.xin[m][l], Lw.norm_in, ws.dh, ws.dx[m], G(Lg.norm_in), M, Hm, st);
         }
+        mark(l);
     }
     // ---- action encoder (vla/modules.py:39-53); dx[2] = d / d (sqrt(A) * linear_3(z))
     {
@@ -1466,7 +1481,11 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         colsum<T>(dyp, A, G(g.prop_b), Mp, A, st);
         PZ_TRY(linear_bwd<T>(h, dyp, A, ws.pp, skp, w.prop_w, nullptr, 0, 0, G(g.prop_w), Mp, A, skp, sc, st));
     }
-    if (!vit_grads) return 0;
+    mark(L);
+    if (!vit_grads) {
+        mark(L + 1 + LV);
+        return 0;
+    }
     // ---- embedding merge (pizero.py:376-414): image rows of the merged sequence are the projector output (the
     // 1/sqrt(H) of the merge and the sqrt(H) of the joint model cancel); token embeddings are frozen (pizero.py:243-249)
     const int n_feat = c.n_images * P;
@@ -1531,12 +1550,14 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         launch_layernorm<T>(ws.xv[i], Lw.ln1_w, Lw.ln1_b, (T *)ws.h, Mv, V, 1e-6f, st);
         PZ_TRY(linear_bwd<T>(h, ws.dqkv, 3 * V, ws.h, V, Lw.w_qkv, ws.dh, V, LIN_OUT_F32, G(Lg.w_qkv), Mv, 3 * V, V, sc, st));
         layernorm_bwd(ws.xv[i], Lw.ln1_w, ws.dh, dxv, G(Lg.ln1_w), G(Lg.ln1_b), Mv, V, st);
+        mark(L + 1 + i);
     }
     // ---- patch embedding (the convolution as a matrix product over unfolded patches) and the position table
     if (g.pos_emb) launch_k(period_sum_kernel, dim3((P * V + 255) / 256), dim3(256), 0, st, (const float *)dxv, G(g.pos_emb), (long)P * V, V, P, n_img);
     cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
     colsum<T>((const T *)ws.dyb, V, G(g.patch_b), Mv, V, st);
     PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.patches, c.patch_k_pad, w.patch_w, nullptr, 0, 0, G(g.patch_w), Mv, V, c.patch_k_pad, sc, st));
+    mark(L + 1 + LV);
     return 0;
 }
 
@@ -1552,7 +1573,8 @@ size_t pz_train_workspace_bytes(const pz_handle *h, int batch) {
 
 int pz_flow_matching_step(pz_handle *h, const int64_t *ids, const void *pixels, const int32_t *valid_len, const float *proprio,
                           const float *actions, const float *noise, const float *t, float sig_min, const pz_weights *grads,
-                          float loss_scale, float *loss, void *ws, size_t ws_bytes, int B, int flags, void *stream) {
+                          float loss_scale, float *loss, void *ws, size_t ws_bytes, int B, int flags, void *const *events, int n_events,
+                          void *stream) {
     if (!h) return PZ_ERR_INVALID;
     if (!h->bound) return fail(h, PZ_ERR_UNBOUND, "pz_bind_weights has not been called");
     if (B < 1 || B > h->cfg.max_batch) return fail(h, PZ_ERR_INVALID, "batch out of range (1..max_batch)");
@@ -1575,9 +1597,9 @@ int pz_flow_matching_step(pz_handle *h, const int64_t *ids, const void *pixels, 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->cfg.dtype == PZ_BF16
                  ? forward_backward<bf16>(h, ids, pixels, valid_len, proprio, actions, noise, t, sig_min, grads ? &gr : nullptr, loss,
-                                          loss_scale, ws, B, flags, st)
+                                          loss_scale, ws, B, flags, events, n_events, st)
                  : forward_backward<float>(h, ids, pixels, valid_len, proprio, actions, noise, t, sig_min, grads ? &gr : nullptr, loss,
-                                           loss_scale, ws, B, flags, st);
+                                           loss_scale, ws, B, flags, events, n_events, st);
     g_launch_counter = nullptr;
     if (rc) return rc;
     cudaError_t e = cudaPeekAtLastError();
@@ -1592,11 +1614,11 @@ int pz_flow_matching_step(pz_handle *h, const int64_t *ids, const void *pixels, 
 int pz_grad_sumsq(const float *d_grad, size_t n, float *d_out, void *stream) {
     if (!d_grad || !d_out) return PZ_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(d_out, 0, sizeof(float), st);
     size_t blocks = (n / 4 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > PZ_SUMSQ_SCRATCH) blocks = PZ_SUMSQ_SCRATCH;
     if (blocks < 1) blocks = 1;
-    launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, d_grad, n, d_out);
+    launch_k(sumsq_kernel, dim3((unsigned)blocks), dim3(256), 0, st, d_grad, n, d_out + 1);
+    launch_k(sumsq_final_kernel, dim3(1), dim3(256), 0, st, (const float *)(d_out + 1), (int)blocks, d_out);
     return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
 }
 

@@ -172,7 +172,7 @@ class GradBuffer:
 
 def flow_matching_step(model, input_ids, pixel_values, proprios, actions, t, *, noise=None, valid_len=None,
                        causal_mask=None, grads: Optional[GradBuffer] = None, loss_scale: float = 1.0,
-                       freeze_vision: bool = False) -> torch.Tensor:
+                       freeze_vision: bool = False, overlap: Optional["OverlappedAllReduce"] = None) -> torch.Tensor:
     """One forward + backward of the flow-matching loss (pizero.py:607-661 followed by `loss.backward()`): returns the loss
     (fp32 scalar tensor on the device) and ACCUMULATES `loss_scale * d loss / d weight` into `grads` (None = loss only)."""
     from .pizero import PzError
@@ -214,7 +214,11 @@ def flow_matching_step(model, input_ids, pixel_values, proprios, actions, t, *, 
         rc = lib.pz_flow_matching_step(model._handle, ids.data_ptr(), pix.data_ptr(), vlen.data_ptr(), prop.data_ptr(),
                                        x1.data_ptr(), x0.data_ptr(), tt.data_ptr(), float(model.flow_sig_min),
                                        C.byref(grads.struct) if grads is not None else None, float(loss_scale),
-                                       loss.data_ptr(), base, nbytes, B, 1 if freeze_vision else 0, stream)
+                                       loss.data_ptr(), base, nbytes, B, 1 if freeze_vision else 0,
+                                       overlap.handles if overlap is not None else None, overlap.n if overlap is not None else 0,
+                                       stream)
+        if overlap is not None and rc == 0:
+            overlap.launch()
     if rc != 0:
         raise PzError(f"pz_flow_matching_step failed ({rc}): {lib.pz_last_error(model._handle).decode()}")
     model.last_launch_count = int(lib.pz_launch_count(model._handle))
@@ -239,7 +243,7 @@ class FusedAdamW:
             grads.view(key, self.master).copy_(grads.packed[key].to(torch.float32))
         self.m = torch.zeros_like(grads.flat)
         self.v = torch.zeros_like(grads.flat)
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1 + 1184, dtype=torch.float32, device=dev)   # [0] the result, then pz_grad_sumsq's per-CTA partials
         offs = [off for _, off, _ in grads.entries] + [grads.numel]
         self._off = torch.tensor(offs, dtype=torch.int64, device=dev)
         self._n = torch.tensor([grads.packed[k].numel() for k, _, _ in grads.entries], dtype=torch.int64, device=dev)
@@ -285,7 +289,7 @@ class FusedAdamW:
 
     def grad_norm(self) -> torch.Tensor:
         """sqrt of the last measured sum of squares (before grad_scale): the value clip_grad_norm_ returns."""
-        return self.sumsq.sqrt()
+        return self.sumsq[0].sqrt()
 
     @torch.no_grad()
     def sync_parameters(self):
@@ -307,10 +311,65 @@ def allreduce_gradients(grads: GradBuffer, bucket_mb: int = 256, group=None, asy
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return []
     n = grads.flat.numel()
-    step = max(1, bucket_mb * (1 << 20) // 4)
+    step = max(1024, bucket_mb * (1 << 20) // 4)
     works = []
     for lo in range(0, n, step):
         w = dist.all_reduce(grads.flat[lo:lo + step], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
             works.append(w)
     return works
+
+
+class OverlappedAllReduce:
+    """The gradient all-reduce of the data-parallel step, overlapped with the backward (what DDP's bucket hooks do for the
+    reference, train.py:119-126): `pz_flow_matching_step` records one event per group of finished gradients (joint layer
+    17 .. 0, the action heads, SigLIP layer 26 .. 0, the rest); a side stream waits for each event and all-reduces that
+    slice of the flat buffer (NCCL over NVLink / NVSwitch) while the main stream keeps computing.  `wait()` makes the
+    current stream wait for all of them (call it before the optimizer step)."""
+
+    def __init__(self, grads: GradBuffer, group=None):
+        d = grads.model.dims
+        L, LV = d["num_layers"], d["vit_layers"]
+        self.grads, self.group = grads, group
+        self.n = L + LV + 2
+        dev = grads.flat.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in range(self.n)]
+        with torch.cuda.device(dev):
+            for e in self.events:       # an event's handle exists after its first record
+                e.record()
+        self.handles = (C.c_void_p * self.n)(*[e.cuda_event for e in self.events])
+        offs = {key: off for key, off, _ in grads.entries}
+        ends = [off for _, off, _ in grads.entries][1:] + [grads.numel]
+        end_of = {key: end for (key, _, _), end in zip(grads.entries, ends)}
+
+        def span(first, last):
+            return (offs[first], end_of[last])
+
+        self.ranges = [[] for _ in range(self.n)]
+        mixes = ("vlm", "action") + (() if grads.tied else ("proprio",))
+        for l in range(L):
+            self.ranges[l] = [span((m, l, MIX_FIELDS[0]), (m, l, MIX_FIELDS[-1])) for m in mixes]
+        self.ranges[L] = [span(("top", TOP_ACTION[0]), ("top", TOP_ACTION[-1]))]
+        for i in range(LV):
+            self.ranges[L + 1 + i] = [span(("vit", i, VIT_FIELDS[0]), ("vit", i, VIT_FIELDS[-1]))]
+        self.ranges[L + 1 + LV] = [span(("top", TOP_VLM[0]), ("top", TOP_VLM[-1]))]
+        self.order = list(range(L - 1, -1, -1)) + [L] + list(range(L + LV, L, -1)) + [L + 1 + LV]   # completion order
+        assert sum(hi - lo for r in self.ranges for lo, hi in r) == grads.numel
+        self._works = []
+
+    def launch(self):
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        flat = self.grads.flat
+        with torch.cuda.stream(self.stream):
+            for idx in self.order:
+                self.stream.wait_event(self.events[idx])
+                for lo, hi in self.ranges[idx]:
+                    self._works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self._works:
+            w.wait()
+        self._works = []

@@ -65,3 +65,106 @@ def test_shard_bounds_cover_batch_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+# ------------------------------------------------------------------ training step: gradient all-reduce (N > 1)
+def _allreduce_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        from open_pi_zero_b200.train import allreduce_gradients
+        n = 3 * 1024 + 17
+        g = torch.Generator().manual_seed(rank)
+        flat = torch.randn(n, generator=g)
+        want = sum(torch.randn(n, generator=torch.Generator().manual_seed(r)) for r in range(world))
+        allreduce_gradients(SimpleNamespace(flat=flat), bucket_mb=0)      # bucket_mb 0 -> the smallest bucket: many buckets
+        if rank == 0:
+            q.put(float((flat - want).abs().max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_allreduce():
+    """train.py:119-126 (DDP): the flat gradient buffer is summed over the ranks bucket by bucket."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-6
+
+
+def _ddp_step_worker(rank, world, port, q):
+    """Both ranks share cuda:0 (gloo moves CUDA tensors through the host): rank r trains on its own micro-batch with the
+    all-reduce overlapped layer by layer; the result must be the sum of the two local gradients."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import SMALL
+        from open_pi_zero_b200.pizero import PiZero
+        from open_pi_zero_b200.train import FusedAdamW, GradBuffer, OverlappedAllReduce, flow_matching_step
+        d = SMALL
+        sd = pz.init_state_dict(d, seed=13, randomize_norms=True, tie_proprio=False)
+        m = PiZero(pz.cfg_from_dims(d), init="empty")
+        m.load_state_dict(sd, strict=True)
+        m = m.to(torch.float32).to("cuda")
+
+        def batch(r):
+            inp = pz.make_inputs(d, 2, seed=40 + r)
+            g = torch.Generator().manual_seed(60 + r)
+            a = torch.rand((2, d["horizon_steps"], d["action_dim"]), generator=g) * 2 - 1
+            n = torch.randn((2, d["horizon_steps"], d["action_dim"]), generator=g)
+            t = torch.rand((2,), generator=g)
+            return inp, a, n, t
+
+        def run(r, gb, ov=None):
+            inp, a, n, t = batch(r)
+            return flow_matching_step(m, inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["proprios"].cuda(), a.cuda(),
+                                      t.cuda(), noise=n.cuda(), valid_len=inp["valid_len"].cuda(), grads=gb, overlap=ov)
+
+        want = GradBuffer(m)
+        for r in range(world):          # the sum of every rank's local gradient, computed locally without communication
+            run(r, want)
+        gb = GradBuffer(m)
+        ov = OverlappedAllReduce(gb)
+        run(rank, gb, ov)
+        ov.wait()
+        torch.cuda.synchronize()
+        err = float((gb.flat - want.flat).norm() / want.flat.norm())
+        # the optimizer step with grad_scale 1 / world leaves identical weights on every rank
+        opt = FusedAdamW(gb, action_lr=1e-3, vlm_lr=1e-3)
+        opt.step(grad_scale=1.0 / world)
+        chk = opt.master.double().sum().reshape(1).cpu()
+        both = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(both, chk)
+        q.put((rank, err, float(both[0]) == float(both[1])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_rank_data_parallel_training_step_overlapped_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_step_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    for _ in range(2):
+        rank, err, same = q.get(timeout=5)
+        assert err < 1e-5, (rank, err)
+        assert same
