@@ -335,6 +335,47 @@ def stage_split_bs1(model, dims, device):
     return res
 
 
+def train_step_extra(model, dims, dev_in, device, Bt, steps=3):
+    """BASELINE configs[4] on one GPU: `pz_flow_matching_step` (forward + backward) and the fused clip + AdamW, CUDA-event
+    timed; next to it the unmodified reference's eager step measured by tools/train_bench.py --reference on the same GPU
+    type (quoted from profiles/, it needs its own process: 65 GB of autograd state)."""
+    from open_pi_zero_b200.train import FusedAdamW, GradBuffer, flow_matching_step
+    g = torch.Generator().manual_seed(7)
+    acts = (torch.rand((Bt, dims["horizon_steps"], dims["action_dim"]), generator=g) * 2 - 1).to(device)
+    x0 = torch.randn((Bt, dims["horizon_steps"], dims["action_dim"]), generator=g).to(device)
+    tt = pz.FlowTimeSampler("beta").sample_fm_time(Bt).to(device)
+    gb = GradBuffer(model)
+    opt = FusedAdamW(gb)
+    kw = dict(noise=x0, valid_len=dev_in["valid_len"][:Bt], grads=gb)
+    args_ = (dev_in["input_ids"][:Bt], dev_in["pixel_values"][:Bt], dev_in["proprios"][:Bt], acts, tt)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    flow_matching_step(model, *args_, **kw)
+    opt.step()
+    torch.cuda.synchronize()
+    fb = op = 0.0
+    for _ in range(steps):
+        ev[0].record()
+        loss = flow_matching_step(model, *args_, **kw)
+        ev[1].record()
+        opt.step()
+        ev[2].record()
+        ev[2].synchronize()
+        fb += ev[0].elapsed_time(ev[1])
+        op += ev[1].elapsed_time(ev[2])
+    ms = (fb + op) / steps
+    out = dict(what="flow-matching training step (BASELINE configs[4]): forward + backward (pz_flow_matching_step) + global-norm clip "
+                    "+ AdamW on fp32 master weights (pz_adamw_step), one GPU, no all-reduce", batch=Bt, ms=ms,
+               fwd_bwd_ms=fb / steps, optimizer_ms=op / steps, samples_per_s=Bt / (ms / 1e3), loss=float(loss),
+               launches_fwd_bwd=model.last_launch_count, parameters_trained=int(gb.flat.numel()))
+    ref_path = os.path.join(ROOT, "profiles", "r02_train_bench_reference.json")
+    if os.path.exists(ref_path):
+        with open(ref_path) as fh:
+            ref = json.load(fh)
+        out["reference_eager_same_gpu_type"] = dict(ms=ref.get("ms_per_step"), samples_per_s=ref.get("value"), source="profiles/r02_train_bench_reference.json")
+    del opt, gb
+    return out
+
+
 def reference_compiled(live):
     """The bar the reference deploys (eval.py:38-40): its model under torch.compile(mode="default").  The first compiled
     call takes minutes, so the default run quotes the committed measurement of tools/ref_compiled.py; --ref-compiled
@@ -667,6 +708,16 @@ def main():
                           if kind == "reference" else "oracle port of the reference") + ", all host threads) after 1 warm-up",
                    max_abs_gpu_vs_cpu=float((got - want).abs().max()))
 
+    # ---- extra: the full training step of BASELINE configs[4] (forward + backward + clip + AdamW, per-GPU batch 32);
+    # LAST, because the optimizer updates the packed weights in place
+    train = None
+    if rank == 0 and not args.skip_latency and extras and args.config == "bridge64":
+        try:
+            train = train_step_extra(model, dims, dev_in, device, min(32, B))
+        except Exception as e:   # noqa: BLE001 -- an extra must not take the headline line down
+            train = dict(error=repr(e)[:300])
+    sync_all()
+
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup,
@@ -676,7 +727,7 @@ def main():
             clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             e2e_stock_signature=e2e_stock,
             gpu_launches=launches, latency_bs1=lat, roofline=roof, roofline_denoise_bs1=roof_denoise,
-            cpu_baseline=cpu, reference_gpu_eager=ref_gpu, reference_gpu_compiled=ref_compiled, train_forward=fm,
+            cpu_baseline=cpu, reference_gpu_eager=ref_gpu, reference_gpu_compiled=ref_compiled, train_forward=fm, train_step=train,
             switches=active_switches(model))
         print(json.dumps(line), flush=True)
     if world > 1:
