@@ -667,6 +667,8 @@ struct AttnBwd2Args {
     int seg, s_v, s_p;                 // segment of the queries (block mask, pizero.py:271-310); valid_len == null: no mask
     float scale, softcap;
     int accumulate, groups;
+    int qsplit;                        // dK/dV kernel: query tiles dealt round-robin to this many CTAs per key block, which
+                                       // then ADD their partial sums with fp32 atomics (qsplit > 1 needs zeroed dK / dV)
 };
 
 constexpr int SLD = 72;               // row pitch of the 64 x 64 score tiles (floats / bf16s)
@@ -756,9 +758,14 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
     const int er = tid >> 2, ec0 = (tid & 3) * 16;      // elementwise mapping: 4 threads per row, 16 columns each
     const bool row_ok = row0 + er < a.NQ && (row0 + er) / a.hpr < tok_limit;
     const int n_kb = (a.NK + 63) / 64;
+    // Soft-capped logits lie in [-cap, cap]: exp(l - cap / 2) can neither overflow nor leave the normal fp32 range, so the
+    // softmax needs no running maximum and dQ is linear in 1 / Z -- ONE pass accumulates the unnormalised sum and Z, the
+    // division happens at the end.  Without a cap (SigLIP) pass A computes the log-sum-exp first.
+    const bool single = a.softcap > 0.f;
+    const float shift = 0.5f * a.softcap;
     // ---- pass A: log-sum-exp of every row
     float m_run = -INFINITY, s_run = 0.f;
-    for (int kb = 0; kb < n_kb; ++kb) {
+    for (int kb = 0; !single && kb < n_kb; ++kb) {
         __syncthreads();
         load_rows64<HDP>(Ks, Kg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
         __syncthreads();
@@ -785,16 +792,11 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
         s_run = (m_run > -INFINITY ? s_run * __expf(m_run - m_new) : 0.f) + sloc;
         m_run = m_new;
     }
-    const float lse = (row_ok && s_run > 0.f) ? m_run + __logf(s_run) : INFINITY;   // +inf: P = exp(l - lse) = 0
+    float lse = (row_ok && s_run > 0.f) ? m_run + __logf(s_run) : INFINITY;   // +inf: P = exp(l - lse) = 0
+    if (single) lse = row_ok ? shift : INFINITY;
     __syncthreads();
-    if ((tid & 3) == 0) {
-        sL[er] = lse;
-        if (row0 + er < a.NQ) {
-            const long o = ((long)b * a.groups + g) * a.NQ + row0 + er;
-            a.lse[o] = lse;
-            a.dvec[o] = sD[er];
-        }
-    }
+    if ((tid & 3) == 0) sL[er] = lse;
+    float z_run = 0.f;
     // ---- pass B: dQ = sum over key blocks of dS K
     constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
     const int wr = warp >> 1, wc = warp & 1;
@@ -816,6 +818,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
             const float l = a.softcap > 0.f ? a.softcap * tanh_hw(sv * inv_cap) : sv;
             const float th = l * inv_cap;
             const float pv = key_visible(a, kb * 64 + ec0 + c, vl) ? __expf(l - Lr) : 0.f;
+            z_run += pv;
             Pb[er * SLD + ec0 + c] = __float2bfloat16_rn(pv * (Df[er * SLD + ec0 + c] - Dr) * (1.f - th * th) * a.scale);
         }
         __syncthreads();
@@ -834,7 +837,19 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
             }
         }
     }
+    // the statistics the dK / dV kernel needs: log-sum-exp and D of every row; single pass: Z is known only now
+    z_run += __shfl_xor_sync(0xffffffffu, z_run, 1);
+    z_run += __shfl_xor_sync(0xffffffffu, z_run, 2);
+    if (single) lse = (row_ok && z_run > 0.f) ? shift + __logf(z_run) : INFINITY;
     __syncthreads();
+    if ((tid & 3) == 0) {
+        sL[er] = single ? ((row_ok && z_run > 0.f) ? 1.f / z_run : 0.f) : 1.f;      // row scale of the accumulated dQ
+        if (row0 + er < a.NQ) {
+            const long o = ((long)b * a.groups + g) * a.NQ + row0 + er;
+            a.lse[o] = lse;
+            a.dvec[o] = sD[er];
+        }
+    }
     float *stage = (float *)Ks;    // 64 x HDP fp32 = the K and V tiles
 #pragma unroll
     for (int t = 0; t < HALF; ++t) {
@@ -845,7 +860,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
     float *dQg = a.dQ + b * a.dq_bs + g * a.dq_gs;
     for (int i = tid; i < 64 * a.hd; i += 256) {
         const int r = i / a.hd, c = i % a.hd;
-        if (row0 + r < a.NQ) dQg[(long)(row0 + r) * a.ld_dq + c] = stage[r * HDP + c];
+        if (row0 + r < a.NQ) dQg[(long)(row0 + r) * a.ld_dq + c] = stage[r * HDP + c] * sL[r];
     }
 }
 
@@ -861,7 +876,8 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     bf16 *Pb = (bf16 *)(Df + 64 * SLD), *dSb = Pb + 64 * SLD;
     float *sD = (float *)(dSb + 64 * SLD), *sL = sD + 64;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int b = blockIdx.z, g = blockIdx.y, key0 = blockIdx.x * 64;
+    const int NS = a.qsplit > 1 ? a.qsplit : 1;
+    const int b = blockIdx.z, g = blockIdx.y, key0 = (blockIdx.x / NS) * 64, split = blockIdx.x % NS;
     const int vl = a.valid_len ? a.valid_len[b] : (1 << 30);
     const int tok_limit = (a.valid_len && a.seg == 0) ? vl : (1 << 30);
     const bf16 *Qg = a.Q + b * a.q_bs + g * a.q_gs, *dOg = a.dO + b * a.o_bs + g * a.o_gs;
@@ -879,7 +895,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     // keys of this block that any query of this segment sees: skip the block if none
     bool any = false;
     for (int j = key0; j < key0 + 64; ++j) any = any || key_visible(a, j, vl);
-    for (int qt = 0; any && qt < n_qt; ++qt) {
+    for (int qt = split; any && qt < n_qt; qt += NS) {
         const int row0 = qt * 64;
         if (a.valid_len && a.seg == 0 && row0 / a.hpr >= vl) break;      // padded tokens only from here on
         __syncthreads();
@@ -934,11 +950,22 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
         }
         __syncthreads();
         float *dst = (which ? a.dK : a.dV) + b * a.dkv_bs + g * a.dkv_gs;
-        for (int i = tid; i < 64 * a.hd; i += 256) {
-            const int r = i / a.hd, c = i % a.hd;
-            if (key0 + r < a.NK) {
-                float *p = dst + (long)(key0 + r) * a.ld_dkv + c;
-                *p = (a.accumulate ? *p : 0.f) + stage[r * HDP + c];
+        if (NS > 1) {
+            // partial sums of this CTA's share of the query tiles: 16-byte fp32 atomics (hd and the row pitch are multiples of 4)
+            for (int i = tid; any && i < 64 * (a.hd / 4); i += 256) {
+                const int r = i / (a.hd / 4), c = (i % (a.hd / 4)) * 4;
+                if (key0 + r < a.NK) {
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + r * HDP + c);
+                    atomicAdd(reinterpret_cast<float4 *>(dst + (long)(key0 + r) * a.ld_dkv + c), v);
+                }
+            }
+        } else {
+            for (int i = tid; i < 64 * a.hd; i += 256) {
+                const int r = i / a.hd, c = i % a.hd;
+                if (key0 + r < a.NK) {
+                    float *p = dst + (long)(key0 + r) * a.ld_dkv + c;
+                    *p = (a.accumulate ? *p : 0.f) + stage[r * HDP + c];
+                }
             }
         }
     }
@@ -953,7 +980,7 @@ int attn_bwd2_launch(const AttnBwd2Args &a, int batch, bool dq, bool dkv, cudaSt
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     if (dq) launch_k(attn_bwd_dq_kernel<HDP>, dim3((a.NQ + 63) / 64, a.groups, batch), dim3(256), smem, st, a);
-    if (dkv) launch_k(attn_bwd_dkv_kernel<HDP>, dim3((a.NK + 63) / 64, a.groups, batch), dim3(256), smem, st, a);
+    if (dkv) launch_k(attn_bwd_dkv_kernel<HDP>, dim3(((a.NK + 63) / 64) * (a.qsplit > 1 ? a.qsplit : 1), a.groups, batch), dim3(256), smem, st, a);
     return 0;
 }
 
@@ -1215,7 +1242,7 @@ TrainWs carve_train(const pz_config &c, int B, void *base) {
     w.dK = b.take<float>((size_t)B * S_all * c.head_dim * 4);
     w.dV = b.take<float>((size_t)B * S_all * c.head_dim * 4);
     {
-        size_t nj = (size_t)B * c.s_vlm * c.n_heads, nv = Mv * c.vit_heads;
+        size_t nj = (size_t)B * (c.s_vlm + c.cond_steps + c.horizon) * c.n_heads, nv = Mv * c.vit_heads;
         w.lse = b.take<float>((nj > nv ? nj : nv) * 4);
         w.dvec = b.take<float>((nj > nv ? nj : nv) * 4);
     }
@@ -1409,16 +1436,39 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             b2.lse = ws.lse; b2.dvec = ws.dvec; b2.valid_len = valid_len; b2.s_v = S_v; b2.s_p = S_p;
             b2.NK = S_all; b2.hd = hd; b2.hpr = nh; b2.groups = 1;
             b2.scale = 1.0f / sqrtf((float)hd); b2.softcap = 50.f;
-            bool first = true;
-            for (int m = 0; m < 3; ++m) {
+            // dK / dV: every (segment, key block, query split) CTA adds its partial sum with atomics into zeroed buffers, so
+            // the three segments are independent: the two small ones (proprio 8, action 32 query rows: latency-bound
+            // launches) run on the side stream beside the vlm segment
+            cudaMemsetAsync(ws.dK, 0, (size_t)B * S_all * hd * 4, st);
+            cudaMemsetAsync(ws.dV, 0, (size_t)B * S_all * hd * 4, st);
+            b2.qsplit = 4;
+            cudaStream_t side = st;
+            if (!last) {
+                if (!h->side && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess)
+                    return fail(h, PZ_ERR_CUDA, "cannot create the side stream");
+                side = h->side;
+                while (h->sync_ev.size() < 2) {
+                    cudaEvent_t e;
+                    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+                    h->sync_ev.push_back(e);
+                }
+                cudaEventRecord(h->sync_ev[0], st);
+                cudaStreamWaitEvent(side, h->sync_ev[0], 0);
+            }
+            for (int m = 2; m >= 0; --m) {
                 if (last && m < 2) continue;
                 // the [tokens, heads * hd] buffers seen as [tokens * heads, hd]: the heads of a token are consecutive query rows
                 b2.Q = (const bf16 *)ws.q[m][l]; b2.q_bs = (long)md[m].rows * qd; b2.ld_q = hd;
                 b2.dO = (const bf16 *)ws.datt[m]; b2.O = (const bf16 *)ws.att[m][l]; b2.o_bs = (long)md[m].rows * qd; b2.ld_o = hd;
                 b2.dQ = ws.dq[m]; b2.dq_bs = (long)md[m].rows * qd; b2.ld_dq = hd;
-                b2.NQ = md[m].rows * nh; b2.seg = m; b2.accumulate = first ? 0 : 1;
-                attn_bwd2_launch<256>(b2, B, true, true, st);
-                first = false;
+                b2.NQ = md[m].rows * nh; b2.seg = m;
+                // every segment has its own slice of the statistics scratch
+                b2.lse = ws.lse + (size_t)B * row_off[m] * nh; b2.dvec = ws.dvec + (size_t)B * row_off[m] * nh;
+                attn_bwd2_launch<256>(b2, B, true, true, m == 0 ? st : side);
+            }
+            if (side != st) {
+                cudaEventRecord(h->sync_ev[1], side);
+                cudaStreamWaitEvent(st, h->sync_ev[1], 0);
             }
         } else {
         cudaMemsetAsync(ws.dK, 0, (size_t)B * S_all * hd * 4, st);
