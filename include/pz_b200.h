@@ -330,6 +330,10 @@ int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const fl
  * Dense test layout: Q,O [B, q_rows, n_heads*hd]; K,V [B, s_cache, kv_heads*hd];
  * K2,V2 [B, n_fresh, kv_heads*hd].  impl: 0 = SIMT reference, 1 = mma.sync tensor-core
  * kernel (bf16), 3 = tcgen05 kernel (prefix vlm rows only; -1 if the shape is not covered).  d_scratch (optional fp32) enables the split-key decode path. */
+/* pz_op_linear with MN-major operands: flags may carry 128 (A stored [K][M], row stride lda) and 256 (W stored [K][N], row
+ * stride ldw) -- how the training step's backward reads dY, X and W in place (impl 0 = SIMT, 1 = tcgen05). */
+int pz_op_linear_ex(int impl, int dtype, const void *d_a, const void *d_w, const float *d_bias, void *d_c, int M, int N, int K,
+                    int lda, int ldc, int ldw, int flags, float alpha, void *stream);
 int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
                     const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
                     int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,

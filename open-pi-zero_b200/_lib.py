@@ -65,7 +65,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_set_pixel_format", "pz_kv_layout", "pz_debug_trace_offset", "pz_sampler_stream_bytes", "pz_sampler_pack", "pz_set_sampler", "pz_infer_action", "pz_embed_prefix",
            "pz_prefill", "pz_denoise", "pz_text_prefill", "pz_text_decode", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss", "pz_train_workspace_bytes", "pz_flow_matching_step", "pz_grad_sumsq", "pz_adamw_step",
-           "pz_launch_count", "pz_fallback_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_attention"]
+           "pz_launch_count", "pz_fallback_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_linear_ex", "pz_op_attention"]
 
 _lib = None
 
@@ -129,6 +129,8 @@ def load(build_if_needed: bool = True):
     lib.pz_timing_end.argtypes = [hp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.pz_op_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_float, vp]
+    lib.pz_op_linear_ex.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]
     lib.pz_op_attention.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp] + \
         [C.c_int] * 9 + [C.c_float, C.c_float, vp, C.c_size_t, vp]
     if lib.pz_abi_version() != PZ_ABI_VERSION:

@@ -900,6 +900,24 @@ int pz_op_linear(int impl, int dtype, const void *d_a, const void *d_w, const fl
     return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
 }
 
+int pz_op_linear_ex(int impl, int dtype, const void *d_a, const void *d_w, const float *d_bias, void *d_c, int M, int N, int K,
+                    int lda, int ldc, int ldw, int flags, float alpha, void *stream) {
+    LinearArgs a = lin(d_a, lda, d_w, d_bias, d_c, ldc, M, N, K, flags, alpha);
+    a.ldw = ldw;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 0) {
+        if (dtype == PZ_BF16) launch_linear_simple<bf16>(a, st); else launch_linear_simple<float>(a, st);
+    } else if (impl == 1) {
+        if (dtype != PZ_BF16 || !gemm_tc_supported(a)) return PZ_ERR_INVALID;
+        const char *e = nullptr;
+        int rc = launch_linear_tc(a, st, &e);
+        if (rc) { g_create_error = e ? e : "tcgen05 gemm failed"; return rc; }
+    } else {
+        return PZ_ERR_INVALID;
+    }
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
 int pz_op_attention(int impl, int dtype, const void *d_q, const void *d_k, const void *d_v,
                     const void *d_k2, const void *d_v2, const int32_t *d_valid_len, void *d_out,
                     int batch, int n_heads, int head_dim, int q_rows, int q_row0, int s_cache,

@@ -127,7 +127,7 @@ static LinearArgs lin(const void *A, int lda, const void *W, const float *bias, 
     LinearArgs a;
     a.A = A; a.W = W; a.bias = bias; a.C = C;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldc = ldc;
-    a.alpha = alpha; a.flags = flags; a.norm_w = nullptr;
+    a.alpha = alpha; a.flags = flags; a.norm_w = nullptr; a.ldw = 0;
     a.cmb_splits = a.cmb_q_rows = a.cmb_heads = a.cmb_hd = 0;
     return a;
 }

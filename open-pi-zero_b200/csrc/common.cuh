@@ -73,6 +73,9 @@ enum : int {
     LIN_SILU = 16,     // silu(acc + bias)
     LIN_NORM_A = 32,   // A is the fp32 residual stream; apply Gemma RMSNorm (norm_w) while loading it
     LIN_COMBINE_A = 64, // A is the split-key attention partials; combine them while loading (skinny only)
+    LIN_A_MN = 128,    // A is stored [K][M] (row stride lda): the M dimension is contiguous ("MN-major" UMMA operand);
+    LIN_W_MN = 256,    // W is stored [K][N] (row stride ldw).  tcgen05 GEMM only: the backward of the training step reads
+                       // dY, X and W in place instead of through transposed copies
 };
 
 struct LinearArgs {
@@ -83,6 +86,7 @@ struct LinearArgs {
     int M, N, K, lda, ldc;
     float alpha;
     int flags;
+    int ldw;            // LIN_W_MN: row stride of the [K][N] storage (otherwise unused)
     const float *norm_w;   // LIN_NORM_A: RMSNorm scale (raw w; 1+w is applied), eps 1e-6
     // LIN_COMBINE_A: A = partials [batch][n_splits][heads*q_rows][hd+2] fp32 (o, m, l) of attn_mma's
     // split-key mode; logical A[m = b*q_rows + tok][k = h*hd + d]

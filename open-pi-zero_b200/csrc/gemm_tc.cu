@@ -51,6 +51,7 @@ struct TcParams {
     bf16 *k_out, *v_out;                // cache rows: base + b*kv_batch_stride + s*256
     long kv_batch_stride;
     int s_x, n_q_tiles;
+    int a_mn, w_mn;                     // operand stored [K][M] / [K][N]: loaded as 64-element x 64-row boxes, MN-major descriptors
 };
 
 constexpr int LIN_ROPE = 1 << 10;       // internal flag of this file
@@ -159,6 +160,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ----
         if (lane == 0) {
+            // one operand tile of a stage: K-major = one box [rows][64 k]; MN-major (operand stored [K][M/N]) = one box
+            // [64 k][64 m] per 64 rows of the tile, 8 KB apart (the LBO of the MN-major descriptor)
+            auto load_w = [&](uint64_t *bar, uint8_t *dst, int kb, int tn) {
+                const int n0 = tn * BN + (CG == 2 ? crank * (BN / 2) : 0);
+                if (!p.w_mn) {
+                    if (CG == 2) tma_load_2d_pair(&map_w, bar, dst, kb * BK, n0, p.w_hint);
+                    else tma_load_2d(&map_w, bar, dst, kb * BK, n0, p.w_hint);
+                } else {
+                    for (int j = 0; j < BN / CG / 64; ++j) {
+                        if (CG == 2) tma_load_2d_pair(&map_w, bar, dst + j * 8192, n0 + 64 * j, kb * BK, p.w_hint);
+                        else tma_load_2d(&map_w, bar, dst + j * 8192, n0 + 64 * j, kb * BK, p.w_hint);
+                    }
+                }
+            };
+            auto load_a = [&](uint64_t *bar, uint8_t *dst, int kb, int tm) {
+                const int m0 = (tm * CG + crank) * BM;
+                if (!p.a_mn) {
+                    if (CG == 2) tma_load_2d_pair(&map_a, bar, dst, kb * BK, m0, p.a_hint);
+                    else tma_load_2d(&map_a, bar, dst, kb * BK, m0, p.a_hint);
+                } else {
+                    for (int j = 0; j < BM / 64; ++j) {
+                        if (CG == 2) tma_load_2d_pair(&map_a, bar, dst + j * 8192, m0 + 64 * j, kb * BK, p.a_hint);
+                        else tma_load_2d(&map_a, bar, dst + j * 8192, m0 + 64 * j, kb * BK, p.a_hint);
+                    }
+                }
+            };
             // PDL: the weight tiles of the first ring pass do not depend on the previous
             // kernel -- issue them before waiting for it; activations (A) only after.
             int pre = 0;
@@ -172,8 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int i = 0; i < pre; ++i) {
                     uint8_t *sa = smem + i * cfg::STAGE_BYTES;
                     if (crank == 0) mbar_expect_tx(&full_bar[i], cfg::STAGE_BYTES * CG);
-                    if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN + crank * (BN / 2), p.w_hint);
-                    else tma_load_2d(&map_w, &full_bar[i], sa + cfg::A_BYTES, (kb0 + i) * BK, tn * BN, p.w_hint);
+                    load_w(&full_bar[i], sa + cfg::A_BYTES, kb0 + i, tn);
                 }
             }
             pdl_wait();
@@ -191,11 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (it >= pre) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (crank == 0) mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES * CG);
-                        if (CG == 2) tma_load_2d_pair(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN + crank * (BN / 2), p.w_hint);
-                        else tma_load_2d(&map_w, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tn * BN, p.w_hint);
+                        load_w(&full_bar[stage], sa + cfg::A_BYTES, kb, tn);
                     }
-                    if (CG == 2) tma_load_2d_pair(&map_a, &full_bar[stage], sa, kb * BK, (tm * CG + crank) * BM, p.a_hint);
-                    else tma_load_2d(&map_a, &full_bar[stage], sa, kb * BK, tm * BM, p.a_hint);
+                    load_a(&full_bar[stage], sa, kb, tm);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -203,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // -------------------------------------------------- MMA issuer ----
         if (lane == 0 && crank == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM * CG, BN);
+            // bits 15 / 16 of the instruction descriptor: A / B operand MN-major
+            const uint32_t idesc = umma_idesc(BM * CG, BN) | (p.a_mn ? (1u << 15) : 0u) | (p.w_mn ? (1u << 16) : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -218,13 +243,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
-                    uint64_t adesc = umma_desc_sw128(sa);
-                    uint64_t bdesc = umma_desc_sw128(sa + cfg::A_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in 16 B units
-                        if (CG == 2) tc_mma_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
-                        else tc_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle atom (+2 in 16 B units);
+                        // MN-major: 16 k-rows of 128 B further down, the next 64 M/N elements 8 KB away
+                        const uint64_t ad = p.a_mn ? umma_desc_sw128_mn(sa + k * 2048, 8192) : adesc + 2 * k;
+                        const uint64_t bd = p.w_mn ? umma_desc_sw128_mn(sa + cfg::A_BYTES + k * 2048, 8192) : bdesc + 2 * k;
+                        if (CG == 2) tc_mma_pair(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
+                        else tc_mma(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
                     }
                     if (CG == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -458,8 +486,11 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
     CUtensorMap ma, mw, mc;
     const bool f32out = a.flags & LIN_OUT_F32;
     const int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
-    if (!make_map(&ma, a.A, a.M, a.K, a.lda, BM) || !make_map(&mw, a.W, a.N, a.K, a.K, BN / CG) ||
-        !make_map(&mc, a.C, a.M, n_out, a.ldc, 32, f32out)) {
+    const bool a_mn = a.flags & LIN_A_MN, w_mn = a.flags & LIN_W_MN;
+    // MN-major operands: the tensor is [K rows][M or N columns]; boxes of 64 columns x 64 k-rows
+    const bool ok_a = a_mn ? make_map(&ma, a.A, a.K, a.M, a.lda, BK) : make_map(&ma, a.A, a.M, a.K, a.lda, BM);
+    const bool ok_w = w_mn ? make_map(&mw, a.W, a.K, a.N, a.ldw, BK) : make_map(&mw, a.W, a.N, a.K, a.K, BN / CG);
+    if (!ok_a || !ok_w || !make_map(&mc, a.C, a.M, n_out, a.ldc, 32, f32out)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return PZ_ERR_CUDA;
     }
@@ -467,6 +498,7 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
     if (extra) p = *extra; else memset(&p, 0, sizeof(p));
     p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc; p.bias = a.bias; p.C = a.C;
     p.alpha = a.alpha; p.flags = a.flags | (extra ? LIN_ROPE : 0);
+    p.a_mn = a_mn; p.w_mn = w_mn;
     p.tiles_m = (a.M + BM * CG - 1) / (BM * CG);   // tiles of the worker (CTA or CTA pair)
     p.tiles_n = (a.N + BN - 1) / BN;
     // split K when the output grid cannot fill the machine and the epilogue is a pure fp32
@@ -570,7 +602,9 @@ bool use_pair(const LinearArgs &a) {
 
 int gemm_tc_supported(const LinearArgs &a) {
     if (a.flags & (LIN_NORM_A | LIN_COMBINE_A)) return 0;
-    if (a.M < 1 || a.K % 8 || a.lda % 8) return 0;          // TMA: 16-byte global strides
+    if ((a.flags & LIN_W_MN) && (a.ldw % 8 || a.ldw < a.N)) return 0;
+    if ((a.flags & LIN_A_MN) && a.lda < a.M) return 0;
+    if (a.M < 1 || (!(a.flags & LIN_W_MN) && a.K % 8) || a.lda % 8) return 0;          // TMA: 16-byte global strides
     if (((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.C) & 15) return 0;
     int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
     if (n_out % 8 || a.ldc % 8) return 0;                    // TMA store: 16-byte global strides

@@ -25,13 +25,13 @@ __global__ void __launch_bounds__(256) linear_simple_kernel(LinearArgs a) {
         for (int i = threadIdx.x; i < BM * BK; i += 256) {
             int r = i / BK, c = i % BK;
             int m = m0 + r, k = k0 + c;
-            sA[c][r] = (m < a.M && k < a.K) ? to_f32<T>(A[(long)m * a.lda + k]) : 0.f;
+            sA[c][r] = (m < a.M && k < a.K) ? to_f32<T>((a.flags & LIN_A_MN) ? A[(long)k * a.lda + m] : A[(long)m * a.lda + k]) : 0.f;
         }
         for (int i = threadIdx.x; i < BN * BK; i += 256) {
             int r = i / BK, c = i % BK;
             int n = n0 + r, k = k0 + c;
             if (!GEGLU) {
-                sW[0][c][r] = (n < a.N && k < a.K) ? to_f32<T>(W[(long)n * a.K + k]) : 0.f;
+                sW[0][c][r] = (n < a.N && k < a.K) ? to_f32<T>((a.flags & LIN_W_MN) ? W[(long)k * a.ldw + n] : W[(long)n * a.K + k]) : 0.f;
             } else {
                 // output column n <- gate row g, up row g + PZ_GU_BLOCK
                 long g = (long)(n / PZ_GU_BLOCK) * (2 * PZ_GU_BLOCK) + (n % PZ_GU_BLOCK);

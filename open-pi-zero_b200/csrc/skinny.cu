@@ -253,6 +253,7 @@ int skinny_supported(const LinearArgs &a) {
     // chunk stay in L2): the 7-wide action decoder.
     // (above ~16 rows the activation fragments no longer stay in registers / L1 cheaply and the
     // tcgen05 GEMM wins even though its fixed cost is higher)
+    if (a.flags & (LIN_A_MN | LIN_W_MN)) return 0;
     if (a.M < 1 || (a.M > 16 && a.N > 64)) return 0;
     if (a.K % 8 || a.lda % 8) return 0;
     if ((a.flags & LIN_NORM_A) && (!a.norm_w || ((uintptr_t)a.norm_w & 15))) return 0;

@@ -1119,6 +1119,24 @@ struct Scratch {          // transposed operands of one backward linear layer
 template <typename T>
 int linear_bwd(pz_handle *h, const void *dY, int ldy, const void *X, int ldx, const void *W, void *dX, int ld_dx,
                int dx_flags, float *dW, int M, int N, int K, const Scratch &sc, cudaStream_t st) {
+    static const bool use_t = [] { const char *e = getenv("PZ_BWD_TRANSPOSE"); return e && e[0] == '1'; }();
+    if (!use_t) {
+        // operands read in place: W [N][K] is the MN-major B operand of dX = dY . W, and dY [M][N], X [M][K] are the
+        // MN-major A / B operands of dW = dY^T . X (tokens are the contraction dimension) -- no transposed copies
+        if (dX) {
+            LinearArgs a = lin(dY, ldy, W, nullptr, dX, ld_dx, M, K, N, dx_flags | LIN_W_MN);
+            a.ldw = K;
+            PZ_TRY(tlin<T>(h, a, st));
+        }
+        if (dW) {
+            PdlOff no_pdl;   // the "weight" operand X was written by the kernel right in front (see PdlOff)
+            LinearArgs a = lin(dY, ldy, X, nullptr, dW, K, N, K, M, LIN_OUT_F32 | LIN_ACCUM | LIN_A_MN | LIN_W_MN);
+            a.ldw = ldx;
+            PZ_TRY(tlin<T>(h, a, st));
+        }
+        return 0;
+    }
+    // PZ_BWD_TRANSPOSE=1: the first version, K-major operands through tiled transposes (kept as a cross-check)
     PdlOff no_pdl;   // the "weight" operand of both products is written by the transpose right in front of them
     if (dX) {
         transpose<T>((const T *)W, K, (T *)sc.wT, rup(N, 8), N, K, st);            // W^T: [K][N]
