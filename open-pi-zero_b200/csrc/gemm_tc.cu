@@ -107,7 +107,10 @@ PZ_DEVINL void tile_coords(const TcParams &p, int tmn, int &tm, int &tn) {
     }
 }
 
-template <int BN, int CG, int EPI>
+// MN: operand storage of this instantiation -- 0: A [M][K], W [N][K] (every inference GEMM; the MMA-issue loop stays free
+// of run-time selects: measured 10 % on the gate|up GEMM when the choice was a kernel parameter), 1: W stored [K][N],
+// 3: A stored [K][M] and W stored [K][N] (the two products of the training step's backward)
+template <int BN, int CG, int EPI, int MN = 0>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
@@ -164,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // [64 k][64 m] per 64 rows of the tile, 8 KB apart (the LBO of the MN-major descriptor)
             auto load_w = [&](uint64_t *bar, uint8_t *dst, int kb, int tn) {
                 const int n0 = tn * BN + (CG == 2 ? crank * (BN / 2) : 0);
-                if (!p.w_mn) {
+                if constexpr (!(MN & 1)) {
                     if (CG == 2) tma_load_2d_pair(&map_w, bar, dst, kb * BK, n0, p.w_hint);
                     else tma_load_2d(&map_w, bar, dst, kb * BK, n0, p.w_hint);
                 } else {
@@ -176,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             };
             auto load_a = [&](uint64_t *bar, uint8_t *dst, int kb, int tm) {
                 const int m0 = (tm * CG + crank) * BM;
-                if (!p.a_mn) {
+                if constexpr (!(MN & 2)) {
                     if (CG == 2) tma_load_2d_pair(&map_a, bar, dst, kb * BK, m0, p.a_hint);
                     else tma_load_2d(&map_a, bar, dst, kb * BK, m0, p.a_hint);
                 } else {
@@ -228,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // -------------------------------------------------- MMA issuer ----
         if (lane == 0 && crank == 0) {
             // bits 15 / 16 of the instruction descriptor: A / B operand MN-major
-            const uint32_t idesc = umma_idesc(BM * CG, BN) | (p.a_mn ? (1u << 15) : 0u) | (p.w_mn ? (1u << 16) : 0u);
+            constexpr uint32_t idesc = umma_idesc(BM * CG, BN) | ((MN & 2) ? (1u << 15) : 0u) | ((MN & 1) ? (1u << 16) : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -249,8 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle atom (+2 in 16 B units);
                         // MN-major: 16 k-rows of 128 B further down, the next 64 M/N elements 8 KB away
-                        const uint64_t ad = p.a_mn ? umma_desc_sw128_mn(sa + k * 2048, 8192) : adesc + 2 * k;
-                        const uint64_t bd = p.w_mn ? umma_desc_sw128_mn(sa + cfg::A_BYTES + k * 2048, 8192) : bdesc + 2 * k;
+                        const uint64_t ad = (MN & 2) ? umma_desc_sw128_mn(sa + k * 2048, 8192) : adesc + 2 * k;
+                        const uint64_t bd = (MN & 1) ? umma_desc_sw128_mn(sa + cfg::A_BYTES + k * 2048, 8192) : bdesc + 2 * k;
                         if (CG == 2) tc_mma_pair(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
                         else tc_mma(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
                     }
@@ -471,12 +474,12 @@ bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld,
 }
 
 
-template <int BN, int CG, int EPI>
+template <int BN, int CG, int EPI, int MN = 0>
 int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcParams *extra = nullptr) {
     using cfg = Cfg<BN, CG>;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cfg::SMEM_BYTES) != cudaSuccess) {
             if (err) *err = "cudaFuncSetAttribute(max dynamic smem) failed";
             return PZ_ERR_CUDA;
@@ -560,7 +563,7 @@ int launch_epi(const LinearArgs &a, cudaStream_t st, const char **err, const TcP
         ++na;
     }
     lc.attrs = attr; lc.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&lc, gemm_tc_kernel<BN, CG, EPI>, ma, mw, mc, p);
+    cudaError_t e = cudaLaunchKernelEx(&lc, gemm_tc_kernel<BN, CG, EPI, MN>, ma, mw, mc, p);
     count_launch();
     if (e != cudaSuccess) {
         if (err) *err = cudaGetErrorString(e);
@@ -580,6 +583,21 @@ int launch(const LinearArgs &a, cudaStream_t st, const char **err, const TcParam
     if (a.flags & LIN_GEGLU) {
         if constexpr (BN == 256) return launch_epi<BN, CG, E_GEGLU>(a, st, err);
         else return PZ_ERR_INVALID;
+    }
+    if (a.flags & (LIN_A_MN | LIN_W_MN)) {
+        // the backward's two products: dX (W in place: MN = 1, bf16 or fp32 output) and dW (both in place: MN = 3, fp32 reduce-add)
+        const bool both = (a.flags & LIN_A_MN) && (a.flags & LIN_W_MN);
+        if (!(a.flags & LIN_W_MN) || (a.flags & (LIN_GELU | LIN_SILU)) || (!(a.flags & LIN_OUT_F32) && a.alpha != 1.f)) {
+            if (err) *err = "tcgen05 gemm: this combination of MN-major operands / epilogue is not instantiated";
+            return PZ_ERR_INVALID;
+        }
+        if (both) {
+            if (a.flags & LIN_OUT_F32) return launch_epi<BN, CG, E_F32, 3>(a, st, err);
+            if (err) *err = "tcgen05 gemm: MN-major A needs an fp32 output";
+            return PZ_ERR_INVALID;
+        }
+        if (a.flags & LIN_OUT_F32) return launch_epi<BN, CG, E_F32, 1>(a, st, err);
+        return launch_epi<BN, CG, E_PLAIN, 1>(a, st, err);
     }
     if (a.flags & LIN_OUT_F32) return launch_epi<BN, CG, E_F32>(a, st, err);
     if (a.alpha == 1.f) {
@@ -603,7 +621,8 @@ bool use_pair(const LinearArgs &a) {
 int gemm_tc_supported(const LinearArgs &a) {
     if (a.flags & (LIN_NORM_A | LIN_COMBINE_A)) return 0;
     if ((a.flags & LIN_W_MN) && (a.ldw % 8 || a.ldw < a.N)) return 0;
-    if ((a.flags & LIN_A_MN) && a.lda < a.M) return 0;
+    if ((a.flags & LIN_A_MN) && (a.lda < a.M || !(a.flags & LIN_W_MN) || !(a.flags & LIN_OUT_F32))) return 0;
+    if ((a.flags & (LIN_A_MN | LIN_W_MN)) && (a.flags & (LIN_GELU | LIN_SILU | LIN_GEGLU))) return 0;
     if (a.M < 1 || (!(a.flags & LIN_W_MN) && a.K % 8) || a.lda % 8) return 0;          // TMA: 16-byte global strides
     if (((uintptr_t)a.A | (uintptr_t)a.W | (uintptr_t)a.C) & 15) return 0;
     int n_out = (a.flags & LIN_GEGLU) ? a.N / 2 : a.N;
