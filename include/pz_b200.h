@@ -260,6 +260,13 @@ int pz_text_prefill(pz_handle *h, const int32_t *d_valid_len, void *d_kcache, vo
 int pz_text_decode(pz_handle *h, const float *d_x, const int32_t *d_valid_len1, int cur_len, void *d_kcache, void *d_vcache,
                    int cache_rows, float *d_logits, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 
+/* Caller-side normalisation folded into the path (env_adapter/base.py:8-49, simpler.py:76-125): the raw proprio
+ * is mapped x -> x * scale[c] + shift[c] (then clipped to [-1, 1] if proprio_clip) inside the kernel that first reads it, and
+ * the clipped action chunk a -> a * scale[c] + shift[c] after the sampler.  Device fp32 vectors [proprio_dim] / [action_dim]
+ * owned by the caller; NULL pairs switch a side off (the default).  Affects pz_prefill / pz_denoise / pz_infer_action. */
+int pz_set_io_normalization(pz_handle *h, const float *d_proprio_scale, const float *d_proprio_shift, int proprio_clip,
+                            const float *d_action_scale, const float *d_action_shift);
+
 /* The flow-matching training step, replaces PiZero.forward + loss.backward() (pizero.py:607-661, train.py:350-368):
  * forward with the activations kept in the training workspace, then the backward (statement: oracle/pizero_backward.py).
  *   d_actions, d_noise  fp32 [batch, horizon, action_dim];  d_t fp32 [batch] (TrainAgent.sample_fm_time, train.py:239-247)

@@ -240,8 +240,8 @@ static int run_prefill(pz_handle *h, const int32_t *valid_len, const float *prop
         if (ext_xp) {
             copy_f32(ws.xp, ext_xp + (size_t)b0 * S_p * A, (size_t)Mp * A, sp);
         } else {
-            launch_cast_pad<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
-                               w.small_k_pad, sp);
+            launch_cast_pad_affine<T>(proprio + (size_t)b0 * S_p * c.proprio_dim, (T *)ws.pp, Mp, c.proprio_dim,
+                                      w.small_k_pad, h->prop_scale, h->prop_shift, h->prop_clip, sp);
             PZ_TRY(Ops<T>::linear(h, lin(ws.pp, w.small_k_pad, w.prop_w, w.prop_b, ws.xp, A, Mp, A,
                                          w.small_k_pad, LIN_OUT_F32, sqrtf((float)A)), sp));
         }
@@ -764,7 +764,19 @@ int pz_denoise(pz_handle *h, const int32_t *valid_len, const float *noise, float
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->cfg.dtype == PZ_BF16 ? run_denoise<bf16>(h, valid_len, noise, out, ws, B, cap, st)
                                      : run_denoise<float>(h, valid_len, noise, out, ws, B, cap, st);
+    // caller-side de-normalisation of the clipped chunk (simpler.py:102-125), when set
+    if (!rc && h->act_scale) launch_affine_cols(out, (long)B * h->cfg.horizon, h->cfg.action_dim, h->act_scale, h->act_shift, st);
     return finish(h, rc);
+}
+
+int pz_set_io_normalization(pz_handle *h, const float *d_proprio_scale, const float *d_proprio_shift, int proprio_clip,
+                            const float *d_action_scale, const float *d_action_shift) {
+    if (!h) return PZ_ERR_INVALID;
+    if ((d_proprio_scale == nullptr) != (d_proprio_shift == nullptr) || (d_action_scale == nullptr) != (d_action_shift == nullptr))
+        return fail(h, PZ_ERR_INVALID, "scale and shift come in pairs");
+    h->prop_scale = d_proprio_scale; h->prop_shift = d_proprio_shift; h->prop_clip = proprio_clip;
+    h->act_scale = d_action_scale; h->act_shift = d_action_shift;
+    return PZ_OK;
 }
 
 int pz_joint_prefix(pz_handle *h, const float *x_vlm, const float *x_proprio, const int32_t *valid_len,

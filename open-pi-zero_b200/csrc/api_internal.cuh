@@ -34,6 +34,9 @@ struct pz_handle {
     int num_sms = 0;
     int sampler = PZ_SAMPLER_AUTO;            // pz_set_sampler
     long long fallbacks = 0;                  // ops that ran on the SIMT kernels under PZ_FLAG_ALLOW_FALLBACK
+    // optional caller-side normalisation folded into the path (pz_set_io_normalization): device vectors or null
+    const float *prop_scale = nullptr, *prop_shift = nullptr, *act_scale = nullptr, *act_shift = nullptr;
+    int prop_clip = 0;
     int timing_tag = 0;                       // 0 = off
     std::vector<cudaEvent_t> ev;              // pairs (start, stop)
     size_t ev_used = 0;

@@ -343,23 +343,54 @@ template void launch_rope_split<bf16>(const bf16 *, int, bf16 *, long, bf16 *, b
                                       cudaStream_t);
 
 // ---- small casts --------------------------------------------------------------
+// optional per-column affine + clip in front of the cast: the caller-side proprio normalisation
+// (env_adapter/base.py:8-49, simpler.py:76-90) folded into the first kernel that touches the raw proprio
 template <typename T>
 __global__ void cast_pad_kernel(const float *__restrict__ src, T *__restrict__ dst, long total,
-                                int cols, int cols_pad) {
+                                int cols, int cols_pad, const float *__restrict__ scale, const float *__restrict__ shift,
+                                int clip) {
     pdl_trigger();
     pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     long r = i / cols_pad;
     int c = i % cols_pad;
-    dst[i] = from_f32<T>(c < cols ? src[r * cols + c] : 0.f);
+    float v = c < cols ? src[r * cols + c] : 0.f;
+    if (scale && c < cols) {
+        v = v * scale[c] + shift[c];
+        if (clip) v = fminf(fmaxf(v, -1.f), 1.f);
+    }
+    dst[i] = from_f32<T>(v);
 }
 template <typename T>
 void launch_cast_pad(const float *src, T *dst, long rows, int cols, int cols_pad,
                      cudaStream_t st) {
     long total = rows * cols_pad;
     launch_k(cast_pad_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, total, cols,
-                                                                       cols_pad);
+             cols_pad, (const float *)nullptr, (const float *)nullptr, 0);
+}
+template <typename T>
+void launch_cast_pad_affine(const float *src, T *dst, long rows, int cols, int cols_pad, const float *scale,
+                            const float *shift, int clip, cudaStream_t st) {
+    long total = rows * cols_pad;
+    launch_k(cast_pad_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, dst, total, cols,
+             cols_pad, scale, shift, clip);
+}
+template void launch_cast_pad_affine<float>(const float *, float *, long, int, int, const float *, const float *, int, cudaStream_t);
+template void launch_cast_pad_affine<bf16>(const float *, bf16 *, long, int, int, const float *, const float *, int, cudaStream_t);
+// x[r][c] = x[r][c] * scale[c] + shift[c]: the caller-side action de-normalisation (simpler.py:102-125)
+__global__ void affine_cols_kernel(float *__restrict__ x, long total, int cols, const float *__restrict__ scale,
+                                   const float *__restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % cols);
+    x[i] = x[i] * scale[c] + shift[c];
+}
+void launch_affine_cols(float *x, long rows, int cols, const float *scale, const float *shift, cudaStream_t st) {
+    long total = rows * cols;
+    launch_k(affine_cols_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, total, cols, scale, shift);
 }
 template void launch_cast_pad<float>(const float *, float *, long, int, int, cudaStream_t);
 template void launch_cast_pad<bf16>(const float *, bf16 *, long, int, int, cudaStream_t);

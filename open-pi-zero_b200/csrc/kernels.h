@@ -33,6 +33,10 @@ void launch_rope_split(const T *qkv, int qkv_ld, T *q_out, long q_batch_stride, 
 template <typename T>
 void launch_cast_pad(const float *src, T *dst, long rows, int cols, int cols_pad, cudaStream_t st);
 template <typename T>
+void launch_cast_pad_affine(const float *src, T *dst, long rows, int cols, int cols_pad, const float *scale,
+                            const float *shift, int clip, cudaStream_t st);
+void launch_affine_cols(float *x, long rows, int cols, const float *scale, const float *shift, cudaStream_t st);
+template <typename T>
 void launch_to_f32(const T *src, float *dst, long n, cudaStream_t st);
 void launch_euler(float *action, const float *vel, int vel_ld, float dt, long rows, int adim,
                   float *vel_capture, cudaStream_t st);

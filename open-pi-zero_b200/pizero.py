@@ -559,9 +559,43 @@ class PiZero(nn.Module):
                     self._sampler_batches.append(b)
         lib.pz_set_sampler(hnd, self._sampler_mode)
         self._handle, self._packed, self._packed_key = hnd, (keep, w), key
+        self._apply_io_normalization()
         self._T = T
         self._workspace, self._ws_batch = None, 0
         self._graphs = {}
+
+    # ------------------------------------------------ caller-side normalisation folded into the kernels
+    def set_io_normalization(self, dataset_statistics: Optional[dict], action_normalization_type: str = "bound",
+                             proprio_normalization_type: str = "bound"):
+        """After this call `infer_action` takes RAW proprios and returns DE-NORMALISED actions: what
+        `SimplerAdapter.preprocess` / `postprocess` do on the host around the model (simpler.py:76-90, 102-125;
+        base.py:8-49) runs inside the kernels instead (adapter.py).  `dataset_statistics` as in the reference's
+        `dataset_statistics.json`: {"proprio": {"p01", "p99", "mean", "std"}, "action": {...}}; None switches it off."""
+        from .adapter import action_affine, proprio_affine
+        if dataset_statistics is None:
+            self.__dict__["_io_norm"] = None
+        else:
+            ps, pb, clip = proprio_affine(dataset_statistics["proprio"], proprio_normalization_type)
+            as_, ab = action_affine(dataset_statistics["action"], action_normalization_type)
+            if len(ps) != self.proprio_dim or len(as_) != self.action_dim:
+                raise ValueError("dataset statistics do not match proprio_dim / action_dim")
+            self.__dict__["_io_norm"] = (ps, pb, clip, as_, ab)
+        self._graphs = {}
+        if self._handle is not None:
+            self._apply_io_normalization()
+
+    def _apply_io_normalization(self):
+        io = self.__dict__.get("_io_norm")
+        lib = _lib.load()
+        if io is None:
+            self.__dict__["_io_norm_dev"] = None
+            lib.pz_set_io_normalization(self._handle, None, None, 0, None, None)
+            return
+        dev = self._packed[0][0].device
+        ps, pb, clip, as_, ab = io
+        t = [torch.tensor(v, dtype=torch.float32, device=dev) for v in (ps, pb, as_, ab)]
+        self.__dict__["_io_norm_dev"] = t
+        lib.pz_set_io_normalization(self._handle, t[0].data_ptr(), t[1].data_ptr(), 1 if clip else 0, t[2].data_ptr(), t[3].data_ptr())
 
     def _destroy_handle(self):
         if getattr(self, "_handle", None) is not None:

@@ -552,3 +552,39 @@ def test_errors_are_python_exceptions():
         PiZero.forward(m, input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda(),
                        proprios=inp["proprios"].cuda(), actions=torch.zeros(2, 1, 1).cuda(), t=torch.zeros(2).cuda())
     assert PzError is not None
+
+
+@pytest.mark.parametrize("kind", ["bound", "gaussian"])
+def test_io_normalization_folded_into_the_kernels(kind):
+    """set_io_normalization: raw proprio in, de-normalised actions out == the host-side adapter arithmetic
+    (simpler.py:76-90, 102-125) around the plain call; eager and CUDA-graph paths."""
+    import numpy as np
+    from open_pi_zero_b200.adapter import BaseEnvAdapter
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=3, randomize_norms=True)
+    inp = pz.make_inputs(d, 3, seed=8)
+    m = _model(d, sd, torch.bfloat16)
+    rng = np.random.default_rng(1)
+    stats = {k: dict(p01=rng.normal(size=7) - 2, p99=rng.normal(size=7) + 2, mean=rng.normal(size=7), std=rng.uniform(0.5, 2, 7))
+             for k in ("proprio", "action")}
+    raw = torch.tensor(rng.normal(size=(3, 1, 7)) * 2, dtype=torch.float32)
+    ad = BaseEnvAdapter()
+    if kind == "bound":
+        norm = ad.normalize_bound(raw.numpy(), stats["proprio"]["p01"], stats["proprio"]["p99"])
+    else:
+        norm = ad.normalize_gaussian(raw.numpy(), stats["proprio"]["mean"], stats["proprio"]["std"])
+    kw = dict(input_ids=inp["input_ids"].cuda(), pixel_values=inp["pixel_values"].cuda().bfloat16(), noise=inp["noise"].cuda(),
+              valid_len=inp["valid_len"].cuda())
+    plain = m(proprios=torch.tensor(norm, dtype=torch.float32).cuda(), **kw).float().cpu().numpy()
+    if kind == "bound":
+        want = ad.denormalize_bound(plain[..., :-1], stats["action"]["p01"][:-1], stats["action"]["p99"][:-1])
+    else:
+        want = ad.denormalize_gaussian(plain[..., :-1], stats["action"]["mean"][:-1], stats["action"]["std"][:-1])
+    want = np.concatenate([want, plain[..., -1:]], -1)
+    m.set_io_normalization(stats, action_normalization_type=kind, proprio_normalization_type=kind)
+    for _ in range(3):      # capture + replay
+        got = m(proprios=raw.cuda(), **kw).float().cpu().numpy()
+        assert np.abs(got - want).max() < 2e-2 * max(1.0, np.abs(want).max())
+    m.set_io_normalization(None)
+    back = m(proprios=torch.tensor(norm, dtype=torch.float32).cuda(), **kw).float().cpu().numpy()
+    assert np.abs(back - plain).max() < 1e-2

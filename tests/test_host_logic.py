@@ -188,3 +188,43 @@ def test_joint_model_forward_rejects_unsupported_patterns_before_touching_inputs
         m.joint_model.forward(mask, {"action": None}, {"action": a}, time_cond=torch.zeros(2, 32),
                               cache_mode="append_non_active")
     assert torch.equal(a, torch.ones(2, 4, 32))
+
+
+def test_adapter_formulas_match_reference_base_adapter():
+    """adapter.py restates env_adapter/base.py:8-49; the affine forms handed to the kernels reproduce SimplerAdapter's
+    preprocess / postprocess arithmetic (simpler.py:76-90, 102-125)."""
+    import numpy as np
+    from open_pi_zero_b200.adapter import BaseEnvAdapter, action_affine, proprio_affine
+    rng = np.random.default_rng(0)
+    stats = {k: dict(p01=rng.normal(size=7) - 2, p99=rng.normal(size=7) + 2, mean=rng.normal(size=7), std=rng.uniform(0.5, 2, 7))
+             for k in ("proprio", "action")}
+    ours = BaseEnvAdapter()
+    x = rng.normal(size=(5, 7)) * 3
+    ref_path = "/root/reference/src/agent/env_adapter/base.py"
+    import os
+    if os.path.exists(ref_path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_base_adapter", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod.BaseEnvAdapter()
+        for name, args in (("normalize_bound", (stats["proprio"]["p01"], stats["proprio"]["p99"])),
+                           ("denormalize_bound", (stats["action"]["p01"], stats["action"]["p99"])),
+                           ("normalize_gaussian", (stats["proprio"]["mean"], stats["proprio"]["std"])),
+                           ("denormalize_gaussian", (stats["action"]["mean"], stats["action"]["std"]))):
+            assert np.array_equal(getattr(ours, name)(x, *args), getattr(ref, name)(x, *args)), name
+    for kind in ("bound", "gaussian"):
+        s, b, clip = proprio_affine(stats["proprio"], kind)
+        got = x * s + b
+        if clip:
+            got = np.clip(got, -1, 1)
+        want = (ours.normalize_bound(x, stats["proprio"]["p01"], stats["proprio"]["p99"]) if kind == "bound"
+                else ours.normalize_gaussian(x, stats["proprio"]["mean"], stats["proprio"]["std"]))
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+        s, b = action_affine(stats["action"], kind)
+        a = np.clip(x, -1, 1)
+        got = a * s + b
+        want = (ours.denormalize_bound(a[:, :-1], stats["action"]["p01"][:-1], stats["action"]["p99"][:-1]) if kind == "bound"
+                else ours.denormalize_gaussian(a[:, :-1], stats["action"]["mean"][:-1], stats["action"]["std"][:-1]))
+        assert np.allclose(got[:, :-1], want, rtol=1e-12, atol=1e-12)
+        assert np.array_equal(got[:, -1], a[:, -1])          # the gripper dimension is passed through
