@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 7
+#define PZ_ABI_VERSION 8
 
 typedef enum pz_status {
     PZ_OK = 0,
@@ -254,11 +254,16 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *d_input_ids, const void *
  *   d_logits  fp32 [batch, s_vlm, vocab] (rows >= q_len are meaningless), or [batch, vocab] = the last prompt token with
  *             last_only != 0, or NULL (cache only)
  * pz_text_decode appends ONE token per sample at cache row cur_len (position cur_len + 1, `cache_mode="append"`,
- * joint_model.py:164-240): d_x fp32 [batch, H] = embedding * sqrt(H); d_valid_len1[b] = cur_len + 1; d_logits [batch, vocab]. */
+ * joint_model.py:164-240): d_x fp32 [batch, H] = embedding * sqrt(H); d_valid_len1[b] = cur_len + 1; d_logits [batch, vocab].
+ * d_hidden (either call, optional): fp32 hidden states after the vlm mixture's final norm, [batch, s_vlm, H] / [batch, H] -- what
+ * `JointModel.forward(embeds_all={"vlm": ...}, cache_mode="append", final_layer_post_attn_skip_names=[])` returns
+ * (joint_model.py:375-380).  d_x_in (prefill, optional): fp32 [batch, s_vlm, H] scaled embeddings to use instead of the
+ * pz_embed_prefix result (the JointModel.forward entry). */
 int pz_text_prefill(pz_handle *h, const int32_t *d_valid_len, void *d_kcache, void *d_vcache, int cache_rows, int q_len,
-                    float *d_logits, int last_only, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+                    float *d_logits, int last_only, float *d_hidden, const float *d_x_in, void *d_workspace, size_t workspace_bytes,
+                    int batch, void *stream);
 int pz_text_decode(pz_handle *h, const float *d_x, const int32_t *d_valid_len1, int cur_len, void *d_kcache, void *d_vcache,
-                   int cache_rows, float *d_logits, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
+                   int cache_rows, float *d_logits, float *d_hidden, void *d_workspace, size_t workspace_bytes, int batch, void *stream);
 
 /* Caller-side normalisation folded into the path (env_adapter/base.py:8-49, simpler.py:76-125): the raw proprio
  * is mapped x -> x * scale[c] + shift[c] (then clipped to [-1, 1] if proprio_clip) inside the kernel that first reads it, and

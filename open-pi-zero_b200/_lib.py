@@ -54,7 +54,7 @@ class PzCapture(C.Structure):
                                   "action_preclip")]
 
 
-PZ_ABI_VERSION = 7
+PZ_ABI_VERSION = 8
 PZ_F32, PZ_BF16 = 0, 1
 PZ_FLAG_SIMPLE_KERNELS = 1
 PZ_FLAG_ALLOW_FALLBACK = 2
@@ -120,8 +120,8 @@ def load(build_if_needed: bool = True):
     lib.pz_grad_sumsq.argtypes = [vp, C.c_size_t, vp, vp]
     lib.pz_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int, vp, C.c_float, C.c_float, C.c_int, vp]
-    lib.pz_text_prefill.argtypes = [hp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_size_t, C.c_int, vp]
-    lib.pz_text_decode.argtypes = [hp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_text_prefill.argtypes = [hp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    lib.pz_text_decode.argtypes = [hp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int, vp]
     lib.pz_launch_count.argtypes = [hp]
     lib.pz_launch_count.restype = C.c_int64
     lib.pz_fallback_count.argtypes = [hp]

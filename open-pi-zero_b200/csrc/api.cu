@@ -505,15 +505,16 @@ static int run_flow_loss(pz_handle *h, const int32_t *valid_len, const float *ac
 // (pizero.py:346-357 "assume no padding"): every sample has q_len valid tokens, positions 1 .. q_len.
 template <typename T>
 static int run_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache, void *vcache, int cache_rows, int q_len,
-                            float *logits, int last_only, void *wsp, int B, cudaStream_t st) {
+                            float *logits, int last_only, float *hidden, const float *ext_x, void *wsp, int B, cudaStream_t st) {
     const pz_config &c = h->cfg;
     const pz_weights &w = h->w;
-    if (!w.vlm_final_norm || !w.lm_head) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head (use_lm_head / mixture.vlm.use_final_norm)");
+    if (!w.vlm_final_norm || (logits && !w.lm_head)) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head (use_lm_head / mixture.vlm.use_final_norm)");
     Workspace ws = carve(c, B, h->prefix_chunk, wsp);
     const int H = c.vlm_hidden, hd = c.head_dim, nh = c.n_heads, S_v = c.s_vlm;
     const int qd = nh * hd, qkvd = (nh + 2 * c.n_kv_heads) * hd;
     const long kv_bs = (long)cache_rows * hd;
     if (q_len < 1 || q_len > S_v || cache_rows < S_v) return fail(h, PZ_ERR_INVALID, "text prefill: 1 <= q_len <= max_image_text_tokens <= cache_rows");
+    if (ext_x) copy_f32(ws.x, ext_x, (size_t)B * S_v * H, st);   // JointModel.forward entry: (scaled) embeddings given
     for (int b0 = 0; b0 < B; b0 += h->prefix_chunk) {
         const int nb = (B - b0 < h->prefix_chunk) ? B - b0 : h->prefix_chunk;
         const int M = nb * S_v;
@@ -544,6 +545,8 @@ static int run_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache
             PZ_TRY(Ops<T>::attention(h, a, st));
             PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, M, H, c.vlm_inter, st));
         }
+        // Mixture.forward_norm (mixture.py:68-77): the hidden states JointModel.forward returns
+        if (hidden) launch_rmsnorm<float>(x, w.vlm_final_norm, hidden + (size_t)b0 * S_v * H, M, H, 1e-6f, st);
         if (!logits) continue;
         if (last_only) {
             // logits of the last prompt token only: [B, vocab]
@@ -566,10 +569,10 @@ static int run_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache
 // `cur_len` of the cache, position cur_len + 1; attends rows 0 .. cur_len (no padding).  logits: [B, vocab].
 template <typename T>
 static int run_text_decode(pz_handle *h, const float *x_in, const int32_t *valid_len1, int cur_len, void *kcache, void *vcache,
-                           int cache_rows, float *logits, void *wsp, int B, cudaStream_t st) {
+                           int cache_rows, float *logits, float *hidden, void *wsp, int B, cudaStream_t st) {
     const pz_config &c = h->cfg;
     const pz_weights &w = h->w;
-    if (!w.vlm_final_norm || !w.lm_head) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head");
+    if (!w.vlm_final_norm || (logits && !w.lm_head)) return fail(h, PZ_ERR_UNBOUND, "text output needs vlm_final_norm and lm_head");
     if (cur_len < 1 || cur_len >= cache_rows || cur_len >= (w.rope_vlm_rows > 0 ? w.rope_vlm_rows : c.s_vlm)) return fail(h, PZ_ERR_INVALID, "text decode: cache / RoPE table exhausted");
     Workspace ws = carve(c, B, h->prefix_chunk, wsp);
     const int H = c.vlm_hidden, hd = c.head_dim, nh = c.n_heads;
@@ -597,8 +600,10 @@ static int run_text_decode(pz_handle *h, const float *x_in, const int32_t *valid
         PZ_TRY(Ops<T>::attention(h, a, st));
         PZ_TRY(post_attention<T>(h, h->vlm[l], x, ws.h, ws.att, ws.mlp, B, H, c.vlm_inter, st));
     }
-    PZ_TRY(norm_linear<T>(h, x, w.vlm_final_norm, ws.h,
-                          lin(nullptr, H, w.lm_head, nullptr, logits, c.vocab_size, B, c.vocab_size, H, LIN_OUT_F32), H, st));
+    if (hidden) launch_rmsnorm<float>(x, w.vlm_final_norm, hidden, B, H, 1e-6f, st);
+    if (logits)
+        PZ_TRY(norm_linear<T>(h, x, w.vlm_final_norm, ws.h,
+                              lin(nullptr, H, w.lm_head, nullptr, logits, c.vocab_size, B, c.vocab_size, H, LIN_OUT_F32), H, st));
     return 0;
 }
 
@@ -842,25 +847,25 @@ int pz_flow_matching_loss(pz_handle *h, const int64_t *ids, const void *pixels, 
 }
 
 int pz_text_prefill(pz_handle *h, const int32_t *valid_len, void *kcache, void *vcache, int cache_rows, int q_len,
-                    float *logits, int last_only, void *ws, size_t ws_bytes, int B, void *stream) {
+                    float *logits, int last_only, float *hidden, const float *x_in, void *ws, size_t ws_bytes, int B, void *stream) {
     PZ_TRY(precheck(h, ws, ws_bytes, B));
     if (!valid_len || !kcache || !vcache) return fail(h, PZ_ERR_INVALID, "null input");
     g_launch_counter = &h->lc;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->cfg.dtype == PZ_BF16
-                 ? run_text_prefill<bf16>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, ws, B, st)
-                 : run_text_prefill<float>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, ws, B, st);
+                 ? run_text_prefill<bf16>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, hidden, x_in, ws, B, st)
+                 : run_text_prefill<float>(h, valid_len, kcache, vcache, cache_rows, q_len, logits, last_only, hidden, x_in, ws, B, st);
     return finish(h, rc);
 }
 
 int pz_text_decode(pz_handle *h, const float *x, const int32_t *valid_len1, int cur_len, void *kcache, void *vcache,
-                   int cache_rows, float *logits, void *ws, size_t ws_bytes, int B, void *stream) {
+                   int cache_rows, float *logits, float *hidden, void *ws, size_t ws_bytes, int B, void *stream) {
     PZ_TRY(precheck(h, ws, ws_bytes, B));
-    if (!x || !valid_len1 || !kcache || !vcache || !logits) return fail(h, PZ_ERR_INVALID, "null input");
+    if (!x || !valid_len1 || !kcache || !vcache || (!logits && !hidden)) return fail(h, PZ_ERR_INVALID, "null input");
     g_launch_counter = &h->lc;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = h->cfg.dtype == PZ_BF16 ? run_text_decode<bf16>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, ws, B, st)
-                                     : run_text_decode<float>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, ws, B, st);
+    int rc = h->cfg.dtype == PZ_BF16 ? run_text_decode<bf16>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, hidden, ws, B, st)
+                                     : run_text_decode<float>(h, x, valid_len1, cur_len, kcache, vcache, cache_rows, logits, hidden, ws, B, st);
     return finish(h, rc);
 }
 

@@ -134,9 +134,10 @@ class JointModel(_Holder):
                 cache_mode="append_non_active", return_caches=False):
         """joint_model.py:328-383 for (a) the prefix pass (vlm + proprio active, caches filled,
         nothing returned for the skipped mixtures), (b) the action pass over the cached prefix
-        (`cache_mode="append_non_active"`) and (c) all three mixtures active with no cache (the training
-        forward, pizero.py:637-652, and infer_action_naive, pizero.py:529-544).  "append" / "no_append"
-        text generation is outside this library's scope.
+        (`cache_mode="append_non_active"`), (c) all three mixtures active with no cache (the training forward,
+        pizero.py:637-652) or with `cache_mode="no_append"` caches (infer_action_naive, pizero.py:529-544: filled by the first
+        call, read by the later ones) and (d) the vlm mixture alone in `cache_mode="append"` with a `TextKVCache`
+        (infer_text, pizero.py:571-583): the prompt first, then one token per call.
         Like the reference, `embeds_all[*]` is scaled by sqrt(hidden) IN PLACE (joint_model.py:355)."""
         assert cache_mode in ["no_append", "append", "append_non_active"], f"Invalid cache mode: {cache_mode}"
         owner = self._owner() if self._owner is not None else None
@@ -150,15 +151,20 @@ class JointModel(_Holder):
             pattern = "prefix"
         elif names == ["action"] and cache_mode == "append_non_active":
             pattern = "action"
-        elif names == ["vlm", "proprio", "action"] and not kv_caches and skip == ("vlm", "proprio"):
+        elif names == ["vlm", "proprio", "action"] and skip == ("vlm", "proprio") and (
+                not kv_caches or cache_mode == "no_append"):
+            # no caches: the training forward; "no_append" with caches: infer_action_naive (pizero.py:529-544) -- the vlm /
+            # proprio K / V are cached by the first call and only READ afterwards (joint_model.py:176-196)
             pattern = "joint"
+        elif names == ["vlm"] and cache_mode == "append" and skip == ():
+            pattern = "text"    # infer_text's call (pizero.py:571-583): the vlm mixture alone, K / V appended to its cache
         if pattern is None:
             raise NotImplementedError(
                 f"JointModel.forward with active mixtures {names} / cache_mode {cache_mode!r} / skip {skip} is outside the "
                 "infer_action / training-forward paths (\"append\" / \"no_append\" text generation is not built)")
         if time_cond is not None:
             raise NotImplementedError("adaLN time conditioning (time_cond) is not built: action_expert_adaptive_mode must be None")
-        if owner.check_inputs not in ("0", "off") and position_ids_all is not None:
+        if owner.check_inputs not in ("0", "off") and position_ids_all is not None and pattern != "text":
             B_ = embeds_all[names[0]].shape[0]
             owner._check_position_ids(B_, position_ids_all.get("vlm"), position_ids_all.get("proprio"),
                                       position_ids_all.get("action"))
@@ -171,7 +177,9 @@ class JointModel(_Holder):
         B = embeds_all[names[0]].shape[0]
         Sv = d["max_image_text_tokens"]
         dev = owner._packed[0][0].device
-        vlen = (attention_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).to(dev).contiguous()
+        vlen = None
+        if pattern != "text":
+            vlen = (attention_mask[:, 0, 0, :Sv] == 0).sum(-1, dtype=torch.int32).to(dev).contiguous()
         ws, ws_bytes = owner._ensure_workspace(B)
         stream = torch.cuda.current_stream(dev).cuda_stream
         f32 = lambda t: t.to(torch.float32).contiguous()   # noqa: E731
@@ -197,6 +205,18 @@ class JointModel(_Holder):
                     raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
                 res = {"action": out.to(embeds_all["action"].dtype)}
                 return (res, kv_caches) if return_caches else res
+            if pattern == "text":
+                return self._forward_text(owner, lib, embeds_all["vlm"], kv_caches, ws, ws_bytes, stream, dev, return_caches)
+            if pattern == "joint" and kv_caches and all(
+                    isinstance(kv_caches.get(n), KVCache) and kv_caches[n].has_item(0) for n in self.cache_names):
+                # "no_append", caches already filled: only the action rows produce anything new
+                xa = f32(embeds_all["action"])
+                out = torch.empty_like(xa)
+                rc = lib.pz_joint_action(owner._handle, xa.data_ptr(), vlen.data_ptr(), out.data_ptr(), ws, ws_bytes, B, stream)
+                if rc != 0:
+                    raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                res = {"action": out.to(embeds_all["action"].dtype)}
+                return (res, kv_caches) if return_caches else res
             if pattern == "joint":
                 # the training call pattern (pizero.py:637-652) and infer_action_naive's (pizero.py:529-544): all three
                 # mixtures active under the full block mask, no cache.  vlm / proprio rows never attend to action keys
@@ -211,9 +231,58 @@ class JointModel(_Holder):
                                          B, stream)
                 if rc != 0:
                     raise PzError(f"pz_joint_action failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+                if cache_mode == "no_append" and kv_caches is not None and len(kv_caches) > 0:
+                    kv_caches.update(owner.kv_caches(B))     # the reference fills the caches it was handed on the first call
                 res = {"action": out.to(embeds_all["action"].dtype)}
                 return (res, kv_caches) if return_caches else res
         raise AssertionError("unreachable")
+
+    def _forward_text(self, owner, lib, emb, kv_caches, ws, ws_bytes, stream, dev, return_caches):
+        """`cache_mode="append"`, vlm only (joint_model.py:164-240, 375-380): returns {"vlm": final-norm hidden states}."""
+        d = owner.dims
+        B, q_len, Hd = emb.shape
+        Sv = d["max_image_text_tokens"]
+        cache = kv_caches.get("vlm") if kv_caches else None
+        if cache is None:
+            cache = TextKVCache()
+        if not isinstance(cache, TextKVCache):
+            raise TypeError('kv_caches["vlm"] must be an open_pi_zero_b200 TextKVCache for cache_mode="append"')
+        if owner.__dict__.get("_packed") is None or owner._packed[1].vlm_final_norm is None:
+            raise PzError('the vlm-only pass needs mixture.vlm.use_final_norm=True')
+        x = emb.to(torch.float32)
+        if cache.num_items() == 0:
+            if q_len > Sv:
+                raise ValueError(f"the prompt has {q_len} tokens, max_image_text_tokens is {Sv}")
+            cap = Sv + owner.text_max_new_tokens
+            if cache.capacity < cap or cache.k.shape[1] != B or cache.k.dtype != owner._T:
+                cache._allocate(d["num_layers"], B, cap, d["head_dim"], owner._T, dev)
+            xin = torch.zeros((B, Sv, Hd), dtype=torch.float32, device=dev)
+            xin[:, :q_len] = x
+            vlen = torch.full((B,), q_len, dtype=torch.int32, device=dev)
+            hid = torch.empty((B, Sv, Hd), dtype=torch.float32, device=dev)
+            rc = lib.pz_text_prefill(owner._handle, vlen.data_ptr(), cache.k.data_ptr(), cache.v.data_ptr(), cache.capacity, q_len,
+                                     None, 0, hid.data_ptr(), xin.data_ptr(), ws, ws_bytes, B, stream)
+            out = hid[:, :q_len]
+        else:
+            if q_len != 1:
+                raise ValueError("Using KV cache so should only use one single token")
+            cur = cache.num_items()
+            if cur + 1 > cache.capacity:
+                raise PzError(f"the text KV cache is full ({cache.capacity} rows)")
+            xin = x[:, 0].contiguous()
+            vlen = torch.full((B,), cur + 1, dtype=torch.int32, device=dev)
+            hid = torch.empty((B, Hd), dtype=torch.float32, device=dev)
+            rc = lib.pz_text_decode(owner._handle, xin.data_ptr(), vlen.data_ptr(), cur, cache.k.data_ptr(), cache.v.data_ptr(),
+                                    cache.capacity, None, hid.data_ptr(), ws, ws_bytes, B, stream)
+            out = hid[:, None]
+        if rc != 0:
+            raise PzError(f"vlm-only pass failed ({rc}): {lib.pz_last_error(owner._handle).decode()}")
+        cache.length = cache.num_items() + q_len
+        owner._inflight = (xin, vlen)
+        if kv_caches is not None:
+            kv_caches["vlm"] = cache
+        res = {"vlm": out.to(emb.dtype)}
+        return (res, kv_caches) if return_caches else res
 
 
 class PiZero(nn.Module):
@@ -501,7 +570,8 @@ class PiZero(nn.Module):
             return fr.cos().to(dev).contiguous(), fr.sin().to(dev).contiguous()
 
         # text decode steps run past the prompt: positions up to max_image_text_tokens + text_max_new_tokens
-        vlm_rope_rows = d["max_image_text_tokens"] + (self.text_max_new_tokens if self.use_lm_head else 0)
+        has_text = self.use_lm_head or "joint_model.mixtures.vlm.norm.weight" in sd
+        vlm_rope_rows = d["max_image_text_tokens"] + (self.text_max_new_tokens if has_text else 0)
         c1, s1 = rope(d["vlm_rope_theta"], vlm_rope_rows)
         c2, s2 = rope(d["act_rope_theta"], d["cond_steps"] + d["horizon_steps"])
         w.rope_vlm_cos, w.rope_vlm_sin = own(c1), own(s1)
@@ -814,7 +884,7 @@ class PiZero(nn.Module):
                 rc = lib.pz_embed_prefix(self._handle, ids.data_ptr(), pix.data_ptr(), ws, ws_bytes, B, None, stream)
                 if rc == 0:
                     rc = lib.pz_text_prefill(self._handle, vlen.data_ptr(), cache.k.data_ptr(), cache.v.data_ptr(), cache.capacity,
-                                             q_len, logits.data_ptr(), 1 if last_token_only else 0, ws, ws_bytes, B, stream)
+                                             q_len, logits.data_ptr(), 1 if last_token_only else 0, None, None, ws, ws_bytes, B, stream)
             if rc != 0:
                 raise PzError(f"infer_text prefill failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
             cache.length = q_len
@@ -834,7 +904,7 @@ class PiZero(nn.Module):
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 rc = lib.pz_text_decode(self._handle, x.data_ptr(), vlen1.data_ptr(), cur, cache.k.data_ptr(), cache.v.data_ptr(),
-                                        cache.capacity, logits.data_ptr(), ws, ws_bytes, B, stream)
+                                        cache.capacity, logits.data_ptr(), None, ws, ws_bytes, B, stream)
             if rc != 0:
                 raise PzError(f"infer_text decode failed ({rc}): {lib.pz_last_error(self._handle).decode()}")
             cache.length = cur + 1

@@ -588,3 +588,30 @@ def test_io_normalization_folded_into_the_kernels(kind):
     m.set_io_normalization(None)
     back = m(proprios=torch.tensor(norm, dtype=torch.float32).cuda(), **kw).float().cpu().numpy()
     assert np.abs(back - plain).max() < 1e-2
+
+
+def test_joint_model_forward_no_append_mode():
+    """`cache_mode="no_append"` with all three mixtures active (infer_action_naive's call, pizero.py:529-544): the first call
+    fills the vlm / proprio caches it was handed, later calls read them; both give what the cache-free joint pass gives."""
+    d = SMALL
+    sd = pz.init_state_dict(d, seed=6, randomize_norms=True)
+    inp = pz.make_inputs(d, 2, seed=12)
+    m = _model(d, sd, torch.float32)
+    mask, vp, pp, ap = m.build_causal_mask_and_position_ids(inp["attention_mask"].cuda(), torch.float32)
+    g = torch.Generator().manual_seed(1)
+    B, Sv, H, A = 2, d["max_image_text_tokens"], d["vlm_hidden"], d["act_hidden"]
+    ev = (torch.randn((B, Sv, H), generator=g) * 0.05).cuda()
+    ep = (torch.randn((B, 1, A), generator=g) * 0.05).cuda()
+    ea = [(torch.randn((B, d["horizon_steps"], A), generator=g) * 0.05).cuda() for _ in range(2)]
+    pos = {"vlm": vp, "proprio": pp, "action": ap}
+    fresh = [m.joint_model(attention_mask=mask, position_ids_all=pos,
+                           embeds_all={"vlm": ev.clone(), "proprio": ep.clone(), "action": e.clone()})["action"] for e in ea]
+    caches = m.joint_model.build_mixture_caches()
+    got = []
+    for e in ea:
+        got.append(m.joint_model(attention_mask=mask, position_ids_all=pos,
+                                 embeds_all={"vlm": ev.clone(), "proprio": ep.clone(), "action": e.clone()}, kv_caches=caches,
+                                 cache_mode="no_append")["action"])
+    assert all(caches[n].has_item(0) for n in ("vlm", "proprio"))
+    for a, b in zip(got, fresh):
+        assert max_abs(a, b) < 1e-5
