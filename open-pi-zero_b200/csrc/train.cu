@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     // keys of this block that any query of this segment sees: skip the block if none
     bool any = false;
     for (int j = key0; j < key0 + 64; ++j) any = any || key_visible(a, j, vl);
+    if (split >= n_qt) return;   // no query tile for this CTA: nothing to add
     for (int qt = split; any && qt < n_qt; qt += NS) {
         const int row0 = qt * 64;
         if (a.valid_len && a.seg == 0 && row0 / a.hpr >= vl) break;      // padded tokens only from here on
@@ -980,7 +981,13 @@ int attn_bwd2_launch(const AttnBwd2Args &a, int batch, bool dq, bool dkv, cudaSt
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     if (dq) launch_k(attn_bwd_dq_kernel<HDP>, dim3((a.NQ + 63) / 64, a.groups, batch), dim3(256), smem, st, a);
-    if (dkv) launch_k(attn_bwd_dkv_kernel<HDP>, dim3(((a.NK + 63) / 64) * (a.qsplit > 1 ? a.qsplit : 1), a.groups, batch), dim3(256), smem, st, a);
+    if (dkv) {
+        AttnBwd2Args k = a;
+        const int n_qt = (a.NQ + 63) / 64;
+        if (k.qsplit > n_qt) k.qsplit = n_qt;      // (a CTA without a query tile would only add zeros; qsplit stays >= 2 when it was:
+        if (a.qsplit > 1 && k.qsplit < 2) k.qsplit = 2;   //  the accumulation into dK / dV must remain atomic)
+        launch_k(attn_bwd_dkv_kernel<HDP>, dim3(((a.NK + 63) / 64) * (k.qsplit > 1 ? k.qsplit : 1), a.groups, batch), dim3(256), smem, st, k);
+    }
     return 0;
 }
 
