@@ -682,15 +682,56 @@ PZ_DEVINL float tanh_hw(float x) {
 // bf16 tiles are [64][HDP + 8]: a row pitch that is an odd multiple of 16 bytes keeps the 8 rows of a fragment load on
 // different banks (a 512-byte pitch put them all on the same ones: measured 27 TFLOP/s)
 template <int HDP>
-PZ_DEVINL void load_rows64(bf16 *dst, const bf16 *src, int ld, int row0, int n_rows, int hd, int hpr, int tok_limit) {
-    // dst[r][0..HDP) <- src[(row0 + r) * ld + 0..hd), zero beyond hd, beyond n_rows and for tokens >= tok_limit
-    constexpr int CH = HDP / 8, LDP = HDP + 8;
-    for (int i = threadIdx.x; i < 64 * CH; i += 256) {
+PZ_DEVINL void load_rows64(bf16 *__restrict__ dst, const bf16 *__restrict__ src, int ld, int row0, int n_rows, int hd, int hpr,
+                           int tok_limit) {
+    // dst[r][0..HDP) <- src[(row0 + r) * ld + 0..hd), zero beyond hd, beyond n_rows and for tokens >= tok_limit.
+    // All of a thread's 16-byte loads are issued before the first shared-memory store (one L2 latency per tile instead of
+    // one per chunk: the stores used to wait for each load in turn), and the row limit is one comparison, no division.
+    constexpr int CH = HDP / 8, LDP = HDP + 8, N = 64 * CH, IT = (N + 255) / 256;
+    const long lim = (long)tok_limit * hpr;
+    const int row_lim = (int)(lim < n_rows ? lim : n_rows);
+    uint4 v[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        const int i = threadIdx.x + k * 256;
         const int r = i / CH, c = (i % CH) * 8;
-        const int row = row0 + r;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (row < n_rows && c < hd && row / hpr < tok_limit) v = *reinterpret_cast<const uint4 *>(src + (long)row * ld + c);
-        *reinterpret_cast<uint4 *>(dst + r * LDP + c) = v;
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < N && row0 + r < row_lim && c < hd) v[k] = __ldg(reinterpret_cast<const uint4 *>(src + (long)(row0 + r) * ld + c));
+    }
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int r = i / CH, c = (i % CH) * 8;
+        if (i < N) *reinterpret_cast<uint4 *>(dst + r * LDP + c) = v[k];
+    }
+}
+
+// two tiles of the same geometry (K and V, or Q and dO): all loads of both in flight together
+template <int HDP>
+PZ_DEVINL void load_rows64x2(bf16 *__restrict__ dst0, const bf16 *__restrict__ src0, int ld0, bf16 *__restrict__ dst1,
+                             const bf16 *__restrict__ src1, int ld1, int row0, int n_rows, int hd, int hpr, int tok_limit) {
+    constexpr int CH = HDP / 8, LDP = HDP + 8, N = 64 * CH, IT = (N + 255) / 256;
+    const long lim = (long)tok_limit * hpr;
+    const int row_lim = (int)(lim < n_rows ? lim : n_rows);
+    uint4 v0[IT], v1[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int r = i / CH, c = (i % CH) * 8;
+        v0[k] = v1[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < N && row0 + r < row_lim && c < hd) {
+            v0[k] = __ldg(reinterpret_cast<const uint4 *>(src0 + (long)(row0 + r) * ld0 + c));
+            v1[k] = __ldg(reinterpret_cast<const uint4 *>(src1 + (long)(row0 + r) * ld1 + c));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int r = i / CH, c = (i % CH) * 8;
+        if (i < N) {
+            *reinterpret_cast<uint4 *>(dst0 + r * LDP + c) = v0[k];
+            *reinterpret_cast<uint4 *>(dst1 + r * LDP + c) = v1[k];
+        }
     }
 }
 
@@ -742,21 +783,20 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
     const int tok_limit = (a.valid_len && a.seg == 0) ? vl : (1 << 30);
     const bf16 *Qg = a.Q + b * a.q_bs + g * a.q_gs, *dOg = a.dO + b * a.o_bs + g * a.o_gs, *Og = a.O + b * a.o_bs + g * a.o_gs;
     const bf16 *Kg = a.K + b * a.kv_bs + g * a.kv_gs, *Vg = a.V + b * a.kv_bs + g * a.kv_gs;
-    load_rows64<HDP>(Qs, Qg, a.ld_q, row0, a.NQ, a.hd, a.hpr, tok_limit);
-    load_rows64<HDP>(dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
+    load_rows64x2<HDP>(Qs, Qg, a.ld_q, dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
     __syncthreads();
     // D = rowsum(dO o O): a warp takes 8 rows
     for (int r = warp * 8; r < warp * 8 + 8; ++r) {
         const int row = row0 + r;
         float acc = 0.f;
-        if (row < a.NQ && row / a.hpr < tok_limit)
+        if (row < a.NQ && (long)row < (long)tok_limit * a.hpr)
             for (int d = lane; d < a.hd; d += 32) acc += __bfloat162float(dOs[r * LDP + d]) * __bfloat162float(Og[(long)row * a.ld_o + d]);
         acc = warp_sum(acc);
         if (lane == 0) sD[r] = acc;
     }
     const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
     const int er = tid >> 2, ec0 = (tid & 3) * 16;      // elementwise mapping: 4 threads per row, 16 columns each
-    const bool row_ok = row0 + er < a.NQ && (row0 + er) / a.hpr < tok_limit;
+    const bool row_ok = row0 + er < a.NQ && (long)(row0 + er) < (long)tok_limit * a.hpr;
     const int n_kb = (a.NK + 63) / 64;
     // Soft-capped logits lie in [-cap, cap]: exp(l - cap / 2) can neither overflow nor leave the normal fp32 range, so the
     // softmax needs no running maximum and dQ is linear in 1 / Z -- ONE pass accumulates the unnormalised sum and Z, the
@@ -805,8 +845,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
     for (int t = 0; t < HALF; ++t) wmma::fill_fragment(accq[t], 0.f);
     for (int kb = 0; kb < n_kb; ++kb) {
         __syncthreads();
-        load_rows64<HDP>(Ks, Kg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
-        load_rows64<HDP>(Vs, Vg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
+        load_rows64x2<HDP>(Ks, Kg, a.ld_kv, Vs, Vg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
         __syncthreads();
         mma_qkT<HDP>(Qs, Ks, Sf, warp);
         mma_qkT<HDP>(dOs, Vs, Df, warp);
@@ -882,8 +921,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     const int tok_limit = (a.valid_len && a.seg == 0) ? vl : (1 << 30);
     const bf16 *Qg = a.Q + b * a.q_bs + g * a.q_gs, *dOg = a.dO + b * a.o_bs + g * a.o_gs;
     const bf16 *Kg = a.K + b * a.kv_bs + g * a.kv_gs, *Vg = a.V + b * a.kv_bs + g * a.kv_gs;
-    load_rows64<HDP>(Ks, Kg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
-    load_rows64<HDP>(Vs, Vg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
+    load_rows64x2<HDP>(Ks, Kg, a.ld_kv, Vs, Vg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
     constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
     const int kr = warp & 3, wc = warp >> 2;          // 16 keys x one half of the feature tiles per warp
     wmma::fragment<wmma::accumulator, 16, 16, 16, float> acck[HALF], accv[HALF];
@@ -898,10 +936,9 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     if (split >= n_qt) return;   // no query tile for this CTA: nothing to add
     for (int qt = split; any && qt < n_qt; qt += NS) {
         const int row0 = qt * 64;
-        if (a.valid_len && a.seg == 0 && row0 / a.hpr >= vl) break;      // padded tokens only from here on
+        if (a.valid_len && a.seg == 0 && (long)row0 >= (long)vl * a.hpr) break;      // padded tokens only from here on
         __syncthreads();
-        load_rows64<HDP>(Qs, Qg, a.ld_q, row0, a.NQ, a.hd, a.hpr, tok_limit);
-        load_rows64<HDP>(dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
+        load_rows64x2<HDP>(Qs, Qg, a.ld_q, dOs, dOg, a.ld_o, row0, a.NQ, a.hd, a.hpr, tok_limit);
         if (tid < 64) {
             const long o = ((long)b * a.groups + g) * a.NQ + row0 + tid;
             const bool ok = row0 + tid < a.NQ;
