@@ -11,8 +11,6 @@
 // on K-major operands produced by a tiled transpose (HBM-bound, ~2 % of the step); nothing is recomputed except the
 // normalised activations (one norm kernel each); 180 GB of HBM hold the ~30 GB of saved activations at 32 samples.
 // The attention backward is one SIMT kernel for both the joint block-masked soft-capped MQA attention and SigLIP's.
-#include <mma.h>
-
 #include "api_internal.cuh"
 
 namespace {
@@ -647,9 +645,8 @@ int attn_bwd(AttnBwdArgs a, cudaStream_t st, const char **err) {
 //   attn_bwd_dkv_kernel: a CTA owns 64 keys and walks the query tiles: dV += P^T dO, dK += dS^T Q in registers.
 // "Query rows" are (token, head) pairs: with one K/V head (MQA) the 8 heads of a token are 8 consecutive rows of the
 // [tokens * heads, head_dim] view of the q buffer, so one CTA serves all heads against one copy of K / V; SigLIP (one K/V
-// head per q head) launches one group per head.  All products are 16x16x16 bf16 MMAs (warp-level `wmma`, fp32
-// accumulation) on shared-memory tiles; P and dS are rounded to bf16 for the second product, as the forward rounds P.
-using namespace nvcuda;
+// head per q head) launches one group per head.  All products are bf16 mma.sync.m16n8k16 (fp32 accumulation) fed by
+// ldmatrix from shared-memory tiles; P and dS are rounded to bf16 for the second product, as the forward rounds P.
 
 struct AttnBwd2Args {
     const bf16 *Q, *dO, *O;
@@ -743,27 +740,69 @@ PZ_DEVINL bool key_visible(const AttnBwd2Args &a, int j, int vl) {
     return a.seg >= 2;
 }
 
+
+// ---- warp-level bf16 MMA plumbing: ldmatrix + mma.sync.m16n8k16 (the `wmma` API loads its fragments with generic LD
+// instructions -- 2.7 per HMMA, 25 % of all issued instructions in the first version of these kernels; ldmatrix is one
+// shared-memory instruction per 16 x 16 tile).  Fragment layouts (g = lane / 4, t = lane % 4):
+//   A 16x16: a0 (g, 2t..) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..);  B 16x8: b0 (k 2t.., n g) b1 (k 2t+8.., n g);
+//   C 16x8 : c0 c1 (g, 2t 2t+1), c2 c3 (g+8, 2t 2t+1).  A "16 x 16 output tile" below is two n8 tiles: c[0..3], c[4..7].
+PZ_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+PZ_DEVINL void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+PZ_DEVINL uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// A tile (rows r0.., k k0..) of a row-major [row][k] array with pitch `ld` elements
+PZ_DEVINL void frag_a(uint32_t (&a)[4], const bf16 *base, int ld, int lane) {
+    ldsm_x4(a, smem_addr(base + ((lane & 7) + 8 * ((lane >> 3) & 1)) * ld + 8 * (lane >> 4)));
+}
+// A tile of an array stored [k][m] (the transpose of what the MMA wants: P^T from P[query][key])
+PZ_DEVINL void frag_a_t(uint32_t (&a)[4], const bf16 *base, int ld, int lane) {
+    ldsm_x4_t(a, smem_addr(base + ((lane & 7) + 8 * (lane >> 4)) * ld + 8 * ((lane >> 3) & 1)));
+}
+// B for two n8 tiles (n n0 .. n0+15, k k0 .. k0+15) of an array stored [n][k]: b[0], b[1] = first n8 tile, b[2], b[3] = second
+PZ_DEVINL void frag_b_nk(uint32_t (&b)[4], const bf16 *base, int ld, int lane) {
+    ldsm_x4(b, smem_addr(base + ((lane & 7) + 8 * (lane >> 4)) * ld + 8 * ((lane >> 3) & 1)));
+}
+// the same of an array stored [k][n]
+PZ_DEVINL void frag_b_kn(uint32_t (&b)[4], const bf16 *base, int ld, int lane) {
+    ldsm_x4_t(b, smem_addr(base + ((lane & 7) + 8 * ((lane >> 3) & 1)) * ld + 8 * (lane >> 4)));
+}
+PZ_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16 x 16 fp32 output tile (two n8 accumulators) -> row-major memory with pitch `ld` floats
+PZ_DEVINL void store_c16(float *base, int ld, const float (&c0)[4], const float (&c1)[4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    *reinterpret_cast<float2 *>(base + g * ld + 2 * t) = make_float2(c0[0], c0[1]);
+    *reinterpret_cast<float2 *>(base + (g + 8) * ld + 2 * t) = make_float2(c0[2], c0[3]);
+    *reinterpret_cast<float2 *>(base + g * ld + 8 + 2 * t) = make_float2(c1[0], c1[1]);
+    *reinterpret_cast<float2 *>(base + (g + 8) * ld + 8 + 2 * t) = make_float2(c1[2], c1[3]);
+}
+
 // S[64 x 64] = A[64 x HDP] . B[64 x HDP]^T into the fp32 tile `out` (8 warps: 4 row tiles x 2 column halves)
 template <int HDP>
 PZ_DEVINL void mma_qkT(const bf16 *A, const bf16 *B, float *out, int warp) {
     constexpr int LDP = HDP + 8;
-    const int wr = warp >> 1, wc = warp & 1;
-    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
-    wmma::fill_fragment(acc[0], 0.f);
-    wmma::fill_fragment(acc[1], 0.f);
+    const int wr = warp >> 1, wc = warp & 1, lane = threadIdx.x & 31;
+    float acc[4][4];      // four n8 tiles: columns wc * 32 + 8 j
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 4
     for (int k = 0; k < HDP / 16; ++k) {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
-        wmma::load_matrix_sync(fa, A + wr * 16 * LDP + k * 16, LDP);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> fb;
-            wmma::load_matrix_sync(fb, B + (wc * 32 + t * 16) * LDP + k * 16, LDP);
-            wmma::mma_sync(acc[t], fa, fb, acc[t]);
-        }
+        uint32_t fa[4], fb0[4], fb1[4];
+        frag_a(fa, A + wr * 16 * LDP + k * 16, LDP, lane);
+        frag_b_nk(fb0, B + (wc * 32) * LDP + k * 16, LDP, lane);
+        frag_b_nk(fb1, B + (wc * 32 + 16) * LDP + k * 16, LDP, lane);
+        mma16816(acc[0], fa, fb0[0], fb0[1]);
+        mma16816(acc[1], fa, fb0[2], fb0[3]);
+        mma16816(acc[2], fa, fb1[0], fb1[1]);
+        mma16816(acc[3], fa, fb1[2], fb1[3]);
     }
-    wmma::store_matrix_sync(out + wr * 16 * SLD + wc * 32, acc[0], SLD, wmma::mem_row_major);
-    wmma::store_matrix_sync(out + wr * 16 * SLD + wc * 32 + 16, acc[1], SLD, wmma::mem_row_major);
+    store_c16(out + wr * 16 * SLD + wc * 32, SLD, acc[0], acc[1], lane);
+    store_c16(out + wr * 16 * SLD + wc * 32 + 16, SLD, acc[2], acc[3], lane);
 }
 
 template <int HDP>
@@ -840,9 +879,12 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
     // ---- pass B: dQ = sum over key blocks of dS K
     constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
     const int wr = warp >> 1, wc = warp & 1;
-    wmma::fragment<wmma::accumulator, 16, 16, 16, float> accq[HALF];
+    const int lane_ = tid & 31;
+    float accq[HALF][2][4];       // [16-column tile][n8 half][fragment]
 #pragma unroll
-    for (int t = 0; t < HALF; ++t) wmma::fill_fragment(accq[t], 0.f);
+    for (int t = 0; t < HALF; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accq[t][0][i] = accq[t][1][i] = 0.f;
     for (int kb = 0; kb < n_kb; ++kb) {
         __syncthreads();
         load_rows64x2<HDP>(Ks, Kg, a.ld_kv, Vs, Vg, a.ld_kv, kb * 64, a.NK, a.hd, 1, 1 << 30);
@@ -863,15 +905,16 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
-            wmma::load_matrix_sync(fa, Pb + wr * 16 * SLD + kk * 16, SLD);
+            uint32_t fa[4];
+            frag_a(fa, Pb + wr * 16 * SLD + kk * 16, SLD, lane_);
 #pragma unroll
             for (int t = 0; t < HALF; ++t) {
                 const int ct = wc * HALF + t;
                 if (ct < NCT) {
-                    wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
-                    wmma::load_matrix_sync(fb, Ks + kk * 16 * LDP + ct * 16, LDP);
-                    wmma::mma_sync(accq[t], fa, fb, accq[t]);
+                    uint32_t fb[4];
+                    frag_b_kn(fb, Ks + kk * 16 * LDP + ct * 16, LDP, lane_);
+                    mma16816(accq[t][0], fa, fb[0], fb[1]);
+                    mma16816(accq[t][1], fa, fb[2], fb[3]);
                 }
             }
         }
@@ -893,7 +936,7 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dq_kernel(co
 #pragma unroll
     for (int t = 0; t < HALF; ++t) {
         const int ct = wc * HALF + t;
-        if (ct < NCT) wmma::store_matrix_sync(stage + wr * 16 * HDP + ct * 16, accq[t], HDP, wmma::mem_row_major);
+        if (ct < NCT) store_c16(stage + wr * 16 * HDP + ct * 16, HDP, accq[t][0], accq[t][1], lane_);
     }
     __syncthreads();
     float *dQg = a.dQ + b * a.dq_bs + g * a.dq_gs;
@@ -924,9 +967,12 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
     load_rows64x2<HDP>(Ks, Kg, a.ld_kv, Vs, Vg, a.ld_kv, key0, a.NK, a.hd, 1, 1 << 30);
     constexpr int NCT = HDP / 16, HALF = (NCT + 1) / 2;
     const int kr = warp & 3, wc = warp >> 2;          // 16 keys x one half of the feature tiles per warp
-    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acck[HALF], accv[HALF];
+    const int lane_ = tid & 31;
+    float acck[HALF][2][4], accv[HALF][2][4];
 #pragma unroll
-    for (int t = 0; t < HALF; ++t) { wmma::fill_fragment(acck[t], 0.f); wmma::fill_fragment(accv[t], 0.f); }
+    for (int t = 0; t < HALF; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acck[t][0][i] = acck[t][1][i] = accv[t][0][i] = accv[t][1][i] = 0.f;
     const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
     const int er = tid >> 2, ec0 = (tid & 3) * 16;
     const int n_qt = (a.NQ + 63) / 64;
@@ -962,18 +1008,20 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
         __syncthreads();
 #pragma unroll
         for (int q0 = 0; q0 < 4; ++q0) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fp, fs;   // P^T, dS^T: (key, query) at [query][key]
-            wmma::load_matrix_sync(fp, Pb + q0 * 16 * SLD + kr * 16, SLD);
-            wmma::load_matrix_sync(fs, dSb + q0 * 16 * SLD + kr * 16, SLD);
+            uint32_t fp[4], fs[4];   // P^T, dS^T: element (key, query) lives at [query][key]
+            frag_a_t(fp, Pb + q0 * 16 * SLD + kr * 16, SLD, lane_);
+            frag_a_t(fs, dSb + q0 * 16 * SLD + kr * 16, SLD, lane_);
 #pragma unroll
             for (int t = 0; t < HALF; ++t) {
                 const int ct = wc * HALF + t;
                 if (ct < NCT) {
-                    wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fo, fq;
-                    wmma::load_matrix_sync(fo, dOs + q0 * 16 * LDP + ct * 16, LDP);
-                    wmma::load_matrix_sync(fq, Qs + q0 * 16 * LDP + ct * 16, LDP);
-                    wmma::mma_sync(accv[t], fp, fo, accv[t]);
-                    wmma::mma_sync(acck[t], fs, fq, acck[t]);
+                    uint32_t fo[4], fq[4];
+                    frag_b_kn(fo, dOs + q0 * 16 * LDP + ct * 16, LDP, lane_);
+                    frag_b_kn(fq, Qs + q0 * 16 * LDP + ct * 16, LDP, lane_);
+                    mma16816(accv[t][0], fp, fo[0], fo[1]);
+                    mma16816(accv[t][1], fp, fo[2], fo[3]);
+                    mma16816(acck[t][0], fs, fq[0], fq[1]);
+                    mma16816(acck[t][1], fs, fq[2], fq[3]);
                 }
             }
         }
@@ -984,7 +1032,10 @@ __global__ void __launch_bounds__(256, HDP <= 128 ? 2 : 1) attn_bwd_dkv_kernel(c
 #pragma unroll
         for (int t = 0; t < HALF; ++t) {
             const int ct = wc * HALF + t;
-            if (ct < NCT) wmma::store_matrix_sync(stage + kr * 16 * HDP + ct * 16, which ? acck[t] : accv[t], HDP, wmma::mem_row_major);
+            if (ct < NCT) {
+                if (which) store_c16(stage + kr * 16 * HDP + ct * 16, HDP, acck[t][0], acck[t][1], lane_);
+                else store_c16(stage + kr * 16 * HDP + ct * 16, HDP, accv[t][0], accv[t][1], lane_);
+            }
         }
         __syncthreads();
         float *dst = (which ? a.dK : a.dV) + b * a.dkv_bs + g * a.dkv_gs;
