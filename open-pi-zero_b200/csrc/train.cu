@@ -200,9 +200,11 @@ __global__ void silu_bwd_kernel(const float *__restrict__ zpre, const float *__r
 //   dx += r (1+w) dy - x r^3 mean(x (1+w) dy);   dw += sum_rows dy x r
 // One CTA walks rows blockIdx.x, + gridDim.x, ...; a thread owns columns tid + 256 k (cols <= 2048) and keeps its dw
 // partials in registers until the end (one atomicAdd per column and CTA).
+template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                           const float *__restrict__ dy, float *__restrict__ dx,
-                                                          float *__restrict__ dw, long rows, int cols, float eps) {
+                                                          float *__restrict__ dw, long rows, int cols, float eps,
+                                                          T *__restrict__ dx_cast) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[32];
@@ -229,7 +231,9 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float *__restric
         for (int k = 0; k < 8; ++k) {
             const int c = threadIdx.x + k * 256;
             if (c < cols) {
-                dx[r * cols + c] += rr * gy[k] * (1.f + w[c]) - xv[k] * k3;
+                const float nv = dx[r * cols + c] + rr * gy[k] * (1.f + w[c]) - xv[k] * k3;
+                dx[r * cols + c] = nv;
+                if (dx_cast) dx_cast[r * cols + c] = from_f32<T>(nv);   // the next product's dY operand (saves a cast pass)
                 dwl[k] += gy[k] * xv[k] * rr;
             }
         }
@@ -242,17 +246,20 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float *__restric
         }
     }
 }
-void rmsnorm_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, long rows, int cols, cudaStream_t st) {
+template <typename T>
+void rmsnorm_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, long rows, int cols, cudaStream_t st,
+                 T *dx_cast = nullptr) {
     unsigned blocks = (unsigned)(rows < 148 * 4 ? rows : 148 * 4);
-    launch_k(rmsnorm_bwd_kernel, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, rows, cols, 1e-6f);
+    launch_k(rmsnorm_bwd_kernel<T>, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, rows, cols, 1e-6f, dx_cast);
 }
 
 // LayerNorm backward (siglip.py:211,217,298): y = xh w + b, xh = (x - mean) rstd
 //   dx += rstd (g - mean g - xh mean(g xh)), g = dy w;   dw += sum dy xh;   db += sum dy
+template <typename T>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ dy, float *__restrict__ dx,
                                                             float *__restrict__ dw, float *__restrict__ db, long rows, int cols,
-                                                            float eps) {
+                                                            float eps, T *__restrict__ dx_cast) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[32];
@@ -287,7 +294,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restr
         for (int k = 0; k < 8; ++k) {
             const int c = threadIdx.x + k * 256;
             if (c < cols) {
-                dx[r * cols + c] += rstd * (gy[k] * w[c] - sg - xv[k] * sgx);
+                const float nv = dx[r * cols + c] + rstd * (gy[k] * w[c] - sg - xv[k] * sgx);
+                dx[r * cols + c] = nv;
+                if (dx_cast) dx_cast[r * cols + c] = from_f32<T>(nv);
                 dwl[k] += gy[k] * xv[k];
                 dbl[k] += gy[k];
             }
@@ -302,10 +311,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restr
         }
     }
 }
+template <typename T>
 void layernorm_bwd(const float *x, const float *w, const float *dy, float *dx, float *dw, float *db, long rows, int cols,
-                   cudaStream_t st) {
+                   cudaStream_t st, T *dx_cast = nullptr) {
     unsigned blocks = (unsigned)(rows < 148 * 4 ? rows : 148 * 4);
-    launch_k(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, db, rows, cols, 1e-6f);
+    launch_k(layernorm_bwd_kernel<T>, dim3(blocks), dim3(256), 0, st, x, w, dy, dx, dw, db, rows, cols, 1e-6f, dx_cast);
 }
 
 // out[c] += sum_r in[r][c] (bias gradients); block (32, 8), grid (column tiles, row slabs)
@@ -1519,7 +1529,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     colsum<T>(dv, 8, G(g.dec_b), Ma, c.action_dim, st);
     PZ_TRY(linear_bwd<T>(h, dv, 8, ws.hfin, A, w.dec_w, ws.dh, A, LIN_OUT_F32, G(g.dec_w), Ma, 8, A, sc, st));
     for (int m = 0; m < 3; ++m) cudaMemsetAsync(ws.dx[m], 0, (size_t)B * md[m].rows * md[m].hidden * 4, st);
-    rmsnorm_bwd(ws.xin[2][L], w.action_final_norm, ws.dh, ws.dx[2], G(g.action_final_norm), Ma, A, st);
+    rmsnorm_bwd<T>(ws.xin[2][L], w.action_final_norm, ws.dh, ws.dx[2], G(g.action_final_norm), Ma, A, st);
     // ---- layers, last to first
     for (int l = L - 1; l >= 0; --l) {
         const bool last = l == L - 1;
@@ -1528,16 +1538,16 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             const int M = B * md[m].rows, Hm = md[m].hidden, Im = md[m].inter;
             const pz_mix_layer &Lw = mixw[m][l];
             const pz_mix_layer &Lg = mixg[m][l];
-            // MLP: x_out = x1 + down(gelu(g) u)
+            // MLP: x_out = x1 + down(gelu(g) u); the model-dtype copy of dx is the dY operand of both products
             cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.mm[m][l], Im, Lw.w_down, ws.d_m, Im, 0, G(Lg.w_down), M, Hm, Im, sc, st));
             launch_k(geglu_bwd_kernel<T>, dim3(ew_blocks((long)M * Im / 8)), dim3(256), 0, st, (const T *)ws.gu[m][l], (const T *)ws.d_m,
                      (T *)ws.dgu, (long)M * Im, Im);
             launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dgu, 2 * Im, ws.h, Hm, Lw.w_gate_up, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_gate_up), M, 2 * Im, Hm, sc, st));
-            rmsnorm_bwd(ws.x1[m][l], Lw.norm_post, ws.dh, ws.dx[m], G(Lg.norm_post), M, Hm, st);   // dx is now d / d x1
+            // dx becomes d / d x1; its model-dtype copy (the dY of the attention output projection) is written by the same kernel
+            rmsnorm_bwd<T>(ws.x1[m][l], Lw.norm_post, ws.dh, ws.dx[m], G(Lg.norm_post), M, Hm, st, (T *)ws.dyb);
             // attention output projection: x1 = x + o_proj(att)
-            cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.att[m][l], qd, Lw.w_o, ws.datt[m], qd, 0, G(Lg.w_o), M, Hm, qd, sc, st));
         }
         // attention
@@ -1614,7 +1624,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
                      (const float *)ws.dK, (const float *)ws.dV, kv_bs, row_off[m], rc_[m], rs_[m], pos0[m], (T *)ws.dqkv, md[m].rows, nh, hd);
             launch_rmsnorm<T>(ws.xin[m][l], Lw.norm_in, (T *)ws.h, M, Hm, 1e-6f, st);
             PZ_TRY(linear_bwd<T>(h, ws.dqkv, qkvd, ws.h, Hm, Lw.w_qkv, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_qkv), M, qkvd, Hm, sc, st));
-            rmsnorm_bwd(ws.xin[m][l], Lw.norm_in, ws.dh, ws.dx[m], G(Lg.norm_in), M, Hm, st);
+            rmsnorm_bwd<T>(ws.xin[m][l], Lw.norm_in, ws.dh, ws.dx[m], G(Lg.norm_in), M, Hm, st);
         }
         mark(l);
     }
@@ -1660,12 +1670,11 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     float *dxv = ws.feats;   // the forward's projector output is no longer needed: fp32 [Mv, H] >= [Mv, V]
     PZ_TRY(linear_bwd<T>(h, dfb, H, ws.hv_post, V, w.proj_w, ws.dh, V, LIN_OUT_F32, G(g.proj_w), Mv, H, V, sc, st));
     cudaMemsetAsync(dxv, 0, (size_t)Mv * V * 4, st);
-    layernorm_bwd(ws.xv[LV], w.post_ln_w, ws.dh, dxv, G(g.post_ln_w), G(g.post_ln_b), Mv, V, st);
+    layernorm_bwd<T>(ws.xv[LV], w.post_ln_w, ws.dh, dxv, G(g.post_ln_w), G(g.post_ln_b), Mv, V, st, (T *)ws.dyb);
     for (int i = LV - 1; i >= 0; --i) {
         const pz_vit_layer &Lw = h->vit[i];
         const pz_vit_layer &Lg = gr->vit[i];
-        // MLP
-        cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
+        // MLP (ws.dyb = the model-dtype copy of dxv, written by the norm backward in front)
         colsum<T>((const T *)ws.dyb, V, G(Lg.b_fc2), Mv, V, st);
         PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.actv[i], VI, Lw.w_fc2, ws.d_m, VI, 0, G(Lg.w_fc2), Mv, V, VI, sc, st));
         launch_k(gelu_bwd_kernel<T>, dim3(ew_blocks((long)Mv * VI)), dim3(256), 0, st, (const T *)ws.f1[i], (const T *)ws.d_m, (T *)ws.dgu,
@@ -1673,9 +1682,8 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         colsum<T>((const T *)ws.dgu, VI, G(Lg.b_fc1), Mv, VI, st);
         launch_layernorm<T>(ws.xv_mid[i], Lw.ln2_w, Lw.ln2_b, (T *)ws.h, Mv, V, 1e-6f, st);
         PZ_TRY(linear_bwd<T>(h, ws.dgu, VI, ws.h, V, Lw.w_fc1, ws.dh, V, LIN_OUT_F32, G(Lg.w_fc1), Mv, VI, V, sc, st));
-        layernorm_bwd(ws.xv_mid[i], Lw.ln2_w, ws.dh, dxv, G(Lg.ln2_w), G(Lg.ln2_b), Mv, V, st);
+        layernorm_bwd<T>(ws.xv_mid[i], Lw.ln2_w, ws.dh, dxv, G(Lg.ln2_w), G(Lg.ln2_b), Mv, V, st, (T *)ws.dyb);
         // attention
-        cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
         colsum<T>((const T *)ws.dyb, V, G(Lg.b_o), Mv, V, st);
         T *dav = (T *)ws.d_m;
         PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.av[i], V, Lw.w_o, dav, V, 0, G(Lg.w_o), Mv, V, V, sc, st));
@@ -1712,12 +1720,11 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         colsum<T>((const T *)ws.dqkv, 3 * V, G(Lg.b_qkv), Mv, 3 * V, st);
         launch_layernorm<T>(ws.xv[i], Lw.ln1_w, Lw.ln1_b, (T *)ws.h, Mv, V, 1e-6f, st);
         PZ_TRY(linear_bwd<T>(h, ws.dqkv, 3 * V, ws.h, V, Lw.w_qkv, ws.dh, V, LIN_OUT_F32, G(Lg.w_qkv), Mv, 3 * V, V, sc, st));
-        layernorm_bwd(ws.xv[i], Lw.ln1_w, ws.dh, dxv, G(Lg.ln1_w), G(Lg.ln1_b), Mv, V, st);
+        layernorm_bwd<T>(ws.xv[i], Lw.ln1_w, ws.dh, dxv, G(Lg.ln1_w), G(Lg.ln1_b), Mv, V, st, (T *)ws.dyb);
         mark(L + 1 + i);
     }
     // ---- patch embedding (the convolution as a matrix product over unfolded patches) and the position table
     if (g.pos_emb) launch_k(period_sum_kernel, dim3((P * V + 255) / 256), dim3(256), 0, st, (const float *)dxv, G(g.pos_emb), (long)P * V, V, P, n_img);
-    cast_scale<T>(dxv, (T *)ws.dyb, (long)Mv * V, 1.f, st);
     colsum<T>((const T *)ws.dyb, V, G(g.patch_b), Mv, V, st);
     PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.patches, c.patch_k_pad, w.patch_w, nullptr, 0, 0, G(g.patch_w), Mv, V, c.patch_k_pad, sc, st));
     mark(L + 1 + LV);

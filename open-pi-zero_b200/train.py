@@ -327,10 +327,13 @@ class OverlappedAllReduce:
     slice of the flat buffer (NCCL over NVLink / NVSwitch) while the main stream keeps computing.  `wait()` makes the
     current stream wait for all of them (call it before the optimizer step)."""
 
-    def __init__(self, grads: GradBuffer, group=None):
+    def __init__(self, grads: GradBuffer, group=None, wire_dtype: torch.dtype = torch.float32):
+        """`wire_dtype=torch.bfloat16`: every slice is rounded to bf16 before it goes over NVLink and widened again after the
+        sum (half the bytes; what DDP moves for the reference's bf16 parameters) -- fp32 (the default) keeps the sum exact."""
         d = grads.model.dims
         L, LV = d["num_layers"], d["vit_layers"]
         self.grads, self.group = grads, group
+        self.wire = None if wire_dtype == torch.float32 else torch.empty(grads.numel, dtype=wire_dtype, device=grads.flat.device)
         self.n = L + LV + 2
         dev = grads.flat.device
         self.stream = torch.cuda.Stream(device=dev)
@@ -367,9 +370,20 @@ class OverlappedAllReduce:
             for idx in self.order:
                 self.stream.wait_event(self.events[idx])
                 for lo, hi in self.ranges[idx]:
-                    self._works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                    if self.wire is None:
+                        self._works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                    else:
+                        w = self.wire[lo:hi]
+                        w.copy_(flat[lo:hi])
+                        dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group, async_op=True).wait()   # orders the side stream
+                        flat[lo:hi].copy_(w)
+            self._done = torch.cuda.Event()
+            self._done.record(self.stream)
 
     def wait(self):
         for w in self._works:
             w.wait()
         self._works = []
+        done = self.__dict__.pop("_done", None)
+        if done is not None:
+            torch.cuda.current_stream(self.grads.flat.device).wait_event(done)

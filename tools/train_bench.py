@@ -42,7 +42,7 @@ def ours(args, d, dev, rank, world):
     actions, noise, t, vlen = actions.to(dev), noise.to(dev), t.to(dev), inp["valid_len"].to(dev)
     gb = GradBuffer(m)
     opt = FusedAdamW(gb)
-    ov = OverlappedAllReduce(gb) if (world > 1 and not args.no_overlap) else None
+    ov = OverlappedAllReduce(gb, wire_dtype=torch.bfloat16 if args.wire_bf16 else torch.float32) if (world > 1 and not args.no_overlap) else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     parts = {"fwd_bwd": 0.0, "allreduce": 0.0, "optimizer": 0.0}
     losses = []
@@ -89,7 +89,7 @@ def ours(args, d, dev, rank, world):
             "metric": "flow-matching training step (forward + backward + gradient all-reduce + clip + AdamW), samples/s",
             "impl": "ours", "value": world * B / (float(ms) / 1e3), "unit": "samples/s", "n_gpus": world, "ms_per_step": float(ms),
             "per_gpu_batch": B, "dtype": "bf16", "layers": [d["vit_layers"], d["num_layers"]],
-            "parts_ms": {k: v / args.steps for k, v in parts.items()}, "allreduce": "overlapped per layer" if ov is not None else "after backward", "launches_fwd_bwd": m.last_launch_count,
+            "parts_ms": {k: v / args.steps for k, v in parts.items()}, "allreduce": ("overlapped per layer" + (", bf16 on the wire" if args.wire_bf16 else ", fp32")) if ov is not None else "after backward", "launches_fwd_bwd": m.last_launch_count,
             "losses_first_last": [losses[0], losses[-1]], "grad_buffer_gb": gb.flat.numel() * 4 / 1e9,
             "train_workspace_gb": m._train_ws.numel() / 1e9, "max_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9}))
 
@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--reference", action="store_true")
+    ap.add_argument("--wire-bf16", action="store_true", help="round the gradients to bf16 for the all-reduce (half the NVLink bytes)")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward instead of layer by layer beside it")
     ap.add_argument("--layers", type=int, default=0, help="debug: shrink to this many Gemma / SigLIP layers")
     args = ap.parse_args()
