@@ -711,7 +711,7 @@ def main():
     # ---- extra: the full training step of BASELINE configs[4] (forward + backward + clip + AdamW, per-GPU batch 32);
     # LAST, because the optimizer updates the packed weights in place
     train = None
-    if rank == 0 and not args.skip_latency and extras and args.config == "bridge64":
+    if rank == 0 and world == 1 and not args.skip_latency and extras and args.config == "bridge64":
         try:
             train = train_step_extra(model, dims, dev_in, device, min(32, B))
         except Exception as e:   # noqa: BLE001 -- an extra must not take the headline line down
