@@ -367,6 +367,13 @@ def train_step_extra(model, dims, dev_in, device, Bt, steps=3):
                     "+ AdamW on fp32 master weights (pz_adamw_step), one GPU, no all-reduce", batch=Bt, ms=ms,
                fwd_bwd_ms=fb / steps, optimizer_ms=op / steps, samples_per_s=Bt / (ms / 1e3), loss=float(loss),
                launches_fwd_bwd=model.last_launch_count, parameters_trained=int(gb.flat.numel()))
+    # roofline of the step: 3 x the forward's FLOPs (1268.2 GF prefix + 2.68 GF for one velocity evaluation per
+    # sample; backward = 2 x) against the measured sustained bf16 rate -- the step is GEMM-bound by construction
+    flops = 3.0 * (1268.2e9 + 26.8e9 / 10) * Bt
+    peaks = measured_peaks()
+    out["roofline"] = dict(bound="tensor", flops_per_step=flops, achieved=flops / (ms * 1e-3) / 1e12, unit="TFLOP/s",
+                           peak=peaks["tflops_sustained"], frac=flops / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                           gemm_share="95 ms of GEMM per step in profiles/r02_train_step_launches.txt = 1284 TFLOP/s")
     ref_path = os.path.join(ROOT, "profiles", "r02_train_bench_reference.json")
     if os.path.exists(ref_path):
         with open(ref_path) as fh:

@@ -5,12 +5,12 @@
 // (fused q|k|v rows, gate|up blocks of 128, padded small matrices), so that an optimizer can update the kernel-side
 // weights in place.
 //
-// B200 plan: every matrix product of the backward runs through the same tcgen05 GEMM as the forward,
-//   dX[M,K] = dY[M,N] . W[N,K]           -> gemm(A = dY,   W' = W^T [K,N])
-//   dW[N,K] = dY[M,N]^T . X[M,K]         -> gemm(A = dY^T, W' = X^T [K,M]), fp32 TMA reduce-add into the gradient
-// on K-major operands produced by a tiled transpose (HBM-bound, ~2 % of the step); nothing is recomputed except the
-// normalised activations (one norm kernel each); 180 GB of HBM hold the ~30 GB of saved activations at 32 samples.
-// The attention backward is one SIMT kernel for both the joint block-masked soft-capped MQA attention and SigLIP's.
+// B200 design: every matrix product of the backward runs through the same tcgen05 GEMM as the forward, with
+// the operands read in place as MN-major UMMA operands (tokens are the contraction dimension of dW = dY^T X; W [out][in] is
+// the MN-major B operand of dX = dY W) and the fp32 TMA reduce-add epilogue accumulating straight into the gradient
+// buffer; nothing is recomputed except the normalised activations (one norm kernel each); 180 GB of HBM hold the ~30 GB of
+// saved activations at 32 samples.  Attention backward: FlashAttention-2 style dQ and dK/dV kernels on mma.sync (bf16),
+// a SIMT kernel for the fp32 build.
 #include "api_internal.cuh"
 
 namespace {
@@ -18,77 +18,6 @@ namespace {
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
 // ============================================================== kernels ====
-// out[c][r] = in[r][c]; out has row stride ld_out >= R, columns R .. ld_out-1 are zero-filled (they are the K padding of
-// the GEMM that consumes `out`).  32 x 32 tiles through shared memory, block (32, 8).
-template <typename T>
-__global__ void transpose_kernel(const T *__restrict__ in, int ld_in, T *__restrict__ out, int ld_out, int R, int C) {
-    pdl_trigger();
-    pdl_wait();
-    __shared__ T tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < R && c < C) ? in[(long)r * ld_in + c] : from_f32<T>(0.f);
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + tx;
-        if (c < C && r < ld_out) out[(long)c * ld_out + r] = tile[tx][i];
-    }
-}
-// bf16 fast path: 64 x 64 tiles, 16-byte global accesses on both sides (needs 16-byte aligned bases and row strides)
-__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16 *__restrict__ in, int ld_in, bf16 *__restrict__ out,
-                                                             int ld_out, int R, int C) {
-    pdl_trigger();
-    pdl_wait();
-    __shared__ unsigned short tile[64][66];
-    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
-    const int t = threadIdx.x;
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int r = pass * 32 + (t >> 3), cs = (t & 7) * 8;
-        const int gr = r0 + r, gc = c0 + cs;
-        unsigned short v[8];
-        if (gr < R && gc + 8 <= C) {
-            const uint4 x = *reinterpret_cast<const uint4 *>(in + (long)gr * ld_in + gc);
-            v[0] = x.x & 0xffff; v[1] = x.x >> 16; v[2] = x.y & 0xffff; v[3] = x.y >> 16;
-            v[4] = x.z & 0xffff; v[5] = x.z >> 16; v[6] = x.w & 0xffff; v[7] = x.w >> 16;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                v[k] = (gr < R && gc + k < C) ? reinterpret_cast<const unsigned short *>(in)[(long)gr * ld_in + gc + k] : (unsigned short)0;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tile[r][cs + k] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int c = pass * 32 + (t >> 3), rs = (t & 7) * 8;
-        const int gc = c0 + c, gr = r0 + rs;
-        if (gc < C && gr < ld_out) {
-            unsigned short v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = tile[rs + k][c];
-            uint4 o;
-            o.x = v[0] | ((unsigned)v[1] << 16); o.y = v[2] | ((unsigned)v[3] << 16);
-            o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
-            *reinterpret_cast<uint4 *>(out + (long)gc * ld_out + gr) = o;
-        }
-    }
-}
-template <typename T>
-void transpose(const T *in, int ld_in, T *out, int ld_out, int R, int C, cudaStream_t st) {
-    if (std::is_same<T, bf16>::value && ld_in % 8 == 0 && ld_out % 8 == 0 &&
-        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-        launch_k(transpose_bf16_kernel, dim3((C + 63) / 64, (ld_out + 63) / 64), dim3(256), 0, st, (const bf16 *)in, ld_in, (bf16 *)out,
-                 ld_out, R, C);
-        return;
-    }
-    launch_k(transpose_kernel<T>, dim3((C + 31) / 32, (ld_out + 31) / 32), dim3(32, 8), 0, st, in, ld_in, out, ld_out, R, C);
-}
-
 // dst = T(scale * src)
 template <typename T>
 __global__ void cast_scale_kernel(const float *__restrict__ src, T *__restrict__ dst, long n, float scale) {
@@ -1213,47 +1142,23 @@ int tlin(pz_handle *h, const LinearArgs &a, cudaStream_t st) {
     return 0;
 }
 
-struct Scratch {          // transposed operands of one backward linear layer
-    void *tA, *tB, *wT;
-};
-
-// Backward of y = x W^T (bias handled by the caller through colsum):
-//   dX [M,K] (fp32 `dx_flags` = LIN_OUT_F32 [| LIN_ACCUM], or T with 0) = dY . W
-//   dW [N,K] fp32 += dY^T . X
-// dY: T [M,N] (ld ldy); X: T [M,K] (ld ldx); W: T [N,K].
+// Backward of y = x W^T (bias handled by the caller through colsum), operands read in place:
+//   dX [M,K] (fp32 `dx_flags` = LIN_OUT_F32 [| LIN_ACCUM], or T with 0) = dY . W    -- W [N][K] is the MN-major B operand
+//   dW [N,K] fp32 += dY^T . X    -- dY [M][N] and X [M][K] are the MN-major A / B operands, tokens the contraction dimension
+// (the first version went through tiled transposes: 14.5 ms per step).  dY: T [M,N] (ld ldy); X: T [M,K] (ld ldx); W: T [N,K].
 template <typename T>
 int linear_bwd(pz_handle *h, const void *dY, int ldy, const void *X, int ldx, const void *W, void *dX, int ld_dx,
-               int dx_flags, float *dW, int M, int N, int K, const Scratch &sc, cudaStream_t st) {
-    static const bool use_t = [] { const char *e = getenv("PZ_BWD_TRANSPOSE"); return e && e[0] == '1'; }();
-    if (!use_t) {
-        // operands read in place: W [N][K] is the MN-major B operand of dX = dY . W, and dY [M][N], X [M][K] are the
-        // MN-major A / B operands of dW = dY^T . X (tokens are the contraction dimension) -- no transposed copies
-        if (dX) {
-            LinearArgs a = lin(dY, ldy, W, nullptr, dX, ld_dx, M, K, N, dx_flags | LIN_W_MN);
-            a.ldw = K;
-            PZ_TRY(tlin<T>(h, a, st));
-        }
-        if (dW) {
-            PdlOff no_pdl;   // the "weight" operand X was written by the kernel right in front (see PdlOff)
-            LinearArgs a = lin(dY, ldy, X, nullptr, dW, K, N, K, M, LIN_OUT_F32 | LIN_ACCUM | LIN_A_MN | LIN_W_MN);
-            a.ldw = ldx;
-            PZ_TRY(tlin<T>(h, a, st));
-        }
-        return 0;
-    }
-    // PZ_BWD_TRANSPOSE=1: the first version, K-major operands through tiled transposes (kept as a cross-check)
-    PdlOff no_pdl;   // the "weight" operand of both products is written by the transpose right in front of them
+               int dx_flags, float *dW, int M, int N, int K, cudaStream_t st) {
     if (dX) {
-        transpose<T>((const T *)W, K, (T *)sc.wT, rup(N, 8), N, K, st);            // W^T: [K][N]
-        LinearArgs a = lin(dY, ldy, sc.wT, nullptr, dX, ld_dx, M, K, rup(N, 8), dx_flags);
-        if (rup(N, 8) != N && ldy < rup(N, 8)) return fail(h, PZ_ERR_INVALID, "linear_bwd: dY row stride smaller than the padded width");
+        LinearArgs a = lin(dY, ldy, W, nullptr, dX, ld_dx, M, K, N, dx_flags | LIN_W_MN);
+        a.ldw = K;
         PZ_TRY(tlin<T>(h, a, st));
     }
     if (dW) {
-        const int Mp = rup(M, 8);
-        transpose<T>((const T *)dY, ldy, (T *)sc.tA, Mp, M, N, st);               // dY^T: [N][Mp]
-        transpose<T>((const T *)X, ldx, (T *)sc.tB, Mp, M, K, st);                // X^T : [K][Mp]
-        PZ_TRY(tlin<T>(h, lin(sc.tA, Mp, sc.tB, nullptr, dW, K, N, K, Mp, LIN_OUT_F32 | LIN_ACCUM), st));
+        PdlOff no_pdl;   // the "weight" operand X was written by the kernel right in front (see PdlOff)
+        LinearArgs a = lin(dY, ldy, X, nullptr, dW, K, N, K, M, LIN_OUT_F32 | LIN_ACCUM | LIN_A_MN | LIN_W_MN);
+        a.ldw = ldx;
+        PZ_TRY(tlin<T>(h, a, st));
     }
     return 0;
 }
@@ -1276,7 +1181,7 @@ struct TrainWs {
     void *a_in, *e1, *temb, *z, *pp, *hfin;     // T
     float *tbias, *zpre, *vel, *psi;
     // scratch
-    void *h, *qkv, *tA, *tB, *wT, *dyb, *d_m, *dgu, *dqkv;
+    void *h, *qkv, *dyb, *d_m, *dgu, *dqkv;
     void *datt[3];
     float *dx[3], *dq[3], *dh, *dK, *dV, *lse, *dvec;
     float *att_scratch; size_t att_scratch_bytes;
@@ -1341,18 +1246,7 @@ TrainWs carve_train(const pz_config &c, int B, void *base) {
     w.zpre = b.take<float>(Ma * A * 4);
     w.vel = b.take<float>(Ma * 8 * 4);
     w.psi = b.take<float>(Ma * c.action_dim * 4);
-    // scratch: sized for the widest operand of any backward linear layer (SigLIP rows included)
-    size_t rows_max = Mmax > Mv ? Mmax : Mv;
-    size_t wide = qkvd;                                  // widest dY / X feature count
-    const size_t cand[] = {(size_t)2 * c.vlm_inter, (size_t)2 * c.act_inter, (size_t)3 * V, (size_t)VI, (size_t)H, (size_t)c.patch_k_pad, qd};
-    for (size_t v : cand) wide = v > wide ? v : wide;
-    const size_t t_elems = wide * (rows_max + 8);
-    size_t w_elems = (size_t)2 * c.vlm_inter * H;
-    const size_t wc[] = {(size_t)2 * c.act_inter * A, (size_t)3 * V * V, (size_t)VI * V, qkvd * H, qd * H, (size_t)H * V, (size_t)V * c.patch_k_pad};
-    for (size_t v : wc) w_elems = v > w_elems ? v : w_elems;
-    w.tA = b.take<void>(t_elems * es);
-    w.tB = b.take<void>(t_elems * es);
-    w.wT = b.take<void>((w_elems + 8 * wide) * es);
+    // scratch
     size_t hmax = MHmax > Mv * V ? MHmax : Mv * V;
     w.h = b.take<void>(hmax * es);
     w.dyb = b.take<void>((hmax > Mv * (size_t)H ? hmax : Mv * (size_t)H) * es);
@@ -1412,7 +1306,6 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     const int skp = w.small_k_pad;
     const bool want_grads = gr != nullptr;
     const bool vit_grads = want_grads && !(flags & PZ_TRAIN_FREEZE_VISION);
-    Scratch sc{ws.tA, ws.tB, ws.wT};
     const char *err = nullptr;
     // "these gradients are final" marks for the caller's bucketed all-reduce: [0, L) joint layer l, L the encoder / decoder
     // heads, L + 1 + i SigLIP layer i, L + 1 + LV everything else (projector, patch embedding, position table)
@@ -1527,7 +1420,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     launch_k(loss_bwd_kernel<T>, dim3((Ma * 8 + 255) / 256), dim3(256), 0, st, (const float *)ws.vel, 8, noise, actions, dv, (long)Ma,
              c.action_dim, sig_min, loss_scale);
     colsum<T>(dv, 8, G(g.dec_b), Ma, c.action_dim, st);
-    PZ_TRY(linear_bwd<T>(h, dv, 8, ws.hfin, A, w.dec_w, ws.dh, A, LIN_OUT_F32, G(g.dec_w), Ma, 8, A, sc, st));
+    PZ_TRY(linear_bwd<T>(h, dv, 8, ws.hfin, A, w.dec_w, ws.dh, A, LIN_OUT_F32, G(g.dec_w), Ma, 8, A, st));
     for (int m = 0; m < 3; ++m) cudaMemsetAsync(ws.dx[m], 0, (size_t)B * md[m].rows * md[m].hidden * 4, st);
     rmsnorm_bwd<T>(ws.xin[2][L], w.action_final_norm, ws.dh, ws.dx[2], G(g.action_final_norm), Ma, A, st);
     // ---- layers, last to first
@@ -1540,15 +1433,15 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             const pz_mix_layer &Lg = mixg[m][l];
             // MLP: x_out = x1 + down(gelu(g) u); the model-dtype copy of dx is the dY operand of both products
             cast_scale<T>(ws.dx[m], (T *)ws.dyb, (long)M * Hm, 1.f, st);
-            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.mm[m][l], Im, Lw.w_down, ws.d_m, Im, 0, G(Lg.w_down), M, Hm, Im, sc, st));
+            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.mm[m][l], Im, Lw.w_down, ws.d_m, Im, 0, G(Lg.w_down), M, Hm, Im, st));
             launch_k(geglu_bwd_kernel<T>, dim3(ew_blocks((long)M * Im / 8)), dim3(256), 0, st, (const T *)ws.gu[m][l], (const T *)ws.d_m,
                      (T *)ws.dgu, (long)M * Im, Im);
             launch_rmsnorm<T>(ws.x1[m][l], Lw.norm_post, (T *)ws.h, M, Hm, 1e-6f, st);
-            PZ_TRY(linear_bwd<T>(h, ws.dgu, 2 * Im, ws.h, Hm, Lw.w_gate_up, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_gate_up), M, 2 * Im, Hm, sc, st));
+            PZ_TRY(linear_bwd<T>(h, ws.dgu, 2 * Im, ws.h, Hm, Lw.w_gate_up, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_gate_up), M, 2 * Im, Hm, st));
             // dx becomes d / d x1; its model-dtype copy (the dY of the attention output projection) is written by the same kernel
             rmsnorm_bwd<T>(ws.x1[m][l], Lw.norm_post, ws.dh, ws.dx[m], G(Lg.norm_post), M, Hm, st, (T *)ws.dyb);
             // attention output projection: x1 = x + o_proj(att)
-            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.att[m][l], qd, Lw.w_o, ws.datt[m], qd, 0, G(Lg.w_o), M, Hm, qd, sc, st));
+            PZ_TRY(linear_bwd<T>(h, ws.dyb, Hm, ws.att[m][l], qd, Lw.w_o, ws.datt[m], qd, 0, G(Lg.w_o), M, Hm, qd, st));
         }
         // attention
         if (tc_attn_bwd && hd == 256) {
@@ -1623,7 +1516,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
             launch_k(rope_bwd_merge_kernel<T>, dim3(M), dim3(256), 0, st, (const float *)((last && m < 2) ? nullptr : ws.dq[m]),
                      (const float *)ws.dK, (const float *)ws.dV, kv_bs, row_off[m], rc_[m], rs_[m], pos0[m], (T *)ws.dqkv, md[m].rows, nh, hd);
             launch_rmsnorm<T>(ws.xin[m][l], Lw.norm_in, (T *)ws.h, M, Hm, 1e-6f, st);
-            PZ_TRY(linear_bwd<T>(h, ws.dqkv, qkvd, ws.h, Hm, Lw.w_qkv, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_qkv), M, qkvd, Hm, sc, st));
+            PZ_TRY(linear_bwd<T>(h, ws.dqkv, qkvd, ws.h, Hm, Lw.w_qkv, ws.dh, Hm, LIN_OUT_F32, G(Lg.w_qkv), M, qkvd, Hm, st));
             rmsnorm_bwd<T>(ws.xin[m][l], Lw.norm_in, ws.dh, ws.dx[m], G(Lg.norm_in), M, Hm, st);
         }
         mark(l);
@@ -1633,26 +1526,26 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         T *dy3 = (T *)ws.dyb;
         cast_scale<T>(ws.dx[2], dy3, (long)Ma * A, sqrtf((float)A), st);
         colsum<T>(dy3, A, G(g.enc_b3), Ma, A, st);
-        PZ_TRY(linear_bwd<T>(h, dy3, A, ws.z, A, w.enc_w3, ws.dh, A, LIN_OUT_F32, G(g.enc_w3), Ma, A, A, sc, st));
+        PZ_TRY(linear_bwd<T>(h, dy3, A, ws.z, A, w.enc_w3, ws.dh, A, LIN_OUT_F32, G(g.enc_w3), Ma, A, A, st));
         T *dzp = (T *)ws.dqkv;
         launch_k(silu_bwd_kernel<T>, dim3(ew_blocks((long)Ma * A)), dim3(256), 0, st, (const float *)ws.zpre, (const float *)ws.tbias,
                  (const float *)ws.dh, dzp, (long)Ma * A, A, Hz);
         colsum<T>(dzp, A, G(g.enc_b2), Ma, A, st);
         T *de1 = (T *)ws.d_m;
-        PZ_TRY(linear_bwd<T>(h, dzp, A, ws.e1, A, w.enc_w2a, de1, A, 0, G(g.enc_w2a), Ma, A, A, sc, st));
+        PZ_TRY(linear_bwd<T>(h, dzp, A, ws.e1, A, w.enc_w2a, de1, A, 0, G(g.enc_w2a), Ma, A, A, st));
         // time half: one input row per sample, its gradient is the sum over the sample's action tokens
         T *dzs = (T *)ws.dgu;
         launch_k(group_sum_kernel<T>, dim3((B * A + 255) / 256), dim3(256), 0, st, (const T *)dzp, dzs, (long)B * A, A, Hz);
-        PZ_TRY(linear_bwd<T>(h, dzs, A, ws.temb, A, w.enc_w2t, nullptr, 0, 0, G(g.enc_w2t), B, A, A, sc, st));
+        PZ_TRY(linear_bwd<T>(h, dzs, A, ws.temb, A, w.enc_w2t, nullptr, 0, 0, G(g.enc_w2t), B, A, A, st));
         colsum<T>(de1, A, G(g.enc_b1), Ma, A, st);
-        PZ_TRY(linear_bwd<T>(h, de1, A, ws.a_in, skp, w.enc_w1, nullptr, 0, 0, G(g.enc_w1), Ma, A, skp, sc, st));
+        PZ_TRY(linear_bwd<T>(h, de1, A, ws.a_in, skp, w.enc_w1, nullptr, 0, 0, G(g.enc_w1), Ma, A, skp, st));
     }
     // ---- proprio encoder (pizero.py:630)
     {
         T *dyp = (T *)ws.dyb;
         cast_scale<T>(ws.dx[1], dyp, (long)Mp * A, sqrtf((float)A), st);
         colsum<T>(dyp, A, G(g.prop_b), Mp, A, st);
-        PZ_TRY(linear_bwd<T>(h, dyp, A, ws.pp, skp, w.prop_w, nullptr, 0, 0, G(g.prop_w), Mp, A, skp, sc, st));
+        PZ_TRY(linear_bwd<T>(h, dyp, A, ws.pp, skp, w.prop_w, nullptr, 0, 0, G(g.prop_w), Mp, A, skp, st));
     }
     mark(L);
     if (!vit_grads) {
@@ -1668,7 +1561,7 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
     cast_scale<T>(dfe, dfb, (long)Mv * H, 1.f, st);
     colsum<T>(dfb, H, G(g.proj_b), Mv, H, st);
     float *dxv = ws.feats;   // the forward's projector output is no longer needed: fp32 [Mv, H] >= [Mv, V]
-    PZ_TRY(linear_bwd<T>(h, dfb, H, ws.hv_post, V, w.proj_w, ws.dh, V, LIN_OUT_F32, G(g.proj_w), Mv, H, V, sc, st));
+    PZ_TRY(linear_bwd<T>(h, dfb, H, ws.hv_post, V, w.proj_w, ws.dh, V, LIN_OUT_F32, G(g.proj_w), Mv, H, V, st));
     cudaMemsetAsync(dxv, 0, (size_t)Mv * V * 4, st);
     layernorm_bwd<T>(ws.xv[LV], w.post_ln_w, ws.dh, dxv, G(g.post_ln_w), G(g.post_ln_b), Mv, V, st, (T *)ws.dyb);
     for (int i = LV - 1; i >= 0; --i) {
@@ -1676,17 +1569,17 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         const pz_vit_layer &Lg = gr->vit[i];
         // MLP (ws.dyb = the model-dtype copy of dxv, written by the norm backward in front)
         colsum<T>((const T *)ws.dyb, V, G(Lg.b_fc2), Mv, V, st);
-        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.actv[i], VI, Lw.w_fc2, ws.d_m, VI, 0, G(Lg.w_fc2), Mv, V, VI, sc, st));
+        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.actv[i], VI, Lw.w_fc2, ws.d_m, VI, 0, G(Lg.w_fc2), Mv, V, VI, st));
         launch_k(gelu_bwd_kernel<T>, dim3(ew_blocks((long)Mv * VI)), dim3(256), 0, st, (const T *)ws.f1[i], (const T *)ws.d_m, (T *)ws.dgu,
                  (long)Mv * VI);
         colsum<T>((const T *)ws.dgu, VI, G(Lg.b_fc1), Mv, VI, st);
         launch_layernorm<T>(ws.xv_mid[i], Lw.ln2_w, Lw.ln2_b, (T *)ws.h, Mv, V, 1e-6f, st);
-        PZ_TRY(linear_bwd<T>(h, ws.dgu, VI, ws.h, V, Lw.w_fc1, ws.dh, V, LIN_OUT_F32, G(Lg.w_fc1), Mv, VI, V, sc, st));
+        PZ_TRY(linear_bwd<T>(h, ws.dgu, VI, ws.h, V, Lw.w_fc1, ws.dh, V, LIN_OUT_F32, G(Lg.w_fc1), Mv, VI, V, st));
         layernorm_bwd<T>(ws.xv_mid[i], Lw.ln2_w, ws.dh, dxv, G(Lg.ln2_w), G(Lg.ln2_b), Mv, V, st, (T *)ws.dyb);
         // attention
         colsum<T>((const T *)ws.dyb, V, G(Lg.b_o), Mv, V, st);
         T *dav = (T *)ws.d_m;
-        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.av[i], V, Lw.w_o, dav, V, 0, G(Lg.w_o), Mv, V, V, sc, st));
+        PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.av[i], V, Lw.w_o, dav, V, 0, G(Lg.w_o), Mv, V, V, st));
         float *dqkv32 = ws.dh;   // fp32 [Mv, 3V]: dq | dk | dv
         if (tc_attn_bwd && hdv == 72) {
             AttnBwd2Args b2;
@@ -1719,14 +1612,14 @@ int forward_backward(pz_handle *h, const int64_t *ids, const void *pixels, const
         cast_scale<T>(dqkv32, (T *)ws.dqkv, (long)Mv * 3 * V, 1.f, st);
         colsum<T>((const T *)ws.dqkv, 3 * V, G(Lg.b_qkv), Mv, 3 * V, st);
         launch_layernorm<T>(ws.xv[i], Lw.ln1_w, Lw.ln1_b, (T *)ws.h, Mv, V, 1e-6f, st);
-        PZ_TRY(linear_bwd<T>(h, ws.dqkv, 3 * V, ws.h, V, Lw.w_qkv, ws.dh, V, LIN_OUT_F32, G(Lg.w_qkv), Mv, 3 * V, V, sc, st));
+        PZ_TRY(linear_bwd<T>(h, ws.dqkv, 3 * V, ws.h, V, Lw.w_qkv, ws.dh, V, LIN_OUT_F32, G(Lg.w_qkv), Mv, 3 * V, V, st));
         layernorm_bwd<T>(ws.xv[i], Lw.ln1_w, ws.dh, dxv, G(Lg.ln1_w), G(Lg.ln1_b), Mv, V, st, (T *)ws.dyb);
         mark(L + 1 + i);
     }
     // ---- patch embedding (the convolution as a matrix product over unfolded patches) and the position table
     if (g.pos_emb) launch_k(period_sum_kernel, dim3((P * V + 255) / 256), dim3(256), 0, st, (const float *)dxv, G(g.pos_emb), (long)P * V, V, P, n_img);
     colsum<T>((const T *)ws.dyb, V, G(g.patch_b), Mv, V, st);
-    PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.patches, c.patch_k_pad, w.patch_w, nullptr, 0, 0, G(g.patch_w), Mv, V, c.patch_k_pad, sc, st));
+    PZ_TRY(linear_bwd<T>(h, ws.dyb, V, ws.patches, c.patch_k_pad, w.patch_w, nullptr, 0, 0, G(g.patch_w), Mv, V, c.patch_k_pad, st));
     mark(L + 1 + LV);
     return 0;
 }
