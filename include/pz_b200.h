@@ -312,6 +312,14 @@ int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t
                   float beta2, float eps, float weight_decay, int step, const float *d_sumsq, float max_grad_norm,
                   float grad_scale, int zero_grad, void *stream);
 
+/* Weight averaging on the flat master buffer (replaces torch.optim.swa_utils.AveragedModel, model_averaging.py:40-66):
+ * d_avg += (d_x - d_avg) * weight; EMA: weight = 1 - ema_decay, SWA: weight = 1 / (n_averaged + 1).
+ * pz_write_packed writes any flat fp32 buffer of the gradient layout (the averaged weights for validation, the master
+ * weights to restore) into the packed weight tensors, rounded to dst_dtype; same entry tables as pz_adamw_step. */
+int pz_average_update(float *d_avg, const float *d_x, size_t n, float weight, void *stream);
+int pz_write_packed(const float *d_flat, size_t begin, size_t end, const long long *d_entry_off, void *const *d_entry_dst,
+                    const long long *d_entry_n, int n_entries, int dst_dtype, void *stream);
+
 /* Number of kernels the last call on this handle launched (bench: gpu_launches). */
 int64_t pz_launch_count(const pz_handle *h);
 

@@ -64,7 +64,7 @@ LIN_GELU, LIN_OUT_F32, LIN_ACCUM, LIN_GEGLU, LIN_SILU = 1, 2, 4, 8, 16
 # every symbol include/pz_b200.h declares
 EXPORTS = ["pz_abi_version", "pz_create", "pz_destroy", "pz_last_error", "pz_bind_weights",
            "pz_workspace_bytes", "pz_set_pixel_format", "pz_set_io_normalization", "pz_kv_layout", "pz_debug_trace_offset", "pz_sampler_stream_bytes", "pz_sampler_pack", "pz_set_sampler", "pz_infer_action", "pz_embed_prefix",
-           "pz_prefill", "pz_denoise", "pz_text_prefill", "pz_text_decode", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss", "pz_train_workspace_bytes", "pz_flow_matching_step", "pz_grad_sumsq", "pz_adamw_step",
+           "pz_prefill", "pz_denoise", "pz_text_prefill", "pz_text_decode", "pz_joint_prefix", "pz_joint_action", "pz_velocity", "pz_flow_matching_loss", "pz_train_workspace_bytes", "pz_flow_matching_step", "pz_grad_sumsq", "pz_adamw_step", "pz_average_update", "pz_write_packed",
            "pz_launch_count", "pz_fallback_count", "pz_timing_begin", "pz_timing_end", "pz_op_linear", "pz_op_linear_ex", "pz_op_attention"]
 
 _lib = None
@@ -117,6 +117,8 @@ def load(build_if_needed: bool = True):
     lib.pz_train_workspace_bytes.argtypes = [hp, C.c_int]
     lib.pz_train_workspace_bytes.restype = C.c_size_t
     lib.pz_flow_matching_step.argtypes = [hp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, C.c_float, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, C.c_int, vp]
+    lib.pz_average_update.argtypes = [vp, vp, C.c_size_t, C.c_float, vp]
+    lib.pz_write_packed.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int, C.c_int, vp]
     lib.pz_grad_sumsq.argtypes = [vp, C.c_size_t, vp, vp]
     lib.pz_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int, vp, C.c_float, C.c_float, C.c_int, vp]

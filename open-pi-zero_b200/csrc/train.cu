@@ -1062,6 +1062,7 @@ struct AdamWArgs {
     const float *sumsq;                // device scalar: sum of squares of the (scaled) gradients, or null = no clipping
     float max_norm, grad_scale;
     int zero_grad;
+    int copy_only;                     // no update: just write `master` (any flat buffer of the layout) into the packed tensors
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
     pdl_trigger();
@@ -1092,8 +1093,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
         const size_t local = i - (size_t)__ldg(a.entry_off + e);
         const size_t n_e = (size_t)__ldg(a.entry_n + e);
         if (i >= a.end || local >= n_e) continue;
-        const float4 g4 = *reinterpret_cast<const float4 *>(a.grad + i);
         const float4 p4 = *reinterpret_cast<const float4 *>(a.master + i);
+        if (a.copy_only) {
+            const int nk_ = (int)(n_e - local < 4 ? n_e - local : 4);
+            const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+            if (a.dst_bf16) {
+                bf16 *dst = (bf16 *)__ldg(reinterpret_cast<const unsigned long long *>(a.entry_dst) + e) + local;
+                for (int k = 0; k < nk_; ++k) dst[k] = __float2bfloat16_rn(pc[k]);
+            } else {
+                float *dst = (float *)__ldg(reinterpret_cast<const unsigned long long *>(a.entry_dst) + e) + local;
+                for (int k = 0; k < nk_; ++k) dst[k] = pc[k];
+            }
+            continue;
+        }
+        const float4 g4 = *reinterpret_cast<const float4 *>(a.grad + i);
         const float4 m4 = *reinterpret_cast<const float4 *>(a.m + i);
         const float4 v4 = *reinterpret_cast<const float4 *>(a.v + i);
         float g[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs}, p[4] = {p4.x, p4.y, p4.z, p4.w};
@@ -1122,6 +1135,25 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
             for (int k = 0; k < nk; ++k) dst[k] = p[k];
         }
     }
+}
+
+
+// avg += (x - avg) * weight over a flat fp32 buffer: EMA (weight = 1 - decay) and SWA (weight = 1 / (n_averaged + 1)) of the
+// master weights (model_averaging.py:40-66, torch.optim.swa_utils)
+__global__ void __launch_bounds__(256) lerp_kernel(float *__restrict__ avg, const float *__restrict__ x, size_t n, float weight) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t n4 = n / 4;
+    float4 *a4 = reinterpret_cast<float4 *>(avg);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = a4[i];
+        const float4 v = x4[i];
+        a.x += (v.x - a.x) * weight; a.y += (v.y - a.y) * weight; a.z += (v.z - a.z) * weight; a.w += (v.w - a.w) * weight;
+        a4[i] = a;
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        avg[i] += (x[i] - avg[i]) * weight;
 }
 
 // ========================================================= host helpers ====
@@ -1700,7 +1732,32 @@ int pz_adamw_step(float *d_master, float *d_grad, float *d_m, float *d_v, size_t
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
     a.bc1 = 1.f - powf(beta1, (float)step);
     a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-    a.sumsq = d_sumsq; a.max_norm = max_grad_norm; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
+    a.sumsq = d_sumsq; a.max_norm = max_grad_norm; a.grad_scale = grad_scale; a.zero_grad = zero_grad; a.copy_only = 0;
+    size_t blocks = (end - begin + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
+
+int pz_average_update(float *d_avg, const float *d_x, size_t n, float weight, void *stream) {
+    if (!d_avg || !d_x) return PZ_ERR_INVALID;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_k(lerp_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, d_avg, d_x, n, weight);
+    return cudaPeekAtLastError() == cudaSuccess ? PZ_OK : PZ_ERR_CUDA;
+}
+
+int pz_write_packed(const float *d_flat, size_t begin, size_t end, const long long *d_entry_off, void *const *d_entry_dst,
+                    const long long *d_entry_n, int n_entries, int dst_dtype, void *stream) {
+    if (!d_flat || !d_entry_off || !d_entry_dst || !d_entry_n || n_entries < 1 || end < begin || (begin & 255)) return PZ_ERR_INVALID;
+    if (end == begin) return PZ_OK;
+    AdamWArgs a;
+    memset(&a, 0, sizeof(a));
+    a.master = const_cast<float *>(d_flat); a.begin = begin; a.end = end;
+    a.entry_off = d_entry_off; a.entry_dst = d_entry_dst; a.entry_n = d_entry_n; a.n_entries = n_entries;
+    a.dst_bf16 = dst_dtype == PZ_BF16; a.copy_only = 1;
     size_t blocks = (end - begin + 1023) / 1024;
     if (blocks > 148 * 8) blocks = 148 * 8;
     launch_k(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);

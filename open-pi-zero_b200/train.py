@@ -387,3 +387,147 @@ class OverlappedAllReduce:
         done = self.__dict__.pop("_done", None)
         if done is not None:
             torch.cuda.current_stream(self.grads.flat.device).wait_event(done)
+
+
+class CosineAnnealingWarmupRestarts:
+    """The reference's learning-rate schedule (`src/utils/optim.py:31-160`, stepped once per optimizer update,
+    train.py:376-379) for one parameter group of a `FusedAdamW`: linear warm-up from `min_lr` to `max_lr`, cosine decay
+    back to `min_lr`, restarts with `cycle_mult` / `gamma`.  Same constructor arguments, `step()`, `get_lr()`,
+    `state_dict()` / `load_state_dict()`; `optimizer` is a `FusedAdamW` and `group` the name of its group."""
+
+    def __init__(self, optimizer: "FusedAdamW", group: str, first_cycle_steps: int, cycle_mult: float = 1.0, max_lr: float = 0.1,
+                 min_lr: float = 0.001, warmup_steps: int = 0, gamma: float = 1.0, last_epoch: int = -1):
+        assert warmup_steps < first_cycle_steps
+        self.first_cycle_steps, self.cycle_mult = first_cycle_steps, cycle_mult
+        self.base_max_lr = self.max_lr = max_lr
+        self.min_lr, self.warmup_steps, self.gamma = min_lr, warmup_steps, gamma
+        self.cur_cycle_steps, self.cycle = first_cycle_steps, 0
+        self.step_in_cycle = self.last_epoch = last_epoch
+        self.optimizer, self.group = optimizer, group
+        self.base_lr = min_lr
+        optimizer.groups[group]["lr"] = min_lr          # init_lr(): the group starts at min_lr
+
+    def state_dict(self):
+        return {k: v for k, v in self.__dict__.items() if k != "optimizer"}
+
+    def load_state_dict(self, state_dict):
+        self.__dict__.update(state_dict)
+
+    def get_lr(self) -> float:
+        import math
+        if self.step_in_cycle == -1:
+            return self.base_lr
+        if self.step_in_cycle < self.warmup_steps:
+            return (self.max_lr - self.base_lr) * self.step_in_cycle / self.warmup_steps + self.base_lr
+        return self.base_lr + (self.max_lr - self.base_lr) * (
+            1 + math.cos(math.pi * (self.step_in_cycle - self.warmup_steps) / (self.cur_cycle_steps - self.warmup_steps))) / 2
+
+    def step(self):
+        import math
+        epoch = self.last_epoch + 1
+        self.step_in_cycle += 1
+        if self.step_in_cycle >= self.cur_cycle_steps:
+            self.cycle += 1
+            self.step_in_cycle -= self.cur_cycle_steps
+            self.cur_cycle_steps = int((self.cur_cycle_steps - self.warmup_steps) * self.cycle_mult) + self.warmup_steps
+        self.max_lr = self.base_max_lr * (self.gamma ** self.cycle)
+        self.last_epoch = math.floor(epoch)
+        self.optimizer.groups[self.group]["lr"] = self.get_lr()
+
+
+def _optimizer_state_dict(self) -> dict:
+    """What `TrainAgent.save_model` stores per optimizer (train.py:520-560): here one entry for both groups."""
+    return dict(master=self.master, exp_avg=self.m, exp_avg_sq=self.v, step=self.step_count,
+                groups={k: dict(lr=g["lr"], weight_decay=g["weight_decay"]) for k, g in self.groups.items()})
+
+
+def _optimizer_load_state_dict(self, sd: dict):
+    """Resume: restores the master weights, both moments and the step count, and rewrites the packed weights from the
+    master weights (the model then computes with exactly the weights the checkpointed optimizer held)."""
+    self.master.copy_(sd["master"])
+    self.m.copy_(sd["exp_avg"])
+    self.v.copy_(sd["exp_avg_sq"])
+    self.step_count = int(sd["step"])
+    for k, g in sd.get("groups", {}).items():
+        self.groups[k].update(g)
+    self.write_packed(self.master)
+
+
+def _optimizer_write_packed(self, flat: torch.Tensor):
+    """Write a flat fp32 buffer of the gradient layout (master weights, averaged weights) into the packed weight tensors."""
+    from .pizero import PzError
+    if self.model._packed is not self._packed_owner:
+        raise PzError("the model was re-packed since this optimizer was built")
+    lib = _lib.load()
+    dev = flat.device
+    with torch.cuda.device(dev):
+        rc = lib.pz_write_packed(flat.data_ptr(), 0, self.grads.numel, self._off.data_ptr(), self._dst.data_ptr(), self._n.data_ptr(),
+                                 len(self.grads.entries), _lib.PZ_BF16 if self.model._T == torch.bfloat16 else _lib.PZ_F32,
+                                 torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        raise PzError(f"pz_write_packed failed ({rc})")
+    self.model._graphs = {}
+
+
+FusedAdamW.state_dict = _optimizer_state_dict
+FusedAdamW.load_state_dict = _optimizer_load_state_dict
+FusedAdamW.write_packed = _optimizer_write_packed
+
+
+class ModelAveraging:
+    """EMA / SWA of the trained weights (`src/agent/model_averaging.py:9-90`: `torch.optim.swa_utils.AveragedModel` with
+    the EMA or the equal-weight SWA rule) kept as ONE flat fp32 buffer in the optimizer's layout and updated by one fused
+    pass (`pz_average_update`).  `averaged_weights()` is a context manager that lets the model compute with the averaged
+    weights (what validation does through `get_model_module()`, train.py:418-433) and puts the trained weights back."""
+
+    def __init__(self, optimizer: FusedAdamW, use_ema: bool = False, use_swa: bool = False, ema_start: int = 0, ema_decay: float = 0.99,
+                 ema_freq: int = 1, swa_start: int = 0, swa_freq: int = 1):
+        assert not (use_ema and use_swa), "Cannot use both EMA and SWA at once"
+        self.opt = optimizer
+        self.use_ema, self.use_swa = use_ema, use_swa
+        self.ema_start, self.ema_decay, self.ema_freq = ema_start, ema_decay, ema_freq
+        self.swa_start, self.swa_freq = swa_start, swa_freq
+        self.avg: Optional[torch.Tensor] = None
+        self.n_averaged = 0
+
+    def maybe_initialize(self, cnt_update: int):
+        if (self.use_swa and cnt_update == self.swa_start) or (self.use_ema and cnt_update == self.ema_start):
+            self.avg = self.opt.master.clone()       # AveragedModel copies the model; the first update_parameters() also copies
+            self.n_averaged = 0
+
+    def maybe_update(self, cnt_update: int):
+        if self.avg is None:
+            return
+        due = (self.use_ema and cnt_update % self.ema_freq == 0) or (self.use_swa and cnt_update % self.swa_freq == 0)
+        if not due:
+            return
+        if self.n_averaged == 0:
+            self.avg.copy_(self.opt.master)
+        else:
+            w = (1.0 - self.ema_decay) if self.use_ema else 1.0 / (self.n_averaged + 1)
+            lib = _lib.load()
+            dev = self.avg.device
+            with torch.cuda.device(dev):
+                lib.pz_average_update(self.avg.data_ptr(), self.opt.master.data_ptr(), self.avg.numel(), float(w),
+                                      torch.cuda.current_stream(dev).cuda_stream)
+        self.n_averaged += 1
+
+    def averaged_weights(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            if self.avg is None:
+                yield self.opt.model
+                return
+            self.opt.write_packed(self.avg)
+            try:
+                yield self.opt.model
+            finally:
+                self.opt.write_packed(self.opt.master)
+        return ctx()
+
+    def state_dict(self) -> dict:
+        if self.avg is None:
+            return {}
+        return dict(averaged=self.avg, n_averaged=self.n_averaged, model_type="ema" if self.use_ema else "swa")

@@ -232,3 +232,52 @@ def test_training_loop_overfits_a_fixed_batch(dtype):
     print(f"[overfit {dtype}] loss {losses[0]:.4f} -> {final:.4f} (min over the run {min(losses):.4f})")
     assert final < 0.35 * losses[0], (losses[0], final)
     assert all(l == l for l in losses)      # no NaN on the way
+
+
+def test_optimizer_checkpoint_resume_and_weight_averaging():
+    """FusedAdamW.state_dict / load_state_dict: a run resumed from the checkpoint continues bit for bit; ModelAveraging (EMA)
+    against the torch.optim.swa_utils rule the reference uses (model_averaging.py:40-66), and the averaged weights are what
+    the kernels compute with inside `averaged_weights()`."""
+    from open_pi_zero_b200.train import FusedAdamW, GradBuffer, ModelAveraging
+    d = SMALL
+    B = 2
+    sd = pz.init_state_dict(d, seed=23, randomize_norms=True, tie_proprio=True)
+    inp = pz.make_inputs(d, B, seed=5)
+    actions, noise, t = _targets(d, B, 6)
+
+    def fresh():
+        m = _model(d, sd, torch.float32)
+        m.tie_action_proprio_weights()
+        gb = GradBuffer(m)
+        return m, gb, FusedAdamW(gb, action_lr=1e-3, vlm_lr=1e-3)
+
+    m, gb, opt = fresh()
+    avg = ModelAveraging(opt, use_ema=True, ema_start=1, ema_decay=0.9)
+    ema_ref = None
+    for it in range(1, 4):
+        _step(m, inp, actions, noise, t, gb)
+        opt.step()
+        avg.maybe_initialize(it)
+        avg.maybe_update(it)
+        cur = opt.master.clone()
+        ema_ref = cur if ema_ref is None else 0.9 * ema_ref + 0.1 * cur      # get_ema_multi_avg_fn: the first update copies
+    assert rel_err(avg.avg, ema_ref) < 1e-6
+    ckpt = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state_dict().items()}
+    l_cont = []
+    for _ in range(2):
+        l_cont.append(float(_step(m, inp, actions, noise, t, gb)))
+        opt.step()
+    # the averaged weights are a different function than the trained ones, and the trained ones come back afterwards
+    l_train = float(_step(m, inp, actions, noise, t, None))
+    with avg.averaged_weights() as me:
+        l_avg = float(_step(me, inp, actions, noise, t, None))
+    assert l_avg != l_train and float(_step(m, inp, actions, noise, t, None)) == l_train
+    # resume in a fresh process-equivalent: new model from the ORIGINAL state dict + optimizer state from the checkpoint
+    m2, gb2, opt2 = fresh()
+    opt2.load_state_dict(ckpt)
+    l_res = []
+    for _ in range(2):
+        l_res.append(float(_step(m2, inp, actions, noise, t, gb2)))
+        opt2.step()
+    assert max(abs(a - b) for a, b in zip(l_cont, l_res)) < 1e-5 * max(l_cont), (l_cont, l_res)
+    assert rel_err(opt2.master, opt.master) < 1e-6

@@ -228,3 +228,30 @@ def test_adapter_formulas_match_reference_base_adapter():
                 else ours.denormalize_gaussian(a[:, :-1], stats["action"]["mean"][:-1], stats["action"]["std"][:-1]))
         assert np.allclose(got[:, :-1], want, rtol=1e-12, atol=1e-12)
         assert np.array_equal(got[:, -1], a[:, -1])          # the gripper dimension is passed through
+
+
+def test_cosine_warmup_schedule_matches_reference():
+    """train.CosineAnnealingWarmupRestarts against src/utils/optim.py:31-160 (the schedule both optimizers of the reference's
+    training loop step once per update, train.py:376-379), including restarts with cycle_mult / gamma."""
+    import importlib.util
+    import os
+    from types import SimpleNamespace
+    from open_pi_zero_b200.train import CosineAnnealingWarmupRestarts as Ours
+    ref_path = "/root/reference/src/utils/optim.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("/root/reference not present")
+    spec = importlib.util.spec_from_file_location("ref_optim", ref_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for kw in (dict(first_cycle_steps=50, max_lr=5e-5, min_lr=1e-8, warmup_steps=10),
+               dict(first_cycle_steps=20, cycle_mult=1.5, max_lr=1e-3, min_lr=1e-5, warmup_steps=3, gamma=0.7)):
+        ref_opt = SimpleNamespace(param_groups=[{"lr": 1.0}])
+        ref = mod.CosineAnnealingWarmupRestarts(ref_opt, **kw)
+        mine_opt = SimpleNamespace(groups={"action": {"lr": 1.0}})
+        mine = Ours(mine_opt, "action", **kw)
+        assert mine_opt.groups["action"]["lr"] == ref_opt.param_groups[0]["lr"]
+        for _ in range(130):
+            ref.step()
+            mine.step()
+            assert abs(mine_opt.groups["action"]["lr"] - ref_opt.param_groups[0]["lr"]) <= 1e-18 + 1e-12 * ref_opt.param_groups[0]["lr"]
+        assert mine.state_dict()["cycle"] == ref.state_dict()["cycle"]
