@@ -9,11 +9,16 @@ from .synth import init_state_dict, make_inputs, state_dict_spec
 
 __all__ = ["BRIDGE_DIMS", "PI0_PAPER_DIMS", "AttrDict", "cfg_from_dims", "dims_from_cfg",
            "make_dims", "init_state_dict", "make_inputs", "state_dict_spec", "PiZero",
-           "PiZeroInference", "JointModel", "KVCache", "FlowTimeSampler"]
+           "PiZeroInference", "JointModel", "KVCache", "TextKVCache", "FlowTimeSampler", "GradBuffer", "FusedAdamW",
+           "OverlappedAllReduce", "ModelAveraging", "CosineAnnealingWarmupRestarts", "flow_matching_step"]
 
 
 def __getattr__(name):   # lazy: importing the package must not need torch.cuda / the .so
-    if name in ("PiZero", "PiZeroInference", "JointModel", "KVCache", "PzError"):
+    if name in ("GradBuffer", "FusedAdamW", "OverlappedAllReduce", "ModelAveraging", "CosineAnnealingWarmupRestarts",
+                "flow_matching_step", "allreduce_gradients"):
+        from . import train
+        return getattr(train, name)
+    if name in ("PiZero", "PiZeroInference", "JointModel", "KVCache", "TextKVCache", "PzError"):
         from . import pizero
         return getattr(pizero, name)
     if name == "FlowTimeSampler":

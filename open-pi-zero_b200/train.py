@@ -80,7 +80,6 @@ class GradBuffer:
         dev = keep[0].device
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         base = self.flat.data_ptr()
-        assert base % 1024 == 0 or True
         # the pointer struct the C ABI reads
         g = _lib.PzWeights()
         for f in TOP_FIELDS:
