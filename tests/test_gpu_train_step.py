@@ -281,3 +281,33 @@ def test_optimizer_checkpoint_resume_and_weight_averaging():
         opt2.step()
     assert max(abs(a - b) for a, b in zip(l_cont, l_res)) < 1e-5 * max(l_cont), (l_cont, l_res)
     assert rel_err(opt2.master, opt.master) < 1e-6
+
+
+def test_multi_image_chunk10_joint_gradients_vs_oracle():
+    """Two images per observation and a 10-step action chunk (the geometry family of BASELINE configs[3]): loss and the
+    gradients of everything downstream of the embeddings (joint model, action encoder / decoder) against
+    `oracle.pizero_backward.flow_matching_backward` (its SigLIP part is single-image)."""
+    from open_pi_zero_b200.train import GradBuffer
+    d = pz.make_dims(SMALL, num_images=2, max_image_text_tokens=40, horizon_steps=10)
+    B = 2
+    sd = pz.init_state_dict(d, seed=29, randomize_norms=True, tie_proprio=False)
+    inp = pz.make_inputs(d, B, seed=41, min_text=2)
+    actions, noise, t = _targets(d, B, 15)
+    want_loss, want, _ = Bk.flow_matching_backward(sd, d, inp["input_ids"], inp["pixel_values"], inp["attention_mask"],
+                                                   inp["proprios"], actions, t, noise)
+    m = _model(d, sd, torch.float32)
+    gb = GradBuffer(m)
+    loss = _step(m, inp, actions, noise, t, gb)
+    assert abs(float(loss) - float(want_loss)) < 1e-4 * max(1.0, float(want_loss))
+    got = gb.unpack()
+    bad, checked = {}, 0
+    for k, g in want.items():
+        if float(g.abs().max()) == 0.0:
+            assert float(got[k].abs().max()) == 0.0, k
+            continue
+        e = rel_err(got[k], g)
+        checked += 1
+        if not e < 2e-3:
+            bad[k] = e
+    print(f"[train step 2 images, chunk 10] loss {float(loss):.6f} vs {float(want_loss):.6f}; {checked} tensors")
+    assert checked >= 50 and not bad, bad
