@@ -319,6 +319,31 @@ def allreduce_gradients(grads: GradBuffer, bucket_mb: int = 256, group=None, asy
     return works
 
 
+def bucket_ranges(entries, numel: int, L: int, LV: int, tied: bool):
+    """The slices of the flat gradient buffer that become final together, indexed like the events of
+    `pz_flow_matching_step` ([l] joint layer l, [L] the action heads, [L + 1 + i] SigLIP layer i, [L + 1 + LV] the rest), and
+    the order in which the backward finishes them.  Pure layout logic (CPU-testable): every element belongs to exactly one."""
+    offs = {key: off for key, off, _ in entries}
+    ends = [off for _, off, _ in entries][1:] + [numel]
+    end_of = {key: end for (key, _, _), end in zip(entries, ends)}
+
+    def span(first, last):
+        return (offs[first], end_of[last])
+
+    n = L + LV + 2
+    ranges = [[] for _ in range(n)]
+    mixes = ("vlm", "action") + (() if tied else ("proprio",))
+    for l in range(L):
+        ranges[l] = [span((m, l, MIX_FIELDS[0]), (m, l, MIX_FIELDS[-1])) for m in mixes]
+    ranges[L] = [span(("top", TOP_ACTION[0]), ("top", TOP_ACTION[-1]))]
+    for i in range(LV):
+        ranges[L + 1 + i] = [span(("vit", i, VIT_FIELDS[0]), ("vit", i, VIT_FIELDS[-1]))]
+    ranges[L + 1 + LV] = [span(("top", TOP_VLM[0]), ("top", TOP_VLM[-1]))]
+    order = list(range(L - 1, -1, -1)) + [L] + list(range(L + LV, L, -1)) + [L + 1 + LV]   # completion order
+    assert sum(hi - lo for r in ranges for lo, hi in r) == numel
+    return ranges, order
+
+
 class OverlappedAllReduce:
     """The gradient all-reduce of the data-parallel step, overlapped with the backward (what DDP's bucket hooks do for the
     reference, train.py:119-126): `pz_flow_matching_step` records one event per group of finished gradients (joint layer
@@ -341,23 +366,7 @@ class OverlappedAllReduce:
             for e in self.events:       # an event's handle exists after its first record
                 e.record()
         self.handles = (C.c_void_p * self.n)(*[e.cuda_event for e in self.events])
-        offs = {key: off for key, off, _ in grads.entries}
-        ends = [off for _, off, _ in grads.entries][1:] + [grads.numel]
-        end_of = {key: end for (key, _, _), end in zip(grads.entries, ends)}
-
-        def span(first, last):
-            return (offs[first], end_of[last])
-
-        self.ranges = [[] for _ in range(self.n)]
-        mixes = ("vlm", "action") + (() if grads.tied else ("proprio",))
-        for l in range(L):
-            self.ranges[l] = [span((m, l, MIX_FIELDS[0]), (m, l, MIX_FIELDS[-1])) for m in mixes]
-        self.ranges[L] = [span(("top", TOP_ACTION[0]), ("top", TOP_ACTION[-1]))]
-        for i in range(LV):
-            self.ranges[L + 1 + i] = [span(("vit", i, VIT_FIELDS[0]), ("vit", i, VIT_FIELDS[-1]))]
-        self.ranges[L + 1 + LV] = [span(("top", TOP_VLM[0]), ("top", TOP_VLM[-1]))]
-        self.order = list(range(L - 1, -1, -1)) + [L] + list(range(L + LV, L, -1)) + [L + 1 + LV]   # completion order
-        assert sum(hi - lo for r in self.ranges for lo, hi in r) == grads.numel
+        self.ranges, self.order = bucket_ranges(grads.entries, grads.numel, L, LV, grads.tied)
         self._works = []
 
     def launch(self):

@@ -168,3 +168,42 @@ def test_two_rank_data_parallel_training_step_overlapped_allreduce():
         rank, err, same = q.get(timeout=5)
         assert err < 1e-5, (rank, err)
         assert same
+
+
+def test_gradient_buckets_cover_the_flat_buffer_exactly_once():
+    """bucket_ranges (what OverlappedAllReduce all-reduces per 'gradients final' event): every element of the flat buffer in
+    exactly one bucket, buckets in the order the backward finishes them, for tied and untied proprio / action weights."""
+    from open_pi_zero_b200.train import MIX_FIELDS, TOP_ACTION, TOP_VLM, VIT_FIELDS, bucket_ranges
+    L, LV = 3, 2
+    for tied in (True, False):
+        entries, off = [], 0
+
+        def add(key, n):
+            nonlocal off
+            entries.append((key, off, (n,)))
+            off += (n + 255) // 256 * 256
+
+        for f in TOP_VLM:
+            add(("top", f), 100)
+        for i in range(LV):
+            for f in VIT_FIELDS:
+                add(("vit", i, f), 300 + i)
+        for mix in ("vlm",):
+            for l in range(L):
+                for f in MIX_FIELDS:
+                    add((mix, l, f), 1000 + l)
+        for f in TOP_ACTION:
+            add(("top", f), 64)
+        for mix in ("action",) + (() if tied else ("proprio",)):
+            for l in range(L):
+                for f in MIX_FIELDS:
+                    add((mix, l, f), 500 + l)
+        ranges, order = bucket_ranges(entries, off, L, LV, tied)
+        assert len(ranges) == L + LV + 2 and sorted(order) == list(range(L + LV + 2))
+        assert order[:L] == list(range(L - 1, -1, -1)) and order[L] == L and order[-1] == L + LV + 1
+        cover = torch.zeros(off, dtype=torch.int32)
+        for r in ranges:
+            for lo, hi in r:
+                cover[lo:hi] += 1
+        assert bool((cover == 1).all())
+        assert len(ranges[0]) == (2 if tied else 3)
