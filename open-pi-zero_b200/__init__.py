@@ -10,7 +10,7 @@ from .synth import init_state_dict, make_inputs, state_dict_spec
 __all__ = ["BRIDGE_DIMS", "PI0_PAPER_DIMS", "AttrDict", "cfg_from_dims", "dims_from_cfg",
            "make_dims", "init_state_dict", "make_inputs", "state_dict_spec", "PiZero",
            "PiZeroInference", "JointModel", "KVCache", "TextKVCache", "FlowTimeSampler", "GradBuffer", "FusedAdamW",
-           "OverlappedAllReduce", "ModelAveraging", "CosineAnnealingWarmupRestarts", "flow_matching_step"]
+           "OverlappedAllReduce", "ModelAveraging", "CosineAnnealingWarmupRestarts", "flow_matching_step", "VLAProcessor"]
 
 
 def __getattr__(name):   # lazy: importing the package must not need torch.cuda / the .so
@@ -21,6 +21,9 @@ def __getattr__(name):   # lazy: importing the package must not need torch.cuda 
     if name in ("PiZero", "PiZeroInference", "JointModel", "KVCache", "TextKVCache", "PzError"):
         from . import pizero
         return getattr(pizero, name)
+    if name == "VLAProcessor":
+        from .processing import VLAProcessor
+        return VLAProcessor
     if name == "FlowTimeSampler":
         from .flow import FlowTimeSampler
         return FlowTimeSampler

@@ -255,3 +255,81 @@ def test_cosine_warmup_schedule_matches_reference():
             mine.step()
             assert abs(mine_opt.groups["action"]["lr"] - ref_opt.param_groups[0]["lr"]) <= 1e-18 + 1e-12 * ref_opt.param_groups[0]["lr"]
         assert mine.state_dict()["cycle"] == ref.state_dict()["cycle"]
+
+
+class _StubTokenizer:
+    """A HuggingFace-shaped tokenizer (only what VLAProcessor touches): special / added tokens get ids, everything else is
+    tokenised per character; right padding to max_length with id 0."""
+    bos_token = "<bos>"
+
+    def __init__(self):
+        self.vocab = {"<pad>": 0, "<bos>": 2}
+        self.special = []
+        self.add_bos_token = self.add_eos_token = True
+        self.calls = []
+
+    def _add(self, toks):
+        for t in toks:
+            if t not in self.vocab:
+                self.vocab[t] = 1000 + len(self.vocab)
+                self.special.append(t)
+
+    def add_special_tokens(self, d):
+        self._add(d["additional_special_tokens"])
+
+    def add_tokens(self, toks):
+        self._add(toks)
+
+    def convert_tokens_to_ids(self, t):
+        return self.vocab[t]
+
+    def __call__(self, strings, return_tensors, max_length, padding, truncation):
+        import torch
+        self.calls.append(dict(return_tensors=return_tensors, max_length=max_length, padding=padding, truncation=truncation))
+        specials = sorted(self.special + ["<bos>"], key=len, reverse=True)
+        ids = []
+        for s in strings:
+            row, i = [], 0
+            while i < len(s):
+                for sp in specials:
+                    if s.startswith(sp, i):
+                        row.append(self.vocab[sp]); i += len(sp)
+                        break
+                else:
+                    row.append(3 + ord(s[i]) % 200); i += 1
+            row = row[:max_length] if truncation else row
+            ids.append(row)
+        n = max_length if padding == "max_length" else max(len(r) for r in ids)
+        mask = [[1] * len(r) + [0] * (n - len(r)) for r in ids]
+        ids = [r + [0] * (n - len(r)) for r in ids]
+        return {"input_ids": torch.tensor(ids), "attention_mask": torch.tensor(mask)}
+
+
+def test_vla_processor_matches_reference():
+    """processing.VLAProcessor against src/model/vla/processing.py:63-136 with the same stub tokenizer: identical prompt strings /
+    ids / masks / pixel values and identical tokenizer arguments; keep_uint8 hands the frames through untouched."""
+    import importlib.util
+    import os
+    import torch
+    from open_pi_zero_b200.processing import VLAProcessor as Ours
+    ref_path = "/root/reference/src/model/vla/processing.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("/root/reference not present")
+    spec = importlib.util.spec_from_file_location("ref_processing", ref_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (2, 3, 28, 28), generator=g, dtype=torch.uint8)
+    text = ["put the carrot on the plate", "open the drawer"]
+    for padding in ("max_length", "longest"):
+        t_ref, t_ours = _StubTokenizer(), _StubTokenizer()
+        ref = mod.VLAProcessor(t_ref, num_image_tokens=4, max_seq_len=48, tokenizer_padding=padding)
+        ours = Ours(t_ours, num_image_tokens=4, max_seq_len=48, tokenizer_padding=padding)
+        a, b = ref(text=text, images=images), ours(text=text, images=images)
+        assert set(a) == set(b) and ours.image_token_id == ref.image_token_id
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        assert t_ref.calls == t_ours.calls and t_ours.add_bos_token is False and t_ours.add_eos_token is False
+        assert int((b["input_ids"][0] == ours.image_token_id).sum()) == 4 and bool((b["input_ids"][:, :4] == ours.image_token_id).all())
+    raw = Ours(_StubTokenizer(), num_image_tokens=4, max_seq_len=48, keep_uint8=True)(text=text, images=images)
+    assert raw["pixel_values"].dtype == torch.uint8 and torch.equal(raw["pixel_values"], images)
