@@ -333,3 +333,23 @@ def test_vla_processor_matches_reference():
         assert int((b["input_ids"][0] == ours.image_token_id).sum()) == 4 and bool((b["input_ids"][:, :4] == ours.image_token_id).all())
     raw = Ours(_StubTokenizer(), num_image_tokens=4, max_seq_len=48, keep_uint8=True)(text=text, images=images)
     assert raw["pixel_values"].dtype == torch.uint8 and torch.equal(raw["pixel_values"], images)
+
+
+def test_action_accuracy_matches_reference_metric():
+    import importlib.util
+    import os
+    import torch
+    from open_pi_zero_b200.metric import eval_stats, get_action_accuracy
+    ref_path = "/root/reference/src/utils/metric.py"
+    g = torch.Generator().manual_seed(0)
+    gt = torch.rand((6, 4, 7), generator=g) * 2 - 1
+    pred = gt + 0.12 * torch.randn((6, 4, 7), generator=g)
+    ours = get_action_accuracy(gt, pred, [0.1, 0.2, 0.5])
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_metric", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert torch.equal(ours, mod.get_action_accuracy(gt, pred, [0.1, 0.2, 0.5]))
+    assert ours[0] <= ours[1] <= ours[2] and 0.0 < float(ours[2]) <= 1.0
+    acc, l1 = eval_stats([pred, pred], [gt, gt], [0.1, 0.2, 0.5])
+    assert torch.allclose(acc, ours) and abs(float(l1) - float((pred - gt).abs().mean())) < 1e-7
