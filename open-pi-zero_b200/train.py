@@ -539,3 +539,41 @@ class ModelAveraging:
         if self.avg is None:
             return {}
         return dict(averaged=self.avg, n_averaged=self.n_averaged, model_type="ema" if self.use_ema else "swa")
+
+
+def preprocess_batch(model, processor, batch: dict, dtype: torch.dtype, device, split_mask: bool, sample_fm_time: bool,
+                     time_sampler=None, dense_masks: bool = True) -> dict:
+    """`TrainAgent.run`'s `preprocess_batch` closure (train.py:271-313): the dataloader's batch (`observation.image_primary`
+    [B, T, H, W, C] uint8, `observation.proprio`, `action`, `task.language_instruction` as bytes) -> the keyword arguments of
+    `PiZero.forward` (`split_mask=False`) or `infer_action` (`split_mask=True`).  `dense_masks=False` is the B200-native form:
+    instead of the O(B S^2) additive masks and the three position-id tensors (which the kernels reduce back to one integer
+    per sample) it returns `valid_len` [B] -- what `flow_matching_step(valid_len=...)` / `infer_action(valid_len=...)` take.
+    `processor`: `processing.VLAProcessor` (with `keep_uint8=True` the frames stay uint8 and are normalised on the device)."""
+    images = batch["observation"]["image_primary"]
+    proprios = batch["observation"]["proprio"]
+    actions = batch["action"].squeeze(1)                                   # remove the time dimension
+    texts = [t.decode("utf-8") if isinstance(t, (bytes, bytearray)) else str(t) for t in batch["task"]["language_instruction"]]
+    B, T, Hh, Ww, Cc = images.shape
+    images = images.permute(0, 1, 4, 2, 3).reshape(B, T * Cc, Hh, Ww)      # "B T H W C -> B (T C) H W"
+    model_inputs = processor(text=texts, images=images)
+    pix = model_inputs["pixel_values"]
+    inputs = {"input_ids": model_inputs["input_ids"],
+              "pixel_values": pix if pix.dtype == torch.uint8 else pix.to(dtype),
+              "proprios": proprios.to(dtype), "actions": actions.to(dtype)}
+    if dense_masks:
+        causal_mask, vlm_pos, proprio_pos, action_pos = model.build_causal_mask_and_position_ids(model_inputs["attention_mask"], dtype)
+        inputs.update(vlm_position_ids=vlm_pos, proprio_position_ids=proprio_pos, action_position_ids=action_pos)
+        if split_mask:
+            inputs["image_text_proprio_mask"], inputs["action_mask"] = model.split_full_mask_into_submasks(causal_mask)
+        else:
+            inputs["causal_mask"] = causal_mask
+    else:
+        inputs["valid_len"] = model_inputs["attention_mask"].sum(dim=1).to(torch.int32)
+    if sample_fm_time:
+        inputs["t"] = (time_sampler or _default_time_sampler()).sample_fm_time(len(texts)).to(dtype)
+    return {k: v.to(device) for k, v in inputs.items()}
+
+
+def _default_time_sampler():
+    from .flow import FlowTimeSampler
+    return FlowTimeSampler("beta")

@@ -353,3 +353,40 @@ def test_action_accuracy_matches_reference_metric():
     assert ours[0] <= ours[1] <= ours[2] and 0.0 < float(ours[2]) <= 1.0
     acc, l1 = eval_stats([pred, pred], [gt, gt], [0.1, 0.2, 0.5])
     assert torch.allclose(acc, ours) and abs(float(l1) - float((pred - gt).abs().mean())) < 1e-7
+
+
+def test_preprocess_batch_mirrors_the_training_loop_closure():
+    """train.preprocess_batch (train.py:271-313): same keys / shapes / values as composing the processor, the mask builder and
+    the time sampler by hand; `dense_masks=False` returns valid_len = the number of image + text tokens."""
+    import torch
+    from open_pi_zero_b200.pizero import PiZero
+    from open_pi_zero_b200.processing import VLAProcessor
+    from open_pi_zero_b200.train import preprocess_batch
+    # a parameter-free stand-in for the model: only the mask builders are used
+    class M:
+        max_image_text_tokens, num_proprio_tokens, num_action_tokens, total_num_tokens = 48, 1, 4, 53
+        build_causal_mask_and_position_ids = PiZero.build_causal_mask_and_position_ids
+        split_full_mask_into_submasks = PiZero.split_full_mask_into_submasks
+    m = M()
+    proc = VLAProcessor(_StubTokenizer(), num_image_tokens=4, max_seq_len=48)
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    batch = {"observation": {"image_primary": torch.randint(0, 256, (B, 1, 28, 28, 3), generator=g, dtype=torch.uint8),
+                             "proprio": torch.rand((B, 1, 7), generator=g)},
+             "action": torch.rand((B, 1, 4, 7), generator=g),
+             "task": {"language_instruction": [b"pick up the spoon", b"open the drawer", b"move left"]}}
+    out = preprocess_batch(m, proc, batch, torch.float32, "cpu", split_mask=False, sample_fm_time=True)
+    assert set(out) == {"input_ids", "pixel_values", "vlm_position_ids", "proprio_position_ids", "action_position_ids", "proprios",
+                        "actions", "causal_mask", "t"}
+    assert out["pixel_values"].shape == (B, 3, 28, 28) and out["actions"].shape == (B, 4, 7) and out["t"].shape == (B,)
+    assert out["causal_mask"].shape == (B, 1, 53, 53)
+    want = proc(text=["pick up the spoon", "open the drawer", "move left"], images=batch["observation"]["image_primary"][:, 0].permute(0, 3, 1, 2))
+    assert torch.equal(out["input_ids"], want["input_ids"]) and torch.equal(out["pixel_values"], want["pixel_values"])
+    inf = preprocess_batch(m, proc, batch, torch.float32, "cpu", split_mask=True, sample_fm_time=False)
+    assert "image_text_proprio_mask" in inf and inf["image_text_proprio_mask"].shape == (B, 1, 49, 49) and inf["action_mask"].shape == (B, 1, 4, 53)
+    lean = preprocess_batch(m, VLAProcessor(_StubTokenizer(), 4, 48, keep_uint8=True), batch, torch.float32, "cpu", split_mask=True,
+                            sample_fm_time=False, dense_masks=False)
+    assert lean["pixel_values"].dtype == torch.uint8 and "action_mask" not in lean
+    assert torch.equal(lean["valid_len"], want["attention_mask"].sum(1).to(torch.int32))
+    # the dense mask's row 0 encodes exactly that count
+    assert torch.equal((out["causal_mask"][:, 0, 0, :48] == 0).sum(-1).to(torch.int32), lean["valid_len"])
