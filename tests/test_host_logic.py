@@ -390,3 +390,33 @@ def test_preprocess_batch_mirrors_the_training_loop_closure():
     assert torch.equal(lean["valid_len"], want["attention_mask"].sum(1).to(torch.int32))
     # the dense mask's row 0 encodes exactly that count
     assert torch.equal((out["causal_mask"][:, 0, 0, :48] == 0).sum(-1).to(torch.int32), lean["valid_len"])
+
+
+def test_c_abi_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/pz_b200.h is the drop-in boundary: it must compile as C99 and as C++17, and a C program that references every
+    declared entry point must link against libpz_b200.so (no compute call: no GPU here)."""
+    import re
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    from open_pi_zero_b200 import _lib
+    header = os.path.join(ROOT, "include", "pz_b200.h")
+    for cmd in (["gcc", "-std=c99", "-fsyntax-only", "-x", "c", header], ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", header]):
+        assert subprocess.run(cmd, capture_output=True).returncode == 0, cmd
+    lib = os.path.join(ROOT, "open-pi-zero_b200", "libpz_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    names = sorted(set(re.findall(r"\b(pz_[a-z0-9_]+)\s*\(", open(header).read())))
+    src = tmp_path / "link.c"
+    src.write_text('#include "pz_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void *p[] = {' +
+                   ", ".join(f"(const void *)&{n}" for n in names) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof(p) / sizeof(p[0])), pz_abi_version());\n  return 0;\n}\n')
+    exe = tmp_path / "link"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), lib,
+                        "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    n, ver = out.stdout.split()
+    assert int(n) == len(names) == len(_lib.EXPORTS) and int(ver) == _lib.PZ_ABI_VERSION
