@@ -225,6 +225,12 @@ def flow_matching_step(model, input_ids, pixel_values, proprios, actions, t, *, 
     return loss
 
 
+def release_training_workspace(model) -> None:
+    """Free the activation workspace `flow_matching_step` keeps on the model between steps (29 GB at 32 samples of the bridge
+    shape), e.g. before a large-batch validation `infer_action`."""
+    model.__dict__.pop("_train_ws", None)
+
+
 class FusedAdamW:
     """clip_grad_norm_ + the two AdamW optimizers of the reference's training loop (train.py:171-199, 371-379) as ONE fused
     pass per parameter group over the flat buffers: fp32 master weights and moments in the GradBuffer layout, the updated
